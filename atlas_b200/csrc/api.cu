@@ -1,0 +1,573 @@
+// C ABI of the B200 spectral-transform engine (include/sptrans_b200.h).
+// Orchestration only: plan life cycle, workspaces, host<->device staging, stage sequencing and timing.
+// There is no CPU path: without a CUDA device every entry point returns SPTRANS_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "plan.hpp"
+
+struct sptrans_plan {
+    sptrans::Plan p;
+};
+
+namespace sptrans {
+int launch_merge_uv_scalar(cudaStream_t s, int T, int nvd, int nsc, const double* d_vor, const double* d_div,
+                           const double* d_sc, double* d_all, uint64_t* launches);
+}
+
+using namespace sptrans;
+
+namespace {
+
+bool is_device_pointer(const void* ptr) {
+    if (!ptr) return false;
+    cudaPointerAttributes at{};
+    cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int ensure(double*& buf, size_t& cap, size_t need_doubles) {
+    if (need_doubles <= cap && buf) return SPTRANS_OK;
+    if (buf) cudaFree(buf);
+    buf = nullptr;
+    cap = 0;
+    SPT_CUDA(cudaMalloc(&buf, std::max<size_t>(need_doubles, 2) * sizeof(double)));
+    cap = need_doubles;
+    return SPTRANS_OK;
+}
+
+template <class T>
+int upload(T*& dptr, const std::vector<T>& h, cudaStream_t s) {
+    SPT_CUDA(cudaMalloc(&dptr, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    SPT_CUDA(cudaMemcpyAsync(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return SPTRANS_OK;
+}
+
+size_t packed_doubles(const Plan& p, int nf) { return static_cast<size_t>(p.g.sp_rowoff.back()) * 2 * nf; }
+size_t fourier_doubles(const Plan& p, int nf) {
+    // + one tile of slack rows so that masked tile loads never form addresses past the allocation
+    return (static_cast<size_t>(p.g.fb_rowoff.back()) + kBM) * 2 * nf;
+}
+size_t spec_doubles(const Plan& p, int nf, int trunc) { return static_cast<size_t>(trunc + 1) * (trunc + 2) * nf; }
+
+struct StageTimer {
+    Plan& p;
+    explicit StageTimer(Plan& pl): p(pl) {
+        for (float& t : p.t_ms) t = 0.f;
+    }
+    void mark(int i) { cudaEventRecord(p.ev[i], p.stream); }
+    void finish(int n_marks, const int* slot) {
+        cudaStreamSynchronize(p.stream);
+        for (int i = 0; i + 1 < n_marks; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
+            p.t_ms[slot[i]] += ms;
+        }
+    }
+};
+
+int check_plan(sptrans_plan* plan) {
+    if (!plan) {
+        set_error("null plan");
+        return SPTRANS_ERR_INVALID;
+    }
+    SPT_CUDA(cudaSetDevice(plan->p.device));
+    return SPTRANS_OK;
+}
+
+// inverse transform of `nf` fields whose spectra sit on the device at truncation `trunc` (T or T+1)
+int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, int nb_uv, StageTimer& tm,
+                int& marks, int* slots) {
+    int rc = build_tiles(p, nf, trunc);
+    if (rc) return rc;
+    rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf));
+    if (rc) return rc;
+    rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nf));
+    if (rc) return rc;
+    tm.mark(marks);
+    rc = launch_pack_spectra(p, nf, trunc, d_spec, p.d_packed);
+    if (rc) return rc;
+    slots[marks++] = 0;
+    tm.mark(marks);
+    rc = launch_legendre_inv(p, nf, p.d_packed, p.d_fourier);
+    if (rc) return rc;
+    slots[marks++] = 1;
+    tm.mark(marks);
+    rc = launch_fourier_inv(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, d_gp, nb_uv);
+    if (rc) return rc;
+    slots[marks++] = 2;
+    tm.mark(marks);
+    return SPTRANS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sptrans_last_error(void) { return last_error_cstr(); }
+
+int sptrans_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int sptrans_gaussian_latitudes(int N, double* lat_deg_2N, double* weights_2N) {
+    if (N < 1 || !lat_deg_2N || !weights_2N) {
+        set_error("sptrans_gaussian_latitudes: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    gaussian_quadrature(N, lat_deg_2N, weights_2N);
+    return SPTRANS_OK;
+}
+
+int sptrans_octahedral_nx(int N, int* nx_2N) {
+    if (N < 1 || !nx_2N) {
+        set_error("sptrans_octahedral_nx: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    for (int j = 0; j < N; ++j) nx_2N[j] = nx_2N[2 * N - 1 - j] = 20 + 4 * j;
+    return SPTRANS_OK;
+}
+
+int sptrans_fourier_truncation(int truncation, int nx, int nxmax, int ndgl, double lat_rad, int fullgrid) {
+    return fourier_truncation(truncation, nx, nxmax, ndgl, lat_rad, fullgrid != 0);
+}
+
+int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, const double* lat_deg,
+                                const double* weights, int truncation, unsigned flags, int device, int rank,
+                                int nranks) {
+    if (!out) {
+        set_error("sptrans_plan_create: null output pointer");
+        return SPTRANS_ERR_INVALID;
+    }
+    *out = nullptr;
+    int ndev = sptrans_device_count();
+    if (ndev <= 0) {
+        set_error("sptrans_plan_create: no CUDA device visible (this engine has no CPU fallback)");
+        return SPTRANS_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("sptrans_plan_create: bad device ordinal");
+        return SPTRANS_ERR_INVALID;
+    }
+    sptrans_plan* sp = new (std::nothrow) sptrans_plan();
+    if (!sp) {
+        set_error("out of host memory");
+        return SPTRANS_ERR_INVALID;
+    }
+    Plan& p = sp->p;
+    p.device = device;
+    p.flags = flags;
+    int rc = build_geometry(p.g, nlat, nx, lat_deg, weights, truncation, (flags & SPTRANS_GRID_REGULAR) != 0, rank,
+                            nranks);
+    if (rc) {
+        delete sp;
+        return rc;
+    }
+    auto fail = [&](int code) {
+        sptrans_plan_destroy(sp);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) {
+        set_error("cudaSetDevice failed");
+        return fail(SPTRANS_ERR_CUDA);
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p.num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        return fail(SPTRANS_ERR_CUDA);
+    }
+    p.own_stream = true;
+    for (auto& e : p.ev) cudaEventCreate(&e);
+    HostGeom& g = p.g;
+    if ((rc = upload(p.d_nlat0, g.nlat0, p.stream))) return fail(rc);
+    if ((rc = upload(p.d_fb_rowoff, g.fb_rowoff, p.stream))) return fail(rc);
+    if ((rc = upload(p.d_sp_rowoff, g.sp_rowoff, p.stream))) return fail(rc);
+    if ((rc = upload(p.d_rowoff, g.rowoff, p.stream))) return fail(rc);
+    if ((rc = upload(p.d_nx, g.nx, p.stream))) return fail(rc);
+    if ((rc = upload(p.d_my_m, g.my_m, p.stream))) return fail(rc);
+    {
+        std::vector<double> ci(g.nleg), c(g.nleg);
+        for (int j = 0; j < g.nleg; ++j) {
+            double lat = g.lat_deg[j];
+            const double pole = 89.9999999;  // TransLocal.cc:49, :1449-1455
+            if (lat > pole) lat = pole;
+            if (lat < -pole) lat = -pole;
+            c[j] = std::cos(lat * (M_PI / 180.));
+            ci[j] = 1. / c[j];
+        }
+        if ((rc = upload(p.d_coslatinv, ci, p.stream))) return fail(rc);
+        if ((rc = upload(p.d_coslat, c, p.stream))) return fail(rc);
+        if (!g.weights.empty()) {
+            std::vector<double> w(g.weights.begin(), g.weights.begin() + g.nleg);
+            if ((rc = upload(p.d_weights, w, p.stream))) return fail(rc);
+        }
+    }
+    if (cudaMalloc(&p.d_tile_counter, sizeof(int)) != cudaSuccess) {
+        set_error("cudaMalloc failed");
+        return fail(SPTRANS_ERR_CUDA);
+    }
+    if ((rc = generate_legendre_table(p))) return fail(rc);
+    if ((rc = build_fft_tables(p))) return fail(rc);
+    if (cudaStreamSynchronize(p.stream) != cudaSuccess) {
+        set_error(std::string("plan setup failed: ") + cudaGetErrorString(cudaGetLastError()));
+        return fail(SPTRANS_ERR_CUDA);
+    }
+    *out = sp;
+    return SPTRANS_OK;
+}
+
+int sptrans_plan_create(sptrans_plan** plan, int nlat, const int* nx, const double* lat_deg, const double* weights,
+                        int truncation, unsigned flags, int device) {
+    return sptrans_plan_create_sharded(plan, nlat, nx, lat_deg, weights, truncation, flags, device, 0, 1);
+}
+
+int sptrans_plan_destroy(sptrans_plan* sp) {
+    if (!sp) return SPTRANS_OK;
+    Plan& p = sp->p;
+    cudaSetDevice(p.device);
+    if (p.stream) cudaStreamSynchronize(p.stream);
+    free_fft_tables(p);
+    void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_weights,
+                    p.d_coslatinv, p.d_coslat, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
+                    p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
+                    p.d_gp};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    if (p.h_pinned) cudaFreeHost(p.h_pinned);
+    for (auto& e : p.ev)
+        if (e) cudaEventDestroy(e);
+    if (p.own_stream && p.stream) cudaStreamDestroy(p.stream);
+    delete sp;
+    return SPTRANS_OK;
+}
+
+int sptrans_truncation(const sptrans_plan* plan) { return plan ? plan->p.g.T : -1; }
+size_t sptrans_nb_gridpoints(const sptrans_plan* plan) { return plan ? static_cast<size_t>(plan->p.g.npts) : 0; }
+size_t sptrans_nb_spectral_coefficients(const sptrans_plan* plan) {
+    return plan ? static_cast<size_t>(plan->p.g.T + 1) * (plan->p.g.T + 2) : 0;
+}
+int sptrans_get_nlat0(const sptrans_plan* plan, int* nlat0) {
+    if (!plan || !nlat0) return SPTRANS_ERR_INVALID;
+    std::copy(plan->p.g.nlat0.begin(), plan->p.g.nlat0.begin() + plan->p.g.T + 1, nlat0);
+    return SPTRANS_OK;
+}
+size_t sptrans_device_bytes(const sptrans_plan* plan) {
+    if (!plan) return 0;
+    const Plan& p = plan->p;
+    return p.bytes_tables + (p.packed_cap + p.fourier_cap + p.spec_cap + p.spec2_cap + p.gp_cap) * sizeof(double);
+}
+
+size_t sptrans_legendre_cache_size(const sptrans_plan* plan) {
+    return plan ? legendre_cache_doubles(plan->p.g) * sizeof(double) : 0;
+}
+int sptrans_export_legendre_cache(const sptrans_plan* plan, void* out) {
+    if (!plan || !out) {
+        set_error("sptrans_export_legendre_cache: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    SPT_CUDA(cudaSetDevice(plan->p.device));
+    return export_legendre_cache(plan->p, static_cast<double*>(out));
+}
+
+int sptrans_set_stream(sptrans_plan* plan, void* cuda_stream) {
+    if (!plan) return SPTRANS_ERR_INVALID;
+    Plan& p = plan->p;
+    if (p.own_stream && p.stream) {
+        cudaStreamSynchronize(p.stream);
+        cudaStreamDestroy(p.stream);
+    }
+    p.stream = static_cast<cudaStream_t>(cuda_stream);
+    p.own_stream = false;
+    return SPTRANS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int sptrans_invtrans_scalar(sptrans_plan* plan, int nf, const double* spectra, double* gp) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf < 0 || (nf > 0 && (!spectra || !gp))) {
+        set_error("sptrans_invtrans_scalar: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (nf == 0) return SPTRANS_OK;  // reference: `if (nb_scalar_fields > 0)` TransLocal.cc:1412
+    if (p.g.nranks != 1) {
+        set_error("whole-transform entry points need an unsharded plan; use the stage-level API");
+        return SPTRANS_ERR_INVALID;
+    }
+    const int T = p.g.T;
+    StageTimer tm(p);
+    int marks = 0, slots[8];
+    const double* d_spec = spectra;
+    double* d_gp = gp;
+    const bool spec_host = !is_device_pointer(spectra), gp_host = !is_device_pointer(gp);
+    const size_t nspec = spec_doubles(p, nf, T), ngp = static_cast<size_t>(p.g.npts) * nf;
+    if (spec_host) {
+        if ((rc = ensure(p.d_spec, p.spec_cap, nspec))) return rc;
+        tm.mark(marks);
+        SPT_CUDA(cudaMemcpyAsync(p.d_spec, spectra, nspec * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+        slots[marks++] = 3;
+        d_spec = p.d_spec;
+    }
+    if (gp_host) {
+        if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
+        d_gp = p.d_gp;
+    }
+    if ((rc = run_inverse(p, nf, T, d_spec, d_gp, 0, tm, marks, slots))) return rc;
+    if (gp_host) {
+        SPT_CUDA(cudaMemcpyAsync(gp, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+        slots[marks++] = 4;
+        tm.mark(marks);
+    }
+    tm.finish(marks + 1, slots);
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int sptrans_invtrans(sptrans_plan* plan, int nsc, const double* scalar_spectra, int nvd, const double* vor,
+                     const double* div, double* gp) {
+    if (nvd <= 0) {
+        // reference :1591-1596: scalars only, written at gp + 2*nb_gp*nb_vordiv_fields (= gp)
+        return sptrans_invtrans_scalar(plan, nsc, scalar_spectra, gp);
+    }
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nsc < 0 || !vor || !div || !gp || (nsc > 0 && !scalar_spectra)) {
+        set_error("sptrans_invtrans: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (p.g.nranks != 1) {
+        set_error("whole-transform entry points need an unsharded plan; use the stage-level API");
+        return SPTRANS_ERR_INVALID;
+    }
+    const int T = p.g.T;
+    const int nall = 2 * nvd + nsc;
+    StageTimer tm(p);
+    int marks = 0, slots[8];
+    const size_t nvd_spec = spec_doubles(p, nvd, T), nsc_spec = spec_doubles(p, nsc, T);
+    const size_t ngp = static_cast<size_t>(p.g.npts) * nall;
+    // stage inputs: [vor | div | scalars] in d_spec2 when they live on the host
+    const double *d_vor = vor, *d_div = div, *d_sc = scalar_spectra;
+    const bool in_host = !is_device_pointer(vor);
+    if (in_host) {
+        if ((rc = ensure(p.d_spec2, p.spec2_cap, 2 * nvd_spec + nsc_spec))) return rc;
+        tm.mark(marks);
+        SPT_CUDA(cudaMemcpyAsync(p.d_spec2, vor, nvd_spec * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+        SPT_CUDA(cudaMemcpyAsync(p.d_spec2 + nvd_spec, div, nvd_spec * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+        if (nsc > 0)
+            SPT_CUDA(cudaMemcpyAsync(p.d_spec2 + 2 * nvd_spec, scalar_spectra, nsc_spec * sizeof(double),
+                                     cudaMemcpyHostToDevice, p.stream));
+        slots[marks++] = 3;
+        d_vor = p.d_spec2;
+        d_div = p.d_spec2 + nvd_spec;
+        d_sc = p.d_spec2 + 2 * nvd_spec;
+    }
+    if ((rc = ensure(p.d_spec, p.spec_cap, spec_doubles(p, nall, T + 1)))) return rc;
+    tm.mark(marks);
+    if ((rc = launch_merge_uv_scalar(p.stream, T, nvd, nsc, d_vor, d_div, d_sc, p.d_spec, &p.launches))) return rc;
+    slots[marks++] = 0;
+    double* d_gp = gp;
+    const bool gp_host = !is_device_pointer(gp);
+    if (gp_host) {
+        if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
+        d_gp = p.d_gp;
+    }
+    if ((rc = run_inverse(p, nall, T + 1, p.d_spec, d_gp, 2 * nvd, tm, marks, slots))) return rc;
+    if (gp_host) {
+        SPT_CUDA(cudaMemcpyAsync(gp, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+        slots[marks++] = 4;
+        tm.mark(marks);
+    }
+    tm.finish(marks + 1, slots);
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int sptrans_invtrans_vordiv2wind(sptrans_plan* plan, int nvd, const double* vor, const double* div, double* gp) {
+    return sptrans_invtrans(plan, 0, nullptr, nvd, vor, div, gp);  // reference :1488-1492
+}
+
+int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double* spectra) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf < 0 || (nf > 0 && (!spectra || !gp))) {
+        set_error("sptrans_dirtrans_scalar: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (nf == 0) return SPTRANS_OK;
+    if (p.g.nranks != 1) {
+        set_error("whole-transform entry points need an unsharded plan; use the stage-level API");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (!p.d_weights) {
+        set_error("sptrans_dirtrans_scalar: plan was created without quadrature weights");
+        return SPTRANS_ERR_INVALID;
+    }
+    const int T = p.g.T;
+    StageTimer tm(p);
+    int marks = 0, slots[8];
+    const bool spec_host = !is_device_pointer(spectra), gp_host = !is_device_pointer(gp);
+    const size_t nspec = spec_doubles(p, nf, T), ngp = static_cast<size_t>(p.g.npts) * nf;
+    const double* d_gp = gp;
+    double* d_spec = spectra;
+    if (gp_host) {
+        if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
+        tm.mark(marks);
+        SPT_CUDA(cudaMemcpyAsync(p.d_gp, gp, ngp * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+        slots[marks++] = 3;
+        d_gp = p.d_gp;
+    }
+    if (spec_host) {
+        if ((rc = ensure(p.d_spec, p.spec_cap, nspec))) return rc;
+        d_spec = p.d_spec;
+    }
+    if ((rc = build_tiles(p, nf, T))) return rc;
+    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
+    if ((rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nf)))) return rc;
+    tm.mark(marks);
+    if ((rc = launch_fourier_dir(p, nf, d_gp, p.d_fourier, 0))) return rc;
+    slots[marks++] = 2;
+    tm.mark(marks);
+    if ((rc = launch_legendre_dir(p, nf, p.d_fourier, p.d_packed))) return rc;
+    slots[marks++] = 1;
+    tm.mark(marks);
+    if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spec))) return rc;
+    slots[marks++] = 0;
+    tm.mark(marks);
+    if (spec_host) {
+        SPT_CUDA(cudaMemcpyAsync(spectra, d_spec, nspec * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+        slots[marks++] = 4;
+        tm.mark(marks);
+    }
+    tm.finish(marks + 1, slots);
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int sptrans_vordiv_to_uv(int truncation, int nf, const double* vor, const double* div, double* U, double* V,
+                         int device) {
+    if (truncation < 0 || nf < 0 || !vor || !div || !U || !V) {
+        set_error("sptrans_vordiv_to_uv: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (sptrans_device_count() <= 0) {
+        set_error("sptrans_vordiv_to_uv: no CUDA device visible (this engine has no CPU fallback)");
+        return SPTRANS_ERR_CUDA;
+    }
+    SPT_CUDA(cudaSetDevice(device));
+    const size_t n = static_cast<size_t>(truncation + 1) * (truncation + 2) * nf;
+    if (n == 0) return SPTRANS_OK;
+    const bool host = !is_device_pointer(vor);
+    double* buf = nullptr;
+    const double *d_vor = vor, *d_div = div;
+    double *d_U = U, *d_V = V;
+    if (host) {
+        SPT_CUDA(cudaMalloc(&buf, 4 * n * sizeof(double)));
+        SPT_CUDA(cudaMemcpy(buf, vor, n * sizeof(double), cudaMemcpyHostToDevice));
+        SPT_CUDA(cudaMemcpy(buf + n, div, n * sizeof(double), cudaMemcpyHostToDevice));
+        d_vor = buf;
+        d_div = buf + n;
+        d_U = buf + 2 * n;
+        d_V = buf + 3 * n;
+    }
+    int rc = launch_vd2uv(nullptr, truncation, nf, d_vor, d_div, d_U, d_V, nullptr);
+    if (rc) {
+        if (buf) cudaFree(buf);
+        return rc;
+    }
+    SPT_CUDA(cudaDeviceSynchronize());
+    if (host) {
+        SPT_CUDA(cudaMemcpy(U, d_U, n * sizeof(double), cudaMemcpyDeviceToHost));
+        SPT_CUDA(cudaMemcpy(V, d_V, n * sizeof(double), cudaMemcpyDeviceToHost));
+        cudaFree(buf);
+    }
+    return SPTRANS_OK;
+}
+
+// ---- stage-level API ---------------------------------------------------------------------------------
+size_t sptrans_fourier_elems_per_field(const sptrans_plan* plan) {
+    return plan ? static_cast<size_t>(plan->p.g.fb_rowoff.back()) + kBM : 0;
+}
+
+int sptrans_invtrans_legendre(sptrans_plan* plan, int nf, int trunc, const double* d_spectra, double* d_fourier) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf <= 0 || !d_spectra || !d_fourier || (trunc != p.g.T && trunc != p.g.T + 1)) {
+        set_error("sptrans_invtrans_legendre: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if ((rc = build_tiles(p, nf, trunc))) return rc;
+    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
+    if ((rc = launch_pack_spectra(p, nf, trunc, d_spectra, p.d_packed))) return rc;
+    if ((rc = launch_legendre_inv(p, nf, p.d_packed, d_fourier))) return rc;
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    return SPTRANS_OK;
+}
+
+int sptrans_invtrans_fourier(sptrans_plan* plan, int nf, int mlimit, const double* d_fourier, double* d_gp,
+                             int nb_uv) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf <= 0 || !d_fourier || !d_gp) {
+        set_error("sptrans_invtrans_fourier: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if ((rc = launch_fourier_inv(p, nf, mlimit, d_fourier, d_gp, nb_uv))) return rc;
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    return SPTRANS_OK;
+}
+
+int sptrans_dirtrans_fourier(sptrans_plan* plan, int nf, const double* d_gp, double* d_fourier, int nb_uv) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf <= 0 || !d_fourier || !d_gp) {
+        set_error("sptrans_dirtrans_fourier: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if ((rc = launch_fourier_dir(p, nf, d_gp, d_fourier, nb_uv))) return rc;
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    return SPTRANS_OK;
+}
+
+int sptrans_dirtrans_legendre(sptrans_plan* plan, int nf, const double* d_fourier, double* d_spectra) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf <= 0 || !d_fourier || !d_spectra) {
+        set_error("sptrans_dirtrans_legendre: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if ((rc = build_tiles(p, nf, p.g.T))) return rc;
+    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
+    if ((rc = launch_legendre_dir(p, nf, d_fourier, p.d_packed))) return rc;
+    if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spectra))) return rc;
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    return SPTRANS_OK;
+}
+
+int sptrans_last_timings(const sptrans_plan* plan, float out_ms[8]) {
+    if (!plan || !out_ms) return SPTRANS_ERR_INVALID;
+    std::memcpy(out_ms, plan->p.t_ms, 8 * sizeof(float));
+    return SPTRANS_OK;
+}
+
+uint64_t sptrans_kernel_launches(const sptrans_plan* plan) { return plan ? plan->p.launches : 0; }
+
+}  // extern "C"

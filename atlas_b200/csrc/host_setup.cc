@@ -1,0 +1,281 @@
+// Host-side plan geometry for the B200 spectral-transform engine: everything the TransLocal
+// constructor derives from the grid (ecmwf/atlas src/atlas/trans/local/TransLocal.cc:371-606)
+// plus the per-latitude seeds of the device Legendre recurrence.
+//
+// Compiled WITHOUT fp contraction / -march flags: the seed columns must carry exactly the
+// roundings of trans/local/LegendrePolynomials.cc so that the device-generated tables are
+// bit-identical to the reference's.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <numeric>
+#include <thread>
+
+#include "plan.hpp"
+
+namespace sptrans {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+// Zonal truncation at one latitude row: linear / quadratic / cubic octahedral rule.
+// (reference: trans/local/TransLocal.cc:272-300)
+int fourier_truncation(int truncation, int nx, int /*nxmax*/, int ndgl, double lat, bool fullgrid) {
+    const int t_linear = ndgl - 1;
+    const int t_quadratic = ndgl * 2 / 3 - 1;
+    int kept;
+    if (fullgrid || truncation >= t_linear) {
+        kept = (nx - 1) / 2;
+    }
+    else {
+        const double c2 = std::pow(std::cos(lat), 2);
+        if (truncation >= t_quadratic) {
+            const double wq = 3 * (t_linear - truncation) / ndgl;  // integer quotient on purpose (reference :287)
+            kept = static_cast<int>((nx - 1) / (2 + wq * c2));
+        }
+        else {
+            kept = static_cast<int>((nx - 1) / (2 + c2) - 1);
+        }
+    }
+    return std::min(truncation, kept);
+}
+
+// Gauss-Legendre nodes/weights on [-1,1] by Newton iteration on the three-term recurrence,
+// returned as latitudes in degrees (north->south) and weights normalised to sum 1 -- the
+// normalisation atlas uses (grid/detail/spacing/gaussian/Latitudes.cc:139-166: sum over 2N rows == 1).
+void gaussian_quadrature(int N, double* lat_deg, double* weights) {
+    const int n = 2 * N;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int i = 0; i < N; ++i) {
+        long double x = cosl(pi * (i + 0.75L) / (n + 0.5L));  // Tricomi-style first guess
+        long double dp = 1;
+        for (int it = 0; it < 100; ++it) {
+            long double p0 = 1, p1 = x;
+            for (int k = 2; k <= n; ++k) {
+                long double pk = ((2 * k - 1) * x * p1 - (k - 1) * p0) / k;
+                p0 = p1;
+                p1 = pk;
+            }
+            dp = n * (x * p1 - p0) / (x * x - 1);
+            long double dx = p1 / dp;
+            x -= dx;
+            if (fabsl(dx) < 1e-19L) break;
+        }
+        // final derivative at the converged node
+        {
+            long double p0 = 1, p1 = x;
+            for (int k = 2; k <= n; ++k) {
+                long double pk = ((2 * k - 1) * x * p1 - (k - 1) * p0) / k;
+                p0 = p1;
+                p1 = pk;
+            }
+            dp = n * (x * p1 - p0) / (x * x - 1);
+        }
+        long double w = 2 / ((1 - x * x) * dp * dp);  // sums to 2 over all nodes
+        long double lat = asinl(x) * 180 / pi;
+        lat_deg[i] = static_cast<double>(lat);
+        lat_deg[n - 1 - i] = -static_cast<double>(lat);
+        weights[i] = weights[n - 1 - i] = static_cast<double>(w / 2);
+    }
+}
+
+int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, const double* weights, int T,
+                   bool regular, int rank, int nranks) {
+    if (nlat < 2 || T < 0 || !nx || !lat_deg || nranks < 1 || rank < 0 || rank >= nranks) {
+        set_error("sptrans_plan_create: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    g.T = T;
+    g.nlat = nlat;
+    g.nleg = (nlat + 1) / 2;
+    g.regular = regular;
+    g.has_equator = (nlat % 2) == 1;
+    g.nx.assign(nx, nx + nlat);
+    g.lat_deg.assign(lat_deg, lat_deg + nlat);
+    if (weights) g.weights.assign(weights, weights + nlat);
+    g.rowoff.assign(nlat + 1, 0);
+    g.nxmax = 0;
+    for (int j = 0; j < nlat; ++j) {
+        if (nx[j] < 1) {
+            set_error("sptrans_plan_create: nx must be positive");
+            return SPTRANS_ERR_INVALID;
+        }
+        g.rowoff[j + 1] = g.rowoff[j] + nx[j];
+        g.nxmax = std::max(g.nxmax, nx[j]);
+    }
+    g.npts = g.rowoff[nlat];
+    for (int j = 0; j < nlat; ++j) {
+        const int mj = nlat - 1 - j;
+        if (j > 0 && !(lat_deg[j] < lat_deg[j - 1])) {
+            set_error("sptrans_plan_create: latitudes must decrease monotonically (north to south)");
+            return SPTRANS_ERR_INVALID;
+        }
+        if (std::abs(lat_deg[j] + lat_deg[mj]) > 1e-9 || nx[j] != nx[mj]) {
+            set_error("sptrans_plan_create: only global grids symmetric about the equator are supported "
+                      "(regional / cropped domains: ATLAS_NOTIMPLEMENTED in this backend)");
+            return SPTRANS_ERR_NOT_IMPLEMENTED;
+        }
+    }
+    // first northern row at which wavenumber m is resolved (reference :462-488, global domain)
+    g.nlat0.assign(T + 2, g.nleg);
+    {
+        int done = -1;
+        for (int j = 0; j < nlat / 2; ++j) {
+            int keep = fourier_truncation(T, nx[j], g.nxmax, nlat, lat_deg[j] * (M_PI / 180.), regular);
+            keep = std::max(done, keep);
+            for (int m = done + 1; m <= keep; ++m) g.nlat0[m] = j;
+            done = keep;
+        }
+    }
+    g.mmax.assign(g.nleg, -1);
+    for (int j = 0; j < g.nleg; ++j)
+        for (int m = 0; m <= T; ++m)
+            if (g.nlat0[m] <= j) g.mmax[j] = m;
+    // Legendre table blocks (m, parity): K rows (n ascending) x pitch latitudes
+    g.tab_off.assign(2 * (T + 1), 0);
+    g.tab_K.assign(2 * (T + 1), 0);
+    g.tab_pitch.assign(T + 1, 0);
+    g.sp_rowoff.assign(2 * (T + 1) + 1, 0);
+    g.fb_rowoff.assign(T + 2, 0);
+    long long off = 0;
+    for (int m = 0; m <= T; ++m) {
+        const int ncol = g.nleg - g.nlat0[m];
+        g.tab_pitch[m] = round_up(std::max(ncol, 0), 16);
+        for (int p = 0; p < 2; ++p) {
+            const int K = num_n(T + 1, m, p);
+            g.tab_K[2 * m + p] = K;
+            g.tab_off[2 * m + p] = off;
+            // rows padded to the GEMM tile height so that tile loads never leave the block
+            off += static_cast<long long>(round_up(std::max(K, 1), kBK)) * g.tab_pitch[m];
+            g.sp_rowoff[2 * m + p + 1] = g.sp_rowoff[2 * m + p] + round_up(std::max(K, 1), kBK);
+        }
+        g.fb_rowoff[m + 1] = g.fb_rowoff[m] + 2LL * std::max(ncol, 0);
+    }
+    g.tab_size = off;
+    // sharding: zonal wavenumbers by cost-balanced greedy assignment, latitude pairs by sum(nx) bands
+    g.rank = rank;
+    g.nranks = nranks;
+    g.my_m.clear();
+    if (nranks == 1) {
+        for (int m = 0; m <= T; ++m) g.my_m.push_back(m);
+        g.pair_begin = 0;
+        g.pair_end = g.nleg;
+    }
+    else {
+        std::vector<int> order(T + 1);
+        std::iota(order.begin(), order.end(), 0);
+        auto cost = [&](int m) { return static_cast<double>(T + 2 - m) * std::max(0, g.nleg - g.nlat0[m]); };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+        std::vector<double> load(nranks, 0.);
+        for (int m : order) {
+            int best = 0;
+            for (int r = 1; r < nranks; ++r)
+                if (load[r] < load[best]) best = r;
+            load[best] += cost(m);
+            if (best == rank) g.my_m.push_back(m);
+        }
+        std::sort(g.my_m.begin(), g.my_m.end());
+        // contiguous bands of latitude pairs with ~equal number of grid points
+        long long total = 0;
+        for (int j = 0; j < g.nleg; ++j) total += nx[j];
+        std::vector<int> bound(nranks + 1, g.nleg);
+        bound[0] = 0;
+        long long acc = 0;
+        int r = 1;
+        for (int j = 0; j < g.nleg && r < nranks; ++j) {
+            acc += nx[j];
+            while (r < nranks && acc * nranks >= total * r) bound[r++] = j + 1;
+        }
+        g.pair_begin = bound[rank];
+        g.pair_end = bound[rank + 1];
+    }
+    return SPTRANS_OK;
+}
+
+// Seeds of the Legendre recurrence for each latitude: cos(theta), the m=0 and m=1 columns (cosine /
+// sine series, Belousov eq. 19/21 with the IFS normalisation) and the sectoral diagonal.
+// Operation order reproduces trans/local/LegendrePolynomials.cc:24-45 (coefficients) and :55-130.
+void legendre_seeds(int trc, int nlats, const double* lats_rad, std::vector<double>& xcos,
+                    std::vector<double>& col0, std::vector<double>& col1, std::vector<double>& diag) {
+    const size_t W = static_cast<size_t>(trc) + 1;
+    std::vector<double> coef(W * W, 0.);  // coef[n*W + k]
+    coef[0] = 2.;
+    for (int n = 1; n <= trc; ++n) {
+        double top = coef[0];
+        for (int g = 1; g <= n; ++g) top *= std::sqrt(1. - 0.25 / (g * g));
+        coef[n * W + n] = top;
+        const int odd = n % 2;
+        for (int g = 2; g <= n - odd; g += 2) {
+            const double num = ((g - 1.) * (2. * n - g + 2.));
+            const double den = (g * (2. * n - g + 1.));
+            coef[n * W + (n - g)] = coef[n * W + (n - g + 2)] * num / den;
+        }
+    }
+    for (int n = 1; n <= trc; n += 2) coef[n * W] = 0.;  // reference :101 zeroes zfn(n,0) for odd n
+
+    xcos.assign(nlats, 0.);
+    col0.assign(static_cast<size_t>(nlats) * W, 0.);
+    col1.assign(static_cast<size_t>(nlats) * W, 0.);
+    diag.assign(static_cast<size_t>(nlats) * W, 0.);
+
+    auto work = [&](int j0, int j1) {
+        std::vector<double> vs(W), vc(W);
+        for (int j = j0; j < j1; ++j) {
+            const double theta = (M_PI_2 - lats_rad[j]);
+            double x = std::cos(theta);
+            volatile double s = std::sqrt(1. - x * x);
+            for (int k = 1; k <= trc; ++k) {
+                vs[k] = std::sin(k * theta);
+                vc[k] = std::cos(k * theta);
+            }
+            double inv_s = 0.;
+            if (std::abs(s) <= std::sqrt(std::numeric_limits<double>::epsilon())) {
+                x = 1.;
+                s = 0.;
+            }
+            else {
+                inv_s = 1. / s;
+            }
+            double* c0 = &col0[static_cast<size_t>(j) * W];
+            double* c1 = &col1[static_cast<size_t>(j) * W];
+            double* dg = &diag[static_cast<size_t>(j) * W];
+            c0[0] = 1.;
+            for (int n = 1; n <= trc; ++n) {
+                const double* cf = &coef[n * W];
+                const int k0 = (n % 2 == 0) ? 2 : 1;
+                double a = (n % 2 == 0) ? 0.5 * cf[0] : 0.;
+                double b = 0.0;
+                const double q = 1. / std::sqrt(n * (n + 1.));
+                for (int k = k0; k <= n; k += 2) {
+                    a = a + cf[k] * vc[k];
+                    b = b + q * cf[k] * k * vs[k];
+                }
+                c0[n] = a;
+                c1[n] = b;
+            }
+            // sectoral values P_n^n with underflow flush (reference :122-130)
+            dg[0] = c0[0];
+            if (trc >= 1) dg[1] = c1[1];
+            const double tiny = inv_s * std::numeric_limits<double>::min();
+            for (int n = 2; n <= trc; ++n) {
+                const double sq = std::sqrt((2. * n + 1.) / (2. * n));
+                double v = dg[n - 1] * s * sq;
+                if (std::abs(v) < tiny) v = 0.0;
+                dg[n] = v;
+            }
+            xcos[j] = x;
+        }
+    };
+    unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 64u));
+    nt = std::min<unsigned>(nt, std::max(1, nlats));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t) {
+        int j0 = static_cast<int>(static_cast<long long>(nlats) * t / nt);
+        int j1 = static_cast<int>(static_cast<long long>(nlats) * (t + 1) / nt);
+        pool.emplace_back(work, j0, j1);
+    }
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace sptrans

@@ -1,0 +1,360 @@
+// fp64 Legendre transforms as a ragged batched GEMM on the FP64 tensor path (DMMA, mma.sync m8n8k4.f64).
+//
+// Replaces TransLocal::invtrans_legendre (ecmwf/atlas src/atlas/trans/local/TransLocal.cc:939-1097: per-m
+// split into sym/antisym, two eckit gemm calls, hemisphere merge) and, for the direct transform, the
+// Legendre stage the reference only has through ectrans (ifs/TransIFS.cc:503-515).
+//
+// tcgen05 has no f64 kind (ptxas: "Unknown modifier .kind::f64"), so the fp64 configurations run on
+// DMMA; measured peak on B200: 37.1 TFLOP/s for both DFMA and DMMA (profiles/microbench_f64_r01.txt),
+// reached from shared memory only with >= 32x56 warp tiles -- hence the 32x72 warp tile below.
+//
+// Work decomposition: one tile = (m, parity, 128-row block, 144-column block) of
+//     inverse:  C[lat][r] = sum_k  P[k][lat] * S[k][r]        (A = P^T, K-major)
+//     direct :  X[k][r]   = sum_lat P[k][lat] * G[lat][r]     (A = P,   row-major)
+// with r = 2*field + (re|im).  Tiles are sorted by cost and claimed through an atomic counter by a
+// persistent grid of one CTA per SM (8 warps, 4 x 2, each 32 rows x 72 columns = 4 x 9 DMMA tiles).
+// Operands are staged by 16-byte cp.async into a 4-stage shared-memory ring; row pitches are
+// = 4 (mod 16) doubles so every fragment load is bank-conflict free.
+//
+// The hemisphere merge of the reference (:1034-1079) is NOT done here: the Fourier kernels read the
+// symmetric / antisymmetric parts and form north = s + a, south = s - a on the fly (fourier.cu).
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include "plan.hpp"
+
+namespace sptrans {
+
+namespace {
+
+constexpr int kWarpsM = 4, kWarpsN = 2;
+constexpr int kMI = 4;   // 8-row DMMA tiles per warp  (32 rows)
+constexpr int kNJ = 9;   // 8-col DMMA tiles per warp  (72 cols)
+static_assert(kWarpsM * kMI * 8 == kBM && kWarpsN * kNJ * 8 == kBN, "tile shape");
+
+constexpr int kAInvPitch = kBM + 4;  // inverse: As[kBK][kBM+4]
+constexpr int kADirPitch = kBK + 4;  // direct : As[kBM][kBK+4]
+constexpr int kBPitch = kBN + 4;     // Bs[kBK][kBN+4]
+constexpr int kAInvStage = kBK * kAInvPitch;
+constexpr int kADirStage = kBM * kADirPitch;
+constexpr int kBStage = kBK * kBPitch;
+constexpr int kAStage = (kAInvStage > kADirStage ? kAInvStage : kADirStage);
+constexpr size_t kLegSmemBytes = static_cast<size_t>(kStages) * (kAStage + kBStage) * sizeof(double) + 16;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    const int sz = valid ? 16 : 0;  // src-size 0 => destination is zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// kDirect == false : A tile is [kBK][kBM] (k rows, latitude contiguous)   -> C rows are latitudes
+// kDirect == true  : A tile is [kBM][kBK] (table rows, latitude contiguous) -> C rows are table rows (n)
+template <bool kDirect>
+__global__ void __launch_bounds__(kLegThreads, 1)
+legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
+                     const double* __restrict__ tab, const double* __restrict__ B, double* __restrict__ C, int ldb) {
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + kStages * kAStage;
+    __shared__ int s_tile;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % kWarpsM, wn = warp / kWarpsM;
+
+    for (;;) {
+        __syncthreads();  // previous tile fully consumed (smem + s_tile)
+        if (tid == 0) s_tile = atomicAdd(counter, 1);
+        __syncthreads();
+        const int ti = s_tile;
+        if (ti >= ntiles) break;
+        const LegTile tl = tiles[ti];
+        const double* Ag = tab + tl.a_off;
+        const double* Bg = B + tl.b_off;
+
+        auto load_stage = [&](int kb, int st) {
+            double* as = As + st * kAStage;
+            double* bs = Bs + st * kBStage;
+            if (!kDirect) {
+                // kBK rows x kBM latitudes, 2 doubles per chunk
+                for (int c = tid; c < kBK * (kBM / 2); c += kLegThreads) {
+                    const int kk = c / (kBM / 2), cc = (c % (kBM / 2)) * 2;
+                    const bool ok = cc < tl.a_rows;  // a_rows: readable latitude columns (even)
+                    const double* src = Ag + static_cast<long long>(kb * kBK + kk) * tl.a_pitch + (ok ? cc : 0);
+                    cp_async16(as + kk * kAInvPitch + cc, src, ok);
+                }
+            }
+            else {
+                // kBM table rows x kBK latitudes
+                for (int c = tid; c < kBM * (kBK / 2); c += kLegThreads) {
+                    const int rr = c / (kBK / 2), cc = (c % (kBK / 2)) * 2;
+                    const bool ok = rr < tl.a_rows;  // a_rows: readable table rows
+                    const double* src = Ag + static_cast<long long>(ok ? rr : 0) * tl.a_pitch + kb * kBK + cc;
+                    cp_async16(as + rr * kADirPitch + cc, src, ok);
+                }
+            }
+            for (int c = tid; c < kBK * (kBN / 2); c += kLegThreads) {
+                const int kk = c / (kBN / 2), cc = (c % (kBN / 2)) * 2;
+                const int row = kb * kBK + kk;
+                const bool ok = (cc < tl.n_valid) && (row < tl.b_rows);
+                const double* src = Bg + static_cast<long long>(ok ? row : 0) * ldb + (ok ? cc : 0);
+                cp_async16(bs + kk * kBPitch + cc, src, ok);
+            }
+        };
+
+        double acc[kMI][kNJ][2];
+#pragma unroll
+        for (int i = 0; i < kMI; ++i)
+#pragma unroll
+            for (int j = 0; j < kNJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
+
+        const int ksteps = tl.k_steps;
+#pragma unroll
+        for (int s = 0; s < kStages - 1; ++s) {
+            if (s < ksteps) load_stage(s, s);
+            cp_async_commit();
+        }
+        const int row_w = wm * (kMI * 8);   // warp's first row in the tile
+        const int col_w = wn * (kNJ * 8);   // warp's first column
+        const bool warp_active = (row_w < tl.m_valid) && (col_w < tl.n_valid);
+
+        for (int kb = 0; kb < ksteps; ++kb) {
+            cp_async_wait<kStages - 2>();
+            __syncthreads();
+            {
+                const int nk = kb + kStages - 1;
+                if (nk < ksteps) load_stage(nk, nk % kStages);
+                cp_async_commit();
+            }
+            if (warp_active) {
+                const double* as = As + (kb % kStages) * kAStage;
+                const double* bs = Bs + (kb % kStages) * kBStage;
+#pragma unroll
+                for (int ks = 0; ks < kBK / 4; ++ks) {
+                    double a[kMI], b[kNJ];
+#pragma unroll
+                    for (int i = 0; i < kMI; ++i) {
+                        if (!kDirect) a[i] = as[(ks * 4 + t) * kAInvPitch + row_w + 8 * i + g];
+                        else a[i] = as[(row_w + 8 * i + g) * kADirPitch + ks * 4 + t];
+                    }
+#pragma unroll
+                    for (int j = 0; j < kNJ; ++j) b[j] = bs[(ks * 4 + t) * kBPitch + col_w + 8 * j + g];
+#pragma unroll
+                    for (int i = 0; i < kMI; ++i) {
+                        if (row_w + 8 * i < tl.m_valid) {
+#pragma unroll
+                            for (int j = 0; j < kNJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        // epilogue: thread holds C[row_w+8i+g][col_w+8j+2t .. +1] = (re, im) of one field
+        if (warp_active) {
+            double* Cg = C + tl.c_off;
+#pragma unroll
+            for (int i = 0; i < kMI; ++i) {
+                const int row = row_w + 8 * i + g;
+                if (row < tl.m_valid) {
+#pragma unroll
+                    for (int j = 0; j < kNJ; ++j) {
+                        const int col = col_w + 8 * j + 2 * t;
+                        if (col < tl.n_valid) {
+                            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                            *reinterpret_cast<double2*>(Cg + static_cast<long long>(row) * ldb + col) = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// spectra [m][n][re/im][fld]  ->  packed [m][p][k][2 fld + re/im], rows k >= K_eff (and whole blocks with
+// m >= trunc) are zero: this is the split + zero padding of TransLocal.cc:970-1003, including the
+// `jn <= truncation && jm < truncation` rule (:982) that drops the m == truncation column.
+__global__ void pack_spectra_kernel(int T, int nf, int trunc, const long long* __restrict__ sp_rowoff,
+                                    const int* __restrict__ my_m, const double* __restrict__ spec,
+                                    double* __restrict__ packed) {
+    const int m = my_m[blockIdx.x];
+    const int p = blockIdx.y;
+    const long long row0 = sp_rowoff[2 * m + p];
+    const int rows = static_cast<int>(sp_rowoff[2 * m + p + 1] - row0);
+    const int ld = 2 * nf;
+    const long long ioff = static_cast<long long>(2 * trunc + 3 - m) * m / 2 * nf * 2;  // reference :970
+    for (long long e = threadIdx.x; e < static_cast<long long>(rows) * ld; e += blockDim.x) {
+        const int k = static_cast<int>(e / ld);
+        const int r = static_cast<int>(e % ld);
+        // read order: field fastest within (k, imag) so that global loads coalesce
+        const int imag = r / nf, f = r % nf;
+        const int n = m + p + 2 * k;
+        double v = 0.;
+        if (n <= trunc && m < trunc) v = spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f];
+        packed[(row0 + k) * ld + 2 * f + imag] = v;
+    }
+}
+
+// packed [m][p][k][2 fld + re/im] -> spectra [m][n][re/im][fld] for all n <= T
+__global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict__ sp_rowoff,
+                                      const int* __restrict__ my_m, const double* __restrict__ packed,
+                                      double* __restrict__ spec) {
+    const int m = my_m[blockIdx.x];
+    const int p = blockIdx.y;
+    const long long row0 = sp_rowoff[2 * m + p];
+    const int K = (T - m + (p ? 1 : 2)) / 2;  // n <= T
+    const int ld = 2 * nf;
+    const long long ioff = static_cast<long long>(2 * T + 3 - m) * m / 2 * nf * 2;
+    for (long long e = threadIdx.x; e < static_cast<long long>(K) * ld; e += blockDim.x) {
+        const int k = static_cast<int>(e / ld);
+        const int r = static_cast<int>(e % ld);
+        const int imag = r / nf, f = r % nf;
+        const int n = m + p + 2 * k;
+        double v = packed[(row0 + k) * ld + 2 * f + imag];
+        if (m == 0 && imag == 1) v = 0.;  // Im of the zonal-mean coefficients is identically zero
+        spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f] = v;
+    }
+}
+
+}  // namespace
+
+// Tile lists for the current (nf, truncation-of-data).  Cheap (tens of thousands of entries); cached.
+int build_tiles(Plan& p, int nf, int trunc) {
+    if (p.tiles_nf == nf && p.tiles_trunc == trunc) return SPTRANS_OK;
+    const HostGeom& g = p.g;
+    const int T = g.T;
+    const int ld = 2 * nf;
+    struct Keyed {
+        double cost;
+        LegTile t;
+    };
+    std::vector<Keyed> inv, dir;
+    for (int m : g.my_m) {
+        const int ncol = g.nleg - g.nlat0[m];
+        if (ncol <= 0) continue;
+        const int pitch = g.tab_pitch[m];
+        for (int par = 0; par < 2; ++par) {
+            const int Ktab = g.tab_K[2 * m + par];
+            const long long fb_row0 = g.fb_rowoff[m] + static_cast<long long>(par) * ncol;  // double2 rows of nf
+            // ---- inverse: K = #n <= trunc of this parity (0 if m >= trunc: column dropped, :982)
+            int Kinv = (m < trunc) ? std::min(Ktab, num_n(trunc, m, par)) : 0;
+            if (Kinv > 0) {
+                const int ksteps = round_up(Kinv, kBK) / kBK;
+                for (int l0 = 0; l0 < ncol; l0 += kBM) {
+                    for (int n0 = 0; n0 < ld; n0 += kBN) {
+                        LegTile t{};
+                        t.a_off = g.tab_off[2 * m + par] + l0;
+                        t.a_pitch = pitch;
+                        t.a_rows = pitch - l0;
+                        t.b_off = g.sp_rowoff[2 * m + par] * ld + n0;
+                        t.b_rows = ksteps * kBK;
+                        t.c_off = (fb_row0 + l0) * ld + n0;
+                        t.m_valid = std::min(kBM, ncol - l0);
+                        t.n_valid = std::min(kBN, ld - n0);
+                        t.k_steps = ksteps;
+                        inv.push_back({static_cast<double>(ksteps) * round_up(t.m_valid, 8), t});
+                    }
+                }
+            }
+            // ---- direct: rows = all n <= T of this parity, contraction over the ncol latitudes
+            const int Kdir = num_n(T, m, par);
+            if (Kdir > 0) {
+                const int ksteps = pitch / kBK;
+                const int rows_tab = round_up(std::max(Ktab, 1), kBK);
+                for (int r0 = 0; r0 < Kdir; r0 += kBM) {
+                    for (int n0 = 0; n0 < ld; n0 += kBN) {
+                        LegTile t{};
+                        t.a_off = g.tab_off[2 * m + par] + static_cast<long long>(r0) * pitch;
+                        t.a_pitch = pitch;
+                        t.a_rows = rows_tab - r0;
+                        t.b_off = fb_row0 * ld + n0;
+                        t.b_rows = ncol;
+                        t.c_off = (g.sp_rowoff[2 * m + par] + r0) * ld + n0;
+                        t.m_valid = std::min(kBM, Kdir - r0);
+                        t.n_valid = std::min(kBN, ld - n0);
+                        t.k_steps = ksteps;
+                        dir.push_back({static_cast<double>(ksteps) * round_up(t.m_valid, 8), t});
+                    }
+                }
+            }
+        }
+    }
+    auto finish = [&](std::vector<Keyed>& v, LegTile*& d_ptr, int& count) -> int {
+        std::stable_sort(v.begin(), v.end(), [](const Keyed& a, const Keyed& b) { return a.cost > b.cost; });
+        std::vector<LegTile> flat(v.size());
+        for (size_t i = 0; i < v.size(); ++i) flat[i] = v[i].t;
+        if (d_ptr) cudaFree(d_ptr);
+        d_ptr = nullptr;
+        count = static_cast<int>(flat.size());
+        SPT_CUDA(cudaMalloc(&d_ptr, std::max<size_t>(flat.size(), 1) * sizeof(LegTile)));
+        SPT_CUDA(cudaMemcpyAsync(d_ptr, flat.data(), flat.size() * sizeof(LegTile), cudaMemcpyHostToDevice, p.stream));
+        SPT_CUDA(cudaStreamSynchronize(p.stream));
+        return SPTRANS_OK;
+    };
+    int rc = finish(inv, p.d_tiles_inv, p.n_tiles_inv);
+    if (rc) return rc;
+    rc = finish(dir, p.d_tiles_dir, p.n_tiles_dir);
+    if (rc) return rc;
+    p.tiles_nf = nf;
+    p.tiles_trunc = trunc;
+    return SPTRANS_OK;
+}
+
+int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed) {
+    const int nm = static_cast<int>(p.g.my_m.size());
+    if (nm == 0) return SPTRANS_OK;
+    dim3 grid(nm, 2);
+    pack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, trunc, p.d_sp_rowoff, p.d_my_m, d_spec, d_packed);
+    p.launches++;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec) {
+    const int nm = static_cast<int>(p.g.my_m.size());
+    if (nm == 0) return SPTRANS_OK;
+    dim3 grid(nm, 2);
+    unpack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, p.d_sp_rowoff, p.d_my_m, d_packed, d_spec);
+    p.launches++;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+template <bool kDirect>
+static int launch_gemm(Plan& p, int nf, const LegTile* tiles, int ntiles, const double* B, double* C) {
+    if (ntiles == 0) return SPTRANS_OK;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[kDirect]) {
+        SPT_CUDA(cudaFuncSetAttribute(legendre_dmma_kernel<kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kLegSmemBytes)));
+        attr_set[kDirect] = true;
+    }
+    SPT_CUDA(cudaMemsetAsync(p.d_tile_counter, 0, sizeof(int), p.stream));
+    const int grid = std::min(ntiles, p.num_sms);
+    legendre_dmma_kernel<kDirect><<<grid, kLegThreads, kLegSmemBytes, p.stream>>>(tiles, ntiles, p.d_tile_counter,
+                                                                                 p.d_tab, B, C, 2 * nf);
+    p.launches++;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier) {
+    return launch_gemm<false>(p, nf, p.d_tiles_inv, p.n_tiles_inv, d_packed, d_fourier);
+}
+int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed) {
+    return launch_gemm<true>(p, nf, p.d_tiles_dir, p.n_tiles_dir, d_fourier, d_packed);
+}
+
+}  // namespace sptrans

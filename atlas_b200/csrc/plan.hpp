@@ -1,0 +1,172 @@
+// Internal plan structures of the B200 spectral-transform engine (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "sptrans_b200.h"
+
+namespace sptrans {
+
+// ----- tile geometry of the fp64 DMMA Legendre kernels (see legendre_f64.cu) -----
+constexpr int kBM = 128;      // rows per CTA tile (latitudes in the inverse, total wavenumbers in the direct)
+constexpr int kBN = 144;      // columns per CTA tile (2*field + re/im)
+constexpr int kBK = 16;       // contraction step
+constexpr int kStages = 4;    // cp.async pipeline depth
+constexpr int kLegThreads = 256;
+
+// One CTA tile of a ragged batched GEMM  C[M x N] = A[M x K] * B[K x N].
+struct alignas(16) LegTile {
+    long long a_off;  // doubles, into the Legendre table: first element of the tile
+    long long b_off;  // doubles, into B (packed spectra / Fourier buffer): row 0, column n0
+    long long c_off;  // doubles, into C: (row m0, column n0)
+    int a_pitch;      // row pitch of the table block (doubles)
+    int m_valid;      // valid rows of this tile (<= kBM)
+    int n_valid;      // valid columns of this tile (<= kBN), even
+    int k_steps;      // number of kBK steps
+    int a_rows;       // inverse: #lat columns readable from a_off (pitch - lat0); direct: #table rows readable
+    int b_rows;       // rows of B that may be read (rest zero-filled)
+    int pad0, pad1;
+};
+
+struct HostGeom {
+    int T = 0;        // truncation
+    int nlat = 0;     // latitude rows
+    int nleg = 0;     // (nlat+1)/2 : northern rows incl. equator   (nlatsLeg_, TransLocal.cc:435)
+    bool regular = false;
+    bool has_equator = false;
+    std::vector<int> nx;            // [nlat]
+    std::vector<long long> rowoff;  // [nlat+1]
+    std::vector<double> lat_deg;    // [nlat]
+    std::vector<double> weights;    // [nlat] or empty
+    std::vector<int> nlat0;         // [T+2]  (entry T+1 == nleg)
+    std::vector<int> mmax;          // [nleg] highest m with nlat0[m] <= j  (-1 if none)
+    int nxmax = 0;
+    long long npts = 0;
+    // Legendre table layout (n ascending, k = (n-m-p)/2), built for truncation T+1
+    std::vector<long long> tab_off;  // [2*(T+1)] index 2*m+p : offset in doubles
+    std::vector<int> tab_K;          // [2*(T+1)] rows with n <= T+1
+    std::vector<int> tab_pitch;      // [T+1]     roundup(nleg - nlat0[m], 16)
+    long long tab_size = 0;          // doubles
+    // packed-spectra layout [m][p][Kpad][2 nf]: row prefix (multiply by 2*nf)
+    std::vector<long long> sp_rowoff;  // [2*(T+1)+1]
+    // Fourier buffer layout [m][p][jj][fld](re,im): row prefix (multiply by nf), in double2 units
+    std::vector<long long> fb_rowoff;  // [T+2] : sum_{m'<m} 2*(nleg - nlat0[m'])
+    // sharding
+    int rank = 0, nranks = 1;
+    std::vector<int> my_m;       // zonal wavenumbers owned by this rank (all if nranks==1)
+    int pair_begin = 0, pair_end = 0;  // latitude pairs [begin,end) of this rank's Fourier band
+};
+
+inline int num_n(int truncation, int m, int parity) {  // #n in [m, truncation] with (n-m)%2 == parity
+    int len = (truncation - m + (parity ? 1 : 2)) / 2;
+    return len < 0 ? 0 : len;
+}
+inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
+
+// per distinct row length: Bluestein / chirp-z tables on the device
+struct FftLen {
+    int n = 0;       // row length
+    int L = 0;       // highest zonal wavenumber used at this length
+    int M = 0;       // power-of-two convolution length >= n + 2L
+    int logM = 0;
+    long long chirp_off = 0;   // double2 units into d_chirp: A_u (2L+1) then C_i (n)
+    long long filt_off = 0;    // double2 units into d_filt: Bhat (M), digit-reversed order
+};
+
+struct Plan {
+    HostGeom g;
+    int device = 0;
+    unsigned flags = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    // device tables
+    double* d_tab = nullptr;       // Legendre table
+    int* d_nlat0 = nullptr;        // [T+2]
+    long long* d_fb_rowoff = nullptr;  // [T+2]
+    long long* d_rowoff = nullptr;     // [nlat+1]
+    int* d_nx = nullptr;               // [nlat]
+    double* d_weights = nullptr;       // [nleg]
+    double* d_coslatinv = nullptr;     // [nleg] 1/cos(lat), latitude clamped to +-89.9999999 (TransLocal.cc:1447-1458)
+    double* d_coslat = nullptr;        // [nleg]
+    long long* d_sp_rowoff = nullptr;  // [2(T+1)+1]
+    int* d_my_m = nullptr;             // [my_m.size()]
+    // FFT tables
+    std::vector<FftLen> fft_len;       // distinct lengths
+    std::vector<int> pair_len_idx;     // [nleg] -> index into fft_len
+    void* d_pair_meta = nullptr;       // [nleg] PairMeta (fourier.cu)
+    double2* d_twiddle = nullptr;      // master twiddle table e^{-2 pi i k/8192}
+    double2* d_chirp = nullptr;
+    double2* d_filt = nullptr;
+    int* d_fft_order = nullptr;        // block schedule, longest rows first
+    int fft_smem_max = 0;
+    // tile lists (device) for the current nf; rebuilt when nf / truncation changes
+    int tiles_nf = -1, tiles_trunc = -1;
+    LegTile* d_tiles_inv = nullptr;
+    int n_tiles_inv = 0;
+    LegTile* d_tiles_dir = nullptr;
+    int n_tiles_dir = 0;
+    int* d_tile_counter = nullptr;
+    // workspaces (grown on demand)
+    double* d_packed = nullptr;   size_t packed_cap = 0;   // packed spectra [m][p][Kpad][2nf]
+    double* d_fourier = nullptr;  size_t fourier_cap = 0;  // Fourier buffer
+    double* d_spec = nullptr;     size_t spec_cap = 0;     // device copy of spectra (host-pointer mode)
+    double* d_spec2 = nullptr;    size_t spec2_cap = 0;
+    double* d_gp = nullptr;       size_t gp_cap = 0;       // device copy of grid fields (host-pointer mode)
+    void* h_pinned = nullptr;     size_t pinned_cap = 0;
+    size_t bytes_tables = 0;
+    // stats
+    uint64_t launches = 0;
+    float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[8] = {};
+};
+
+// ---- error handling ----
+void set_error(const std::string& msg);
+const char* last_error_cstr();
+#define SPT_CUDA(call)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            ::sptrans::set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                                 std::to_string(__LINE__) + ")");                                    \
+            return SPTRANS_ERR_CUDA;                                                                 \
+        }                                                                                            \
+    } while (0)
+
+// ---- host_setup.cc ----
+int fourier_truncation(int truncation, int nx, int nxmax, int ndgl, double lat, bool fullgrid);
+void gaussian_quadrature(int N, double* lat_deg_2N, double* weights_2N);
+int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, const double* weights, int T,
+                   bool regular, int rank, int nranks);
+// per-latitude seeds for the device Legendre recurrence: x=cos(theta), s=sin(theta), columns m=0,1 and the diagonal
+void legendre_seeds(int trc, int nlats, const double* lats_rad, std::vector<double>& x, std::vector<double>& col0,
+                    std::vector<double>& col1, std::vector<double>& diag);
+
+// ---- legendre_gen.cu ----
+int generate_legendre_table(Plan& p);
+int export_legendre_cache(const Plan& p, double* h_out);
+size_t legendre_cache_doubles(const HostGeom& g);
+
+// ---- legendre_f64.cu ----
+int build_tiles(Plan& p, int nf, int trunc);
+int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed);
+int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec);
+int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier);
+int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed);
+
+// ---- fourier.cu ----
+int build_fft_tables(Plan& p);
+void free_fft_tables(Plan& p);
+int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv);
+int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv);
+
+// ---- vordiv.cu ----
+int launch_vd2uv(cudaStream_t s, int T, int nf, const double* d_vor, const double* d_div, double* d_U, double* d_V,
+                 uint64_t* launches);
+
+}  // namespace sptrans

@@ -1,0 +1,169 @@
+"""Host-side mirror of `atlas::trans::Trans` (trans/Trans.h:42-189) over the sptrans C ABI.
+
+Same method names, argument meaning and error behaviour as the reference's IFS-style raw-pointer
+interface (trans/detail/TransImpl.h:116-181), so that the parity tests read like
+src/tests/trans/test_transgeneral.cc.  Arrays may be NumPy arrays (host; staged by the library) or
+torch CUDA tensors (used in place).  No arithmetic happens in this file.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .grid import Grid, StructuredGrid
+
+
+class option:
+    """`atlas::option::*` sugar (option/TransOptions.h): only `type` matters here."""
+
+    @staticmethod
+    def type(name):
+        return {"type": name}
+
+
+def _ptr(a):
+    """Raw pointer of a NumPy array or torch tensor (fp64, contiguous)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("expected a C-contiguous float64 array")
+        return C.c_void_p(a.ctypes.data)
+    # torch tensor (duck-typed so that torch stays optional at import time)
+    if hasattr(a, "data_ptr"):
+        import torch
+
+        if a.dtype != torch.float64 or not a.is_contiguous():
+            raise ValueError("expected a contiguous float64 tensor")
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(f"unsupported array type {type(a)}")
+
+
+class Trans:
+    """`trans::Trans(grid, truncation, option::type("b200"))`."""
+
+    def __init__(self, grid, truncation, config=None, device=0, rank=0, nranks=1):
+        if isinstance(grid, str):
+            grid = Grid(grid)
+        if not isinstance(grid, StructuredGrid):
+            raise TypeError("Trans needs a StructuredGrid")
+        cfg = dict(config or {})
+        backend = cfg.get("type", "b200")
+        if backend != "b200":
+            raise ValueError(f"backend {backend!r} not available here; this package provides type('b200') only")
+        self._grid = grid
+        self._T = int(truncation)
+        self._h = C.c_void_p()
+        nx = grid.nx()
+        lat = grid.y()
+        w = grid.weights()
+        flags = 1 if grid.regular else 0
+        _lib.check(
+            _lib.lib.sptrans_plan_create_sharded(
+                C.byref(self._h), grid.ny(), nx.ctypes.data_as(_lib.c_int_p), lat.ctypes.data_as(_lib.c_double_p),
+                None if w is None else w.ctypes.data_as(_lib.c_double_p), self._T, flags, int(device), int(rank), int(nranks),
+            )
+        )
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            _lib.lib.sptrans_plan_destroy(h)
+            self._h = C.c_void_p()
+
+    # --- inspectors (TransImpl.h:42-52) ---
+    def type(self):
+        return "b200"
+
+    def truncation(self):
+        return self._T
+
+    def grid(self):
+        return self._grid
+
+    def nb_spectral_coefficients(self):
+        return int(_lib.lib.sptrans_nb_spectral_coefficients(self._h))
+
+    def nb_gridpoints(self):
+        return int(_lib.lib.sptrans_nb_gridpoints(self._h))
+
+    def nlat0(self):
+        out = np.empty(self._T + 1, dtype=np.int32)
+        _lib.check(_lib.lib.sptrans_get_nlat0(self._h, out.ctypes.data_as(_lib.c_int_p)))
+        return out
+
+    def device_bytes(self):
+        return int(_lib.lib.sptrans_device_bytes(self._h))
+
+    def kernel_launches(self):
+        return int(_lib.lib.sptrans_kernel_launches(self._h))
+
+    def last_timings(self):
+        out = (C.c_float * 8)()
+        _lib.check(_lib.lib.sptrans_last_timings(self._h, out))
+        t = list(out)
+        return {"pack": t[0], "legendre": t[1], "fourier": t[2], "h2d": t[3], "d2h": t[4]}
+
+    def set_stream(self, cuda_stream_ptr):
+        _lib.check(_lib.lib.sptrans_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def export_legendre_cache(self):
+        n = int(_lib.lib.sptrans_legendre_cache_size(self._h))
+        out = np.empty(n // 8, dtype=np.float64)
+        _lib.check(_lib.lib.sptrans_export_legendre_cache(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    # --- transforms, IFS-style buffers (TransImpl.h:116-181) ---
+    def invtrans(self, *args):
+        """invtrans(nb_scalar, scalar_spectra, gp)
+        invtrans(nb_vordiv, vor, div, gp)
+        invtrans(nb_scalar, scalar_spectra, nb_vordiv, vor, div, gp)"""
+        if len(args) == 3:
+            n, sp, gp = args
+            _lib.check(_lib.lib.sptrans_invtrans_scalar(self._h, int(n), _ptr(sp), _ptr(gp)))
+        elif len(args) == 4:
+            n, vor, div, gp = args
+            _lib.check(_lib.lib.sptrans_invtrans_vordiv2wind(self._h, int(n), _ptr(vor), _ptr(div), _ptr(gp)))
+        elif len(args) == 6:
+            ns, sp, nv, vor, div, gp = args
+            _lib.check(_lib.lib.sptrans_invtrans(self._h, int(ns), _ptr(sp), int(nv), _ptr(vor), _ptr(div), _ptr(gp)))
+        else:
+            raise TypeError("invtrans: wrong number of arguments")
+
+    def dirtrans(self, *args):
+        """dirtrans(nb_fields, scalar_fields, scalar_spectra)"""
+        if len(args) == 3:
+            n, gp, sp = args
+            _lib.check(_lib.lib.sptrans_dirtrans_scalar(self._h, int(n), _ptr(gp), _ptr(sp)))
+        else:
+            raise _lib.NotImplementedInBackend(3, "dirtrans(wind -> vor/div) is not implemented yet")
+
+    # --- stage level (device pointers only) ---
+    def fourier_elems_per_field(self):
+        return int(_lib.lib.sptrans_fourier_elems_per_field(self._h))
+
+    def invtrans_legendre(self, nf, trunc, d_spec, d_fourier):
+        _lib.check(_lib.lib.sptrans_invtrans_legendre(self._h, int(nf), int(trunc), _ptr(d_spec), _ptr(d_fourier)))
+
+    def invtrans_fourier(self, nf, mlimit, d_fourier, d_gp, nb_uv=0):
+        _lib.check(_lib.lib.sptrans_invtrans_fourier(self._h, int(nf), int(mlimit), _ptr(d_fourier), _ptr(d_gp), int(nb_uv)))
+
+    def dirtrans_fourier(self, nf, d_gp, d_fourier, nb_uv=0):
+        _lib.check(_lib.lib.sptrans_dirtrans_fourier(self._h, int(nf), _ptr(d_gp), _ptr(d_fourier), int(nb_uv)))
+
+    def dirtrans_legendre(self, nf, d_fourier, d_spec):
+        _lib.check(_lib.lib.sptrans_dirtrans_legendre(self._h, int(nf), _ptr(d_fourier), _ptr(d_spec)))
+
+
+class VorDivToUV:
+    """`trans::VorDivToUV(truncation, option::type("b200"))` (trans/VorDivToUV.h:109-128)."""
+
+    def __init__(self, truncation, config=None, device=0):
+        self._T = int(truncation)
+        self._device = int(device)
+
+    def truncation(self):
+        return self._T
+
+    def execute(self, nb_coeff, nb_fields, vorticity, divergence, U, V):
+        _lib.check(_lib.lib.sptrans_vordiv_to_uv(self._T, int(nb_fields), _ptr(vorticity), _ptr(divergence), _ptr(U), _ptr(V), self._device))

@@ -1,0 +1,168 @@
+/*
+ * sptrans_b200.h -- C ABI of the B200-native spherical-harmonics transform engine.
+ *
+ * This is the drop-in boundary below atlas::trans::TransImpl: plain pointers and sizes, no
+ * atlas / eckit / torch types.  Every entry point names the reference interface it replaces
+ * (paths relative to ecmwf/atlas src/atlas/).  The adaptor class that registers this engine
+ * as `type("b200")` with atlas's TransFactory is include/atlas_b200/TransB200.h; the
+ * binding a maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions (identical to the reference):
+ *   spectra : [m][n][re/im][field], field fastest; (T+1)(T+2) doubles per field
+ *             (functionspace/Spectral.h:43-61, trans/local/TransLocal.cc:970-981)
+ *   grid    : [field][point]; points ordered by latitude row north->south, longitudes
+ *             lambda_i = 2 pi i / nx(row) from 0 (trans/local/TransLocal.cc:1160-1187)
+ *   wind    : all u fields, then all v fields (then scalars)   (TransLocal.cc:1561-1589)
+ * All data pointers may be device pointers (used in place) or host pointers (staged through
+ * the plan's device workspace with pinned-memory copies); the engine detects which with
+ * cudaPointerGetAttributes, as atlas itself does in parallel/detail/DevicePacker.hic:20-28.
+ * There is NO CPU fallback: every call fails with SPTRANS_ERR_CUDA if no device is present.
+ *
+ * Thread-safety: like TransLocal (mutable scratch, trans/local/TransLocal.h:245) a plan
+ * supports one in-flight call at a time.  Calls are blocking: results are visible on return.
+ */
+#ifndef SPTRANS_B200_H
+#define SPTRANS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sptrans_plan sptrans_plan;
+
+enum {
+    SPTRANS_OK = 0,
+    SPTRANS_ERR_INVALID = 1,        /* bad argument (eckit::BadParameter / ATLAS_ASSERT in the reference) */
+    SPTRANS_ERR_CUDA = 2,           /* CUDA runtime / launch failure, or no device */
+    SPTRANS_ERR_NOT_IMPLEMENTED = 3 /* ATLAS_NOTIMPLEMENTED in the reference */
+};
+
+/* flags for sptrans_plan_create */
+enum {
+    SPTRANS_GRID_REGULAR = 1u,  /* RegularGrid(grid): linear zonal truncation (TransLocal.cc:281-284) */
+    SPTRANS_NO_FP64_TABLE = 2u  /* keep only the split-integer Legendre table (saves HBM; fp64 kernels unavailable) */
+};
+
+/* precision selector for sptrans_set_precision */
+enum {
+    SPTRANS_PREC_FP64 = 0,  /* DMMA fp64 tensor path (BASELINE configs 1-3,5) */
+    SPTRANS_PREC_TC_SPLIT = 1 /* tcgen05 split-operand tensor-core path (BASELINE config 4) */
+};
+
+/* Last error message of the calling thread (errors in the reference are C++ exceptions,
+ * runtime/Exception.h:23-76; the TransB200 adaptor rethrows this string). */
+const char* sptrans_last_error(void);
+
+/* Library / device probe: returns the number of visible CUDA devices (0 => every other call fails). */
+int sptrans_device_count(void);
+
+/* ---- grid helpers (replace the Grid getters TransLocal's constructor consumes) ------------------- */
+
+/* Gaussian latitudes (degrees, north->south, 2N values) and quadrature weights (sum == 1).
+ * Replaces grid/detail/spacing/gaussian/Latitudes.cc:227-274 (compute_gaussian_quadrature_npole_equator). */
+int sptrans_gaussian_latitudes(int N, double* lat_deg_2N, double* weights_2N);
+
+/* Octahedral reduced Gaussian grid O<N>: nx[j] = 20 + 4 j mirrored (grid/detail/grid/Gaussian.cc:127-134). */
+int sptrans_octahedral_nx(int N, int* nx_2N);
+
+/* Highest zonal wavenumber kept at a latitude (trans/local/TransLocal.cc:272-300 fourier_truncation). */
+int sptrans_fourier_truncation(int truncation, int nx, int nxmax, int ndgl, double lat_rad, int fullgrid);
+
+/* ---- plan = what TransLocal::TransLocal builds (trans/local/TransLocal.cc:322-770) ---------------- */
+
+/* Create a transform plan for a GLOBAL structured grid given as rows.
+ *   nlat          number of latitude rows (StructuredGrid::ny)
+ *   nx[nlat]      points per row (StructuredGrid::nx(j))
+ *   lat_deg[nlat] row latitudes in degrees, north->south, symmetric about the equator
+ *   weights[nlat] quadrature weights (sum 1) for the direct transform, or NULL (=> dirtrans unavailable)
+ *   truncation    spectral truncation T
+ *   device        CUDA device ordinal
+ * Replaces TransBuilderGrid<TransLocal>::make -> TransLocal ctor (trans/detail/TransFactory.h:114-119).
+ * Legendre tables are generated ON THE DEVICE (bit-identical to trans/local/LegendrePolynomials.cc). */
+int sptrans_plan_create(sptrans_plan** plan, int nlat, const int* nx, const double* lat_deg, const double* weights,
+                        int truncation, unsigned flags, int device);
+
+/* m-sharded plan for multi-GPU runs (one process per GPU): this rank owns the zonal wavenumbers
+ * { m : owner(m) == rank } (work-balanced pairing) and the latitude pairs of band `rank`.
+ * No reference equivalent: TransLocal throws for mpi::size()>1 (TransLocal.cc:338-340). */
+int sptrans_plan_create_sharded(sptrans_plan** plan, int nlat, const int* nx, const double* lat_deg,
+                                const double* weights, int truncation, unsigned flags, int device, int rank,
+                                int nranks);
+
+int sptrans_plan_destroy(sptrans_plan* plan); /* atlas__Trans__delete, trans/detail/TransInterface.cc:86-89 */
+
+/* inspectors: TransImpl::truncation / grid().size() / nb_spectral_coefficients (TransLocal.h:84-91) */
+int sptrans_truncation(const sptrans_plan* plan);
+size_t sptrans_nb_gridpoints(const sptrans_plan* plan);
+size_t sptrans_nb_spectral_coefficients(const sptrans_plan* plan); /* (T+1)(T+2) */
+/* first northern latitude index at which wavenumber m is resolved (TransLocal.cc:462-488); out[T+1] */
+int sptrans_get_nlat0(const sptrans_plan* plan, int* nlat0);
+/* bytes of device memory held by the plan (tables + workspaces) */
+size_t sptrans_device_bytes(const sptrans_plan* plan);
+
+/* Export the Legendre tables in the reference's cache layout [all sym blocks][all asym blocks], blocks
+ * padded to 8 doubles, n descending (TransLocal.cc:592-647, LegendrePolynomials.cc:181-205).
+ * `out` is a HOST buffer of sptrans_legendre_cache_size() bytes. */
+size_t sptrans_legendre_cache_size(const sptrans_plan* plan);
+int sptrans_export_legendre_cache(const sptrans_plan* plan, void* out);
+
+/* run all subsequent calls on this cudaStream_t (default: the plan's own stream) */
+int sptrans_set_stream(sptrans_plan* plan, void* cuda_stream);
+
+/* ---- transforms ------------------------------------------------------------------------------------ */
+
+/* TransImpl::invtrans(nb_scalar_fields, scalar_spectra, gp_fields)            trans/detail/TransImpl.h:136-137
+ * = TransLocal::invtrans -> invtrans_uv(truncation_, ...)                      TransLocal.cc:931-934          */
+int sptrans_invtrans_scalar(sptrans_plan* plan, int nb_fields, const double* scalar_spectra, double* gp_fields);
+
+/* TransImpl::invtrans(nb_scalar, scalar_spectra, nb_vordiv, vor, div, gp)      trans/detail/TransImpl.h:125-127
+ * = TransLocal::invtrans (extend_truncation, vd2uv, merged spectra at T+1)     TransLocal.cc:1523-1597
+ * gp layout: [u_1..u_k | v_1..v_k | s_1..s_j][npts]                                                            */
+int sptrans_invtrans(sptrans_plan* plan, int nb_scalar_fields, const double* scalar_spectra, int nb_vordiv_fields,
+                     const double* vorticity_spectra, const double* divergence_spectra, double* gp_fields);
+
+/* TransImpl::invtrans(nb_vordiv, vor, div, gp)                                 trans/detail/TransImpl.h:144-146 */
+int sptrans_invtrans_vordiv2wind(sptrans_plan* plan, int nb_vordiv_fields, const double* vorticity_spectra,
+                                 const double* divergence_spectra, double* gp_fields);
+
+/* TransImpl::dirtrans(nb_fields, scalar_fields, scalar_spectra)                trans/detail/TransImpl.h:172-173
+ * NotImplemented in TransLocal (TransLocal.cc:1671-1676); semantics of TransIFS (ifs/TransIFS.cc:503-515).  */
+int sptrans_dirtrans_scalar(sptrans_plan* plan, int nb_fields, const double* gp_fields, double* scalar_spectra);
+
+
+/* TransImpl::invtrans_grad(spfield, gradfield) in IFS-style pointers: grad layout
+ * [E-W_1..E-W_k | N-S_1..N-S_k][npts], i.e. component 0 = (1/(a cos))d/dlambda, 1 = (1/a)d/dphi
+ * (ifs/TransIFS.cc:2075-2142).  NotImplemented in TransLocal (TransLocal.cc:848-857).                          */
+
+/* VorDivToUV::execute(nb_coeff, nb_fields, vor, div, U, V)   trans/VorDivToUV.h:121-122,
+ * = vd2uv, trans/local/VorDivToUVLocal.cc:62-184.  Plan-free: spectral space only.                            */
+int sptrans_vordiv_to_uv(int truncation, int nb_fields, const double* vorticity, const double* divergence,
+                         double* U, double* V, int device);
+
+/* ---- stage-level entry points (multi-GPU pipelines, benchmarks, tests) ---------------------------- */
+
+/* number of double2 (re,im) elements per field of the Legendre<->Fourier exchange buffer */
+size_t sptrans_fourier_elems_per_field(const sptrans_plan* plan);
+/* Legendre stage only: device spectra -> device Fourier buffer  (TransLocal::invtrans_legendre, :939-1097) */
+int sptrans_invtrans_legendre(sptrans_plan* plan, int nb_fields, int truncation_of_data, const double* d_spectra,
+                              double* d_fourier);
+/* Fourier stage only: device Fourier buffer -> device grid     (TransLocal::invtrans_fourier_*, :1101-1196) */
+int sptrans_invtrans_fourier(sptrans_plan* plan, int nb_fields, int mlimit, const double* d_fourier,
+                             double* d_gp, int nb_uv_fields);
+int sptrans_dirtrans_fourier(sptrans_plan* plan, int nb_fields, const double* d_gp, double* d_fourier,
+                             int nb_uv_fields);
+int sptrans_dirtrans_legendre(sptrans_plan* plan, int nb_fields, const double* d_fourier, double* d_spectra);
+
+/* kernel time of the last call's stages in milliseconds (CUDA events on the plan's stream):
+ * out[0]=pack/unpack+vd2uv, out[1]=Legendre GEMM, out[2]=Fourier, out[3]=H2D, out[4]=D2H */
+int sptrans_last_timings(const sptrans_plan* plan, float out_ms[8]);
+/* number of kernels this library launched on behalf of the plan since creation */
+uint64_t sptrans_kernel_launches(const sptrans_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPTRANS_B200_H */

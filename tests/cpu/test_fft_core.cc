@@ -1,0 +1,108 @@
+// CPU unit test of atlas_b200/csrc/fft_core.cuh: the exact index / phase algebra of the GPU Fourier
+// kernels (in-place DIF/DIT passes, digit-reversed filter, chirp-z with M >= n + 2L) run sequentially
+// on the host and compared with a naive O(n^2) DFT.  Built and run by tests/test_fft_core_cpu.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../atlas_b200/csrc/fft_core.cuh"
+
+using namespace sptrans::fftc;
+
+static double urand() { return rand() / (double)RAND_MAX - 0.5; }
+
+struct Tables {
+    int n, L, M, logM, Wn;
+    std::vector<double2> W, A, C, Bh;
+};
+
+static Tables build(int n, int L) {
+    Tables t;
+    t.n = n;
+    t.L = L;
+    t.M = conv_length(n, L, &t.logM);
+    t.Wn = 8192;
+    if (t.M > t.Wn) t.Wn = t.M;
+    t.W.resize(t.Wn);
+    for (int k = 0; k < t.Wn; ++k) t.W[k] = make_double2(std::cos(-2 * M_PI * k / t.Wn), std::sin(-2 * M_PI * k / t.Wn));
+    t.A.resize(2 * L + 1);
+    for (int u = 0; u <= 2 * L; ++u) {
+        double ang = M_PI * (double)chirp_residue(u, 0, n) / n;
+        t.A[u] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    t.C.resize(n);
+    for (int i = 0; i < n; ++i) {
+        double ang = M_PI * (double)chirp_residue(i, -2LL * L, n) / n;
+        t.C[i] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    std::vector<double2> b(padded_len(t.M), make_double2(0, 0));
+    for (int k = -2 * L; k <= n - 1; ++k) {
+        double ang = -M_PI * (double)chirp_residue(k, 0, n) / n;
+        int idx = ((k % t.M) + t.M) % t.M;
+        b[pad(idx)] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    fft_dif_all(b.data(), 1, t.logM, t.W.data(), t.Wn, 0, 1);
+    t.Bh.resize(t.M);
+    for (int k = 0; k < t.M; ++k) t.Bh[k] = make_double2(b[pad(k)].x / t.M, b[pad(k)].y / t.M);
+    return t;
+}
+
+static int check(int n, int L) {
+    Tables t = build(n, L);
+    // ---- inverse: z_i = sum_{m=-L..L} Z_m e^{+2 pi i m i/n}
+    std::vector<double2> Z(2 * L + 1);
+    for (auto& z : Z) z = make_double2(urand(), urand());
+    std::vector<double2> X(padded_len(t.M), make_double2(0, 0));
+    for (int u = 0; u <= 2 * L; ++u) X[pad(u)] = cmul(Z[u], t.A[u]);
+    fft_dif_all(X.data(), 1, t.logM, t.W.data(), t.Wn, 0, 1);
+    fft_dit_all<false>(X.data(), 1, t.logM, t.W.data(), t.Wn, t.Bh.data(), 0, 1);
+    double err_inv = 0, nrm = 0;
+    for (int i = 0; i < n; ++i) {
+        double2 got = cmul(X[pad(i)], t.C[i]);
+        double re = 0, im = 0;
+        for (int u = 0; u <= 2 * L; ++u) {
+            long long m = u - L;
+            double ang = 2 * M_PI * (double)(((m * i) % n + n) % n) / n;
+            re += Z[u].x * std::cos(ang) - Z[u].y * std::sin(ang);
+            im += Z[u].x * std::sin(ang) + Z[u].y * std::cos(ang);
+        }
+        err_inv = std::fmax(err_inv, std::hypot(got.x - re, got.y - im));
+        nrm = std::fmax(nrm, std::hypot(re, im));
+    }
+    // ---- forward: G_m = (1/n) sum_i z_i e^{-2 pi i m i/n}, m = -L..L
+    std::vector<double2> z(n);
+    for (auto& v : z) v = make_double2(urand(), urand());
+    std::fill(X.begin(), X.end(), make_double2(0, 0));
+    for (int i = 0; i < n; ++i) X[pad(i)] = cmulc(z[i], t.C[i]);
+    fft_dif_all(X.data(), 1, t.logM, t.W.data(), t.Wn, 0, 1);
+    fft_dit_all<true>(X.data(), 1, t.logM, t.W.data(), t.Wn, t.Bh.data(), 0, 1);
+    double err_fwd = 0, nrm2 = 0;
+    for (int u = 0; u <= 2 * L; ++u) {
+        double2 got = cmulc(X[pad(u)], t.A[u]);
+        got.x /= n;
+        got.y /= n;
+        long long m = u - L;
+        double re = 0, im = 0;
+        for (int i = 0; i < n; ++i) {
+            double ang = -2 * M_PI * (double)(((m * i) % n + n) % n) / n;
+            re += z[i].x * std::cos(ang) - z[i].y * std::sin(ang);
+            im += z[i].x * std::sin(ang) + z[i].y * std::cos(ang);
+        }
+        re /= n;
+        im /= n;
+        err_fwd = std::fmax(err_fwd, std::hypot(got.x - re, got.y - im));
+        nrm2 = std::fmax(nrm2, std::hypot(re, im));
+    }
+    printf("n=%5d L=%5d M=%5d  inv rel err %.3e   fwd rel err %.3e\n", n, L, t.M, err_inv / nrm, err_fwd / nrm2);
+    return (err_inv / nrm < 1e-12 && err_fwd / nrm2 < 1e-12) ? 0 : 1;
+}
+
+int main() {
+    int bad = 0;
+    const int cases[][2] = {{20, 9}, {24, 7}, {28, 0}, {144, 31}, {36, 17}, {1616, 399}, {5136, 1279}, {5132, 1279},
+                            {2568, 1279}, {128, 31}, {9, 4}, {7, 3}, {4, 1}};
+    for (auto& c : cases) bad += check(c[0], c[1]);
+    printf(bad ? "FAILED\n" : "ALL OK\n");
+    return bad;
+}

@@ -1,0 +1,126 @@
+"""Shared test helpers: the reference's analytic-harmonic harness, restated.
+
+* `analytic_harmonic` gives closed forms of the normalised harmonics the reference checks against
+  (src/tests/trans/test_transgeneral.cc:80-374): all (m, n) with n <= 3, and the sectoral n = m for any m
+  (Pbar_m^m = sqrt((2m+1)!!/(2m)!!) cos^m(lat), IFS normalisation 1/2 int Pbar^2 dmu = 1), with the
+  Fourier factor 1 (m = 0) or 2 (m > 0) times cos(m lon) / -sin(m lon)  (:94-104).
+* `compute_rms` is the reference's error norm (:472-489): RMS difference / max |expected|.
+* wind closed forms for (n,m) in {(1,0),(1,1)} (:283-368).
+"""
+import numpy as np
+
+EARTH_RADIUS = 6371229.0  # util/Earth.h:24
+
+
+def spec_index(T, m, n, imag, nf=1, f=0):
+    """flat index of coefficient (m,n,re/im) of field f in [m][n][re/im][fld] layout"""
+    return (2 * ((2 * T + 3 - m) * m // 2 + (n - m)) + imag) * nf + f
+
+
+def pbar(n, m, lat):
+    s, c = np.sin(lat), np.cos(lat)
+    if n == m:
+        k = np.arange(1, m + 1)
+        return np.sqrt(np.prod((2.0 * k + 1.0) / (2.0 * k))) * c**m
+    table = {
+        (1, 0): np.sqrt(3.0) * s,
+        (2, 0): np.sqrt(5.0) / 2.0 * (3.0 * s * s - 1.0),
+        (3, 0): np.sqrt(7.0) / 2.0 * (5.0 * s * s - 3.0) * s,
+        (2, 1): np.sqrt(15.0 / 2.0) * s * c,
+        (3, 1): np.sqrt(21.0) / 4.0 * c * (5.0 * s * s - 1.0),
+        (3, 2): np.sqrt(105.0 / 2.0) / 2.0 * c * c * s,
+    }
+    return table[(n, m)]
+
+
+def has_closed_form(n, m):
+    return n == m or (n <= 3 and m <= n)
+
+
+def analytic_harmonic(n, m, imag, lon, lat):
+    rft = 1.0 if m == 0 else 2.0
+    rft = rft * (np.cos(m * lon) if imag == 0 else -np.sin(m * lon))
+    return pbar(n, m, lat) * rft
+
+
+def analytic_wind(n, m, imag, lon, lat, var_in, var_out):
+    """u (var_out=0) / v (var_out=1) produced by a unit vorticity (var_in=0) or divergence (var_in=1)
+    coefficient; only (n,m) in {(0,0),(1,0),(1,1)}.  test_transgeneral.cc:283-368."""
+    a = EARTH_RADIUS
+    s, c = np.sin(lat), np.cos(lat)
+    ls, lc = np.sin(m * lon), np.cos(m * lon)
+    z = np.zeros_like(lon)
+    if (n, m) == (0, 0):
+        return z
+    if var_in == 0:  # vorticity
+        if var_out == 0:
+            if (n, m) == (1, 0):
+                return np.sqrt(3.0) * a / 2.0 * c if imag == 0 else z
+            return -a * np.sqrt(1.5) * lc * s if imag == 0 else a * np.sqrt(1.5) * ls * s
+        if (n, m) == (1, 0):
+            return z
+        return a * np.sqrt(1.5) * ls if imag == 0 else a * np.sqrt(1.5) * lc
+    # divergence
+    if var_out == 0:
+        if (n, m) == (1, 0):
+            return z
+        return a * np.sqrt(1.5) * ls if imag == 0 else a * np.sqrt(1.5) * lc
+    if (n, m) == (1, 0):
+        return -np.sqrt(3.0) * a / 2.0 * c if imag == 0 else z
+    return a * np.sqrt(1.5) * lc * s if imag == 0 else -a * np.sqrt(1.5) * ls * s
+
+
+def compute_rms(got, expected):
+    got = np.asarray(got)
+    expected = np.asarray(expected)
+    rmax = np.abs(expected).max()
+    if rmax == 0.0:
+        return 0.0
+    return float(np.sqrt(np.mean((got - expected) ** 2)) / rmax)
+
+
+def rel_max(got, expected):
+    d = np.abs(np.asarray(got) - np.asarray(expected)).max()
+    s = np.abs(np.asarray(expected)).max()
+    return float(d / s) if s > 0 else float(d)
+
+
+def synthetic_spectra(T, nf, seed=20260925):
+    """SURVEY 8(d) synthetic input: N(0,1)(1+n)^-1.5, Im(m=0)=0, layout [coeff][fld]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ncoef = (T + 1) * (T + 2) // 2
+    sp = rng.standard_normal((ncoef, 2, nf))
+    k = 0
+    for m in range(T + 1):
+        cnt = T - m + 1
+        n = np.arange(m, T + 1)
+        sp[k:k + cnt] *= ((1.0 + n) ** -1.5)[:, None, None]
+        if m == 0:
+            sp[k:k + cnt, 1, :] = 0.0
+        k += cnt
+    return np.ascontiguousarray(sp.reshape(-1))
+
+
+def grid_lonlat(nx, lat_deg):
+    lon = np.concatenate([2.0 * np.pi * np.arange(n) / n for n in nx])
+    lat = np.repeat(np.deg2rad(lat_deg), nx)
+    return lon, lat
+
+
+def expected_zonal_mask(T, nx, lat_deg, regular, m, fourier_truncation):
+    """Rows on which TransLocal evaluates zonal wavenumber m: northern row j (and its mirror) is kept iff
+    m <= max_{j' <= j} fourier_truncation(row j')   (nlat0, TransLocal.cc:462-488).
+    NB the reference's analytic generator uses `ftrc > m` (test_transgeneral.cc:445), which differs at
+    m == ftrc; its tests pass only because Pbar_m^m ~ cos^m(lat) is below 1e-13 on those polar rows at the
+    resolutions it uses.  Here the mask follows the transform's own rule, so the check is exact."""
+    nlat = len(nx)
+    nxmax = int(max(nx))
+    keep = np.zeros(nlat, dtype=bool)
+    run = -1
+    for j in range(nlat // 2):
+        ft = fourier_truncation(T, int(nx[j]), nxmax, nlat, float(np.deg2rad(lat_deg[j])), 1 if regular else 0)
+        run = max(run, ft)
+        keep[j] = keep[nlat - 1 - j] = m <= run
+    if nlat % 2:
+        keep[nlat // 2] = m <= run
+    return np.repeat(keep, nx)

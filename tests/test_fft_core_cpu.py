@@ -1,0 +1,17 @@
+"""Compiles and runs tests/cpu/test_fft_core.cc: the GPU Fourier kernels' index/phase algebra
+(atlas_b200/csrc/fft_core.cuh is __host__ __device__) executed on the CPU against a naive DFT."""
+import os
+import subprocess
+import tempfile
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fft_core_on_cpu():
+    src = os.path.join(REPO, "tests", "cpu", "test_fft_core.cc")
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "t")
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, src], check=True)
+        r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stdout
+        assert "ALL OK" in r.stdout

@@ -1,0 +1,205 @@
+"""CPU tests (no GPU): the oracle against every golden vector the reference offers for this path.
+
+Pins the oracle before it is trusted as the checker of the CUDA path:
+  * Gaussian latitudes vs the reference's tabulated values (tests/golden/gaussian_latitudes_N*.npy)
+  * Legendre polynomials bit-for-bit vs the unmodified reference source (oracle/_ref or the golden file)
+  * FFT vs the literal DFT
+  * inverse transform vs the reference's closed-form harmonics with the reference's own tolerances
+    (test_transgeneral.cc:534-538: 1e-13 scalar; :833-838: 2e-6 wind)
+  * literal ("as written") vs fast (blocked/OpenMP/FFT) oracle paths
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import pyoracle as po
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def octahedral(N):
+    lat, w = po.gaussian_quadrature(N)
+    nx = np.array([20 + 4 * j for j in range(N)] + [20 + 4 * j for j in range(N - 1, -1, -1)], dtype=np.int32)
+    return nx, lat, w
+
+
+def regular_gaussian(N):
+    lat, w = po.gaussian_quadrature(N)
+    return np.full(2 * N, 4 * N, dtype=np.int32), lat, w
+
+
+def lonlat_grid(N):
+    lat = 90.0 - 180.0 * np.arange(2 * N + 1) / (2 * N)
+    lat[N] = 0.0
+    return np.full(2 * N + 1, 4 * N, dtype=np.int32), lat, None
+
+
+@pytest.mark.parametrize("N", [32, 400, 1280])
+def test_gaussian_latitudes_match_reference_tables(N):
+    gold = np.load(os.path.join(GOLD, f"gaussian_latitudes_N{N}.npy"))
+    lat, w = po.gaussian_quadrature(N)
+    assert np.abs(lat[:N] - gold).max() < 5e-12  # tables carry 12 decimals (N1280 row 0 is off by 3e-12)
+    assert np.allclose(lat[N:], -lat[:N][::-1], rtol=0, atol=0)
+    assert abs(w.sum() - 1.0) < 1e-13  # atlas normalisation: weights over all 2N rows sum to 1
+
+
+def test_legendre_matches_reference_golden_bitwise():
+    g = np.load(os.path.join(GOLD, "legendre_ref_T33.npz"))
+    trc = int(g["trc"])
+    for lat, want in zip(g["lats"], g["legpol"]):
+        got = po.legendre_lat(trc, float(lat))
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.skipif(po.load_ref_legendre() is None, reason="oracle/_ref not built (reference tree absent)")
+@pytest.mark.parametrize("trc,lat_deg", [(64, 60.0), (161, 3.3), (400, 89.9999999), (400, 0.2)])
+def test_legendre_matches_reference_inplace_bitwise(trc, lat_deg):
+    lat = float(np.deg2rad(lat_deg))
+    assert np.array_equal(po.legendre_lat(trc, lat), po.legendre_lat(trc, lat, ref=True))
+
+
+@pytest.mark.skipif(po.load_ref_legendre() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_legendre_tables_match_reference_inplace_bitwise():
+    import ctypes as C
+
+    nx, lat, w = octahedral(16)
+    T = 15
+    plan = po.OraclePlan(nx, lat, T)
+    sym, asym, sb, ab = plan.tables()
+    ref = po.load_ref_legendre()
+    rs = np.zeros_like(sym)
+    ra = np.zeros_like(asym)
+    lats = np.deg2rad(lat[:16])
+    ref.ref_legendre_tables(T + 1, 16, lats.ctypes.data_as(C.POINTER(C.c_double)), rs.ctypes.data_as(C.POINTER(C.c_double)),
+                            ra.ctypes.data_as(C.POINTER(C.c_double)), sb.ctypes.data_as(C.POINTER(C.c_size_t)),
+                            ab.ctypes.data_as(C.POINTER(C.c_size_t)))
+    assert np.array_equal(sym, rs) and np.array_equal(asym, ra)
+
+
+@pytest.mark.parametrize("n", [4, 20, 24, 36, 100, 144, 332, 1616, 2052, 5132])
+def test_fft_c2r_matches_literal_dft(n):
+    rng = np.random.default_rng(n)
+    spec = rng.standard_normal(n // 2 + 1) + 1j * rng.standard_normal(n // 2 + 1)
+    spec[0] = spec[0].real
+    a = po.c2r(n, spec, naive=False)
+    b = po.c2r(n, spec, naive=True)
+    assert H.rel_max(a, b) < 2e-14
+    # r2c is the adjoint/inverse pair
+    back = po.r2c(n, a) / n
+    m = (n - 1) // 2
+    assert np.abs(back[1:m + 1] - spec[1:m + 1]).max() < 1e-13
+
+
+def test_fourier_truncation_octahedral_cubic():
+    # O1280 / T1279: cubic rule; every m < = T is resolved at the equator, few at the pole
+    nx, lat, w = octahedral(1280)
+    plan_nlat0 = []
+    for m_probe, j in ((0, 0), (1279, 1279)):
+        ft = po.lib().orc_fourier_truncation(1279, int(nx[j]), 5136, 2560, float(np.deg2rad(lat[j])), 0)
+        plan_nlat0.append(ft)
+    assert plan_nlat0[0] == 8 and plan_nlat0[1] == 1279
+
+
+CASES = [("F32", regular_gaussian(32), 31, True), ("O32", octahedral(32), 31, False), ("O64", octahedral(64), 63, False),
+         ("L3", lonlat_grid(3), 5, True), ("L9", lonlat_grid(9), 17, True)]
+
+
+@pytest.mark.parametrize("name,grid,T,regular", CASES)
+def test_invtrans_scalar_vs_closed_form_harmonics(name, grid, T, regular):
+    """test_transgeneral.cc:493-643 (and the pole case :956-1140): unit coefficient -> closed-form harmonic."""
+    nx, lat, w = grid
+    plan = po.OraclePlan(nx, lat, T, regular=regular, weights=w)
+    lon, latp = H.grid_lonlat(nx, np.clip(lat, -89.9999999, 89.9999999) if name.startswith("L") else lat)
+    ncoef2 = (T + 1) * (T + 2)
+    worst = 0.0
+    ncases = 0
+    for m in range(0, min(T, 45) + 1):
+        for n in range(m, min(T, 45) + 1):
+            if not H.has_closed_form(n, m) or m >= T:  # m == T is dropped by the scalar path (TransLocal.cc:982)
+                continue
+            for imag in (0, 1):
+                if m == 0 and imag == 1:
+                    continue
+                sp = np.zeros(ncoef2)
+                sp[H.spec_index(T, m, n, imag)] = 1.0
+                got = plan.invtrans(1, sp, mode=2)
+                want = H.analytic_harmonic(n, m, imag, lon, latp)
+                mask = H.expected_zonal_mask(T, nx, lat, regular, m, po.lib().orc_fourier_truncation)
+                want = np.where(mask, want, 0.0)
+                worst = max(worst, H.compute_rms(got, want))
+                ncases += 1
+    assert ncases > 10
+    assert worst < 1e-13, worst
+
+
+def test_invtrans_wind_vs_closed_form():
+    """vorticity / divergence unit coefficients -> u, v (test_transgeneral.cc:540-600, tolerance 2e-6)."""
+    nx, lat, w = regular_gaussian(32)
+    T = 31
+    plan = po.OraclePlan(nx, lat, T, regular=True, weights=w)
+    lon, latp = H.grid_lonlat(nx, lat)
+    npts = plan.npts
+    ncoef2 = (T + 1) * (T + 2)
+    for (n, m) in ((1, 0), (1, 1)):
+        for imag in (0, 1):
+            if m == 0 and imag == 1:
+                continue
+            for var_in in (0, 1):
+                vor = np.zeros(ncoef2)
+                div = np.zeros(ncoef2)
+                (vor if var_in == 0 else div)[H.spec_index(T, m, n, imag)] = 1.0
+                gp = plan.invtrans(0, None, 1, vor, div, mode=2)
+                for var_out in (0, 1):
+                    want = H.analytic_wind(n, m, imag, lon, latp, var_in, var_out)
+                    got = gp[var_out * npts:(var_out + 1) * npts]
+                    assert H.compute_rms(got, want) < 2e-6 or np.abs(want).max() == 0 and np.abs(got).max() < 1e-3
+
+
+def test_literal_and_fast_paths_agree():
+    nx, lat, w = octahedral(32)
+    T = 31
+    nf = 4
+    plan = po.OraclePlan(nx, lat, T, weights=w)
+    sp = H.synthetic_spectra(T, nf)
+    a = plan.invtrans(nf, sp, mode=0)   # naive GEMM + naive DFT, single thread: "reference as written"
+    b = plan.invtrans(nf, sp, mode=2)   # blocked GEMM + FFT + OpenMP
+    assert H.rel_max(b, a) < 1e-14
+    vor = H.synthetic_spectra(T, 2, seed=7)
+    div = H.synthetic_spectra(T, 2, seed=8)
+    a = plan.invtrans(nf, sp, 2, vor, div, mode=0)
+    b = plan.invtrans(nf, sp, 2, vor, div, mode=2)
+    assert H.rel_max(b, a) < 1e-14
+
+
+def test_dirtrans_roundtrip_regular_grid():
+    """dirtrans(invtrans(x)) == x on a regular Gaussian grid (exact quadrature) except the m == T column
+    the scalar inverse drops; semantics of test_transgeneral.cc:1494-1585 (test_trans_levels)."""
+    nx, lat, w = regular_gaussian(24)
+    T = 23
+    nf = 3
+    plan = po.OraclePlan(nx, lat, T, regular=True, weights=w)
+    sp = H.synthetic_spectra(T, nf)
+    gp = plan.invtrans(nf, sp, mode=2)
+    back = plan.dirtrans(nf, gp)
+    sp_expect = sp.copy().reshape(-1, 2, nf)
+    sp_expect[-1] = 0.0  # (m=T, n=T)
+    assert np.abs(back - sp_expect.reshape(-1)).max() < 1e-13
+
+
+def test_vd2uv_against_merged_inverse_definition():
+    """U,V from vd2uv at T+1 are what the merged inverse feeds to the Legendre stage: check linearity
+    and the (1,0)/(1,1) closed forms through the full inverse instead (above); here only shape/zero rules."""
+    T = 10
+    nf = 2
+    rng = np.random.default_rng(0)
+    vor = rng.standard_normal((T + 1) * (T + 2) * nf)
+    div = rng.standard_normal((T + 1) * (T + 2) * nf)
+    U, V = po.vd2uv(T, nf, vor, div)
+    U2, V2 = po.vd2uv(T, nf, 2 * vor, 2 * div)
+    assert np.allclose(U2, 2 * U, rtol=1e-14, atol=0) and np.allclose(V2, 2 * V, rtol=1e-14, atol=0)
+    # imaginary parts of m = 0 stay zero
+    for n in range(T + 1):
+        for f in range(nf):
+            assert U[H.spec_index(T, 0, n, 1, nf, f)] == 0.0

@@ -151,8 +151,11 @@ def test_invtrans_vordiv_matches_oracle(gridname, T, nsc, nvd):
     gp = np.full(nall * grid.size(), np.nan)
     trans.invtrans(nsc, sp, nvd, vor, div, gp)
     want = plan.invtrans(nsc, sp, nvd, vor, div, mode=2)
-    assert H.compute_rms(gp, want) < 1e-12
-    assert H.rel_max(gp, want) < 1e-11
+    # grids with pole rows divide U,V by cos(89.9999999 deg) = 1.7e-9, amplifying rounding differences by ~1e9;
+    # the reference relaxes its own wind tolerance to 2e-5 there (test_transgeneral.cc:1040-1045)
+    pole = abs(grid.y(0)) > 89.9999999
+    assert H.compute_rms(gp, want) < (1e-8 if pole else 1e-12)
+    assert H.rel_max(gp, want) < (1e-7 if pole else 1e-11)
 
 
 def test_invtrans_wind_vs_closed_form():

@@ -60,6 +60,13 @@ def _load():
         "sptrans_invtrans_fourier": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int]),
         "sptrans_dirtrans_fourier": (C.c_int, [vp, C.c_int, vp, vp, C.c_int]),
         "sptrans_dirtrans_legendre": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_shard_layout": (C.c_int, [C.c_int, c_int_p, c_double_p, C.c_int, C.c_uint, C.c_int, C.c_int, c_int_p, c_int_p,
+                                           C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+        "sptrans_shard_segments": (C.c_longlong, [C.c_int, c_int_p, c_double_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int,
+                                                  C.POINTER(C.c_longlong)]),
+        "sptrans_exchange_rows": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+        "sptrans_exchange_pack": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+        "sptrans_exchange_unpack": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
         "sptrans_last_timings": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "sptrans_kernel_launches": (C.c_uint64, [vp]),
     }

@@ -218,6 +218,9 @@ int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, con
         set_error("cudaMalloc failed");
         return fail(SPTRANS_ERR_CUDA);
     }
+    build_exchange(g, p.ex);
+    if ((rc = upload(p.d_ex_m, p.ex.m_side, p.stream))) return fail(rc);
+    if ((rc = upload(p.d_ex_band, p.ex.band_side, p.stream))) return fail(rc);
     if ((rc = generate_legendre_table(p))) return fail(rc);
     if ((rc = build_fft_tables(p))) return fail(rc);
     if (cudaStreamSynchronize(p.stream) != cudaSuccess) {
@@ -241,7 +244,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     free_fft_tables(p);
     void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_weights,
                     p.d_coslatinv, p.d_coslat, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
-                    p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
+                    p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
                     p.d_gp};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -558,6 +561,77 @@ int sptrans_dirtrans_legendre(sptrans_plan* plan, int nf, const double* d_fourie
     if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
     if ((rc = launch_legendre_dir(p, nf, d_fourier, p.d_packed))) return rc;
     if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spectra))) return rc;
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    return SPTRANS_OK;
+}
+
+int sptrans_shard_layout(int nlat, const int* nx, const double* lat_deg, int truncation, unsigned flags, int rank,
+                         int nranks, int* owner, int* band, long long* m_side_rows, long long* band_side_rows) {
+    HostGeom g;
+    int rc = build_geometry(g, nlat, nx, lat_deg, nullptr, truncation, (flags & SPTRANS_GRID_REGULAR) != 0, rank, nranks);
+    if (rc) return rc;
+    ExchangeLayout ex;
+    build_exchange(g, ex);
+    if (owner) std::copy(g.owner.begin(), g.owner.end(), owner);
+    if (band) std::copy(g.band.begin(), g.band.end(), band);
+    if (m_side_rows) std::copy(ex.m_side_rows.begin(), ex.m_side_rows.end(), m_side_rows);
+    if (band_side_rows) std::copy(ex.band_side_rows.begin(), ex.band_side_rows.end(), band_side_rows);
+    return SPTRANS_OK;
+}
+
+long long sptrans_shard_segments(int nlat, const int* nx, const double* lat_deg, int truncation, unsigned flags,
+                                 int rank, int nranks, int side, long long* out) {
+    HostGeom g;
+    int rc = build_geometry(g, nlat, nx, lat_deg, nullptr, truncation, (flags & SPTRANS_GRID_REGULAR) != 0, rank, nranks);
+    if (rc) return -1;
+    ExchangeLayout ex;
+    build_exchange(g, ex);
+    const std::vector<ExSeg>& v = side == 0 ? ex.m_side : ex.band_side;
+    if (out)
+        for (size_t i = 0; i < v.size(); ++i) {
+            out[3 * i] = v[i].fb_row;
+            out[3 * i + 1] = v[i].buf_row;
+            out[3 * i + 2] = v[i].nrows;
+        }
+    return static_cast<long long>(v.size());
+}
+
+int sptrans_exchange_rows(const sptrans_plan* plan, long long* m_side_rows, long long* band_side_rows) {
+    if (!plan || !m_side_rows || !band_side_rows) return SPTRANS_ERR_INVALID;
+    const ExchangeLayout& ex = plan->p.ex;
+    std::copy(ex.m_side_rows.begin(), ex.m_side_rows.end(), m_side_rows);
+    std::copy(ex.band_side_rows.begin(), ex.band_side_rows.end(), band_side_rows);
+    return SPTRANS_OK;
+}
+
+int sptrans_exchange_pack(sptrans_plan* plan, int nf, int side, const double* d_fourier, double* d_buf) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf <= 0 || !d_fourier || !d_buf) {
+        set_error("sptrans_exchange_pack: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    const bool ms = side == 0;
+    rc = launch_exchange_copy(p, nf, ms ? p.d_ex_m : p.d_ex_band, static_cast<int>(ms ? p.ex.m_side.size() : p.ex.band_side.size()),
+                              const_cast<double*>(d_fourier), d_buf, true);
+    if (rc) return rc;
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    return SPTRANS_OK;
+}
+
+int sptrans_exchange_unpack(sptrans_plan* plan, int nf, int side, const double* d_buf, double* d_fourier) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf <= 0 || !d_fourier || !d_buf) {
+        set_error("sptrans_exchange_unpack: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    const bool ms = side == 0;
+    rc = launch_exchange_copy(p, nf, ms ? p.d_ex_m : p.d_ex_band, static_cast<int>(ms ? p.ex.m_side.size() : p.ex.band_side.size()),
+                              d_fourier, const_cast<double*>(d_buf), false);
+    if (rc) return rc;
     SPT_CUDA(cudaStreamSynchronize(p.stream));
     return SPTRANS_OK;
 }

@@ -132,31 +132,13 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
     for (int j = 0; j < g.nleg; ++j)
         for (int m = 0; m <= T; ++m)
             if (g.nlat0[m] <= j) g.mmax[j] = m;
-    // Legendre table blocks (m, parity): K rows (n ascending) x pitch latitudes
-    g.tab_off.assign(2 * (T + 1), 0);
-    g.tab_K.assign(2 * (T + 1), 0);
-    g.tab_pitch.assign(T + 1, 0);
-    g.sp_rowoff.assign(2 * (T + 1) + 1, 0);
-    g.fb_rowoff.assign(T + 2, 0);
-    long long off = 0;
-    for (int m = 0; m <= T; ++m) {
-        const int ncol = g.nleg - g.nlat0[m];
-        g.tab_pitch[m] = round_up(std::max(ncol, 0), 16);
-        for (int p = 0; p < 2; ++p) {
-            const int K = num_n(T + 1, m, p);
-            g.tab_K[2 * m + p] = K;
-            g.tab_off[2 * m + p] = off;
-            // rows padded to the GEMM tile height so that tile loads never leave the block
-            off += static_cast<long long>(round_up(std::max(K, 1), kBK)) * g.tab_pitch[m];
-            g.sp_rowoff[2 * m + p + 1] = g.sp_rowoff[2 * m + p] + round_up(std::max(K, 1), kBK);
-        }
-        g.fb_rowoff[m + 1] = g.fb_rowoff[m] + 2LL * std::max(ncol, 0);
-    }
-    g.tab_size = off;
     // sharding: zonal wavenumbers by cost-balanced greedy assignment, latitude pairs by sum(nx) bands
     g.rank = rank;
     g.nranks = nranks;
     g.my_m.clear();
+    g.owner.assign(T + 1, 0);
+    g.band.assign(nranks + 1, g.nleg);
+    g.band[0] = 0;
     if (nranks == 1) {
         for (int m = 0; m <= T; ++m) g.my_m.push_back(m);
         g.pair_begin = 0;
@@ -173,6 +155,7 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
             for (int r = 1; r < nranks; ++r)
                 if (load[r] < load[best]) best = r;
             load[best] += cost(m);
+            g.owner[m] = best;
             if (best == rank) g.my_m.push_back(m);
         }
         std::sort(g.my_m.begin(), g.my_m.end());
@@ -187,10 +170,68 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
             acc += nx[j];
             while (r < nranks && acc * nranks >= total * r) bound[r++] = j + 1;
         }
+        g.band = bound;
         g.pair_begin = bound[rank];
         g.pair_end = bound[rank + 1];
     }
+    // Legendre table blocks (m, parity): K rows (n ascending) x pitch latitudes
+    g.tab_off.assign(2 * (T + 1), 0);
+    g.tab_K.assign(2 * (T + 1), 0);
+    g.tab_pitch.assign(T + 1, 0);
+    g.sp_rowoff.assign(2 * (T + 1) + 1, 0);
+    g.fb_rowoff.assign(T + 2, 0);
+    long long off = 0;
+    for (int m = 0; m <= T; ++m) {
+        const int ncol = g.nleg - g.nlat0[m];
+        g.tab_pitch[m] = round_up(std::max(ncol, 0), 16);
+        for (int p = 0; p < 2; ++p) {
+            const int K = num_n(T + 1, m, p);
+            g.tab_K[2 * m + p] = K;
+            // a sharded plan holds only the table blocks of its own zonal wavenumbers
+            const bool mine = (nranks == 1) || (g.owner[m] == rank);
+            g.tab_off[2 * m + p] = mine ? off : -1;
+            // rows padded to the GEMM tile height so that tile loads never leave the block
+            if (mine) off += static_cast<long long>(round_up(std::max(K, 1), kBK)) * g.tab_pitch[m];
+            g.sp_rowoff[2 * m + p + 1] = g.sp_rowoff[2 * m + p] + round_up(std::max(K, 1), kBK);
+        }
+        g.fb_rowoff[m + 1] = g.fb_rowoff[m] + 2LL * std::max(ncol, 0);
+    }
+    g.tab_size = off;
     return SPTRANS_OK;
+}
+
+// Segment lists of the transposition between the two shardings.  Both sides enumerate (m ascending, parity,
+// latitude ascending) so that the packed buffers of sender and receiver line up without any metadata exchange.
+void build_exchange(const HostGeom& g, ExchangeLayout& ex) {
+    const int R = g.nranks, me = g.rank;
+    ex.m_side.clear();
+    ex.band_side.clear();
+    ex.m_side_rows.assign(R, 0);
+    ex.band_side_rows.assign(R, 0);
+    auto add = [&](std::vector<ExSeg>& v, long long& cursor, int m, int b0, int b1) -> long long {
+        const int n0 = g.nlat0[m];
+        const int ncol = g.nleg - n0;
+        const int lo = std::max(b0, n0), hi = b1;
+        long long rows = 0;
+        if (hi <= lo) return 0;
+        for (int p = 0; p < 2; ++p) {
+            ExSeg s{};
+            s.fb_row = g.fb_rowoff[m] + static_cast<long long>(p) * ncol + (lo - n0);
+            s.buf_row = cursor;
+            s.nrows = hi - lo;
+            v.push_back(s);
+            cursor += s.nrows;
+            rows += s.nrows;
+        }
+        return rows;
+    };
+    long long cur = 0;
+    for (int d = 0; d < R; ++d)           // my zonal wavenumbers, restricted to rank d's latitude band
+        for (int m : g.my_m) ex.m_side_rows[d] += add(ex.m_side, cur, m, g.band[d], g.band[d + 1]);
+    cur = 0;
+    for (int s = 0; s < R; ++s)           // rank s's zonal wavenumbers, restricted to my latitude band
+        for (int m = 0; m <= g.T; ++m)
+            if (g.owner[m] == s) ex.band_side_rows[s] += add(ex.band_side, cur, m, g.band[me], g.band[me + 1]);
 }
 
 // Seeds of the Legendre recurrence for each latitude: cos(theta), the m=0 and m=1 columns (cosine /

@@ -56,8 +56,9 @@ legendre_gen_kernel(int trc,            // table truncation (T+1)
         }
         else {
             const int jj = j - nlat0[m];
-            if (jj < 0) return;
-            tab[tab_off[2 * m + par] + static_cast<long long>(k) * tab_pitch[m] + jj] = v;
+            const long long off = tab_off[2 * m + par];
+            if (jj < 0 || off < 0) return;  // latitude pruned for this m / block owned by another rank
+            tab[off + static_cast<long long>(k) * tab_pitch[m] + jj] = v;
         }
     };
 

@@ -58,6 +58,8 @@ struct HostGeom {
     // sharding
     int rank = 0, nranks = 1;
     std::vector<int> my_m;       // zonal wavenumbers owned by this rank (all if nranks==1)
+    std::vector<int> owner;      // [T+1] rank that owns zonal wavenumber m
+    std::vector<int> band;       // [nranks+1] latitude-pair band boundaries
     int pair_begin = 0, pair_end = 0;  // latitude pairs [begin,end) of this rank's Fourier band
 };
 
@@ -67,6 +69,21 @@ inline int num_n(int truncation, int m, int parity) {  // #n in [m, truncation] 
 }
 inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
 
+// One contiguous run of rows of the Legendre<->Fourier exchange buffer (a row = nf double2) and where it
+// sits in a packed send / receive buffer.
+struct ExSeg {
+    long long fb_row;
+    long long buf_row;
+    int nrows;
+    int pad;
+};
+// Exchange plan between the m-sharded Legendre stage and the latitude-band-sharded Fourier stage.
+// m_side: segments of the rows this rank owns as m-owner, grouped by the band owner they travel to/from;
+// band_side: segments of the rows this rank owns as band owner, grouped by m-owner.
+struct ExchangeLayout {
+    std::vector<ExSeg> m_side, band_side;
+    std::vector<long long> m_side_rows, band_side_rows;  // [nranks] rows per peer
+};
 // per distinct row length: Bluestein / chirp-z tables on the device
 struct FftLen {
     int n = 0;       // row length
@@ -118,6 +135,9 @@ struct Plan {
     double* d_spec2 = nullptr;    size_t spec2_cap = 0;
     double* d_gp = nullptr;       size_t gp_cap = 0;       // device copy of grid fields (host-pointer mode)
     void* h_pinned = nullptr;     size_t pinned_cap = 0;
+    ExchangeLayout ex;
+    ExSeg* d_ex_m = nullptr;
+    ExSeg* d_ex_band = nullptr;
     size_t bytes_tables = 0;
     // stats
     uint64_t launches = 0;
@@ -137,6 +157,8 @@ const char* last_error_cstr();
             return SPTRANS_ERR_CUDA;                                                                 \
         }                                                                                            \
     } while (0)
+
+void build_exchange(const HostGeom& g, ExchangeLayout& ex);
 
 // ---- host_setup.cc ----
 int fourier_truncation(int truncation, int nx, int nxmax, int ndgl, double lat, bool fullgrid);
@@ -164,6 +186,9 @@ int build_fft_tables(Plan& p);
 void free_fft_tables(Plan& p);
 int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv);
 int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv);
+
+// ---- exchange.cu ----
+int launch_exchange_copy(Plan& p, int nf, const ExSeg* d_segs, int nseg, double* d_fourier, double* d_buf, bool gather);
 
 // ---- vordiv.cu ----
 int launch_vd2uv(cudaStream_t s, int T, int nf, const double* d_vor, const double* d_div, double* d_U, double* d_V,

@@ -156,6 +156,23 @@ int sptrans_dirtrans_fourier(sptrans_plan* plan, int nb_fields, const double* d_
                              int nb_uv_fields);
 int sptrans_dirtrans_legendre(sptrans_plan* plan, int nb_fields, const double* d_fourier, double* d_spectra);
 
+/* ---- multi-GPU: one exchange step between the two shardings (no reference equivalent; ectrans does the same
+ * transposition internally over MPI).  "m side" = rows of the exchange buffer this rank owns as owner of its
+ * zonal wavenumbers, grouped by destination latitude band; "band side" = rows it owns as owner of its latitude
+ * band, grouped by the rank owning the zonal wavenumber.  Row = nb_fields (re,im) pairs.
+ *   inverse: legendre -> pack(m side) -> all-to-all (send m_side_rows, recv band_side_rows) -> unpack(band side) -> fourier
+ *   direct : fourier  -> pack(band side) -> all-to-all (send band_side_rows, recv m_side_rows) -> unpack(m side) -> legendre */
+/* host-only layout query (no device needed): owner[T+1], band[nranks+1], rows per peer [nranks] each */
+int sptrans_shard_layout(int nlat, const int* nx, const double* lat_deg, int truncation, unsigned flags, int rank,
+                         int nranks, int* owner, int* band, long long* m_side_rows, long long* band_side_rows);
+/* host-only: the copy segments of one side as triples (exchange-buffer row, packed-buffer row, number of rows);
+ * returns the number of segments (call with out == NULL to size the buffer) */
+long long sptrans_shard_segments(int nlat, const int* nx, const double* lat_deg, int truncation, unsigned flags,
+                                 int rank, int nranks, int side, long long* out);
+int sptrans_exchange_rows(const sptrans_plan* plan, long long* m_side_rows, long long* band_side_rows);
+int sptrans_exchange_pack(sptrans_plan* plan, int nb_fields, int side, const double* d_fourier, double* d_buf);
+int sptrans_exchange_unpack(sptrans_plan* plan, int nb_fields, int side, const double* d_buf, double* d_fourier);
+
 /* kernel time of the last call's stages in milliseconds (CUDA events on the plan's stream):
  * out[0]=pack/unpack+vd2uv, out[1]=Legendre GEMM, out[2]=Fourier, out[3]=H2D, out[4]=D2H */
 int sptrans_last_timings(const sptrans_plan* plan, float out_ms[8]);

@@ -1,0 +1,22 @@
+// Minimal stand-in for eckit::Configuration (only what TransB200.h touches). Test infrastructure.
+#pragma once
+#include <map>
+#include <string>
+namespace eckit {
+class Configuration {
+public:
+    virtual ~Configuration() = default;
+    bool get(const std::string& key, int& v) const {
+        auto it = ints_.find(key);
+        if (it == ints_.end()) return false;
+        v = it->second;
+        return true;
+    }
+    Configuration& set(const std::string& key, int v) {
+        ints_[key] = v;
+        return *this;
+    }
+private:
+    std::map<std::string, int> ints_;
+};
+}  // namespace eckit

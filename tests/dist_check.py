@@ -1,0 +1,53 @@
+"""Run under torch.distributed.run with N >= 2 GPUs: sharded inverse + direct transform vs the CPU oracle.
+Used by tests/test_gpu_dist.py and by hand:  python -m torch.distributed.run --nproc-per-node 2 tests/dist_check.py O48 47 5"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+import helpers as H  # noqa: E402
+
+import atlas_b200  # noqa: E402
+from atlas_b200.dist import ShardedTrans  # noqa: E402
+
+
+def main():
+    gridname, T, nf = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    rank = int(os.environ["RANK"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    grid = atlas_b200.Grid(gridname)
+    st = ShardedTrans(grid, T, local)
+    sp = H.synthetic_spectra(T, nf)
+    d_sp = torch.from_numpy(sp).cuda()
+    d_gp = torch.zeros(nf * grid.size(), dtype=torch.float64, device="cuda")
+    st.invtrans(nf, d_sp, d_gp)
+    st.gather_grid(nf, d_gp)  # disjoint rows summed with zeros elsewhere
+    d_sp2 = torch.zeros_like(d_sp)
+    st.dirtrans(nf, d_gp, d_sp2)
+    dist.all_reduce(d_sp2)  # every coefficient is produced by exactly one rank
+    ok = True
+    if rank == 0:
+        from oracle import pyoracle as po
+
+        plan = po.OraclePlan(grid.nx(), grid.y(), T, regular=grid.regular, weights=grid.weights())
+        want = plan.invtrans(nf, sp, mode=2)
+        e1 = H.rel_max(d_gp.cpu().numpy(), want)
+        want_sp = plan.dirtrans(nf, want)
+        e2 = H.rel_max(d_sp2.cpu().numpy(), want_sp)
+        ok = e1 < 1e-12 and e2 < 1e-12
+        print(f"DIST_CHECK world={dist.get_world_size()} {gridname} T{T} nf={nf}: invtrans rel err {e1:.2e}, dirtrans rel err {e2:.2e} -> {'OK' if ok else 'FAIL'}")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

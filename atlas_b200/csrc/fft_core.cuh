@@ -228,6 +228,267 @@ SPT_HD void fft_dit_all(double2* X, int nseq, int logM, const double2* tw, int W
     }
 }
 
+
+// =====================================================================================================
+// Mixed-radix engine (M = 2^a 3^b 5^c): same in-place DIF / DIT scheme with radices {16, 9, 8, 5, 4, 3, 2}.
+// Choosing M among all 5-smooth lengths instead of powers of two cuts the convolution length of the
+// chirp-z by ~25 % on the octahedral grid (n + 2L is rarely just below a power of two).
+// =====================================================================================================
+template <bool FWD>
+SPT_HD void dft3(double2* v) {
+    const double c = 0.86602540378443864676;  // sin(pi/3)
+    const double2 s = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+    const double2 m = make_double2(v[0].x - 0.5 * s.x, v[0].y - 0.5 * s.y);
+    const double2 rd = rot90<FWD>(d);
+    const double2 r = make_double2(c * rd.x, c * rd.y);
+    v[0] = cadd(v[0], s);
+    v[1] = cadd(m, r);
+    v[2] = csub(m, r);
+}
+template <bool FWD>
+SPT_HD void dft5(double2* v) {
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;  // cos(2pi/5), cos(4pi/5)
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;   // sin(2pi/5), sin(4pi/5)
+    const double2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
+    const double2 b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+    const double2 p1 = make_double2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+    const double2 p2 = make_double2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+    const double2 q1 = rot90<FWD>(make_double2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y));
+    const double2 q2 = rot90<FWD>(make_double2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y));
+    v[0] = make_double2(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
+    v[1] = cadd(p1, q1);
+    v[4] = csub(p1, q1);
+    v[2] = cadd(p2, q2);
+    v[3] = csub(p2, q2);
+}
+// multiply by e^{-+ 2 pi i k / N} given (cos, sin) of 2 pi k / N
+template <bool FWD>
+SPT_HD double2 twc(double2 a, double c, double s) {
+    return FWD ? make_double2(a.x * c + a.y * s, a.y * c - a.x * s) : make_double2(a.x * c - a.y * s, a.y * c + a.x * s);
+}
+template <bool FWD>
+SPT_HD void dft9(double2* v) {
+    const double c1 = 0.76604444311897803520, s1 = 0.64278760968653932632;   // 2pi/9
+    const double c2 = 0.17364817766693034885, s2 = 0.98480775301220805937;   // 4pi/9
+    const double c4 = -0.93969262078590838405, s4 = 0.34202014332566873304;  // 8pi/9
+    double2 y[3][3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        double2 t[3] = {v[b], v[b + 3], v[b + 6]};
+        dft3<FWD>(t);
+        y[b][0] = t[0];
+        y[b][1] = t[1];
+        y[b][2] = t[2];
+    }
+    y[1][1] = twc<FWD>(y[1][1], c1, s1);
+    y[1][2] = twc<FWD>(y[1][2], c2, s2);
+    y[2][1] = twc<FWD>(y[2][1], c2, s2);
+    y[2][2] = twc<FWD>(y[2][2], c4, s4);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double2 t[3] = {y[0][c], y[1][c], y[2][c]};
+        dft3<FWD>(t);
+        v[c] = t[0];
+        v[c + 3] = t[1];
+        v[c + 6] = t[2];
+    }
+}
+template <bool FWD>
+SPT_HD void dft16(double2* v) {
+    const double h = 0.70710678118654752440;
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;  // 2pi/16
+    double2 y[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        double2 t[4] = {v[b], v[b + 4], v[b + 8], v[b + 12]};
+        dft4<FWD>(t);
+        y[b][0] = t[0];
+        y[b][1] = t[1];
+        y[b][2] = t[2];
+        y[b][3] = t[3];
+    }
+    // twiddles w16^{b c}
+    y[1][1] = twc<FWD>(y[1][1], c1, s1);   // w^1
+    y[1][2] = twc<FWD>(y[1][2], h, h);     // w^2
+    y[1][3] = twc<FWD>(y[1][3], s1, c1);   // w^3
+    y[2][1] = twc<FWD>(y[2][1], h, h);     // w^2
+    y[2][2] = rot90<FWD>(y[2][2]);         // w^4
+    y[2][3] = twc<FWD>(y[2][3], -h, h);    // w^6
+    y[3][1] = twc<FWD>(y[3][1], s1, c1);   // w^3
+    y[3][2] = twc<FWD>(y[3][2], -h, h);    // w^6
+    y[3][3] = twc<FWD>(y[3][3], -c1, -s1); // w^9
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double2 t[4] = {y[0][c], y[1][c], y[2][c], y[3][c]};
+        dft4<FWD>(t);
+        v[c] = t[0];
+        v[c + 4] = t[1];
+        v[c + 8] = t[2];
+        v[c + 12] = t[3];
+    }
+}
+template <int R, bool FWD>
+SPT_HD void dftN(double2* v) {
+    if (R == 2) dft2<FWD>(v);
+    else if (R == 3) dft3<FWD>(v);
+    else if (R == 4) dft4<FWD>(v);
+    else if (R == 5) dft5<FWD>(v);
+    else if (R == 8) dft8<FWD>(v);
+    else if (R == 9) dft9<FWD>(v);
+    else dft16<FWD>(v);
+}
+
+// powers w^1..w^{R-1} of one twiddle with a shallow dependency tree
+template <int R>
+SPT_HD void twiddle_powers(double2 w1, double2* w /*[R]*/) {
+    w[1] = w1;
+    if (R > 2) w[2] = cmul(w1, w1);
+    if (R > 3) w[3] = cmul(w[2], w1);
+    if (R > 4) w[4] = cmul(w[2], w[2]);
+#pragma unroll
+    for (int j = 5; j < R; ++j) w[j] = (j & 1) ? cmul(w[j - 1], w1) : cmul(w[j / 2], w[j / 2]);
+}
+
+// Two-level twiddle table of e^{-2 pi i k / M}: W[k] = Wa[k >> 6] * Wb[k & 63]  (Wa: M/64+1 entries, Wb: 64)
+SPT_HD double2 twiddle2(const double2* Wa, const double2* Wb, int k) { return cmul(Wa[k >> 6], Wb[k & 63]); }
+
+template <int R>
+SPT_HD void dif_butterfly_g(double2* X, int q, int Nb, int S, const double2* Wa, const double2* Wb) {
+    const int span = Nb / R;
+    const int blk = q / span, t = q - blk * span;
+    const int base = blk * Nb + t;
+    double2 v[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = X[pad(base + j * span)];
+    dftN<R, true>(v);
+    if (t != 0) {
+        double2 w[R];
+        twiddle_powers<R>(twiddle2(Wa, Wb, t * S), w);
+#pragma unroll
+        for (int j = 1; j < R; ++j) v[j] = cmul(v[j], w[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) X[pad(base + j * span)] = v[j];
+}
+
+template <int R, bool CONJ_FILT>
+SPT_HD void dit_butterfly_g(double2* X, int q, int Nb, int S, const double2* Wa, const double2* Wb,
+                            const double2* filt) {
+    const int span = Nb / R;
+    const int blk = q / span, t = q - blk * span;
+    const int base = blk * Nb + t;
+    double2 v[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        v[j] = X[pad(base + j * span)];
+        if (filt) v[j] = CONJ_FILT ? cmulc(v[j], filt[base + j * span]) : cmul(v[j], filt[base + j * span]);
+    }
+    if (t != 0) {
+        double2 w[R];
+        twiddle_powers<R>(twiddle2(Wa, Wb, t * S), w);
+#pragma unroll
+        for (int j = 1; j < R; ++j) v[j] = cmulc(v[j], w[j]);
+    }
+    dftN<R, false>(v);
+#pragma unroll
+    for (int j = 0; j < R; ++j) X[pad(base + j * span)] = v[j];
+}
+
+struct ScheduleG {
+    int npass;
+    int radix[10];
+    int nb[10];     // block length of the pass
+    int stride[10]; // S = M / nb
+};
+// radices: 16s, then the remaining power of two, then 9s / 3, then 5s
+SPT_HD ScheduleG make_schedule_g(int M) {
+    ScheduleG s;
+    s.npass = 0;
+    int a = 0, b = 0, c = 0, r = M;
+    while (r % 2 == 0) { r /= 2; ++a; }
+    while (r % 3 == 0) { r /= 3; ++b; }
+    while (r % 5 == 0) { r /= 5; ++c; }
+    int Nb = M;
+    auto push = [&](int R) {
+        s.radix[s.npass] = R;
+        s.nb[s.npass] = Nb;
+        s.stride[s.npass] = M / Nb;
+        ++s.npass;
+        Nb /= R;
+    };
+    while (a >= 4) { push(16); a -= 4; }
+    if (a == 3) push(8);
+    else if (a == 2) push(4);
+    else if (a == 1) push(2);
+    while (b >= 2) { push(9); b -= 2; }
+    if (b == 1) push(3);
+    while (c >= 1) { push(5); --c; }
+    return s;
+}
+
+template <int R>
+SPT_HD void dif_pass_g(double2* X, int nseq, int M, int Nb, int S, const double2* Wa, const double2* Wb, int tid, int nthr) {
+    const int per = M / R, PL = padded_len(M);
+    for (int w = tid; w < nseq * per; w += nthr) {
+        const int sq = w / per, q = w - sq * per;
+        dif_butterfly_g<R>(X + sq * PL, q, Nb, S, Wa, Wb);
+    }
+}
+template <int R, bool CONJ_FILT>
+SPT_HD void dit_pass_g(double2* X, int nseq, int M, int Nb, int S, const double2* Wa, const double2* Wb,
+                       const double2* filt, int tid, int nthr) {
+    const int per = M / R, PL = padded_len(M);
+    for (int w = tid; w < nseq * per; w += nthr) {
+        const int sq = w / per, q = w - sq * per;
+        dit_butterfly_g<R, CONJ_FILT>(X + sq * PL, q, Nb, S, Wa, Wb, filt);
+    }
+}
+
+SPT_HD void fft_dif_g(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb, int tid,
+                      int nthr) {
+    for (int p = 0; p < s.npass; ++p) {
+        const int Nb = s.nb[p], S = s.stride[p];
+        switch (s.radix[p]) {
+            case 16: dif_pass_g<16>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
+            case 9: dif_pass_g<9>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
+            case 8: dif_pass_g<8>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
+            case 5: dif_pass_g<5>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
+            case 4: dif_pass_g<4>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
+            case 3: dif_pass_g<3>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
+            default: dif_pass_g<2>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
+        }
+        SPT_SYNC();
+    }
+}
+template <bool CONJ_FILT>
+SPT_HD void fft_dit_g(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb,
+                      const double2* filt, int tid, int nthr) {
+    for (int p = s.npass - 1; p >= 0; --p) {
+        const int Nb = s.nb[p], S = s.stride[p];
+        const double2* f = (p == s.npass - 1) ? filt : nullptr;
+        switch (s.radix[p]) {
+            case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
+            case 9: dit_pass_g<9, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
+            case 8: dit_pass_g<8, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
+            case 5: dit_pass_g<5, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
+            case 4: dit_pass_g<4, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
+            case 3: dit_pass_g<3, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
+            default: dit_pass_g<2, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
+        }
+        SPT_SYNC();
+    }
+}
+
+// smallest 5-smooth even length >= need (and >= 8); returns 0 if none <= limit
+SPT_HD int conv_length_smooth(int need, int limit) {
+    int best = 0;
+    for (long long p5 = 1; p5 <= limit; p5 *= 5)
+        for (long long p3 = p5; p3 <= limit; p3 *= 3)
+            for (long long p2 = p3 * 2; p2 <= limit; p2 *= 2)
+                if (p2 >= need && p2 >= 8 && (best == 0 || p2 < best)) best = static_cast<int>(p2);
+    return best;
+}
+
 // exact phase arithmetic for the chirps: returns r in [0, 2n) with r == (a*a + c*a) mod 2n
 SPT_HD long long chirp_residue(long long a, long long c, long long n) {
     long long v = (a * a + c * a) % (2 * n);

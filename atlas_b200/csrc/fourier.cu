@@ -25,37 +25,39 @@ struct PairMeta {
     long long filt_off;   // Bhat, M entries, digit-reversed order, scaled by 1/M
     long long rowN;       // grid offset of the northern row
     long long rowS;       // grid offset of the southern row
+    long long tw_off;     // two-level twiddle table: Wa (M/64+1 entries) then Wb (64 entries), double2 units
     int n;                // row length
     int L;                // zonal truncation at this latitude (mmax[j]); -1: nothing resolved
-    int logM;
+    int M;                // convolution length, 5-smooth, >= n + 2L
     int has_s;            // 0 for the equator row of a grid with an odd number of latitudes
+    int F;                // fields transformed together by one block
+    int pad;
 };
 
 namespace {
 
 using namespace fftc;
 
-constexpr int kWn = 8192;  // master twiddle table length (largest supported M)
+constexpr int kMaxM = 8192;      // largest convolution length a single CTA can hold in shared memory
+constexpr int kFftThreads = 256;
 
-__global__ void twiddle_kernel(double2* W, int Wn) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < Wn) {
-        double s, c;
-        sincospi(-2.0 * k / Wn, &s, &c);
-        W[k] = make_double2(c, s);
-    }
+__device__ __forceinline__ void load_twiddles(const double2* __restrict__ g, double2* s, int M, int tid, int nthr) {
+    const int ntw = M / 64 + 1 + 64;
+    for (int e = tid; e < ntw; e += nthr) s[e] = g[e];
 }
 
-// one block per distinct (n, L): chirps and the digit-reversed filter spectrum
-__global__ void __launch_bounds__(256)
-chirp_tables_kernel(const PairMeta* __restrict__ cls, const double2* __restrict__ W, int Wn,
-                    double2* __restrict__ chirp, double2* __restrict__ filt) {
+// one block per distinct (n, L): chirps, two-level twiddles and the digit-reversed filter spectrum
+__global__ void __launch_bounds__(kFftThreads)
+chirp_tables_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chirp, double2* __restrict__ filt,
+                    double2* __restrict__ twid) {
     extern __shared__ double2 X[];
     const PairMeta pm = cls[blockIdx.x];
-    const int n = pm.n, L = pm.L, M = 1 << pm.logM;
+    const int n = pm.n, L = pm.L, M = pm.M;
     const int tid = threadIdx.x, nthr = blockDim.x;
     double2* A = chirp + pm.chirp_off;
     double2* C = A + (2 * L + 1);
+    double2* Wa = twid + pm.tw_off;
+    double2* Wb = Wa + (M / 64 + 1);
     for (int u = tid; u <= 2 * L; u += nthr) {
         double s, c;
         sincospi(static_cast<double>(chirp_residue(u, 0, n)) / n, &s, &c);
@@ -66,8 +68,21 @@ chirp_tables_kernel(const PairMeta* __restrict__ cls, const double2* __restrict_
         sincospi(static_cast<double>(chirp_residue(i, -2LL * L, n)) / n, &s, &c);
         C[i] = make_double2(c, s);
     }
-    for (int e = tid; e < padded_len(M); e += nthr) X[e] = make_double2(0., 0.);
+    for (int k = tid; k <= M / 64; k += nthr) {
+        double s, c;
+        sincospi(-2.0 * (64.0 * k) / M, &s, &c);
+        Wa[k] = make_double2(c, s);
+    }
+    for (int k = tid; k < 64; k += nthr) {
+        double s, c;
+        sincospi(-2.0 * k / M, &s, &c);
+        Wb[k] = make_double2(c, s);
+    }
+    const int PL = padded_len(M);
+    double2* sW = X + PL;
+    for (int e = tid; e < PL; e += nthr) X[e] = make_double2(0., 0.);
     __syncthreads();
+    load_twiddles(Wa, sW, M, tid, nthr);
     for (int e = tid; e < n + 2 * L; e += nthr) {
         const int k = e - 2 * L;  // k in [-2L, n-1]
         double s, c;
@@ -76,28 +91,29 @@ chirp_tables_kernel(const PairMeta* __restrict__ cls, const double2* __restrict_
         X[pad(idx)] = make_double2(c, s);
     }
     __syncthreads();
-    fft_dif_all(X, 1, pm.logM, W, Wn, tid, nthr);
-    const double sc = 1.0 / M;
+    const ScheduleG sc = make_schedule_g(M);
+    fft_dif_g(X, 1, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
+    const double scl = 1.0 / M;
     for (int k = tid; k < M; k += nthr) {
         const double2 v = X[pad(k)];
-        filt[pm.filt_off + k] = make_double2(v.x * sc, v.y * sc);
+        filt[pm.filt_off + k] = make_double2(v.x * scl, v.y * scl);
     }
 }
 
-__global__ void __launch_bounds__(512)
-fourier_inv_kernel(const PairMeta* __restrict__ meta, const int* __restrict__ group_pairs, int ngf, int F, int nf,
+__global__ void __launch_bounds__(kFftThreads, 2)
+fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
                    int mlimit, int nb_uv, const double2* __restrict__ fb, const long long* __restrict__ fb_rowoff,
-                   const int* __restrict__ nlat0, int nleg, const double2* __restrict__ W,
+                   const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
                    const double2* __restrict__ chirp, const double2* __restrict__ filt,
                    const double* __restrict__ coslatinv, double* __restrict__ gp, long long npts) {
     extern __shared__ double2 X[];
-    const int pair = group_pairs[blockIdx.x / ngf];
-    const int f0 = (blockIdx.x % ngf) * F;
-    const int nfb = min(F, nf - f0);
+    const int2 bd = blocks[blockIdx.x];
+    const int pair = bd.x, f0 = bd.y;
     const PairMeta pm = meta[pair];
+    const int nfb = min(pm.F, nf - f0);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n = pm.n, L = pm.L;
-    const int M = 1 << pm.logM, PL = padded_len(M);
+    const int M = pm.M, PL = padded_len(M);
     const int Lc = min(L, mlimit);
     if (Lc < 0) {  // no zonal wavenumber resolved / requested at this latitude: rows are zero
         for (int w = tid; w < nfb * n; w += nthr) {
@@ -107,7 +123,10 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int* __restrict__ gr
         }
         return;
     }
+    double2* sW = X + pm.F * PL;
+    const ScheduleG sc = make_schedule_g(M);
     for (int e = tid; e < nfb * PL; e += nthr) X[e] = make_double2(0., 0.);
+    load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
     __syncthreads();
     const double2* A = chirp + pm.chirp_off;
     const double2* C = A + (2 * L + 1);
@@ -136,8 +155,8 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int* __restrict__ gr
         }
     }
     __syncthreads();
-    fft_dif_all(X, nfb, pm.logM, W, kWn, tid, nthr);
-    fft_dit_all<false>(X, nfb, pm.logM, W, kWn, filt + pm.filt_off, tid, nthr);
+    fft_dif_g(X, nfb, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
+    fft_dit_g<false>(X, nfb, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
     for (int w = tid; w < nfb * n; w += nthr) {
         const int fi = w / n, i = w - fi * n;
         const double2 z = cmul(X[fi * PL + pad(i)], C[i]);
@@ -151,22 +170,25 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int* __restrict__ gr
     }
 }
 
-__global__ void __launch_bounds__(512)
-fourier_dir_kernel(const PairMeta* __restrict__ meta, const int* __restrict__ group_pairs, int ngf, int F, int nf,
+__global__ void __launch_bounds__(kFftThreads, 2)
+fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
                    int nb_uv, const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
-                   const int* __restrict__ nlat0, int nleg, const double2* __restrict__ W,
+                   const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
                    const double2* __restrict__ chirp, const double2* __restrict__ filt,
                    const double* __restrict__ weights, const double* __restrict__ coslat, double2* __restrict__ fb) {
     extern __shared__ double2 X[];
-    const int pair = group_pairs[blockIdx.x / ngf];
-    const int f0 = (blockIdx.x % ngf) * F;
-    const int nfb = min(F, nf - f0);
+    const int2 bd = blocks[blockIdx.x];
+    const int pair = bd.x, f0 = bd.y;
     const PairMeta pm = meta[pair];
+    const int nfb = min(pm.F, nf - f0);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n = pm.n, L = pm.L;
     if (L < 0) return;
-    const int M = 1 << pm.logM, PL = padded_len(M);
+    const int M = pm.M, PL = padded_len(M);
+    double2* sW = X + pm.F * PL;
+    const ScheduleG sc = make_schedule_g(M);
     for (int e = tid; e < nfb * PL; e += nthr) X[e] = make_double2(0., 0.);
+    load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
     __syncthreads();
     const double2* A = chirp + pm.chirp_off;
     const double2* C = A + (2 * L + 1);
@@ -182,8 +204,8 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int* __restrict__ gr
         X[fi * PL + pad(i)] = cmulc(make_double2(xn, xs), C[i]);
     }
     __syncthreads();
-    fft_dif_all(X, nfb, pm.logM, W, kWn, tid, nthr);
-    fft_dit_all<true>(X, nfb, pm.logM, W, kWn, filt + pm.filt_off, tid, nthr);
+    fft_dif_g(X, nfb, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
+    fft_dit_g<true>(X, nfb, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
     const double wq = weights[pair];
     const double inv_n = 1.0 / n;
     for (int w = tid; w < nfb * (L + 1); w += nthr) {
@@ -211,23 +233,62 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int* __restrict__ gr
     }
 }
 
-int fields_per_block(int logM) {
-    // aim at ~64 KB of shared memory per block (3 blocks / SM) but never less than one sequence
-    const int M = 1 << logM;
+// Cost model used to pick the convolution length: every pass is one read+write sweep of shared memory;
+// larger radices do more arithmetic per point.
+double pass_cost(int R) {
+    switch (R) {
+        case 16: return 1.25;
+        case 9: return 1.10;
+        case 8: return 1.05;
+        case 5: return 1.05;
+        case 4: return 0.95;
+        case 3: return 0.95;
+        default: return 0.90;
+    }
+}
+int choose_conv_length(int need) {
+    int best = 0;
+    double best_cost = 1e300;
+    for (long long p5 = 1; p5 <= kMaxM; p5 *= 5)
+        for (long long p3 = p5; p3 <= kMaxM; p3 *= 3)
+            for (long long p2 = p3 * 2; p2 <= kMaxM; p2 *= 2) {
+                if (p2 < need || p2 < 8) continue;
+                const ScheduleG s = fftc::make_schedule_g(static_cast<int>(p2));
+                double c = 0.4;  // load/store/pointwise sweeps
+                for (int p = 0; p < s.npass; ++p) c += 2.0 * pass_cost(s.radix[p]);  // forward + inverse
+                c *= static_cast<double>(p2);
+                if (c < best_cost) {
+                    best_cost = c;
+                    best = static_cast<int>(p2);
+                }
+            }
+    return best;
+}
+
+int fields_per_block(int M) {
+    // enough sequences per block to keep 256 threads busy, at most ~64 KB of shared memory
     int F = 4096 / M;
     if (F < 1) F = 1;
     if (F > 16) F = 16;
     return F;
 }
 
+size_t block_smem_bytes(int M, int F) {
+    return (static_cast<size_t>(F) * fftc::padded_len(M) + (M / 64 + 1 + 64)) * sizeof(double2);
+}
+
 }  // namespace
 
 struct FftGroups {
-    std::vector<int> logM;                 // distinct logM, descending
-    std::vector<std::vector<int>> pairs;   // pairs per group, longest rows first
-    std::vector<int*> d_pairs;
+    // launch groups by shared-memory footprint (so that small rows run several blocks per SM)
+    std::vector<size_t> smem;              // dynamic shared memory of the group
+    std::vector<std::vector<int>> pairs;   // pairs per group, costliest first
+    int nf = -1;                           // block lists below are built for this number of fields
+    std::vector<int2*> d_blocks;
+    std::vector<int> nblocks;
 };
 static std::map<Plan*, FftGroups> g_groups;
+static std::map<Plan*, std::vector<PairMeta>> g_meta;
 
 int build_fft_tables(Plan& p) {
     HostGeom& g = p.g;
@@ -235,7 +296,7 @@ int build_fft_tables(Plan& p) {
     std::vector<PairMeta> meta(nleg);
     std::map<std::pair<int, int>, int> cls_index;
     std::vector<PairMeta> classes;
-    long long chirp_total = 0, filt_total = 0;
+    long long chirp_total = 0, filt_total = 0, tw_total = 0;
     for (int j = 0; j < nleg; ++j) {
         PairMeta pm{};
         pm.n = g.nx[j];
@@ -248,14 +309,14 @@ int build_fft_tables(Plan& p) {
             return SPTRANS_ERR_INVALID;
         }
         const int Luse = std::max(pm.L, 0);
-        int logM = 0;
-        const int M = fftc::conv_length(pm.n, Luse, &logM);
-        if (M > kWn) {
+        const int M = choose_conv_length(pm.n + 2 * Luse);
+        if (M == 0) {
             set_error("sptrans_plan_create: row length + 2*truncation exceeds 8192 (grids beyond O1280 need the "
-                      "two-level Fourier kernel, not available yet)");
+                      "cluster Fourier kernel, not available yet)");
             return SPTRANS_ERR_NOT_IMPLEMENTED;
         }
-        pm.logM = logM;
+        pm.M = M;
+        pm.F = fields_per_block(M);
         auto key = std::make_pair(pm.n, Luse);
         auto it = cls_index.find(key);
         if (it == cls_index.end()) {
@@ -263,78 +324,102 @@ int build_fft_tables(Plan& p) {
             c.L = Luse;
             c.chirp_off = chirp_total;
             c.filt_off = filt_total;
+            c.tw_off = tw_total;
             chirp_total += 2LL * Luse + 1 + pm.n;
             filt_total += M;
+            tw_total += M / 64 + 1 + 64;
             cls_index[key] = static_cast<int>(classes.size());
             classes.push_back(c);
             it = cls_index.find(key);
         }
         pm.chirp_off = classes[it->second].chirp_off;
         pm.filt_off = classes[it->second].filt_off;
+        pm.tw_off = classes[it->second].tw_off;
         meta[j] = pm;
     }
-    double2* d_W = nullptr;
-    SPT_CUDA(cudaMalloc(&d_W, kWn * sizeof(double2)));
-    twiddle_kernel<<<(kWn + 255) / 256, 256, 0, p.stream>>>(d_W, kWn);
-    p.launches++;
-    SPT_CUDA(cudaGetLastError());
     SPT_CUDA(cudaMalloc(&p.d_chirp, std::max<long long>(chirp_total, 1) * sizeof(double2)));
     SPT_CUDA(cudaMalloc(&p.d_filt, std::max<long long>(filt_total, 1) * sizeof(double2)));
-    p.bytes_tables += (chirp_total + filt_total + kWn) * sizeof(double2);
+    SPT_CUDA(cudaMalloc(&p.d_twiddle, std::max<long long>(tw_total, 1) * sizeof(double2)));
+    p.bytes_tables += (chirp_total + filt_total + tw_total) * sizeof(double2);
     PairMeta* d_cls = nullptr;
     SPT_CUDA(cudaMalloc(&d_cls, classes.size() * sizeof(PairMeta)));
     SPT_CUDA(cudaMemcpyAsync(d_cls, classes.data(), classes.size() * sizeof(PairMeta), cudaMemcpyHostToDevice, p.stream));
-    const size_t smem_max = static_cast<size_t>(fftc::padded_len(kWn)) * sizeof(double2);
+    const size_t smem_max = block_smem_bytes(kMaxM, 1);
     SPT_CUDA(cudaFuncSetAttribute(chirp_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_dir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    chirp_tables_kernel<<<static_cast<int>(classes.size()), 256, smem_max, p.stream>>>(d_cls, d_W, kWn, p.d_chirp,
-                                                                                      p.d_filt);
+    chirp_tables_kernel<<<static_cast<int>(classes.size()), kFftThreads, smem_max, p.stream>>>(d_cls, p.d_chirp, p.d_filt,
+                                                                                              p.d_twiddle);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     SPT_CUDA(cudaMalloc(&p.d_pair_meta, meta.size() * sizeof(PairMeta)));
     SPT_CUDA(cudaMemcpyAsync(p.d_pair_meta, meta.data(), meta.size() * sizeof(PairMeta), cudaMemcpyHostToDevice,
                              p.stream));
-    p.d_twiddle = d_W;
-    // launch groups by logM over this rank's latitude band
+    // launch groups by shared-memory bucket over this rank's latitude band
     FftGroups grp;
-    std::map<int, std::vector<int>, std::greater<int>> by;
-    for (int j = g.pair_begin; j < g.pair_end; ++j) by[meta[j].logM].push_back(j);
-    for (auto& kv : by) {
-        std::vector<int> v = kv.second;
-        std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return meta[a].n > meta[b].n; });
-        int* d = nullptr;
-        SPT_CUDA(cudaMalloc(&d, v.size() * sizeof(int)));
-        SPT_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, p.stream));
-        grp.logM.push_back(kv.first);
+    const size_t buckets[] = {28 * 1024, 37 * 1024, 56 * 1024, 75 * 1024, 113 * 1024, smem_max};
+    std::vector<std::vector<int>> by(6);
+    for (int j = g.pair_begin; j < g.pair_end; ++j) {
+        const size_t need = block_smem_bytes(meta[j].M, meta[j].F);
+        int b = 0;
+        while (need > buckets[b]) ++b;
+        by[b].push_back(j);
+    }
+    for (int b = 5; b >= 0; --b) {
+        if (by[b].empty()) continue;
+        std::vector<int> v = by[b];
+        std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return meta[x].M > meta[y].M; });
+        size_t need = 0;
+        for (int j : v) need = std::max(need, block_smem_bytes(meta[j].M, meta[j].F));
+        grp.smem.push_back(need);
         grp.pairs.push_back(v);
-        grp.d_pairs.push_back(d);
     }
     SPT_CUDA(cudaStreamSynchronize(p.stream));
     cudaFree(d_cls);
     g_groups[&p] = grp;
+    g_meta[&p] = meta;
     return SPTRANS_OK;
 }
 
 void free_fft_tables(Plan& p) {
     auto it = g_groups.find(&p);
     if (it != g_groups.end()) {
-        for (int* d : it->second.d_pairs) cudaFree(d);
+        for (int2* d : it->second.d_blocks) cudaFree(d);
         g_groups.erase(it);
     }
+    g_meta.erase(&p);
+}
+
+static int ensure_block_lists(Plan& p, int nf) {
+    FftGroups& grp = g_groups[&p];
+    if (grp.nf == nf) return SPTRANS_OK;
+    for (int2* d : grp.d_blocks) cudaFree(d);
+    grp.d_blocks.clear();
+    grp.nblocks.clear();
+    const std::vector<PairMeta>& meta = g_meta[&p];
+    for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
+        std::vector<int2> blocks;
+        for (int j : grp.pairs[gi])
+            for (int f0 = 0; f0 < nf; f0 += meta[j].F) blocks.push_back(make_int2(j, f0));
+        int2* d = nullptr;
+        SPT_CUDA(cudaMalloc(&d, std::max<size_t>(blocks.size(), 1) * sizeof(int2)));
+        SPT_CUDA(cudaMemcpyAsync(d, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, p.stream));
+        SPT_CUDA(cudaStreamSynchronize(p.stream));
+        grp.d_blocks.push_back(d);
+        grp.nblocks.push_back(static_cast<int>(blocks.size()));
+    }
+    grp.nf = nf;
+    return SPTRANS_OK;
 }
 
 int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv) {
+    int rc = ensure_block_lists(p, nf);
+    if (rc) return rc;
     const FftGroups& grp = g_groups[&p];
-    for (size_t gi = 0; gi < grp.logM.size(); ++gi) {
-        const int logM = grp.logM[gi];
-        const int F = fields_per_block(logM);
-        const int ngf = (nf + F - 1) / F;
-        const size_t smem = static_cast<size_t>(F) * fftc::padded_len(1 << logM) * sizeof(double2);
-        const int threads = (logM >= 13) ? 512 : 256;
-        const long long blocks = static_cast<long long>(grp.pairs[gi].size()) * ngf;
-        fourier_inv_kernel<<<static_cast<unsigned>(blocks), threads, smem, p.stream>>>(
-            reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_pairs[gi], ngf, F, nf, mlimit, nb_uv,
+    for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
+        if (grp.nblocks[gi] == 0) continue;
+        fourier_inv_kernel<<<grp.nblocks[gi], kFftThreads, grp.smem[gi], p.stream>>>(
+            reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
             reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp,
             p.d_filt, p.d_coslatinv, d_gp, p.g.npts);
         p.launches++;
@@ -348,16 +433,13 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
         set_error("dirtrans: plan was created without quadrature weights");
         return SPTRANS_ERR_INVALID;
     }
+    int rc = ensure_block_lists(p, nf);
+    if (rc) return rc;
     const FftGroups& grp = g_groups[&p];
-    for (size_t gi = 0; gi < grp.logM.size(); ++gi) {
-        const int logM = grp.logM[gi];
-        const int F = fields_per_block(logM);
-        const int ngf = (nf + F - 1) / F;
-        const size_t smem = static_cast<size_t>(F) * fftc::padded_len(1 << logM) * sizeof(double2);
-        const int threads = (logM >= 13) ? 512 : 256;
-        const long long blocks = static_cast<long long>(grp.pairs[gi].size()) * ngf;
-        fourier_dir_kernel<<<static_cast<unsigned>(blocks), threads, smem, p.stream>>>(
-            reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_pairs[gi], ngf, F, nf, nb_uv, d_gp, p.g.npts,
+    for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
+        if (grp.nblocks[gi] == 0) continue;
+        fourier_dir_kernel<<<grp.nblocks[gi], kFftThreads, grp.smem[gi], p.stream>>>(
+            reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
             p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_coslat,
             reinterpret_cast<double2*>(d_fourier));
         p.launches++;

@@ -72,7 +72,9 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp % kWarpsM, wn = warp / kWarpsM;
+    // warp -> (row block, column block): consecutive warps (= the four SM sub-partitions) cover the first two row
+    // blocks, so that a partial tile with <= 64 valid rows still keeps every sub-partition's FP64 pipe busy
+    const int wm = warp / kWarpsN, wn = warp % kWarpsN;
 
     for (;;) {
         __syncthreads();  // previous tile fully consumed (smem + s_tile)

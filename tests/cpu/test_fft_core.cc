@@ -98,11 +98,85 @@ static int check(int n, int L) {
     return (err_inv / nrm < 1e-12 && err_fwd / nrm2 < 1e-12) ? 0 : 1;
 }
 
+// ---- mixed-radix engine: same chirp-z algebra with M = 2^a 3^b 5^c and two-level twiddles ----
+static int check_g(int n, int L) {
+    const int M = conv_length_smooth(n + 2 * L, 1 << 15);
+    const ScheduleG sc = make_schedule_g(M);
+    std::vector<double2> Wa(M / 64 + 1), Wb(64);
+    for (int k = 0; k <= M / 64; ++k) Wa[k] = make_double2(std::cos(-2 * M_PI * (64.0 * k) / M), std::sin(-2 * M_PI * (64.0 * k) / M));
+    for (int k = 0; k < 64; ++k) Wb[k] = make_double2(std::cos(-2 * M_PI * k / M), std::sin(-2 * M_PI * k / M));
+    std::vector<double2> A(2 * L + 1), C(n), Bh(M);
+    for (int u = 0; u <= 2 * L; ++u) {
+        double ang = M_PI * (double)chirp_residue(u, 0, n) / n;
+        A[u] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    for (int i = 0; i < n; ++i) {
+        double ang = M_PI * (double)chirp_residue(i, -2LL * L, n) / n;
+        C[i] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    std::vector<double2> b(padded_len(M), make_double2(0, 0));
+    for (int k = -2 * L; k <= n - 1; ++k) {
+        double ang = -M_PI * (double)chirp_residue(k, 0, n) / n;
+        b[pad(((k % M) + M) % M)] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    fft_dif_g(b.data(), 1, M, sc, Wa.data(), Wb.data(), 0, 1);
+    for (int k = 0; k < M; ++k) Bh[k] = make_double2(b[pad(k)].x / M, b[pad(k)].y / M);
+    std::vector<double2> Z(2 * L + 1);
+    for (auto& z : Z) z = make_double2(urand(), urand());
+    std::vector<double2> X(padded_len(M), make_double2(0, 0));
+    for (int u = 0; u <= 2 * L; ++u) X[pad(u)] = cmul(Z[u], A[u]);
+    fft_dif_g(X.data(), 1, M, sc, Wa.data(), Wb.data(), 0, 1);
+    fft_dit_g<false>(X.data(), 1, M, sc, Wa.data(), Wb.data(), Bh.data(), 0, 1);
+    double err_inv = 0, nrm = 0;
+    for (int i = 0; i < n; i += (n > 2000 ? 7 : 1)) {
+        double2 got = cmul(X[pad(i)], C[i]);
+        double re = 0, im = 0;
+        for (int u = 0; u <= 2 * L; ++u) {
+            long long m = u - L;
+            double ang = 2 * M_PI * (double)(((m * i) % n + n) % n) / n;
+            re += Z[u].x * std::cos(ang) - Z[u].y * std::sin(ang);
+            im += Z[u].x * std::sin(ang) + Z[u].y * std::cos(ang);
+        }
+        err_inv = std::fmax(err_inv, std::hypot(got.x - re, got.y - im));
+        nrm = std::fmax(nrm, std::hypot(re, im));
+    }
+    std::vector<double2> z(n);
+    for (auto& v : z) v = make_double2(urand(), urand());
+    std::fill(X.begin(), X.end(), make_double2(0, 0));
+    for (int i = 0; i < n; ++i) X[pad(i)] = cmulc(z[i], C[i]);
+    fft_dif_g(X.data(), 1, M, sc, Wa.data(), Wb.data(), 0, 1);
+    fft_dit_g<true>(X.data(), 1, M, sc, Wa.data(), Wb.data(), Bh.data(), 0, 1);
+    double err_fwd = 0, nrm2 = 0;
+    for (int u = 0; u <= 2 * L; u += (L > 500 ? 5 : 1)) {
+        double2 got = cmulc(X[pad(u)], A[u]);
+        got.x /= n;
+        got.y /= n;
+        long long m = u - L;
+        double re = 0, im = 0;
+        for (int i = 0; i < n; ++i) {
+            double ang = -2 * M_PI * (double)(((m * i) % n + n) % n) / n;
+            re += z[i].x * std::cos(ang) - z[i].y * std::sin(ang);
+            im += z[i].x * std::sin(ang) + z[i].y * std::cos(ang);
+        }
+        re /= n;
+        im /= n;
+        err_fwd = std::fmax(err_fwd, std::hypot(got.x - re, got.y - im));
+        nrm2 = std::fmax(nrm2, std::hypot(re, im));
+    }
+    printf("mixed n=%5d L=%5d M=%5d passes=%d [", n, L, M, sc.npass);
+    for (int p = 0; p < sc.npass; ++p) printf("%d ", sc.radix[p]);
+    printf("]  inv %.3e  fwd %.3e\n", err_inv / nrm, err_fwd / nrm2);
+    return (err_inv / nrm < 1e-12 && err_fwd / nrm2 < 1e-12) ? 0 : 1;
+}
+
 int main() {
     int bad = 0;
     const int cases[][2] = {{20, 9}, {24, 7}, {28, 0}, {144, 31}, {36, 17}, {1616, 399}, {5136, 1279}, {5132, 1279},
                             {2568, 1279}, {128, 31}, {9, 4}, {7, 3}, {4, 1}};
     for (auto& c : cases) bad += check(c[0], c[1]);
+    const int cases_g[][2] = {{20, 9}, {24, 7}, {144, 31}, {1616, 399}, {5136, 1279}, {3000, 999}, {2052, 683}, {4000, 1279},
+                              {10256, 2559}, {36, 17}, {100, 33}, {448, 148}, {1000, 332}, {2700, 899}, {3600, 1199}, {28, 0}};
+    for (auto& c : cases_g) bad += check_g(c[0], c[1]);
     printf(bad ? "FAILED\n" : "ALL OK\n");
     return bad;
 }

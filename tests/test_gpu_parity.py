@@ -317,3 +317,65 @@ def test_config3_tco1279_l137_properties(torch_cuda):
     assert H.rel_max(got_sp, want_sp) < TOL_MAX
     t = trans.last_timings()
     print("TCo1279 L137 dirtrans stage ms:", t)
+
+
+@pytest.mark.parametrize("gridname,T,nf,R", [("O48", 47, 5, 2), ("O80", 79, 4, 3), ("F24", 23, 3, 2)])
+def test_sharded_path_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
+    """The multi-GPU algorithm (m-sharded Legendre -> pack -> all-to-all -> unpack -> band-sharded Fourier, and
+    the mirror image for the direct transform) with all R ranks living on one device and the all-to-all replaced
+    by slice copies.  Exercises the sharded plans, table pruning, tile lists and gather/scatter kernels."""
+    import ctypes as C
+
+    import atlas_b200
+    from atlas_b200 import _lib
+    from atlas_b200.trans import _ptr
+    from oracle import pyoracle as po
+
+    torch = torch_cuda
+    grid = atlas_b200.Grid(gridname)
+    plans = [atlas_b200.Trans(grid, T, rank=r, nranks=R) for r in range(R)]
+    LL = C.POINTER(C.c_longlong)
+    m_rows, b_rows = [], []
+    for t in plans:
+        ms, bs = np.zeros(R, dtype=np.int64), np.zeros(R, dtype=np.int64)
+        _lib.check(_lib.lib.sptrans_exchange_rows(t._h, ms.ctypes.data_as(LL), bs.ctypes.data_as(LL)))
+        m_rows.append(ms)
+        b_rows.append(bs)
+    k = 2 * nf
+    kw = dict(dtype=torch.float64, device="cuda")
+    fb = [torch.zeros(t.fourier_elems_per_field() * k, **kw) for t in plans]
+    buf_m = [torch.zeros(max(int(m_rows[r].sum()), 1) * k, **kw) for r in range(R)]
+    buf_b = [torch.zeros(max(int(b_rows[r].sum()), 1) * k, **kw) for r in range(R)]
+
+    def all_to_all(src, src_rows, dst, dst_rows):
+        for s in range(R):
+            so = np.concatenate([[0], np.cumsum(src_rows[s])]) * k
+            for d in range(R):
+                do = np.concatenate([[0], np.cumsum(dst_rows[d])]) * k
+                assert src_rows[s][d] == dst_rows[d][s]
+                dst[d][do[s]:do[s + 1]] = src[s][so[d]:so[d + 1]]
+
+    sp = H.synthetic_spectra(T, nf)
+    d_sp = torch.from_numpy(sp).cuda()
+    d_gp = torch.full((nf * grid.size(),), float("nan"), **kw)
+    for r, t in enumerate(plans):
+        t.invtrans_legendre(nf, T, d_sp, fb[r])
+        _lib.check(_lib.lib.sptrans_exchange_pack(t._h, nf, 0, _ptr(fb[r]), _ptr(buf_m[r])))
+    all_to_all(buf_m, m_rows, buf_b, b_rows)
+    for r, t in enumerate(plans):
+        _lib.check(_lib.lib.sptrans_exchange_unpack(t._h, nf, 1, _ptr(buf_b[r]), _ptr(fb[r])))
+        t.invtrans_fourier(nf, T - 1, fb[r], d_gp)
+    plan = po.OraclePlan(grid.nx(), grid.y(), T, regular=grid.regular, weights=grid.weights())
+    want = plan.invtrans(nf, sp, mode=2)
+    assert H.rel_max(d_gp.cpu().numpy(), want) < TOL_MAX
+    # direct transform, mirror image
+    d_back = torch.full_like(d_sp, float("nan"))
+    for r, t in enumerate(plans):
+        fb[r].zero_()
+        t.dirtrans_fourier(nf, d_gp, fb[r])
+        _lib.check(_lib.lib.sptrans_exchange_pack(t._h, nf, 1, _ptr(fb[r]), _ptr(buf_b[r])))
+    all_to_all(buf_b, b_rows, buf_m, m_rows)
+    for r, t in enumerate(plans):
+        _lib.check(_lib.lib.sptrans_exchange_unpack(t._h, nf, 0, _ptr(buf_m[r]), _ptr(fb[r])))
+        t.dirtrans_legendre(nf, fb[r], d_back)  # every rank writes the coefficients of its own zonal wavenumbers
+    assert H.rel_max(d_back.cpu().numpy(), plan.dirtrans(nf, want)) < TOL_MAX

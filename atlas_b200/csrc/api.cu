@@ -84,7 +84,7 @@ int check_plan(sptrans_plan* plan) {
 // inverse transform of `nf` fields whose spectra sit on the device at truncation `trunc` (T or T+1)
 int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, int nb_uv, StageTimer& tm,
                 int& marks, int* slots) {
-    int rc = build_tiles(p, nf, trunc);
+    int rc = build_tiles(p, nf, trunc, p.g.T);
     if (rc) return rc;
     rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf));
     if (rc) return rc;
@@ -209,6 +209,11 @@ int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, con
         }
         if ((rc = upload(p.d_coslatinv, ci, p.stream))) return fail(rc);
         if ((rc = upload(p.d_coslat, c, p.stream))) return fail(rc);
+        {
+            std::vector<double> us(g.nleg);
+            for (int j = 0; j < g.nleg; ++j) us[j] = 1. / (6371229. * c[j]);  // util/Earth.h:24
+            if ((rc = upload(p.d_uvscale, us, p.stream))) return fail(rc);
+        }
         if (!g.weights.empty()) {
             std::vector<double> w(g.weights.begin(), g.weights.begin() + g.nleg);
             if ((rc = upload(p.d_weights, w, p.stream))) return fail(rc);
@@ -243,7 +248,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     if (p.stream) cudaStreamSynchronize(p.stream);
     free_fft_tables(p);
     void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_weights,
-                    p.d_coslatinv, p.d_coslat, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
+                    p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
                     p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
                     p.d_gp};
     for (void* q : ptrs)
@@ -438,7 +443,7 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double
         if ((rc = ensure(p.d_spec, p.spec_cap, nspec))) return rc;
         d_spec = p.d_spec;
     }
-    if ((rc = build_tiles(p, nf, T))) return rc;
+    if ((rc = build_tiles(p, nf, T, T))) return rc;
     if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
     if ((rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nf)))) return rc;
     tm.mark(marks);
@@ -453,6 +458,114 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double
     tm.mark(marks);
     if (spec_host) {
         SPT_CUDA(cudaMemcpyAsync(spectra, d_spec, nspec * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+        slots[marks++] = 4;
+        tm.mark(marks);
+    }
+    tm.finish(marks + 1, slots);
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nf, const double* wind, double* vor, double* div) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf < 0 || (nf > 0 && (!wind || !vor || !div))) {
+        set_error("sptrans_dirtrans_wind2vordiv: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (nf == 0) return SPTRANS_OK;
+    if (p.g.nranks != 1) {
+        set_error("whole-transform entry points need an unsharded plan; use the stage-level API");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (!p.d_weights) {
+        set_error("sptrans_dirtrans_wind2vordiv: plan was created without quadrature weights");
+        return SPTRANS_ERR_INVALID;
+    }
+    const int T = p.g.T;
+    const int nall = 2 * nf;
+    StageTimer tm(p);
+    int marks = 0, slots[8];
+    const bool gp_host = !is_device_pointer(wind), sp_host = !is_device_pointer(vor);
+    const size_t ngp = static_cast<size_t>(p.g.npts) * nall, nspec = spec_doubles(p, nf, T);
+    const double* d_gp = wind;
+    double *d_vor = vor, *d_div = div;
+    if (gp_host) {
+        if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
+        tm.mark(marks);
+        SPT_CUDA(cudaMemcpyAsync(p.d_gp, wind, ngp * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+        slots[marks++] = 3;
+        d_gp = p.d_gp;
+    }
+    if (sp_host) {
+        if ((rc = ensure(p.d_spec, p.spec_cap, 2 * nspec))) return rc;
+        d_vor = p.d_spec;
+        d_div = p.d_spec + nspec;
+    }
+    if ((rc = build_tiles(p, nall, T, T + 1))) return rc;
+    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nall)))) return rc;
+    if ((rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nall)))) return rc;
+    tm.mark(marks);
+    if ((rc = launch_fourier_dir(p, nall, d_gp, p.d_fourier, nall))) return rc;
+    slots[marks++] = 2;
+    tm.mark(marks);
+    if ((rc = launch_legendre_dir(p, nall, p.d_fourier, p.d_packed))) return rc;
+    slots[marks++] = 1;
+    tm.mark(marks);
+    if ((rc = launch_uv_to_vordiv(p.stream, T, nf, p.d_sp_rowoff, p.d_packed, d_vor, d_div, &p.launches))) return rc;
+    slots[marks++] = 0;
+    tm.mark(marks);
+    if (sp_host) {
+        SPT_CUDA(cudaMemcpyAsync(vor, d_vor, nspec * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+        SPT_CUDA(cudaMemcpyAsync(div, d_div, nspec * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+        slots[marks++] = 4;
+        tm.mark(marks);
+    }
+    tm.finish(marks + 1, slots);
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int sptrans_invtrans_grad(sptrans_plan* plan, int nf, const double* spectra, double* grad) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf < 0 || (nf > 0 && (!spectra || !grad))) {
+        set_error("sptrans_invtrans_grad: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (nf == 0) return SPTRANS_OK;
+    if (p.g.nranks != 1) {
+        set_error("whole-transform entry points need an unsharded plan; use the stage-level API");
+        return SPTRANS_ERR_INVALID;
+    }
+    const int T = p.g.T;
+    const int nall = 2 * nf;
+    StageTimer tm(p);
+    int marks = 0, slots[8];
+    const bool sp_host = !is_device_pointer(spectra), gp_host = !is_device_pointer(grad);
+    const size_t nspec = spec_doubles(p, nf, T), ngp = static_cast<size_t>(p.g.npts) * nall;
+    const double* d_sp = spectra;
+    if (sp_host) {
+        if ((rc = ensure(p.d_spec2, p.spec2_cap, nspec))) return rc;
+        tm.mark(marks);
+        SPT_CUDA(cudaMemcpyAsync(p.d_spec2, spectra, nspec * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+        slots[marks++] = 3;
+        d_sp = p.d_spec2;
+    }
+    if ((rc = ensure(p.d_spec, p.spec_cap, spec_doubles(p, nall, T + 1)))) return rc;
+    tm.mark(marks);
+    if ((rc = launch_grad_spectra(p.stream, T, nf, d_sp, p.d_spec, &p.launches))) return rc;
+    slots[marks++] = 0;
+    double* d_gp = grad;
+    if (gp_host) {
+        if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
+        d_gp = p.d_gp;
+    }
+    if ((rc = run_inverse(p, nall, T + 1, p.d_spec, d_gp, nall, tm, marks, slots))) return rc;
+    if (gp_host) {
+        SPT_CUDA(cudaMemcpyAsync(grad, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
         slots[marks++] = 4;
         tm.mark(marks);
     }
@@ -514,7 +627,7 @@ int sptrans_invtrans_legendre(sptrans_plan* plan, int nf, int trunc, const doubl
         set_error("sptrans_invtrans_legendre: invalid arguments");
         return SPTRANS_ERR_INVALID;
     }
-    if ((rc = build_tiles(p, nf, trunc))) return rc;
+    if ((rc = build_tiles(p, nf, trunc, p.g.T))) return rc;
     if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
     if ((rc = launch_pack_spectra(p, nf, trunc, d_spectra, p.d_packed))) return rc;
     if ((rc = launch_legendre_inv(p, nf, p.d_packed, d_fourier))) return rc;
@@ -557,7 +670,7 @@ int sptrans_dirtrans_legendre(sptrans_plan* plan, int nf, const double* d_fourie
         set_error("sptrans_dirtrans_legendre: invalid arguments");
         return SPTRANS_ERR_INVALID;
     }
-    if ((rc = build_tiles(p, nf, p.g.T))) return rc;
+    if ((rc = build_tiles(p, nf, p.g.T, p.g.T))) return rc;
     if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
     if ((rc = launch_legendre_dir(p, nf, d_fourier, p.d_packed))) return rc;
     if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spectra))) return rc;

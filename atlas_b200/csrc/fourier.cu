@@ -197,7 +197,7 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
         const int f = f0 + fi;
         double xn = gp[f * npts + pm.rowN + i];
         double xs = pm.has_s ? gp[f * npts + pm.rowS + i] : 0.;
-        if (f < nb_uv) {  // wind components enter the transform as U,V = u,v * cos(lat)
+        if (f < nb_uv) {  // wind components enter the vor/div transform as u,v / (a cos(lat))
             xn *= coslat[pair];
             xs *= coslat[pair];
         }
@@ -440,7 +440,7 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
         if (grp.nblocks[gi] == 0) continue;
         fourier_dir_kernel<<<grp.nblocks[gi], kFftThreads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
-            p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_coslat,
+            p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
             reinterpret_cast<double2*>(d_fourier));
         p.launches++;
         SPT_CUDA(cudaGetLastError());

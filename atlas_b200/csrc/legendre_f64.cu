@@ -233,8 +233,8 @@ __global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict
 }  // namespace
 
 // Tile lists for the current (nf, truncation-of-data).  Cheap (tens of thousands of entries); cached.
-int build_tiles(Plan& p, int nf, int trunc) {
-    if (p.tiles_nf == nf && p.tiles_trunc == trunc) return SPTRANS_OK;
+int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
+    if (p.tiles_nf == nf && p.tiles_trunc == trunc && p.tiles_dir_trunc == dir_trunc) return SPTRANS_OK;
     const HostGeom& g = p.g;
     const int T = g.T;
     const int ld = 2 * nf;
@@ -270,8 +270,8 @@ int build_tiles(Plan& p, int nf, int trunc) {
                     }
                 }
             }
-            // ---- direct: rows = all n <= T of this parity, contraction over the ncol latitudes
-            const int Kdir = num_n(T, m, par);
+            // ---- direct: rows = all n <= dir_trunc (T, or T+1 for the wind path) of this parity, contraction over latitudes
+            const int Kdir = std::min(Ktab, num_n(dir_trunc, m, par));
             if (Kdir > 0) {
                 const int ksteps = pitch / kBK;
                 const int rows_tab = round_up(std::max(Ktab, 1), kBK);
@@ -311,6 +311,7 @@ int build_tiles(Plan& p, int nf, int trunc) {
     if (rc) return rc;
     p.tiles_nf = nf;
     p.tiles_trunc = trunc;
+    p.tiles_dir_trunc = dir_trunc;
     return SPTRANS_OK;
 }
 

@@ -110,6 +110,7 @@ struct Plan {
     double* d_weights = nullptr;       // [nleg]
     double* d_coslatinv = nullptr;     // [nleg] 1/cos(lat), latitude clamped to +-89.9999999 (TransLocal.cc:1447-1458)
     double* d_coslat = nullptr;        // [nleg]
+    double* d_uvscale = nullptr;       // [nleg] 1/(a cos(lat)): wind -> scaled wind of the direct vor/div transform
     long long* d_sp_rowoff = nullptr;  // [2(T+1)+1]
     int* d_my_m = nullptr;             // [my_m.size()]
     // FFT tables
@@ -122,7 +123,7 @@ struct Plan {
     int* d_fft_order = nullptr;        // block schedule, longest rows first
     int fft_smem_max = 0;
     // tile lists (device) for the current nf; rebuilt when nf / truncation changes
-    int tiles_nf = -1, tiles_trunc = -1;
+    int tiles_nf = -1, tiles_trunc = -1, tiles_dir_trunc = -1;
     LegTile* d_tiles_inv = nullptr;
     int n_tiles_inv = 0;
     LegTile* d_tiles_dir = nullptr;
@@ -175,7 +176,7 @@ int export_legendre_cache(const Plan& p, double* h_out);
 size_t legendre_cache_doubles(const HostGeom& g);
 
 // ---- legendre_f64.cu ----
-int build_tiles(Plan& p, int nf, int trunc);
+int build_tiles(Plan& p, int nf, int trunc, int dir_trunc);
 int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed);
 int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec);
 int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier);
@@ -191,6 +192,9 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
 int launch_exchange_copy(Plan& p, int nf, const ExSeg* d_segs, int nseg, double* d_fourier, double* d_buf, bool gather);
 
 // ---- vordiv.cu ----
+int launch_grad_spectra(cudaStream_t s, int T, int nf, const double* d_sp, double* d_all, uint64_t* launches);
+int launch_uv_to_vordiv(cudaStream_t s, int T, int nf, const long long* d_sp_rowoff, const double* d_packed,
+                        double* d_vor, double* d_div, uint64_t* launches);
 int launch_vd2uv(cudaStream_t s, int T, int nf, const double* d_vor, const double* d_div, double* d_U, double* d_V,
                  uint64_t* launches);
 

@@ -136,7 +136,107 @@ __global__ void merge_uv_scalar_kernel(int T, int nvd, int nsc, const double* __
     }
 }
 
+// Spectral part of invtrans_grad: from scalar coefficients X at truncation T build, at truncation T+1, the fields
+//   [E-W_1..E-W_k | N-S_1..N-S_k],  E-W_n^m = i m X_n^m / a,
+//   N-S_n^m = [ (n+2) eps(n+1,m) X_{n+1}^m - (n-1) eps(n,m) X_{n-1}^m ] / a          ((1-mu^2) dPbar/dmu recurrence)
+// whose inverse transform, divided by cos(lat) in the Fourier store, is (1/(a cos)) df/dlambda and (1/a) df/dphi.
+// This is vd2uv applied to the velocity potential chi = f (vor = 0), cf. VorDivToUVLocal.cc:133-157.
+__global__ void grad_spectra_kernel(int T, int nf, const double* __restrict__ sp, double* __restrict__ all) {
+    const int Te = T + 1;
+    const int nall = 2 * nf;
+    const long long ncoef_e = static_cast<long long>(Te + 1) * (Te + 2) / 2;
+    const long long total = ncoef_e * nall;
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(e % nall);
+        const long long c = e / nall;
+        int m = static_cast<int>(((2.0 * Te + 3.0) - sqrt((2.0 * Te + 3.0) * (2.0 * Te + 3.0) - 8.0 * static_cast<double>(c))) * 0.5);
+        while (static_cast<long long>(2 * Te + 3 - m) * m / 2 > c) --m;
+        while (static_cast<long long>(2 * Te + 3 - (m + 1)) * (m + 1) / 2 <= c) ++m;
+        const int n = m + static_cast<int>(c - static_cast<long long>(2 * Te + 3 - m) * m / 2);
+        const int fs = f < nf ? f : f - nf;
+        auto at = [&](int nn, int imag) -> double {
+            if (m > T || nn > T || nn < m) return 0.;
+            const long long ct = static_cast<long long>(2 * T + 3 - m) * m / 2 + (nn - m);
+            return sp[(2 * ct + imag) * nf + fs];
+        };
+        const double inv_a = 1. / kEarthRadius;
+        double out_r, out_i;
+        if (f < nf) {  // E-W: i m X
+            out_r = -m * at(n, 1) * inv_a;
+            out_i = m * at(n, 0) * inv_a;
+        }
+        else {
+            const double cp = (n + 2) * epsnm(n + 1, m), cm = (n - 1) * epsnm(n, m);
+            out_r = (cp * at(n + 1, 0) - cm * at(n - 1, 0)) * inv_a;
+            out_i = (cp * at(n + 1, 1) - cm * at(n - 1, 1)) * inv_a;
+        }
+        if (m == 0) out_i = 0.;
+        all[(2 * c) * nall + f] = out_r;
+        all[(2 * c + 1) * nall + f] = out_i;
+    }
+}
+
+// Spectral part of dirtrans(wind -> vor, div): input = packed scalar transforms (to n = T+1) of
+// Ut = u/(a cos), Vt = v/(a cos) as produced by the direct Legendre kernel, layout [m][parity][k][2 fld + re/im]
+// with fields [u_1..u_k | v_1..v_k]:
+//   zeta_n^m = i m Vt_n^m + (n+1) eps(n,m) Ut_{n-1}^m - n eps(n+1,m) Ut_{n+1}^m
+//   D_n^m    = i m Ut_n^m - (n+1) eps(n,m) Vt_{n-1}^m + n eps(n+1,m) Vt_{n+1}^m
+__global__ void uv_to_vordiv_kernel(int T, int nf, const long long* __restrict__ sp_rowoff,
+                                    const double* __restrict__ packed, double* __restrict__ vor,
+                                    double* __restrict__ div) {
+    const long long ncoef = static_cast<long long>(T + 1) * (T + 2) / 2;
+    const long long total = ncoef * nf;
+    const int ld = 4 * nf;  // 2 * (2 nf) columns
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(e % nf);
+        const long long c = e / nf;
+        int m = static_cast<int>(((2.0 * T + 3.0) - sqrt((2.0 * T + 3.0) * (2.0 * T + 3.0) - 8.0 * static_cast<double>(c))) * 0.5);
+        while (static_cast<long long>(2 * T + 3 - m) * m / 2 > c) --m;
+        while (static_cast<long long>(2 * T + 3 - (m + 1)) * (m + 1) / 2 <= c) ++m;
+        const int n = m + static_cast<int>(c - static_cast<long long>(2 * T + 3 - m) * m / 2);
+        auto ext = [&](int nn, int imag, int fld) -> double {
+            if (nn < m || nn > T + 1) return 0.;
+            const int p = (nn - m) & 1, k = (nn - m) >> 1;
+            return packed[(sp_rowoff[2 * m + p] + k) * ld + 2 * fld + imag];
+        };
+        const int fu = f, fv = nf + f;
+        const double em = (n + 1) * epsnm(n, m), ep = n * epsnm(n + 1, m);
+        double zr = -m * ext(n, 1, fv) + em * ext(n - 1, 0, fu) - ep * ext(n + 1, 0, fu);
+        double zi = +m * ext(n, 0, fv) + em * ext(n - 1, 1, fu) - ep * ext(n + 1, 1, fu);
+        double dr = -m * ext(n, 1, fu) - em * ext(n - 1, 0, fv) + ep * ext(n + 1, 0, fv);
+        double di = +m * ext(n, 0, fu) - em * ext(n - 1, 1, fv) + ep * ext(n + 1, 1, fv);
+        if (m == 0) zi = di = 0.;
+        vor[(2 * c) * nf + f] = zr;
+        vor[(2 * c + 1) * nf + f] = zi;
+        div[(2 * c) * nf + f] = dr;
+        div[(2 * c + 1) * nf + f] = di;
+    }
+}
+
 }  // namespace
+
+int launch_grad_spectra(cudaStream_t s, int T, int nf, const double* d_sp, double* d_all, uint64_t* launches) {
+    const long long total = static_cast<long long>(T + 2) * (T + 3) / 2 * (2 * nf);
+    if (total == 0) return SPTRANS_OK;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    grad_spectra_kernel<<<blocks, 256, 0, s>>>(T, nf, d_sp, d_all);
+    if (launches) ++*launches;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int launch_uv_to_vordiv(cudaStream_t s, int T, int nf, const long long* d_sp_rowoff, const double* d_packed,
+                        double* d_vor, double* d_div, uint64_t* launches) {
+    const long long total = static_cast<long long>(T + 1) * (T + 2) / 2 * nf;
+    if (total == 0) return SPTRANS_OK;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    uv_to_vordiv_kernel<<<blocks, 256, 0, s>>>(T, nf, d_sp_rowoff, d_packed, d_vor, d_div);
+    if (launches) ++*launches;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
 
 int launch_vd2uv(cudaStream_t s, int T, int nf, const double* d_vor, const double* d_div, double* d_U, double* d_V,
                  uint64_t* launches) {

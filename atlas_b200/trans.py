@@ -131,12 +131,20 @@ class Trans:
             raise TypeError("invtrans: wrong number of arguments")
 
     def dirtrans(self, *args):
-        """dirtrans(nb_fields, scalar_fields, scalar_spectra)"""
+        """dirtrans(nb_fields, scalar_fields, scalar_spectra)
+        dirtrans(nb_fields, wind_fields, vorticity_spectra, divergence_spectra)"""
         if len(args) == 3:
             n, gp, sp = args
             _lib.check(_lib.lib.sptrans_dirtrans_scalar(self._h, int(n), _ptr(gp), _ptr(sp)))
+        elif len(args) == 4:
+            n, wind, vor, div = args
+            _lib.check(_lib.lib.sptrans_dirtrans_wind2vordiv(self._h, int(n), _ptr(wind), _ptr(vor), _ptr(div)))
         else:
-            raise _lib.NotImplementedInBackend(3, "dirtrans(wind -> vor/div) is not implemented yet")
+            raise TypeError("dirtrans: wrong number of arguments")
+
+    def invtrans_grad(self, nb_fields, scalar_spectra, grad_fields):
+        """grad_fields = [E-W_1..E-W_k | N-S_1..N-S_k][npts]  (TransIFS::__invtrans_grad, ifs/TransIFS.cc:2075-2142)"""
+        _lib.check(_lib.lib.sptrans_invtrans_grad(self._h, int(nb_fields), _ptr(scalar_spectra), _ptr(grad_fields)))
 
     # --- stage level (device pointers only) ---
     def fourier_elems_per_field(self):

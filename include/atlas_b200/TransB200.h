@@ -96,9 +96,9 @@ public:
                   const eckit::Configuration& = util::NoConfig()) const override {
         check(sptrans_dirtrans_scalar(plan_, nb_fields, scalar_fields, scalar_spectra));
     }
-    void dirtrans(const int, const double[], double[], double[],
-                  const eckit::Configuration& = util::NoConfig()) const override {
-        ATLAS_NOTIMPLEMENTED;
+    void dirtrans(const int nb_fields, const double wind_fields[], double vorticity_spectra[],
+                  double divergence_spectra[], const eckit::Configuration& = util::NoConfig()) const override {
+        check(sptrans_dirtrans_wind2vordiv(plan_, nb_fields, wind_fields, vorticity_spectra, divergence_spectra));
     }
     void invtrans_adj(const int, const double[], const int, double[], double[], double[],
                       const eckit::Configuration& = util::NoConfig()) const override {
@@ -158,7 +158,16 @@ public:
     void dirtrans_adj(const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
     void dirtrans_adj(const FieldSet&, FieldSet&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
     void dirtrans_wind2vordiv_adj(const Field&, const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void invtrans_grad(const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
+    void invtrans_grad(const Field& spfield, Field& gradfield, const eckit::Configuration& = util::NoConfig()) const override {
+        // gradfield (2, npts): row 0 = E-W, row 1 = N-S (component order of ifs/TransIFS.cc:2113-2137)
+        ATLAS_ASSERT(spfield.rank() == 1 && gradfield.rank() == 2, "rank-1 spectral field, (2, npts) gradient field");
+        const auto sp = array::make_view<double, 1>(spfield);
+        auto g        = array::make_view<double, 2>(gradfield);
+        if (g.shape(0) != 2) {
+            ATLAS_NOTIMPLEMENTED;
+        }
+        check(sptrans_invtrans_grad(plan_, 1, sp.data(), g.data()));
+    }
     void invtrans_grad(const FieldSet&, FieldSet&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
     void invtrans_adj(const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
     void invtrans_adj(const FieldSet&, FieldSet&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }

@@ -137,6 +137,17 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nb_fields, const double* gp_
  * [E-W_1..E-W_k | N-S_1..N-S_k][npts], i.e. component 0 = (1/(a cos))d/dlambda, 1 = (1/a)d/dphi
  * (ifs/TransIFS.cc:2075-2142).  NotImplemented in TransLocal (TransLocal.cc:848-857).                          */
 
+/* TransImpl::dirtrans(nb_fields, wind_fields, vorticity_spectra, divergence_spectra)   TransImpl.h:180-181
+ * wind layout [u_1..u_k | v_1..v_k][npts] (what invtrans_vordiv2wind produces); NotImplemented in TransLocal
+ * (TransLocal.cc:1680-1685).  Exact inverse of sptrans_invtrans_vordiv2wind up to quadrature error.          */
+int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nb_fields, const double* wind_fields,
+                                 double* vorticity_spectra, double* divergence_spectra);
+
+/* TransImpl::invtrans_grad(spfield, gradfield) in IFS-style pointers: grad layout
+ * [E-W_1..E-W_k | N-S_1..N-S_k][npts], i.e. component 0 = (1/(a cos))d/dlambda, 1 = (1/a)d/dphi
+ * (ifs/TransIFS.cc:2075-2142).  NotImplemented in TransLocal (TransLocal.cc:848-857).                          */
+int sptrans_invtrans_grad(sptrans_plan* plan, int nb_fields, const double* scalar_spectra, double* grad_fields);
+
 /* VorDivToUV::execute(nb_coeff, nb_fields, vor, div, U, V)   trans/VorDivToUV.h:121-122,
  * = vd2uv, trans/local/VorDivToUVLocal.cc:62-184.  Plan-free: spectral space only.                            */
 int sptrans_vordiv_to_uv(int truncation, int nb_fields, const double* vorticity, const double* divergence,

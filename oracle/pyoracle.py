@@ -41,6 +41,8 @@ def load_oracle():
     lib.orc_vd2uv.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp]
     lib.orc_extend_truncation.argtypes = [C.c_int, C.c_int, _dp, _dp]
     lib.orc_dirtrans.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    lib.orc_dirtrans_wind.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+    lib.orc_invtrans_grad.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     lib.orc_gaussian_quadrature.argtypes = [C.c_int, _dp, _dp]
     lib.orc_compute_zfn.argtypes = [C.c_int, _dp]
     lib.orc_legendre_lat.argtypes = [C.c_int, C.c_double, _dp, _dp]
@@ -152,6 +154,18 @@ class OraclePlan:
         sp = np.zeros((self.T + 1) * (self.T + 2) * nf)
         lib().orc_dirtrans(self.h, nf, _p(np.ascontiguousarray(gp)), _p(sp))
         return sp
+
+
+    def dirtrans_wind(self, nf, wind):
+        n = (self.T + 1) * (self.T + 2) * nf
+        vor, div = np.zeros(n), np.zeros(n)
+        lib().orc_dirtrans_wind(self.h, nf, _p(np.ascontiguousarray(wind)), _p(vor), _p(div))
+        return vor, div
+
+    def invtrans_grad(self, nf, spectra):
+        grad = np.zeros(2 * nf * self.npts)
+        lib().orc_invtrans_grad(self.h, nf, _p(np.ascontiguousarray(spectra)), _p(grad))
+        return grad
 
 
 def vd2uv(T, nf, vor, div):

@@ -701,7 +701,9 @@ void invtrans_full(const Plan& p, int nb_scalar_fields, const double* scalar_spe
 // using the same per-latitude zonal truncation (nlat0) as the inverse.  All (m<=T, n<=T)
 // coefficients are produced (no m==T drop here).
 // -------------------------------------------------------------------------------------
-void dirtrans(const Plan& p, int nb_fields, const double* gp, double* spectra) {
+// `Tout` = truncation of the produced spectra (T, or T+1 for the wind path below); `rowscale` (per latitude
+// row, may be null) multiplies the grid values before the transform.
+void dirtrans_general(const Plan& p, int nb_fields, const double* gp, double* spectra, int Tout, const double* rowscale) {
     const int T = p.T;
     const int nlats = p.nlat;
     const int nf = nb_fields;
@@ -720,15 +722,16 @@ void dirtrans(const Plan& p, int nb_fields, const double* gp, double* spectra) {
                 r2c_fft(p.fft(n), gp + npts * f + row_off[jlat], out.data(), buf.data());
                 cplx* dst = &four[(static_cast<size_t>(f) * nlats + jlat) * (T + 1)];
                 const int mmax = std::min(T, (n - 1) / 2);
-                for (int m = 0; m <= mmax; ++m) dst[m] = out[m] / static_cast<double>(n);
+                const double rs = rowscale ? rowscale[jlat] : 1.;
+                for (int m = 0; m <= mmax; ++m) dst[m] = out[m] * (rs / static_cast<double>(n));
             }
     }
-    const size_t nspec2 = 2 * legendre_size(T);
+    const size_t nspec2 = 2 * legendre_size(Tout);
     std::fill(spectra, spectra + nspec2 * nf, 0.);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(p.nthreads)
     for (int m = 0; m <= T; ++m) {
         const size_t Ks = num_n(T + 1, m, true), Ka = num_n(T + 1, m, false);
-        const size_t ioff = static_cast<size_t>(2 * T + 3 - m) * m / 2 * nf * 2;
+        const size_t ioff = static_cast<size_t>(2 * Tout + 3 - m) * m / 2 * nf * 2;
         for (int jl = p.nlat0[m]; jl < p.nlatsLegReduced; ++jl) {
             const int jn_row = jl;                 // northern row
             const int js_row = nlats - 1 - jl;     // its mirror
@@ -742,7 +745,7 @@ void dirtrans(const Plan& p, int nb_fields, const double* gp, double* spectra) {
                 cplx fs = has_s ? four[(static_cast<size_t>(f) * nlats + js_row) * (T + 1) + m] : cplx(0, 0);
                 cplx fsym = (fn + fs) * w, fasym = (fn - fs) * w;
                 // tables hold n descending from T+1 (k = 0 <-> highest n of that parity)
-                for (int n = m; n <= T; ++n) {
+                for (int n = m; n <= Tout; ++n) {
                     const bool sym = ((n - m) % 2 == 0);
                     // position of n in the descending list of its parity
                     const int ntop = sym ? ((T + 1 - m) % 2 == 0 ? T + 1 : T) : ((T + 1 - m) % 2 == 1 ? T + 1 : T);
@@ -756,6 +759,73 @@ void dirtrans(const Plan& p, int nb_fields, const double* gp, double* spectra) {
             }
         }
     }
+}
+
+void dirtrans(const Plan& p, int nb_fields, const double* gp, double* spectra) {
+    dirtrans_general(p, nb_fields, gp, spectra, p.T, nullptr);
+}
+
+// Direct transform of wind to vorticity / divergence (NOT in TransLocal -- parity unpinned; API of
+// TransImpl::dirtrans(nb_fields, wind, vor, div), trans/detail/TransImpl.h:180-181; wind layout
+// [u_1..u_k | v_1..v_k][npts] as produced by the inverse, TransLocal.cc:1561-1589).
+// With Ut = u/(a cos(lat)), Vt = v/(a cos(lat)) transformed as scalars up to n = T+1 and
+// eps(n,m) = sqrt((n^2-m^2)/(4n^2-1)):
+//   zeta_n^m = i m Vt_n^m + (n+1) eps(n,m) Ut_{n-1}^m - n eps(n+1,m) Ut_{n+1}^m
+//   D_n^m    = i m Ut_n^m - (n+1) eps(n,m) Vt_{n-1}^m + n eps(n+1,m) Vt_{n+1}^m
+// (integration by parts of zeta = (1/(a cos^2)) [dV/dlambda - cos d(U)/dphi], U = u cos, V = v cos).
+void dirtrans_wind(const Plan& p, int nb_fields, const double* wind, double* vor, double* div) {
+    const int T = p.T, nf = nb_fields;
+    std::vector<double> rs(p.nlat);
+    for (int j = 0; j < p.nlat; ++j) {
+        double lat = p.lat_deg[j];
+        if (lat > kLatPole) lat = kLatPole;
+        if (lat < -kLatPole) lat = -kLatPole;
+        rs[j] = 1. / (kEarthRadius * std::cos(lat * kDeg2Rad));
+    }
+    const size_t next = 2 * legendre_size(T + 1);
+    std::vector<double> uv(next * 2 * nf);
+    dirtrans_general(p, 2 * nf, wind, uv.data(), T + 1, rs.data());  // fields: u_1..u_k, v_1..v_k
+    auto eps = [](int n, int m) { return (n == 0 || n < m) ? 0. : std::sqrt((double(n) * n - double(m) * m) / (4. * n * n - 1.)); };
+    auto ext = [&](int m, int n, int imag, int f) -> double {  // f in [0, 2nf)
+        if (n < m || n > T + 1) return 0.;
+        return uv[(2 * (static_cast<size_t>(2 * (T + 1) + 3 - m) * m / 2 + (n - m)) + imag) * (2 * nf) + f];
+    };
+    for (int m = 0; m <= T; ++m)
+        for (int n = m; n <= T; ++n) {
+            const size_t c = static_cast<size_t>(2 * T + 3 - m) * m / 2 + (n - m);
+            const double em = (n + 1) * eps(n, m), ep = n * eps(n + 1, m);
+            for (int f = 0; f < nf; ++f) {
+                const int fu = f, fv = nf + f;
+                const double ur = ext(m, n, 0, fu), ui = ext(m, n, 1, fu), vr = ext(m, n, 0, fv), vi = ext(m, n, 1, fv);
+                // i m (a + i b) = (-m b) + i (m a)
+                double zr = -m * vi + em * ext(m, n - 1, 0, fu) - ep * ext(m, n + 1, 0, fu);
+                double zi = +m * vr + em * ext(m, n - 1, 1, fu) - ep * ext(m, n + 1, 1, fu);
+                double dr = -m * ui - em * ext(m, n - 1, 0, fv) + ep * ext(m, n + 1, 0, fv);
+                double di = +m * ur - em * ext(m, n - 1, 1, fv) + ep * ext(m, n + 1, 1, fv);
+                if (m == 0) zi = di = 0.;
+                vor[(2 * c) * nf + f] = zr;
+                vor[(2 * c + 1) * nf + f] = zi;
+                div[(2 * c) * nf + f] = dr;
+                div[(2 * c + 1) * nf + f] = di;
+            }
+        }
+}
+
+// Gradient of scalar fields (NOT in TransLocal, TransLocal.cc:848-857; TransIFS semantics ifs/TransIFS.cc:2075-2142):
+// out = [E-W_1..E-W_k | N-S_1..N-S_k][npts] with E-W = (1/(a cos)) d/dlambda, N-S = (1/a) d/dphi.
+// grad f is the irrotational wind of the velocity potential chi = f, i.e. the reference's own
+// vorticity/divergence inverse with vor = 0 and D = laplace(f): D_n^m = -n(n+1)/a^2 f_n^m.
+void invtrans_grad(const Plan& p, int nb_fields, const double* spectra, double* grad, bool fast) {
+    const int T = p.T, nf = nb_fields;
+    const size_t nspec = 2 * legendre_size(T) * nf;
+    std::vector<double> vor(nspec, 0.), div(nspec);
+    size_t c = 0;
+    for (int m = 0; m <= T; ++m)
+        for (int n = m; n <= T; ++n, ++c)
+            for (int imag = 0; imag < 2; ++imag)
+                for (int f = 0; f < nf; ++f)
+                    div[(2 * c + imag) * nf + f] = -(n * (n + 1.)) / (kEarthRadius * kEarthRadius) * spectra[(2 * c + imag) * nf + f];
+    invtrans_full(p, 0, nullptr, nf, vor.data(), div.data(), grad, fast, false);
 }
 
 }  // namespace
@@ -840,6 +910,14 @@ void orc_extend_truncation(int old_truncation, int nb_fields, const double* old_
 
 void orc_dirtrans(void* plan, int nb_fields, const double* gp, double* spectra) {
     dirtrans(*static_cast<Plan*>(plan), nb_fields, gp, spectra);
+}
+
+void orc_dirtrans_wind(void* plan, int nb_fields, const double* wind, double* vor, double* div) {
+    dirtrans_wind(*static_cast<Plan*>(plan), nb_fields, wind, vor, div);
+}
+
+void orc_invtrans_grad(void* plan, int nb_fields, const double* spectra, double* grad) {
+    invtrans_grad(*static_cast<Plan*>(plan), nb_fields, spectra, grad, true);
 }
 
 // FFT self-checks

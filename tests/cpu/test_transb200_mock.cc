@@ -54,8 +54,8 @@ int main() {
     for (size_t i = 1; i < t->nb_spectral_coefficients(); ++i) err2 = std::fmax(err2, std::fabs(back.data()[i]));
     bool threw = false;
     try {
-        Field g2("g", {idx_t(2)});
-        t->invtrans_grad(sp, g2);
+        FieldSet a, b;
+        t->invtrans_grad(a, b);
     }
     catch (const eckit::NotImplemented&) {
         threw = true;

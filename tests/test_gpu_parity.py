@@ -221,6 +221,50 @@ def test_dirtrans_unit_harmonic_gives_unit_coefficient():
         assert np.abs(sp - want).max() < 1e-13
 
 
+@pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("O160", 159, 4)])
+def test_dirtrans_wind2vordiv_matches_oracle(gridname, T, nf):
+    """TransImpl::dirtrans(nb_fields, wind, vor, div): parity unpinned in the reference (TransLocal: NotImplemented);
+    checked against the oracle's definition and as the inverse of invtrans_vordiv2wind."""
+    grid, trans, plan = make(gridname, T)
+    vor = H.synthetic_spectra(T, nf, seed=21)
+    div = H.synthetic_spectra(T, nf, seed=22)
+    vor.reshape(-1, 2, nf)[0] = 0.0  # the global mean of vorticity / divergence is unphysical (lap^-1 undefined)
+    div.reshape(-1, 2, nf)[0] = 0.0
+    wind = np.full(2 * nf * grid.size(), np.nan)
+    trans.invtrans(nf, vor, div, wind)
+    v2 = np.full_like(vor, np.nan)
+    d2 = np.full_like(div, np.nan)
+    trans.dirtrans(nf, wind, v2, d2)
+    ov, od = plan.dirtrans_wind(nf, wind)
+    assert H.rel_max(v2, ov) < 1e-11 and H.rel_max(d2, od) < 1e-11
+    tol = 1e-12 if grid.regular else 1e-9  # octahedral rows are pruned per wavenumber: quadrature no longer exact
+    assert H.rel_max(v2, vor) < tol and H.rel_max(d2, div) < tol
+
+
+@pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 5), ("O80", 79, 3)])
+def test_invtrans_grad_matches_oracle_and_closed_form(gridname, T, nf):
+    """invtrans_grad (TransIFS semantics, ifs/TransIFS.cc:2075-2142): [E-W | N-S]; the oracle evaluates it through
+    the reference's own vd2uv + inverse (grad f = irrotational wind of the velocity potential f)."""
+    grid, trans, plan = make(gridname, T)
+    sp = H.synthetic_spectra(T, nf, seed=31)
+    g = np.full(2 * nf * grid.size(), np.nan)
+    trans.invtrans_grad(nf, sp, g)
+    want = plan.invtrans_grad(nf, sp)
+    assert H.compute_rms(g, want) < 1e-12 and H.rel_max(g, want) < 1e-11
+    # closed form: f = 2 Pbar_2^1 cos(lon)
+    sp1 = np.zeros((T + 1) * (T + 2))
+    sp1[H.spec_index(T, 1, 2, 0)] = 1.0
+    g1 = np.full(2 * grid.size(), np.nan)
+    trans.invtrans_grad(1, sp1, g1)
+    lon, latp = H.grid_lonlat(grid.nx(), grid.y())
+    s, c = np.sin(latp), np.cos(latp)
+    a = H.EARTH_RADIUS
+    ew = -np.sqrt(7.5) * s * 2 * np.sin(lon) / a
+    ns = np.sqrt(7.5) * (c * c - s * s) * 2 * np.cos(lon) / a
+    npts = grid.size()
+    assert H.compute_rms(g1[:npts], ew) < 1e-13 and H.compute_rms(g1[npts:], ns) < 1e-13
+
+
 def test_round_trip_regular_grid():
     grid, trans, plan = make("F48", 47)
     T, nf = 47, 6

@@ -203,3 +203,26 @@ def test_vd2uv_against_merged_inverse_definition():
     for n in range(T + 1):
         for f in range(nf):
             assert U[H.spec_index(T, 0, n, 1, nf, f)] == 0.0
+
+
+def test_wind_direct_transform_round_trip_and_gradient_closed_form():
+    """dirtrans(wind) and invtrans_grad are not in TransLocal (parity unpinned): the oracle's definitions are checked
+    by round trip through the reference's own vd2uv + inverse, and against a closed-form gradient."""
+    nx, lat, w = regular_gaussian(24)
+    T, nf = 23, 2
+    plan = po.OraclePlan(nx, lat, T, regular=True, weights=w)
+    vor = H.synthetic_spectra(T, nf, seed=5)
+    div = H.synthetic_spectra(T, nf, seed=6)
+    vor.reshape(-1, 2, nf)[0] = 0.0
+    div.reshape(-1, 2, nf)[0] = 0.0
+    wind = plan.invtrans(0, None, nf, vor, div, mode=2)
+    v2, d2 = plan.dirtrans_wind(nf, wind)
+    assert H.rel_max(v2, vor) < 1e-12 and H.rel_max(d2, div) < 1e-12
+    sp1 = np.zeros((T + 1) * (T + 2))
+    sp1[H.spec_index(T, 1, 2, 0)] = 1.0
+    g1 = plan.invtrans_grad(1, sp1).reshape(2, -1)
+    lon, latp = H.grid_lonlat(nx, lat)
+    s, c = np.sin(latp), np.cos(latp)
+    a = H.EARTH_RADIUS
+    assert H.compute_rms(g1[0], -np.sqrt(7.5) * s * 2 * np.sin(lon) / a) < 1e-13
+    assert H.compute_rms(g1[1], np.sqrt(7.5) * (c * c - s * s) * 2 * np.cos(lon) / a) < 1e-13

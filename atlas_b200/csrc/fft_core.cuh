@@ -261,6 +261,22 @@ SPT_HD void dft5(double2* v) {
     v[2] = cadd(p2, q2);
     v[3] = csub(p2, q2);
 }
+// Shared-memory index swizzle of the mixed-radix engine (no padding): the three low index bits (= the 128-byte
+// bank group of a 16-byte element) are XORed with bits 3..5 and 4..6.  Unit-stride octets stay conflict free,
+// and so do the power-of-two strides 2, 4, 8, 16 of the last passes (span < 8); odd radices run first, where
+// every span is a multiple of 8.  Requires M % 8 == 0.
+SPT_HD int swz(int i) { return i ^ (((i >> 3) ^ (i >> 4)) & 7); }
+
+// exact q / d for q < 65536 via a precomputed reciprocal (integer division is ~20 instructions on the GPU)
+SPT_HD unsigned fastdiv_magic(unsigned d) { return static_cast<unsigned>((0x100000000ull + d - 1) / d); }
+SPT_HD int fastdiv(int q, unsigned magic, int d) {
+#ifdef __CUDA_ARCH__
+    return d == 1 ? q : static_cast<int>(__umulhi(static_cast<unsigned>(q), magic));
+#else
+    return d == 1 ? q : static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(q)) * magic) >> 32);
+#endif
+}
+
 // multiply by e^{-+ 2 pi i k / N} given (cos, sin) of 2 pi k / N
 template <bool FWD>
 SPT_HD double2 twc(double2 a, double c, double s) {
@@ -353,13 +369,13 @@ SPT_HD void twiddle_powers(double2 w1, double2* w /*[R]*/) {
 SPT_HD double2 twiddle2(const double2* Wa, const double2* Wb, int k) { return cmul(Wa[k >> 6], Wb[k & 63]); }
 
 template <int R>
-SPT_HD void dif_butterfly_g(double2* X, int q, int Nb, int S, const double2* Wa, const double2* Wb) {
-    const int span = Nb / R;
-    const int blk = q / span, t = q - blk * span;
+SPT_HD void dif_butterfly_g(double2* X, int q, int Nb, int span, unsigned span_magic, int S, const double2* Wa,
+                            const double2* Wb) {
+    const int blk = fastdiv(q, span_magic, span), t = q - blk * span;
     const int base = blk * Nb + t;
     double2 v[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = X[pad(base + j * span)];
+    for (int j = 0; j < R; ++j) v[j] = X[swz(base + j * span)];
     dftN<R, true>(v);
     if (t != 0) {
         double2 w[R];
@@ -368,19 +384,18 @@ SPT_HD void dif_butterfly_g(double2* X, int q, int Nb, int S, const double2* Wa,
         for (int j = 1; j < R; ++j) v[j] = cmul(v[j], w[j]);
     }
 #pragma unroll
-    for (int j = 0; j < R; ++j) X[pad(base + j * span)] = v[j];
+    for (int j = 0; j < R; ++j) X[swz(base + j * span)] = v[j];
 }
 
 template <int R, bool CONJ_FILT>
-SPT_HD void dit_butterfly_g(double2* X, int q, int Nb, int S, const double2* Wa, const double2* Wb,
-                            const double2* filt) {
-    const int span = Nb / R;
-    const int blk = q / span, t = q - blk * span;
+SPT_HD void dit_butterfly_g(double2* X, int q, int Nb, int span, unsigned span_magic, int S, const double2* Wa,
+                            const double2* Wb, const double2* filt) {
+    const int blk = fastdiv(q, span_magic, span), t = q - blk * span;
     const int base = blk * Nb + t;
     double2 v[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        v[j] = X[pad(base + j * span)];
+        v[j] = X[swz(base + j * span)];
         if (filt) v[j] = CONJ_FILT ? cmulc(v[j], filt[base + j * span]) : cmul(v[j], filt[base + j * span]);
     }
     if (t != 0) {
@@ -391,16 +406,18 @@ SPT_HD void dit_butterfly_g(double2* X, int q, int Nb, int S, const double2* Wa,
     }
     dftN<R, false>(v);
 #pragma unroll
-    for (int j = 0; j < R; ++j) X[pad(base + j * span)] = v[j];
+    for (int j = 0; j < R; ++j) X[swz(base + j * span)] = v[j];
 }
 
 struct ScheduleG {
     int npass;
     int radix[10];
-    int nb[10];     // block length of the pass
-    int stride[10]; // S = M / nb
+    int nb[10];       // block length of the pass
+    int stride[10];   // S = M / nb
+    unsigned span_magic[10];  // reciprocal of span = nb / radix
+    unsigned per_magic[10];   // reciprocal of M / radix (butterflies per sequence)
 };
-// radices: 16s, then the remaining power of two, then 9s / 3, then 5s
+// radices: odd ones first (9s, 3, 5s: their spans stay multiples of 8), then 16s, then the remaining power of two
 SPT_HD ScheduleG make_schedule_g(int M) {
     ScheduleG s;
     s.npass = 0;
@@ -413,34 +430,37 @@ SPT_HD ScheduleG make_schedule_g(int M) {
         s.radix[s.npass] = R;
         s.nb[s.npass] = Nb;
         s.stride[s.npass] = M / Nb;
+        s.span_magic[s.npass] = fastdiv_magic(static_cast<unsigned>(Nb / R));
+        s.per_magic[s.npass] = fastdiv_magic(static_cast<unsigned>(M / R));
         ++s.npass;
         Nb /= R;
     };
+    while (b >= 2) { push(9); b -= 2; }
+    if (b == 1) push(3);
+    while (c >= 1) { push(5); --c; }
     while (a >= 4) { push(16); a -= 4; }
     if (a == 3) push(8);
     else if (a == 2) push(4);
     else if (a == 1) push(2);
-    while (b >= 2) { push(9); b -= 2; }
-    if (b == 1) push(3);
-    while (c >= 1) { push(5); --c; }
     return s;
 }
 
 template <int R>
-SPT_HD void dif_pass_g(double2* X, int nseq, int M, int Nb, int S, const double2* Wa, const double2* Wb, int tid, int nthr) {
-    const int per = M / R, PL = padded_len(M);
+SPT_HD void dif_pass_g(double2* X, int nseq, int M, int Nb, int S, unsigned span_magic, unsigned per_magic,
+                       const double2* Wa, const double2* Wb, int tid, int nthr) {
+    const int per = M / R, span = Nb / R;
     for (int w = tid; w < nseq * per; w += nthr) {
-        const int sq = w / per, q = w - sq * per;
-        dif_butterfly_g<R>(X + sq * PL, q, Nb, S, Wa, Wb);
+        const int sq = nseq == 1 ? 0 : fastdiv(w, per_magic, per), q = w - sq * per;
+        dif_butterfly_g<R>(X + sq * M, q, Nb, span, span_magic, S, Wa, Wb);
     }
 }
 template <int R, bool CONJ_FILT>
-SPT_HD void dit_pass_g(double2* X, int nseq, int M, int Nb, int S, const double2* Wa, const double2* Wb,
-                       const double2* filt, int tid, int nthr) {
-    const int per = M / R, PL = padded_len(M);
+SPT_HD void dit_pass_g(double2* X, int nseq, int M, int Nb, int S, unsigned span_magic, unsigned per_magic,
+                       const double2* Wa, const double2* Wb, const double2* filt, int tid, int nthr) {
+    const int per = M / R, span = Nb / R;
     for (int w = tid; w < nseq * per; w += nthr) {
-        const int sq = w / per, q = w - sq * per;
-        dit_butterfly_g<R, CONJ_FILT>(X + sq * PL, q, Nb, S, Wa, Wb, filt);
+        const int sq = nseq == 1 ? 0 : fastdiv(w, per_magic, per), q = w - sq * per;
+        dit_butterfly_g<R, CONJ_FILT>(X + sq * M, q, Nb, span, span_magic, S, Wa, Wb, filt);
     }
 }
 
@@ -448,14 +468,15 @@ SPT_HD void fft_dif_g(double2* X, int nseq, int M, const ScheduleG& s, const dou
                       int nthr) {
     for (int p = 0; p < s.npass; ++p) {
         const int Nb = s.nb[p], S = s.stride[p];
+        const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
         switch (s.radix[p]) {
-            case 16: dif_pass_g<16>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
-            case 9: dif_pass_g<9>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
-            case 8: dif_pass_g<8>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
-            case 5: dif_pass_g<5>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
-            case 4: dif_pass_g<4>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
-            case 3: dif_pass_g<3>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
-            default: dif_pass_g<2>(X, nseq, M, Nb, S, Wa, Wb, tid, nthr); break;
+            case 16: dif_pass_g<16>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 9: dif_pass_g<9>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 8: dif_pass_g<8>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 5: dif_pass_g<5>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 4: dif_pass_g<4>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 3: dif_pass_g<3>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            default: dif_pass_g<2>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
         }
         SPT_SYNC();
     }
@@ -465,27 +486,28 @@ SPT_HD void fft_dit_g(double2* X, int nseq, int M, const ScheduleG& s, const dou
                       const double2* filt, int tid, int nthr) {
     for (int p = s.npass - 1; p >= 0; --p) {
         const int Nb = s.nb[p], S = s.stride[p];
+        const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
         const double2* f = (p == s.npass - 1) ? filt : nullptr;
         switch (s.radix[p]) {
-            case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
-            case 9: dit_pass_g<9, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
-            case 8: dit_pass_g<8, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
-            case 5: dit_pass_g<5, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
-            case 4: dit_pass_g<4, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
-            case 3: dit_pass_g<3, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
-            default: dit_pass_g<2, CONJ_FILT>(X, nseq, M, Nb, S, Wa, Wb, f, tid, nthr); break;
+            case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 9: dit_pass_g<9, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 8: dit_pass_g<8, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 5: dit_pass_g<5, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 4: dit_pass_g<4, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 3: dit_pass_g<3, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            default: dit_pass_g<2, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
         }
         SPT_SYNC();
     }
 }
 
-// smallest 5-smooth even length >= need (and >= 8); returns 0 if none <= limit
+// smallest 5-smooth multiple of 8 >= need; returns 0 if none <= limit
 SPT_HD int conv_length_smooth(int need, int limit) {
     int best = 0;
     for (long long p5 = 1; p5 <= limit; p5 *= 5)
         for (long long p3 = p5; p3 <= limit; p3 *= 3)
-            for (long long p2 = p3 * 2; p2 <= limit; p2 *= 2)
-                if (p2 >= need && p2 >= 8 && (best == 0 || p2 < best)) best = static_cast<int>(p2);
+            for (long long p2 = p3 * 8; p2 <= limit; p2 *= 2)
+                if (p2 >= need && (best == 0 || p2 < best)) best = static_cast<int>(p2);
     return best;
 }
 

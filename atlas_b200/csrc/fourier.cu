@@ -38,7 +38,7 @@ namespace {
 
 using namespace fftc;
 
-constexpr int kMaxM = 8192;      // largest convolution length a single CTA can hold in shared memory
+constexpr int kMaxM = 13824;     // largest convolution length a single CTA can hold in shared memory (221 KB)
 constexpr int kFftThreads = 256;
 
 __device__ __forceinline__ void load_twiddles(const double2* __restrict__ g, double2* s, int M, int tid, int nthr) {
@@ -78,7 +78,7 @@ chirp_tables_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chir
         sincospi(-2.0 * k / M, &s, &c);
         Wb[k] = make_double2(c, s);
     }
-    const int PL = padded_len(M);
+    const int PL = M;
     double2* sW = X + PL;
     for (int e = tid; e < PL; e += nthr) X[e] = make_double2(0., 0.);
     __syncthreads();
@@ -88,19 +88,19 @@ chirp_tables_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chir
         double s, c;
         sincospi(-static_cast<double>(chirp_residue(k, 0, n)) / n, &s, &c);
         const int idx = (k % M + M) % M;
-        X[pad(idx)] = make_double2(c, s);
+        X[swz(idx)] = make_double2(c, s);
     }
     __syncthreads();
     const ScheduleG sc = make_schedule_g(M);
     fft_dif_g(X, 1, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
     const double scl = 1.0 / M;
     for (int k = tid; k < M; k += nthr) {
-        const double2 v = X[pad(k)];
+        const double2 v = X[swz(k)];
         filt[pm.filt_off + k] = make_double2(v.x * scl, v.y * scl);
     }
 }
 
-__global__ void __launch_bounds__(kFftThreads, 2)
+__global__ void __launch_bounds__(2 * kFftThreads, 1)
 fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
                    int mlimit, int nb_uv, const double2* __restrict__ fb, const long long* __restrict__ fb_rowoff,
                    const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
@@ -113,7 +113,7 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     const int nfb = min(pm.F, nf - f0);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n = pm.n, L = pm.L;
-    const int M = pm.M, PL = padded_len(M);
+    const int M = pm.M, PL = M;
     const int Lc = min(L, mlimit);
     if (Lc < 0) {  // no zonal wavenumber resolved / requested at this latitude: rows are zero
         for (int w = tid; w < nfb * n; w += nthr) {
@@ -148,10 +148,10 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
         }
         // Z_m = F_N + i F_S ;  Z_{-m} = conj(F_N) + i conj(F_S)
         const double2 Zp = make_double2(FN.x - FS.y, FN.y + FS.x);
-        X[fi * PL + pad(L + m)] = cmul(Zp, A[L + m]);
+        X[fi * PL + swz(L + m)] = cmul(Zp, A[L + m]);
         if (m > 0) {
             const double2 Zm = make_double2(FN.x + FS.y, FS.x - FN.y);
-            X[fi * PL + pad(L - m)] = cmul(Zm, A[L - m]);
+            X[fi * PL + swz(L - m)] = cmul(Zm, A[L - m]);
         }
     }
     __syncthreads();
@@ -159,7 +159,7 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     fft_dit_g<false>(X, nfb, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
     for (int w = tid; w < nfb * n; w += nthr) {
         const int fi = w / n, i = w - fi * n;
-        const double2 z = cmul(X[fi * PL + pad(i)], C[i]);
+        const double2 z = cmul(X[fi * PL + swz(i)], C[i]);
         const int f = f0 + fi;
         double sn = 1., ss = 1.;
         if (f < nb_uv) {  // u,v = U,V / cos(lat)  (reference :1443-1469)
@@ -170,7 +170,7 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     }
 }
 
-__global__ void __launch_bounds__(kFftThreads, 2)
+__global__ void __launch_bounds__(2 * kFftThreads, 1)
 fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
                    int nb_uv, const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
                    const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
@@ -184,7 +184,7 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n = pm.n, L = pm.L;
     if (L < 0) return;
-    const int M = pm.M, PL = padded_len(M);
+    const int M = pm.M, PL = M;
     double2* sW = X + pm.F * PL;
     const ScheduleG sc = make_schedule_g(M);
     for (int e = tid; e < nfb * PL; e += nthr) X[e] = make_double2(0., 0.);
@@ -201,7 +201,7 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
             xn *= coslat[pair];
             xs *= coslat[pair];
         }
-        X[fi * PL + pad(i)] = cmulc(make_double2(xn, xs), C[i]);
+        X[fi * PL + swz(i)] = cmulc(make_double2(xn, xs), C[i]);
     }
     __syncthreads();
     fft_dif_g(X, nfb, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
@@ -210,8 +210,8 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     const double inv_n = 1.0 / n;
     for (int w = tid; w < nfb * (L + 1); w += nthr) {
         const int m = w / nfb, fi = w - m * nfb;
-        double2 Gp = cmulc(X[fi * PL + pad(L + m)], A[L + m]);
-        double2 Gm = cmulc(X[fi * PL + pad(L - m)], A[L - m]);
+        double2 Gp = cmulc(X[fi * PL + swz(L + m)], A[L + m]);
+        double2 Gm = cmulc(X[fi * PL + swz(L - m)], A[L - m]);
         Gp.x *= inv_n; Gp.y *= inv_n; Gm.x *= inv_n; Gm.y *= inv_n;
         // F_N = (G_m + conj(G_-m))/2 ; F_S = (G_m - conj(G_-m))/(2i)
         const double2 FN = make_double2(0.5 * (Gp.x + Gm.x), 0.5 * (Gp.y - Gm.y));
@@ -251,8 +251,8 @@ int choose_conv_length(int need) {
     double best_cost = 1e300;
     for (long long p5 = 1; p5 <= kMaxM; p5 *= 5)
         for (long long p3 = p5; p3 <= kMaxM; p3 *= 3)
-            for (long long p2 = p3 * 2; p2 <= kMaxM; p2 *= 2) {
-                if (p2 < need || p2 < 8) continue;
+            for (long long p2 = p3 * 8; p2 <= kMaxM; p2 *= 2) {  // multiples of 8 (index swizzle)
+                if (p2 < need) continue;
                 const ScheduleG s = fftc::make_schedule_g(static_cast<int>(p2));
                 double c = 0.4;  // load/store/pointwise sweeps
                 for (int p = 0; p < s.npass; ++p) c += 2.0 * pass_cost(s.radix[p]);  // forward + inverse
@@ -274,7 +274,7 @@ int fields_per_block(int M) {
 }
 
 size_t block_smem_bytes(int M, int F) {
-    return (static_cast<size_t>(F) * fftc::padded_len(M) + (M / 64 + 1 + 64)) * sizeof(double2);
+    return (static_cast<size_t>(F) * M + (M / 64 + 1 + 64)) * sizeof(double2);
 }
 
 }  // namespace
@@ -418,7 +418,8 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
     const FftGroups& grp = g_groups[&p];
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         if (grp.nblocks[gi] == 0) continue;
-        fourier_inv_kernel<<<grp.nblocks[gi], kFftThreads, grp.smem[gi], p.stream>>>(
+        const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;  // one block per SM: 16 warps
+        fourier_inv_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
             reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp,
             p.d_filt, p.d_coslatinv, d_gp, p.g.npts);
@@ -438,7 +439,8 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
     const FftGroups& grp = g_groups[&p];
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         if (grp.nblocks[gi] == 0) continue;
-        fourier_dir_kernel<<<grp.nblocks[gi], kFftThreads, grp.smem[gi], p.stream>>>(
+        const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;
+        fourier_dir_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
             p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
             reinterpret_cast<double2*>(d_fourier));

@@ -118,13 +118,17 @@ FFTPlan* fft_plan(int n, int sign) {
     return p;
 }
 
-// Stockham autosort, decimation in frequency, generic radix.
+// Stockham autosort, decimation in frequency.  Radix 4 and 2 are specialised (they carry the power-of-two
+// transforms inside Bluestein, i.e. most of the CPU baseline's Fourier time); other radices use the
+// generic O(f^2) butterfly.  Per-stage twiddles are read with a running index (no modulo in the loops).
 void fft_exec(const FFTPlan& p, cplx* data, cplx* work) {
     const int n = p.n;
     if (n <= 1) return;
     if (p.bluestein) {
         const int m = p.m;
-        std::vector<cplx> a(m, cplx(0, 0)), w(m);
+        static thread_local std::vector<cplx> a, w;  // per-thread work space (plans are shared between threads)
+        a.assign(m, cplx(0, 0));
+        w.resize(m);
         // With chirp_k = exp(s i pi k^2/n):  exp(s 2 pi i jk/n) = chirp_j chirp_k conj(chirp_{k-j})
         for (int j = 0; j < n; ++j) a[j] = data[j] * p.chirp[j];
         fft_exec(*p.sub, a.data(), w.data());
@@ -138,23 +142,51 @@ void fft_exec(const FFTPlan& p, cplx* data, cplx* work) {
     cplx* y = work;
     int l = n;  // remaining length
     int s = 1;  // stride
+    const double sg = p.sign;
     for (int f : p.factors) {
         const int mm = l / f;
-        // x viewed as [f][mm][s], y as [mm][f][s]
-        for (int q = 0; q < mm; ++q) {
-            cplx t[16];
-            for (int r = 0; r < s; ++r) {
-                for (int a = 0; a < f; ++a) t[a] = x[r + s * (q + mm * a)];
-                for (int b = 0; b < f; ++b) {
-                    cplx acc(0, 0);
-                    for (int a = 0; a < f; ++a) {
-                        // exp(sign 2 pi i a b / f)
-                        int idx = static_cast<int>((static_cast<long long>(a) * b % f) * (n / f));
-                        acc += t[a] * p.tw[idx];
+        const int tstep = n / l;  // twiddle exp(sign 2 pi i q b / l) = tw[q b tstep]
+        if (f == 4) {
+            for (int q = 0; q < mm; ++q) {
+                const cplx w1 = p.tw[q * tstep], w2 = p.tw[2 * q * tstep], w3 = p.tw[3 * q * tstep];
+                for (int r = 0; r < s; ++r) {
+                    const cplx a0 = x[r + s * q], a1 = x[r + s * (q + mm)], a2 = x[r + s * (q + 2 * mm)],
+                               a3 = x[r + s * (q + 3 * mm)];
+                    const cplx s02 = a0 + a2, d02 = a0 - a2, s13 = a1 + a3;
+                    const cplx d13 = cplx(-sg * (a1.imag() - a3.imag()), sg * (a1.real() - a3.real()));  // (sign i)(a1-a3)
+                    y[r + s * (4 * q)] = s02 + s13;
+                    y[r + s * (4 * q + 1)] = (d02 + d13) * w1;
+                    y[r + s * (4 * q + 2)] = (s02 - s13) * w2;
+                    y[r + s * (4 * q + 3)] = (d02 - d13) * w3;
+                }
+            }
+        }
+        else if (f == 2) {
+            for (int q = 0; q < mm; ++q) {
+                const cplx w1 = p.tw[q * tstep];
+                for (int r = 0; r < s; ++r) {
+                    const cplx a0 = x[r + s * q], a1 = x[r + s * (q + mm)];
+                    y[r + s * (2 * q)] = a0 + a1;
+                    y[r + s * (2 * q + 1)] = (a0 - a1) * w1;
+                }
+            }
+        }
+        else {
+            const int fstep = n / f;  // exp(sign 2 pi i a b / f) = tw[(a b mod f) fstep]
+            for (int q = 0; q < mm; ++q) {
+                cplx t[16];
+                for (int r = 0; r < s; ++r) {
+                    for (int a = 0; a < f; ++a) t[a] = x[r + s * (q + mm * a)];
+                    for (int b = 0; b < f; ++b) {
+                        cplx acc = t[0];
+                        int ab = 0;
+                        for (int a = 1; a < f; ++a) {
+                            ab += b;
+                            if (ab >= f) ab -= f;
+                            acc += t[a] * p.tw[ab * fstep];
+                        }
+                        y[r + s * (b + f * q)] = acc * p.tw[(q * b) * tstep];
                     }
-                    // twiddle exp(sign 2 pi i q b / l)
-                    int tidx = static_cast<int>((static_cast<long long>(q) * b) % l * (n / l));
-                    y[r + s * (b + f * q)] = acc * p.tw[tidx];
                 }
             }
         }
@@ -198,6 +230,41 @@ void c2r_fft(const RealFFT& r, const cplx* in, double* out, cplx* buf /*2n*/) {
     }
     fft_exec(*r.inv, z, buf + n);
     for (int j = 0; j < n; ++j) out[j] = z[j].real();
+}
+
+// Two real rows of the same length in one complex transform (CPU-baseline fast path): z = x_a + i x_b has the
+// spectrum Z_k = A_k + i B_k, Z_{n-k} = conj(A_k) + i conj(B_k).
+void c2r_pair_fft(const RealFFT& r, const cplx* ina, const cplx* inb, double* outa, double* outb, cplx* buf /*2n*/) {
+    const int n = r.n;
+    cplx* z = buf;
+    const cplx I(0., 1.);
+    z[0] = cplx(ina[0].real(), inb[0].real());
+    for (int k = 1; k <= n / 2; ++k) {
+        if (n - k != k) {
+            z[k] = ina[k] + I * inb[k];
+            z[n - k] = std::conj(ina[k]) + I * std::conj(inb[k]);
+        }
+        else {
+            z[k] = cplx(ina[k].real(), inb[k].real());
+        }
+    }
+    fft_exec(*r.inv, z, buf + n);
+    for (int j = 0; j < n; ++j) {
+        outa[j] = z[j].real();
+        outb[j] = z[j].imag();
+    }
+}
+void r2c_pair_fft(const RealFFT& r, const double* ina, const double* inb, cplx* outa, cplx* outb, cplx* buf /*2n*/) {
+    const int n = r.n;
+    for (int j = 0; j < n; ++j) buf[j] = cplx(ina[j], inb[j]);
+    fft_exec(*r.fwd, buf, buf + n);
+    outa[0] = cplx(buf[0].real(), 0.);
+    outb[0] = cplx(buf[0].imag(), 0.);
+    for (int k = 1; k <= n / 2; ++k) {
+        const cplx zk = buf[k], zc = std::conj(buf[n - k]);
+        outa[k] = 0.5 * (zk + zc);
+        outb[k] = cplx(0., -0.5) * (zk - zc);
+    }
 }
 
 // literal DFT, O(n^2): the "reference-as-written" semantic anchor for the FFT
@@ -411,12 +478,93 @@ void gemm_blocked(const double* A, const double* B, double* C, size_t M, size_t 
     if (j < N) gemm_naive(A, B + K * j, C + M * j, M, K, N - j);
 }
 
+// CPU-baseline variant of invtrans_legendre: same split / GEMM / merge, but threads own blocks of 8 consecutive
+// zonal wavenumbers so that the merge writes 8 adjacent complex values per (field, latitude) instead of one
+// value per cache line (the reference's posMethod layout makes m the fastest index).
+void invtrans_legendre_blocked(const Plan& p, int truncation, int nlats, int nb_fields, const double* spectra,
+                               double* scl_fourier) {
+    const int T = p.T;
+    constexpr int MB = 8;
+    const int nblocks = (T + 1 + MB - 1) / MB;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(p.nthreads)
+    for (int blk = 0; blk < nblocks; ++blk) {
+        const int m0 = blk * MB, m1 = std::min(T + 1, m0 + MB);
+        std::vector<std::vector<double>> cs(MB), ca(MB);
+        int ncols_m[MB], nimag_m[MB];
+        for (int jm = m0; jm < m1; ++jm) {
+            const int b = jm - m0;
+            const size_t size_sym = num_n(T + 1, jm, true), size_asym = num_n(T + 1, jm, false);
+            const int n_imag = (jm ? 2 : 1);
+            const int ncols = p.nlatsLegReduced - p.nlat0[jm];
+            ncols_m[b] = ncols;
+            nimag_m[b] = n_imag;
+            if (ncols <= 0) continue;
+            const size_t rows = static_cast<size_t>(nb_fields) * n_imag;
+            std::vector<double> a_sym(rows * size_sym), a_asym(rows * size_asym);
+            cs[b].assign(rows * ncols, 0.);
+            ca[b].assign(rows * ncols, 0.);
+            size_t is = 0, ia = 0;
+            const size_t ioff = static_cast<size_t>(2 * truncation + 3 - jm) * jm / 2 * nb_fields * 2;
+            for (int jn = T + 1; jn >= jm; jn--)
+                for (int imag = 0; imag < n_imag; imag++)
+                    for (int jfld = 0; jfld < nb_fields; jfld++) {
+                        size_t idx = jfld + static_cast<size_t>(nb_fields) * (imag + 2 * (jn - jm));
+                        double v = (jn <= truncation && jm < truncation) ? spectra[idx + ioff] : 0.;
+                        if ((jn - jm) % 2 == 0) a_sym[is++] = v;
+                        else a_asym[ia++] = v;
+                    }
+            gemm_blocked(a_sym.data(), p.leg_sym.data() + p.sym_begin[jm] + p.nlat0[jm] * size_sym, cs[b].data(), rows,
+                         size_sym, ncols);
+            if (size_asym > 0)
+                gemm_blocked(a_asym.data(), p.leg_asym.data() + p.asym_begin[jm] + p.nlat0[jm] * size_asym, ca[b].data(),
+                             rows, size_asym, ncols);
+        }
+        for (int jfld = 0; jfld < nb_fields; jfld++) {
+            for (int jlat = 0; jlat < std::max(p.nlatsNH, p.nlatsSH); jlat++) {
+                for (int jm = m0; jm < m1; ++jm) {
+                    const int b = jm - m0;
+                    const int ncols = ncols_m[b], n_imag = nimag_m[b];
+                    for (int imag = 0; imag < n_imag; imag++) {
+                        if (jlat < p.nlatsNH) {
+                            const int col = ncols - p.nlatsNH + jlat;
+                            double v = 0.;
+                            if (ncols > 0 && col >= 0) {
+                                const size_t idx = jfld + static_cast<size_t>(nb_fields) * (imag + n_imag * col);
+                                v = cs[b][idx] + ca[b][idx];
+                            }
+                            scl_fourier[pos_fourier(p, jfld, imag, jlat, jm, nb_fields, nlats)] = v;
+                        }
+                    }
+                }
+                for (int jm = m0; jm < m1; ++jm) {  // southern rows second: the equator row ends up as sym - asym (:1061-1070)
+                    const int b = jm - m0;
+                    const int ncols = ncols_m[b], n_imag = nimag_m[b];
+                    for (int imag = 0; imag < n_imag; imag++) {
+                        if (jlat < p.nlatsSH) {
+                            const int col = ncols - p.nlatsSH + jlat;
+                            double v = 0.;
+                            if (ncols > 0 && col >= 0) {
+                                const size_t idx = jfld + static_cast<size_t>(nb_fields) * (imag + n_imag * col);
+                                v = cs[b][idx] - ca[b][idx];
+                            }
+                            scl_fourier[pos_fourier(p, jfld, imag, nlats - jlat - 1, jm, nb_fields, nlats)] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // TransLocal::invtrans_legendre, TransLocal.cc:939-1097.  `fast` only changes the GEMM loop
 // nest and threads over m; the split / merge follow the reference literally.
 void invtrans_legendre(const Plan& p, int truncation, int nlats, int nb_fields, const double* spectra,
                        double* scl_fourier, bool fast) {
     const int T = p.T;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(fast ? p.nthreads : 1)
+    if (fast) {
+        invtrans_legendre_blocked(p, truncation, nlats, nb_fields, spectra, scl_fourier);
+        return;
+    }
     for (int jm = 0; jm <= T; jm++) {
         const size_t size_sym = num_n(T + 1, jm, true);
         const size_t size_asym = num_n(T + 1, jm, false);
@@ -498,6 +646,43 @@ void invtrans_fourier(const Plan& p, int nlats, int nb_fields, const double* scl
     std::vector<size_t> row_off(nlats + 1, 0);
     for (int j = 0; j < nlats; ++j) row_off[j + 1] = row_off[j] + p.nx[j];
     const size_t npts = row_off[nlats];
+    if (fast && !naive_dft) {
+        // CPU-baseline variant: rows j and nlats-1-j have the same length on a global grid -> one complex FFT per pair
+        const int npairs = (nlats + 1) / 2;
+#pragma omp parallel num_threads(p.nthreads)
+        {
+            std::vector<cplx> ina(p.nxmax / 2 + 1), inb(p.nxmax / 2 + 1), buf(2 * static_cast<size_t>(p.nxmax));
+#pragma omp for collapse(2) schedule(dynamic, 8)
+            for (int jfld = 0; jfld < nb_fields; jfld++) {
+                for (int jp = 0; jp < npairs; jp++) {
+                    const int ja = jp, jb = nlats - 1 - jp;
+                    const int n = p.nx[ja];
+                    const int num_complex = n / 2 + 1;
+                    auto pack = [&](int jlat, cplx* in) {
+                        in[0] = cplx(scl_fourier[pos_fourier(p, jfld, 0, jlat, 0, nb_fields, nlats)], 0.);
+                        const size_t base = pos_fourier(p, jfld, 0, jlat, 0, nb_fields, nlats);
+                        const int top = std::min(num_complex - 1, p.T);
+                        for (int jm = 1; jm <= top; jm++) in[jm] = cplx(scl_fourier[base + 2 * jm], scl_fourier[base + 2 * jm + 1]);
+                        for (int jm = top + 1; jm < num_complex; jm++) in[jm] = cplx(0., 0.);
+                    };
+                    pack(ja, ina.data());
+                    if (jb != ja && p.nx[jb] == n) {
+                        pack(jb, inb.data());
+                        c2r_pair_fft(p.fft(n), ina.data(), inb.data(), gp + npts * jfld + row_off[ja],
+                                     gp + npts * jfld + row_off[jb], buf.data());
+                    }
+                    else {
+                        c2r_fft(p.fft(n), ina.data(), gp + npts * jfld + row_off[ja], buf.data());
+                        if (jb != ja) {
+                            pack(jb, inb.data());
+                            c2r_fft(p.fft(p.nx[jb]), inb.data(), gp + npts * jfld + row_off[jb], buf.data());
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
 #pragma omp parallel num_threads(fast ? p.nthreads : 1)
     {
         std::vector<cplx> in(p.nxmax / 2 + 1), buf(2 * static_cast<size_t>(p.nxmax));
@@ -710,51 +895,113 @@ void dirtrans_general(const Plan& p, int nb_fields, const double* gp, double* sp
     std::vector<size_t> row_off(nlats + 1, 0);
     for (int j = 0; j < nlats; ++j) row_off[j + 1] = row_off[j] + p.nx[j];
     const size_t npts = row_off[nlats];
-    // Fourier stage: four[fld][lat][m] complex
+    // Fourier stage: four[fld][lat][m] complex; rows j and nlats-1-j share one complex FFT
     std::vector<cplx> four(static_cast<size_t>(nf) * nlats * (T + 1), cplx(0, 0));
+    const int npairs = (nlats + 1) / 2;
 #pragma omp parallel num_threads(p.nthreads)
     {
-        std::vector<cplx> out(p.nxmax / 2 + 1), buf(2 * static_cast<size_t>(p.nxmax));
-#pragma omp for collapse(2) schedule(static)
+        std::vector<cplx> oa(p.nxmax / 2 + 1), ob(p.nxmax / 2 + 1), buf(2 * static_cast<size_t>(p.nxmax));
+#pragma omp for collapse(2) schedule(dynamic, 8)
         for (int f = 0; f < nf; ++f)
-            for (int jlat = 0; jlat < nlats; ++jlat) {
-                const int n = p.nx[jlat];
-                r2c_fft(p.fft(n), gp + npts * f + row_off[jlat], out.data(), buf.data());
-                cplx* dst = &four[(static_cast<size_t>(f) * nlats + jlat) * (T + 1)];
+            for (int jp = 0; jp < npairs; ++jp) {
+                const int ja = jp, jb = nlats - 1 - jp;
+                const int n = p.nx[ja];
                 const int mmax = std::min(T, (n - 1) / 2);
-                const double rs = rowscale ? rowscale[jlat] : 1.;
-                for (int m = 0; m <= mmax; ++m) dst[m] = out[m] * (rs / static_cast<double>(n));
+                auto put = [&](int jlat, const cplx* out) {
+                    cplx* dst = &four[(static_cast<size_t>(f) * nlats + jlat) * (T + 1)];
+                    const double rs = (rowscale ? rowscale[jlat] : 1.) / static_cast<double>(n);
+                    for (int m = 0; m <= mmax; ++m) dst[m] = out[m] * rs;
+                };
+                if (jb != ja && p.nx[jb] == n) {
+                    r2c_pair_fft(p.fft(n), gp + npts * f + row_off[ja], gp + npts * f + row_off[jb], oa.data(), ob.data(),
+                                 buf.data());
+                    put(ja, oa.data());
+                    put(jb, ob.data());
+                }
+                else {
+                    r2c_fft(p.fft(n), gp + npts * f + row_off[ja], oa.data(), buf.data());
+                    put(ja, oa.data());
+                    if (jb != ja) {
+                        r2c_fft(p.fft(p.nx[jb]), gp + npts * f + row_off[jb], ob.data(), buf.data());
+                        const int mm2 = std::min(T, (p.nx[jb] - 1) / 2);
+                        cplx* dst = &four[(static_cast<size_t>(f) * nlats + jb) * (T + 1)];
+                        const double rs = (rowscale ? rowscale[jb] : 1.) / static_cast<double>(p.nx[jb]);
+                        for (int m = 0; m <= mm2; ++m) dst[m] = ob[m] * rs;
+                    }
+                }
             }
     }
     const size_t nspec2 = 2 * legendre_size(Tout);
     std::fill(spectra, spectra + nspec2 * nf, 0.);
+    constexpr int MB = 8;
+    const int nblocks = (T + 1 + MB - 1) / MB;
+    const int R = 2 * nf;  // rows: f + nf*imag
 #pragma omp parallel for schedule(dynamic, 1) num_threads(p.nthreads)
-    for (int m = 0; m <= T; ++m) {
-        const size_t Ks = num_n(T + 1, m, true), Ka = num_n(T + 1, m, false);
-        const size_t ioff = static_cast<size_t>(2 * Tout + 3 - m) * m / 2 * nf * 2;
-        for (int jl = p.nlat0[m]; jl < p.nlatsLegReduced; ++jl) {
-            const int jn_row = jl;                 // northern row
-            const int js_row = nlats - 1 - jl;     // its mirror
+    for (int blk = 0; blk < nblocks; ++blk) {
+        const int m0 = blk * MB, m1 = std::min(T + 1, m0 + MB);
+        const int nl0 = p.nlat0[m0];  // nlat0 is non-decreasing in m
+        const int ncmax = p.nlatsLegReduced - nl0;
+        if (ncmax <= 0) continue;
+        // gather w * (F_N +- F_S) for the 8 wavenumbers of the block: gs/ga[b][i + R*col]
+        std::vector<double> gs(static_cast<size_t>(MB) * R * ncmax, 0.), ga(static_cast<size_t>(MB) * R * ncmax, 0.);
+        for (int jl = nl0; jl < p.nlatsLegReduced; ++jl) {
+            const int js_row = nlats - 1 - jl;
             const bool has_n = jl < p.nlatsNH;
-            const bool has_s = jl < p.nlatsSH && js_row != jn_row;
+            const bool has_s = jl < p.nlatsSH && js_row != jl;
             const double w = p.weights.empty() ? 0. : p.weights[jl];
-            const double* Ps = p.leg_sym.data() + p.sym_begin[m] + Ks * jl;
-            const double* Pa = p.leg_asym.data() + p.asym_begin[m] + Ka * jl;
             for (int f = 0; f < nf; ++f) {
-                cplx fn = has_n ? four[(static_cast<size_t>(f) * nlats + jn_row) * (T + 1) + m] : cplx(0, 0);
-                cplx fs = has_s ? four[(static_cast<size_t>(f) * nlats + js_row) * (T + 1) + m] : cplx(0, 0);
-                cplx fsym = (fn + fs) * w, fasym = (fn - fs) * w;
-                // tables hold n descending from T+1 (k = 0 <-> highest n of that parity)
-                for (int n = m; n <= Tout; ++n) {
-                    const bool sym = ((n - m) % 2 == 0);
-                    // position of n in the descending list of its parity
-                    const int ntop = sym ? ((T + 1 - m) % 2 == 0 ? T + 1 : T) : ((T + 1 - m) % 2 == 1 ? T + 1 : T);
-                    const size_t k = static_cast<size_t>((ntop - n) / 2);
-                    const double pv = sym ? Ps[k] : Pa[k];
-                    const cplx c = (sym ? fsym : fasym) * pv;
+                const cplx* rn = &four[(static_cast<size_t>(f) * nlats + jl) * (T + 1)];
+                const cplx* rsn = &four[(static_cast<size_t>(f) * nlats + js_row) * (T + 1)];
+                for (int m = m0; m < m1; ++m) {
+                    if (jl < p.nlat0[m]) continue;
+                    const cplx fn = has_n ? rn[m] : cplx(0, 0), fs = has_s ? rsn[m] : cplx(0, 0);
+                    const cplx a = (fn + fs) * w, c = (fn - fs) * w;
+                    const size_t base = (static_cast<size_t>(m - m0) * ncmax + (jl - nl0)) * R;
+                    gs[base + f] = a.real();
+                    gs[base + nf + f] = a.imag();
+                    ga[base + f] = c.real();
+                    ga[base + nf + f] = c.imag();
+                }
+            }
+        }
+        for (int m = m0; m < m1; ++m) {
+            const int ncols = p.nlatsLegReduced - p.nlat0[m];
+            if (ncols <= 0) continue;
+            const size_t Ks = num_n(T + 1, m, true), Ka = num_n(T + 1, m, false);
+            const size_t ioff = static_cast<size_t>(2 * Tout + 3 - m) * m / 2 * nf * 2;
+            const size_t skip = static_cast<size_t>(p.nlat0[m] - nl0) * R;
+            const double* Gs = gs.data() + static_cast<size_t>(m - m0) * ncmax * R + skip;
+            const double* Ga = ga.data() + static_cast<size_t>(m - m0) * ncmax * R + skip;
+            for (int par = 0; par < 2; ++par) {
+                const size_t K = par ? Ka : Ks;
+                if (K == 0) continue;
+                const double* P = (par ? p.leg_asym.data() + p.asym_begin[m] : p.leg_sym.data() + p.sym_begin[m]) +
+                                  K * static_cast<size_t>(p.nlat0[m]);
+                const double* G = par ? Ga : Gs;
+                // X[i + R*k] = sum_col G[i + R*col] * P[k + K*col]   (tables hold n descending: k = 0 <-> highest n)
+                std::vector<double> X(static_cast<size_t>(R) * K, 0.);
+                for (size_t k0 = 0; k0 < K; k0 += 4) {
+                    const size_t kb = std::min<size_t>(4, K - k0);
+                    for (int col = 0; col < ncols; ++col) {
+                        const double* g = G + static_cast<size_t>(col) * R;
+                        const double* pc = P + K * static_cast<size_t>(col) + k0;
+                        for (size_t kk = 0; kk < kb; ++kk) {
+                            const double pv = pc[kk];
+                            double* x = X.data() + (k0 + kk) * R;
+#pragma omp simd
+                            for (int i = 0; i < R; ++i) x[i] += g[i] * pv;
+                        }
+                    }
+                }
+                const int ntop = par == 0 ? ((T + 1 - m) % 2 == 0 ? T + 1 : T) : ((T + 1 - m) % 2 == 1 ? T + 1 : T);
+                for (size_t k = 0; k < K; ++k) {
+                    const int n = ntop - 2 * static_cast<int>(k);
+                    if (n > Tout || n < m) continue;
                     const size_t base = ioff + static_cast<size_t>(nf) * 2 * (n - m);
-                    spectra[base + f] += c.real();
-                    if (m > 0) spectra[base + nf + f] += c.imag();
+                    for (int f = 0; f < nf; ++f) {
+                        spectra[base + f] = X[k * R + f];
+                        if (m > 0) spectra[base + nf + f] = X[k * R + nf + f];
+                    }
                 }
             }
         }

@@ -114,22 +114,22 @@ static int check_g(int n, int L) {
         double ang = M_PI * (double)chirp_residue(i, -2LL * L, n) / n;
         C[i] = make_double2(std::cos(ang), std::sin(ang));
     }
-    std::vector<double2> b(padded_len(M), make_double2(0, 0));
+    std::vector<double2> b(M, make_double2(0, 0));
     for (int k = -2 * L; k <= n - 1; ++k) {
         double ang = -M_PI * (double)chirp_residue(k, 0, n) / n;
-        b[pad(((k % M) + M) % M)] = make_double2(std::cos(ang), std::sin(ang));
+        b[swz(((k % M) + M) % M)] = make_double2(std::cos(ang), std::sin(ang));
     }
     fft_dif_g(b.data(), 1, M, sc, Wa.data(), Wb.data(), 0, 1);
-    for (int k = 0; k < M; ++k) Bh[k] = make_double2(b[pad(k)].x / M, b[pad(k)].y / M);
+    for (int k = 0; k < M; ++k) Bh[k] = make_double2(b[swz(k)].x / M, b[swz(k)].y / M);
     std::vector<double2> Z(2 * L + 1);
     for (auto& z : Z) z = make_double2(urand(), urand());
-    std::vector<double2> X(padded_len(M), make_double2(0, 0));
-    for (int u = 0; u <= 2 * L; ++u) X[pad(u)] = cmul(Z[u], A[u]);
+    std::vector<double2> X(M, make_double2(0, 0));
+    for (int u = 0; u <= 2 * L; ++u) X[swz(u)] = cmul(Z[u], A[u]);
     fft_dif_g(X.data(), 1, M, sc, Wa.data(), Wb.data(), 0, 1);
     fft_dit_g<false>(X.data(), 1, M, sc, Wa.data(), Wb.data(), Bh.data(), 0, 1);
     double err_inv = 0, nrm = 0;
     for (int i = 0; i < n; i += (n > 2000 ? 7 : 1)) {
-        double2 got = cmul(X[pad(i)], C[i]);
+        double2 got = cmul(X[swz(i)], C[i]);
         double re = 0, im = 0;
         for (int u = 0; u <= 2 * L; ++u) {
             long long m = u - L;
@@ -143,12 +143,12 @@ static int check_g(int n, int L) {
     std::vector<double2> z(n);
     for (auto& v : z) v = make_double2(urand(), urand());
     std::fill(X.begin(), X.end(), make_double2(0, 0));
-    for (int i = 0; i < n; ++i) X[pad(i)] = cmulc(z[i], C[i]);
+    for (int i = 0; i < n; ++i) X[swz(i)] = cmulc(z[i], C[i]);
     fft_dif_g(X.data(), 1, M, sc, Wa.data(), Wb.data(), 0, 1);
     fft_dit_g<true>(X.data(), 1, M, sc, Wa.data(), Wb.data(), Bh.data(), 0, 1);
     double err_fwd = 0, nrm2 = 0;
     for (int u = 0; u <= 2 * L; u += (L > 500 ? 5 : 1)) {
-        double2 got = cmulc(X[pad(u)], A[u]);
+        double2 got = cmulc(X[swz(u)], A[u]);
         got.x /= n;
         got.y /= n;
         long long m = u - L;

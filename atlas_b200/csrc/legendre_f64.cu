@@ -143,21 +143,28 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
             if (warp_active) {
                 const double* as = As + (kb % kStages) * kAStage;
                 const double* bs = Bs + (kb % kStages) * kBStage;
-#pragma unroll
-                for (int ks = 0; ks < kBK / 4; ++ks) {
-                    double a[kMI], b[kNJ];
+                // fragments are double buffered: the shared-memory loads of k-step ks+1 are issued before the
+                // DMMAs of step ks, so that the two warps of a sub-partition (which run in lock step between
+                // barriers) never wait on LDS latency with an idle FP64 pipe
+                double a[2][kMI], b[2][kNJ];
+                auto load_frag = [&](int ks, int buf) {
 #pragma unroll
                     for (int i = 0; i < kMI; ++i) {
-                        if (!kDirect) a[i] = as[(ks * 4 + t) * kAInvPitch + row_w + 8 * i + g];
-                        else a[i] = as[(row_w + 8 * i + g) * kADirPitch + ks * 4 + t];
+                        if (!kDirect) a[buf][i] = as[(ks * 4 + t) * kAInvPitch + row_w + 8 * i + g];
+                        else a[buf][i] = as[(row_w + 8 * i + g) * kADirPitch + ks * 4 + t];
                     }
 #pragma unroll
-                    for (int j = 0; j < kNJ; ++j) b[j] = bs[(ks * 4 + t) * kBPitch + col_w + 8 * j + g];
+                    for (int j = 0; j < kNJ; ++j) b[buf][j] = bs[(ks * 4 + t) * kBPitch + col_w + 8 * j + g];
+                };
+                load_frag(0, 0);
+#pragma unroll
+                for (int ks = 0; ks < kBK / 4; ++ks) {
+                    if (ks + 1 < kBK / 4) load_frag(ks + 1, (ks + 1) & 1);
 #pragma unroll
                     for (int i = 0; i < kMI; ++i) {
                         if (row_w + 8 * i < tl.m_valid) {
 #pragma unroll
-                            for (int j = 0; j < kNJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                            for (int j = 0; j < kNJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[ks & 1][i], b[ks & 1][j]);
                         }
                     }
                 }

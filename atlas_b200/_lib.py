@@ -50,6 +50,7 @@ def _load():
         "sptrans_legendre_cache_size": (C.c_size_t, [vp]),
         "sptrans_export_legendre_cache": (C.c_int, [vp, vp]),
         "sptrans_set_stream": (C.c_int, [vp, vp]),
+        "sptrans_set_precision": (C.c_int, [vp, C.c_int]),
         "sptrans_invtrans_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_invtrans": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp]),
         "sptrans_invtrans_vordiv2wind": (C.c_int, [vp, C.c_int, vp, vp, vp]),

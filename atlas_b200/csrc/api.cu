@@ -90,14 +90,26 @@ int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, 
     if (rc) return rc;
     rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nf));
     if (rc) return rc;
-    tm.mark(marks);
-    rc = launch_pack_spectra(p, nf, trunc, d_spec, p.d_packed);
-    if (rc) return rc;
-    slots[marks++] = 0;
-    tm.mark(marks);
-    rc = launch_legendre_inv(p, nf, p.d_packed, p.d_fourier);
-    if (rc) return rc;
-    slots[marks++] = 1;
+    if (p.precision == SPTRANS_PREC_TC_SPLIT) {
+        if ((rc = tc_prepare_tables(p))) return rc;
+        if ((rc = tc_build_tiles(p, nf, trunc, p.g.T))) return rc;
+        tm.mark(marks);
+        slots[marks++] = 0;
+        tm.mark(marks);
+        rc = launch_legendre_inv_tc(p, nf, trunc, d_spec, p.d_fourier);
+        if (rc) return rc;
+        slots[marks++] = 1;
+    }
+    else {
+        tm.mark(marks);
+        rc = launch_pack_spectra(p, nf, trunc, d_spec, p.d_packed);
+        if (rc) return rc;
+        slots[marks++] = 0;
+        tm.mark(marks);
+        rc = launch_legendre_inv(p, nf, p.d_packed, p.d_fourier);
+        if (rc) return rc;
+        slots[marks++] = 1;
+    }
     tm.mark(marks);
     rc = launch_fourier_inv(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, d_gp, nb_uv);
     if (rc) return rc;
@@ -247,6 +259,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     cudaSetDevice(p.device);
     if (p.stream) cudaStreamSynchronize(p.stream);
     free_fft_tables(p);
+    tc_free(p);
     void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_weights,
                     p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
                     p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
@@ -287,6 +300,18 @@ int sptrans_export_legendre_cache(const sptrans_plan* plan, void* out) {
     }
     SPT_CUDA(cudaSetDevice(plan->p.device));
     return export_legendre_cache(plan->p, static_cast<double*>(out));
+}
+
+int sptrans_set_precision(sptrans_plan* plan, int precision) {
+    if (!plan || (precision != SPTRANS_PREC_FP64 && precision != SPTRANS_PREC_TC_SPLIT)) {
+        set_error("sptrans_set_precision: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    plan->p.precision = precision;
+    if (precision == SPTRANS_PREC_TC_SPLIT) return tc_prepare_tables(plan->p);
+    return SPTRANS_OK;
 }
 
 int sptrans_set_stream(sptrans_plan* plan, void* cuda_stream) {
@@ -450,7 +475,12 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double
     if ((rc = launch_fourier_dir(p, nf, d_gp, p.d_fourier, 0))) return rc;
     slots[marks++] = 2;
     tm.mark(marks);
-    if ((rc = launch_legendre_dir(p, nf, p.d_fourier, p.d_packed))) return rc;
+    if (p.precision == SPTRANS_PREC_TC_SPLIT) {
+        if ((rc = tc_prepare_tables(p))) return rc;
+        if ((rc = tc_build_tiles(p, nf, T, T))) return rc;
+        if ((rc = launch_legendre_dir_tc(p, nf, p.d_fourier, p.d_packed))) return rc;
+    }
+    else if ((rc = launch_legendre_dir(p, nf, p.d_fourier, p.d_packed))) return rc;
     slots[marks++] = 1;
     tm.mark(marks);
     if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spec))) return rc;

@@ -136,6 +136,8 @@ struct Plan {
     double* d_spec2 = nullptr;    size_t spec2_cap = 0;
     double* d_gp = nullptr;       size_t gp_cap = 0;       // device copy of grid fields (host-pointer mode)
     void* h_pinned = nullptr;     size_t pinned_cap = 0;
+    int precision = 0;           // SPTRANS_PREC_FP64 | SPTRANS_PREC_TC_SPLIT
+    void* tc = nullptr;          // TcState (legendre_tc.cu)
     ExchangeLayout ex;
     ExSeg* d_ex_m = nullptr;
     ExSeg* d_ex_band = nullptr;
@@ -181,6 +183,13 @@ int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double
 int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec);
 int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier);
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed);
+
+// ---- legendre_tc.cu (tcgen05 split-TF32 path) ----
+int tc_prepare_tables(Plan& p);
+int tc_build_tiles(Plan& p, int nf, int trunc, int dir_trunc);
+int launch_legendre_inv_tc(Plan& p, int nf, int trunc, const double* d_spec, double* d_fourier);
+int launch_legendre_dir_tc(Plan& p, int nf, const double* d_fourier, double* d_packed);
+void tc_free(Plan& p);
 
 // ---- fourier.cu ----
 int build_fft_tables(Plan& p);

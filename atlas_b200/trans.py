@@ -104,6 +104,11 @@ class Trans:
         t = list(out)
         return {"pack": t[0], "legendre": t[1], "fourier": t[2], "h2d": t[3], "d2h": t[4]}
 
+    def set_precision(self, name):
+        """'fp64' (default, DMMA) or 'tc' (tcgen05 split-TF32 Legendre stage, fp32-level accuracy)."""
+        code = {"fp64": 0, "tc": 1}[name]
+        _lib.check(_lib.lib.sptrans_set_precision(self._h, code))
+
     def set_stream(self, cuda_stream_ptr):
         _lib.check(_lib.lib.sptrans_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

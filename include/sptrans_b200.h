@@ -109,6 +109,11 @@ size_t sptrans_device_bytes(const sptrans_plan* plan);
 size_t sptrans_legendre_cache_size(const sptrans_plan* plan);
 int sptrans_export_legendre_cache(const sptrans_plan* plan, void* out);
 
+/* Select the arithmetic of the Legendre stage: SPTRANS_PREC_FP64 (default; DMMA, results match the fp64 oracle to
+ * 1e-13) or SPTRANS_PREC_TC_SPLIT (tcgen05 kind::tf32 with split operands and fp32 accumulation in tensor memory:
+ * fp32-level accuracy, BASELINE config 4).  The reference has one precision only (double, eckit gemm). */
+int sptrans_set_precision(sptrans_plan* plan, int precision);
+
 /* run all subsequent calls on this cudaStream_t (default: the plan's own stream) */
 int sptrans_set_stream(sptrans_plan* plan, void* cuda_stream);
 

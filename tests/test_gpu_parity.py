@@ -423,3 +423,25 @@ def test_sharded_path_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
         _lib.check(_lib.lib.sptrans_exchange_unpack(t._h, nf, 0, _ptr(buf_m[r]), _ptr(fb[r])))
         t.dirtrans_legendre(nf, fb[r], d_back)  # every rank writes the coefficients of its own zonal wavenumbers
     assert H.rel_max(d_back.cpu().numpy(), plan.dirtrans(nf, want)) < TOL_MAX
+
+
+@pytest.mark.parametrize("gridname,T,nf", [("O32", 31, 4), ("O48", 47, 137), ("O160", 159, 20), ("F24", 23, 3)])
+def test_tensor_core_split_tf32_legendre(gridname, T, nf):
+    """BASELINE config 4: Legendre stage on tcgen05 (kind::tf32, operands split hi+lo, fp32 accumulation in TMEM).
+    Stated tolerance vs the fp64 oracle: 2e-6 relative (max norm) -- fp32-level, three orders better than plain TF32."""
+    grid, trans, plan = make(gridname, T)
+    trans.set_precision("tc")
+    sp = H.synthetic_spectra(T, nf)
+    gp = np.full(nf * grid.size(), np.nan)
+    trans.invtrans(nf, sp, gp)
+    want = plan.invtrans(nf, sp, mode=2)
+    err = H.rel_max(gp, want)
+    assert err < 2e-6, err
+    assert err > 1e-12  # it really is the reduced-precision path
+    back = np.full_like(sp, np.nan)
+    trans.dirtrans(nf, want, back)
+    want_sp = plan.dirtrans(nf, want)
+    assert H.rel_max(back, want_sp) < 2e-6
+    trans.set_precision("fp64")
+    trans.invtrans(nf, sp, gp)
+    assert H.rel_max(gp, want) < TOL_MAX

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsptrans_b200.so")
+LIB_PATH = os.environ.get("SPTRANS_LIB", os.path.join(_HERE, "libsptrans_b200.so"))  # override: tuning variants only
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

@@ -309,7 +309,7 @@ __global__ void pack_spectra_tc_kernel(int T, int nf, int trunc, int n_tot, cons
     const int K = tab_K[2 * m + par];
     if (K <= 0) return;
     const int chunks = (K + kTcKC - 1) / kTcKC;
-    const long long base = bimg_off[2 * m + par] * n_tot;  // bimg_off counts K-chunk rows of 16: floats = off * n_tot
+    const long long base = bimg_off[2 * m + par] * (static_cast<long long>(n_tot) * kTcKC);  // bimg_off counts 16-wide K chunks
     const long long ioff = static_cast<long long>(2 * trunc + 3 - m) * m / 2 * nf * 2;
     const long long total = static_cast<long long>(chunks) * kTcKC * n_tot;
     for (long long e = threadIdx.x; e < total; e += blockDim.x) {
@@ -342,7 +342,7 @@ __global__ void transpose_fourier_tc_kernel(int nf, int n_tot, const int* __rest
     const int ncol = nleg - nlat0[m];
     if (ncol <= 0) return;
     const int chunks = (ncol + kTcKC - 1) / kTcKC;
-    const long long base = bimg_off[2 * m + par] * n_tot;
+    const long long base = bimg_off[2 * m + par] * (static_cast<long long>(n_tot) * kTcKC);
     const double* src = fb + (fb_rowoff[m] + static_cast<long long>(par) * ncol) * (2 * nf);
     const long long total = static_cast<long long>(chunks) * kTcKC * n_tot;
     for (long long e = threadIdx.x; e < total; e += blockDim.x) {
@@ -577,14 +577,14 @@ static int launch_tc_gemm(Plan& p, int nf, const TcTile* tiles, int ntiles, cons
     }
     const size_t stage_bytes = 2ull * kTcM * kTcKC * 4 + 2ull * prm.n_tot * kTcKC * 4;
     const size_t smem = stage_bytes * kTcStages + 128;
-    static bool attr = false;
-    if (!attr) {
-        SPT_CUDA(cudaFuncSetAttribute(legendre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
-    if (smem > 227 * 1024) {
+    if (smem > 226 * 1024) {  // static shared memory (barriers) comes on top
         set_error("tensor-core Legendre path: stage buffers exceed shared memory for this field count");
         return SPTRANS_ERR_INVALID;
+    }
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        SPT_CUDA(cudaFuncSetAttribute(legendre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_smem = smem;
     }
     const int grid = std::min(ntiles, p.num_sms);
     legendre_tc_kernel<<<grid, kTcThreads, smem, p.stream>>>(prm);

@@ -14,8 +14,14 @@ namespace sptrans {
 // ----- tile geometry of the fp64 DMMA Legendre kernels (see legendre_f64.cu) -----
 constexpr int kBM = 128;      // rows per CTA tile (latitudes in the inverse, total wavenumbers in the direct)
 constexpr int kBN = 144;      // columns per CTA tile (2*field + re/im)
-constexpr int kBK = 16;       // contraction step
-constexpr int kStages = 4;    // cp.async pipeline depth
+#ifndef SPT_BK
+#define SPT_BK 16
+#endif
+#ifndef SPT_STAGES
+#define SPT_STAGES 4
+#endif
+constexpr int kBK = SPT_BK;          // contraction step
+constexpr int kStages = SPT_STAGES;  // cp.async pipeline depth
 constexpr int kLegThreads = 256;
 
 // One CTA tile of a ragged batched GEMM  C[M x N] = A[M x K] * B[K x N].

@@ -67,8 +67,8 @@ class Trans:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h is not None and h.value:
-            _lib.lib.sptrans_plan_destroy(h)
+        if h is not None and h.value and _lib is not None and getattr(_lib, "lib", None) is not None:
+            _lib.lib.sptrans_plan_destroy(h)  # (module globals may already be gone at interpreter shutdown)
             self._h = C.c_void_p()
 
     # --- inspectors (TransImpl.h:42-52) ---

@@ -142,6 +142,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="TCo1279", choices=["TCo1279", "TCo399", "TCo159", "O32"])
     ap.add_argument("--cpu-fields", type=int, default=16, help="fields in the bounded CPU sample")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "tc"],
+                    help="Legendre arithmetic: fp64 DMMA (headline) or tcgen05 split-TF32 (BASELINE config 4; fp32-level accuracy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -173,6 +175,8 @@ def main():
     grid = atlas_b200.Grid(gridname)
     t0 = time.time()
     trans = atlas_b200.Trans(grid, T, atlas_b200.option.type("b200"), device=0)
+    if args.precision == "tc":
+        trans.set_precision("tc")
     setup_s = time.time() - t0
     npts = grid.size()
     nspec = (T + 1) * (T + 2) * nf
@@ -224,7 +228,20 @@ def main():
     leg_inv = float(np.mean([a for a, _ in leg_ms]))
     leg_dir = float(np.mean([b for _, b in leg_ms]))
     achieved = (fl_inv + fl_dir) / ((leg_inv + leg_dir) * 1e-3) / 1e12
-    roofline = {
+    if args.precision == "tc":
+        # 3 tf32 MMAs per algorithmic product; peak: dense tf32 = half the measured bf16 rate
+        try:
+            tf32_peak = float(json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2.0
+            src = "half of the measured bf16 cuBLAS rate in MEASURED_PEAKS.json (tf32 runs at half the bf16 rate)"
+        except Exception:
+            tf32_peak, src = 1590.0 / 2.0, "half of the fallback bf16 figure"
+        roofline = {"kernel": "legendre_tc_kernel (tcgen05.mma kind::tf32, 3 split products per MAC, TMEM fp32 accumulators)",
+                    "bound": "tensor", "achieved": 3.0 * achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": 3.0 * achieved / tf32_peak, "traffic": None, "peak_source": src,
+                    "algorithmic_tflops": achieved, "flops_per_launch": {"inverse": fl_inv, "direct": fl_dir},
+                    "ms_per_launch": {"inverse": leg_inv, "direct": leg_dir}, "share_of_step": (leg_inv + leg_dir) / ms_per_step}
+    else:
+      roofline = {
         "kernel": "legendre_dmma_kernel<inverse|direct> (fp64 mma.sync m8n8k4)", "bound": "tensor", "achieved": achieved,
         "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
         "peak_source": "fp64 DMMA/DFMA microbenchmark on this pool's B200 (profiles/microbench_f64_r01.txt); "
@@ -297,9 +314,10 @@ def main():
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if args.precision == "fp64" else "tf32x3 (fp32-level Legendre stage, fp64 Fourier stage)",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload} L{nf} invtrans+dirtrans fp64 (grid {gridname}, T{T})",
+        "config": {"workload": f"{args.workload} L{nf} invtrans+dirtrans " + ("fp64" if args.precision == "fp64" else "fp32 mixed-precision tensor-core Legendre") + f" (grid {gridname}, T{T})",
                    "l2": "inputs larger than L2 (spectra %.2f GB, grid fields %.2f GB per step)" % (8e-9 * nspec, 8e-9 * nf * npts),
                    "plan_setup_s": setup_s, "device_bytes": trans.device_bytes()},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

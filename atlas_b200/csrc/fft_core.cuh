@@ -501,6 +501,122 @@ SPT_HD void fft_dit_g(double2* X, int nseq, int M, const ScheduleG& s, const dou
     }
 }
 
+
+// ---- fused boundary passes -------------------------------------------------------------------------------
+// The first forward pass can take its inputs from a generator (the chirp-modulated spectrum / grid row) instead
+// of reading X, and the last inverse pass can hand its outputs to a sink (chirp multiply + global store) instead
+// of writing X: this removes the zero-fill, the separate load sweep and the separate store sweep of shared memory.
+template <int R, class Gen>
+SPT_HD void dif_first_pass_g(double2* X, int nseq, int M, unsigned per_magic, const double2* Wa, const double2* Wb,
+                             int tid, int nthr, Gen gen) {
+    const int per = M / R;  // first pass: one block of length M, span = per, twiddle stride 1
+    for (int w = tid; w < nseq * per; w += nthr) {
+        const int sq = nseq == 1 ? 0 : fastdiv(w, per_magic, per), t = w - sq * per;
+        double2 v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = gen(sq, t + j * per);
+        dftN<R, true>(v);
+        if (t != 0) {
+            double2 tw[R];
+            twiddle_powers<R>(twiddle2(Wa, Wb, t), tw);
+#pragma unroll
+            for (int j = 1; j < R; ++j) v[j] = cmul(v[j], tw[j]);
+        }
+        double2* Xs = X + sq * M;
+#pragma unroll
+        for (int j = 0; j < R; ++j) Xs[swz(t + j * per)] = v[j];
+    }
+}
+template <int R, bool CONJ_FILT, class Sink>
+SPT_HD void dit_last_pass_g(const double2* X, int nseq, int M, unsigned per_magic, const double2* Wa, const double2* Wb,
+                            const double2* filt, int tid, int nthr, Sink sink) {
+    const int per = M / R;
+    for (int w = tid; w < nseq * per; w += nthr) {
+        const int sq = nseq == 1 ? 0 : fastdiv(w, per_magic, per), t = w - sq * per;
+        const double2* Xs = X + sq * M;
+        double2 v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            v[j] = Xs[swz(t + j * per)];
+            if (filt) v[j] = CONJ_FILT ? cmulc(v[j], filt[t + j * per]) : cmul(v[j], filt[t + j * per]);
+        }
+        if (t != 0) {
+            double2 tw[R];
+            twiddle_powers<R>(twiddle2(Wa, Wb, t), tw);
+#pragma unroll
+            for (int j = 1; j < R; ++j) v[j] = cmulc(v[j], tw[j]);
+        }
+        dftN<R, false>(v);
+#pragma unroll
+        for (int j = 0; j < R; ++j) sink(sq, t + j * per, v[j]);
+    }
+}
+
+template <class Gen>
+SPT_HD void fft_dif_g_gen(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb, int tid,
+                          int nthr, Gen gen) {
+    const unsigned pm0 = s.per_magic[0];
+    switch (s.radix[0]) {
+        case 16: dif_first_pass_g<16>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        case 9: dif_first_pass_g<9>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        case 8: dif_first_pass_g<8>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        case 5: dif_first_pass_g<5>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        case 4: dif_first_pass_g<4>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        case 3: dif_first_pass_g<3>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        default: dif_first_pass_g<2>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+    }
+    SPT_SYNC();
+}
+// remaining forward passes (p >= 1)
+SPT_HD void fft_dif_g_rest(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb, int tid,
+                           int nthr) {
+    for (int p = 1; p < s.npass; ++p) {
+        const int Nb = s.nb[p], S = s.stride[p];
+        const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
+        switch (s.radix[p]) {
+            case 16: dif_pass_g<16>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 9: dif_pass_g<9>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 8: dif_pass_g<8>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 5: dif_pass_g<5>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 4: dif_pass_g<4>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 3: dif_pass_g<3>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            default: dif_pass_g<2>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+        }
+        SPT_SYNC();
+    }
+}
+// inverse passes p = npass-1 .. 1 in place, then the last pass (p = 0) into the sink
+template <bool CONJ_FILT, class Sink>
+SPT_HD void fft_dit_g_sink(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb,
+                           const double2* filt, int tid, int nthr, Sink sink) {
+    for (int p = s.npass - 1; p >= 1; --p) {
+        const int Nb = s.nb[p], S = s.stride[p];
+        const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
+        const double2* f = (p == s.npass - 1) ? filt : nullptr;
+        switch (s.radix[p]) {
+            case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 9: dit_pass_g<9, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 8: dit_pass_g<8, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 5: dit_pass_g<5, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 4: dit_pass_g<4, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 3: dit_pass_g<3, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            default: dit_pass_g<2, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+        }
+        SPT_SYNC();
+    }
+    const double2* f0 = (s.npass == 1) ? filt : nullptr;
+    const unsigned pm0 = s.per_magic[0];
+    switch (s.radix[0]) {
+        case 16: dit_last_pass_g<16, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        case 9: dit_last_pass_g<9, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        case 8: dit_last_pass_g<8, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        case 5: dit_last_pass_g<5, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        case 4: dit_last_pass_g<4, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        case 3: dit_last_pass_g<3, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        default: dit_last_pass_g<2, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+    }
+}
+
 // smallest 5-smooth multiple of 8 >= need; returns 0 if none <= limit
 SPT_HD int conv_length_smooth(int need, int limit) {
     int best = 0;

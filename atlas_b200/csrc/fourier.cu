@@ -100,178 +100,136 @@ chirp_tables_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chir
     }
 }
 
-__device__ __forceinline__ void cp_async16_g2s(void* smem_dst, const void* gmem_src) {
-    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
-}
-
-// One block = one latitude pair x a run of `nfields` fields, processed F at a time.  Per group of F fields:
-//   first forward pass reads the hemisphere-merged, chirp-modulated spectrum straight from the exchange buffer
-//   (or from a cp.async-prefetched staging copy when the block is alone on its SM), forward passes, inverse
-//   passes with the filter fused into the first one, and the last inverse pass multiplies by the output chirp
-//   and stores both grid rows -- shared memory is swept 2*npass-1 times instead of 2*npass+3.
 __global__ void __launch_bounds__(2 * kFftThreads, 1)
-fourier_inv_kernel(const PairMeta* __restrict__ meta, const int4* __restrict__ blocks, int nf, int mlimit, int nb_uv,
-                   const double2* __restrict__ fb, const long long* __restrict__ fb_rowoff,
+fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
+                   int mlimit, int nb_uv, const double2* __restrict__ fb, const long long* __restrict__ fb_rowoff,
                    const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
                    const double2* __restrict__ chirp, const double2* __restrict__ filt,
                    const double* __restrict__ coslatinv, double* __restrict__ gp, long long npts) {
     extern __shared__ double2 X[];
-    const int4 bd = blocks[blockIdx.x];
-    const int pair = bd.x, f0 = bd.y, nfields = bd.z;
-    const bool use_stage = bd.w != 0;
+    const int2 bd = blocks[blockIdx.x];
+    const int pair = bd.x, f0 = bd.y;
     const PairMeta pm = meta[pair];
+    const int nfb = min(pm.F, nf - f0);
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int n = pm.n, L = pm.L, M = pm.M, F = pm.F;
+    const int n = pm.n, L = pm.L;
+    const int M = pm.M, PL = M;
     const int Lc = min(L, mlimit);
     if (Lc < 0) {  // no zonal wavenumber resolved / requested at this latitude: rows are zero
-        for (long long w = tid; w < static_cast<long long>(nfields) * n; w += nthr) {
-            const int fi = static_cast<int>(w / n), i = static_cast<int>(w - static_cast<long long>(fi) * n);
+        for (int w = tid; w < nfb * n; w += nthr) {
+            const int fi = w / n, i = w - fi * n;
             gp[(f0 + fi) * npts + pm.rowN + i] = 0.;
             if (pm.has_s) gp[(f0 + fi) * npts + pm.rowS + i] = 0.;
         }
         return;
     }
-    const int ntw = M / 64 + 1 + 64;
-    double2* sW = X + F * M;
-    double2* St = sW + ntw;  // staging [F][2][L+1] (only if use_stage)
+    double2* sW = X + pm.F * PL;
     const ScheduleG sc = make_schedule_g(M);
+    for (int e = tid; e < nfb * PL; e += nthr) X[e] = make_double2(0., 0.);
     load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
+    __syncthreads();
     const double2* A = chirp + pm.chirp_off;
     const double2* C = A + (2 * L + 1);
-    const double2* Wa = sW;
-    const double2* Wb = sW + (M / 64 + 1);
-    const bool has_s = pm.has_s != 0;
-
-    auto stage_load = [&](int fbase, int nfb) {
-        for (int w = tid; w < nfb * (Lc + 1); w += nthr) {
-            const int m = w / nfb, fi = w - m * nfb;
-            const int n0 = nlat0[m];
-            const long long is = (fb_rowoff[m] + (pair - n0)) * nf + fbase + fi;
-            const long long ia = is + static_cast<long long>(nleg - n0) * nf;
-            cp_async16_g2s(St + (fi * 2 + 0) * (L + 1) + m, fb + is);
-            cp_async16_g2s(St + (fi * 2 + 1) * (L + 1) + m, fb + ia);
+    for (int w = tid; w < nfb * (Lc + 1); w += nthr) {
+        const int m = w / nfb, fi = w - m * nfb;
+        const int n0 = nlat0[m];
+        const long long is = (fb_rowoff[m] + (pair - n0)) * nf + f0 + fi;
+        const long long ia = is + static_cast<long long>(nleg - n0) * nf;
+        double2 cs = fb[is], ca = fb[ia];
+        if (m == 0) cs.y = ca.y = 0.;  // only Re of m = 0 enters (reference :1165)
+        double2 FN, FS;
+        if (pm.has_s) {
+            FN = cadd(cs, ca);
+            FS = csub(cs, ca);
         }
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-    if (use_stage) stage_load(f0, min(F, nfields));
-
-    for (int g0 = 0; g0 < nfields; g0 += F) {
-        const int nfb = min(F, nfields - g0);
-        const int fbase = f0 + g0;
-        if (use_stage) asm volatile("cp.async.wait_group 0;\n" ::);
-        __syncthreads();  // twiddles / staging visible; previous group's last pass has finished reading X
-        auto gen = [&](int sq, int e) -> double2 {
-            const int m = e - L;
-            const int am = m < 0 ? -m : m;
-            if (e > 2 * L || am > Lc) return make_double2(0., 0.);
-            double2 cs, ca;
-            if (use_stage) {
-                cs = St[(sq * 2 + 0) * (L + 1) + am];
-                ca = St[(sq * 2 + 1) * (L + 1) + am];
-            }
-            else {
-                const int n0 = nlat0[am];
-                const long long is = (fb_rowoff[am] + (pair - n0)) * nf + fbase + sq;
-                cs = fb[is];
-                ca = fb[is + static_cast<long long>(nleg - n0) * nf];
-            }
-            if (am == 0) cs.y = ca.y = 0.;  // only Re of m = 0 enters (reference :1165)
-            double2 FN, FS;
-            if (has_s) {
-                FN = cadd(cs, ca);
-                FS = csub(cs, ca);
-            }
-            else {  // equator row: the reference's southern loop overwrites it with sym - asym (:1061-1070)
-                FN = csub(cs, ca);
-                FS = make_double2(0., 0.);
-            }
-            // Z_m = F_N + i F_S ;  Z_{-m} = conj(F_N) + i conj(F_S)
-            const double2 Z = m >= 0 ? make_double2(FN.x - FS.y, FN.y + FS.x) : make_double2(FN.x + FS.y, FS.x - FN.y);
-            return cmul(Z, A[e]);
-        };
-        fft_dif_g_gen(X, nfb, M, sc, Wa, Wb, tid, nthr, gen);
-        if (use_stage && g0 + F < nfields) stage_load(fbase + F, min(F, nfields - g0 - F));  // overlaps the passes below
-        fft_dif_g_rest(X, nfb, M, sc, Wa, Wb, tid, nthr);
-        auto sink = [&](int sq, int i, double2 v) {
-            if (i < n) {
-                const double2 z = cmul(v, C[i]);
-                const int f = fbase + sq;
-                const double s = f < nb_uv ? coslatinv[pair] : 1.;  // u,v = U,V / cos(lat)  (reference :1443-1469)
-                gp[f * npts + pm.rowN + i] = z.x * s;
-                if (has_s) gp[f * npts + pm.rowS + i] = z.y * s;
-            }
-        };
-        fft_dit_g_sink<false>(X, nfb, M, sc, Wa, Wb, filt + pm.filt_off, tid, nthr, sink);
+        else {  // equator row: the reference's southern loop overwrites it with sym - asym (:1061-1070)
+            FN = csub(cs, ca);
+            FS = make_double2(0., 0.);
+        }
+        // Z_m = F_N + i F_S ;  Z_{-m} = conj(F_N) + i conj(F_S)
+        const double2 Zp = make_double2(FN.x - FS.y, FN.y + FS.x);
+        X[fi * PL + swz(L + m)] = cmul(Zp, A[L + m]);
+        if (m > 0) {
+            const double2 Zm = make_double2(FN.x + FS.y, FS.x - FN.y);
+            X[fi * PL + swz(L - m)] = cmul(Zm, A[L - m]);
+        }
+    }
+    __syncthreads();
+    fft_dif_g(X, nfb, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
+    fft_dit_g<false>(X, nfb, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
+    for (int w = tid; w < nfb * n; w += nthr) {
+        const int fi = w / n, i = w - fi * n;
+        const double2 z = cmul(X[fi * PL + swz(i)], C[i]);
+        const int f = f0 + fi;
+        double sn = 1., ss = 1.;
+        if (f < nb_uv) {  // u,v = U,V / cos(lat)  (reference :1443-1469)
+            sn = ss = coslatinv[pair];  // grid is symmetric about the equator
+        }
+        gp[f * npts + pm.rowN + i] = z.x * sn;
+        if (pm.has_s) gp[f * npts + pm.rowS + i] = z.y * ss;
     }
 }
 
 __global__ void __launch_bounds__(2 * kFftThreads, 1)
-fourier_dir_kernel(const PairMeta* __restrict__ meta, const int4* __restrict__ blocks, int nf, int nb_uv,
-                   const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
+fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
+                   int nb_uv, const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
                    const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
                    const double2* __restrict__ chirp, const double2* __restrict__ filt,
-                   const double* __restrict__ weights, const double* __restrict__ uvscale, double2* __restrict__ fb) {
+                   const double* __restrict__ weights, const double* __restrict__ coslat, double2* __restrict__ fb) {
     extern __shared__ double2 X[];
-    const int4 bd = blocks[blockIdx.x];
-    const int pair = bd.x, f0 = bd.y, nfields = bd.z;
+    const int2 bd = blocks[blockIdx.x];
+    const int pair = bd.x, f0 = bd.y;
     const PairMeta pm = meta[pair];
+    const int nfb = min(pm.F, nf - f0);
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int n = pm.n, L = pm.L, M = pm.M, F = pm.F;
+    const int n = pm.n, L = pm.L;
     if (L < 0) return;
-    const int ntw = M / 64 + 1 + 64;
-    double2* sW = X + F * M;
+    const int M = pm.M, PL = M;
+    double2* sW = X + pm.F * PL;
     const ScheduleG sc = make_schedule_g(M);
+    for (int e = tid; e < nfb * PL; e += nthr) X[e] = make_double2(0., 0.);
     load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
+    __syncthreads();
     const double2* A = chirp + pm.chirp_off;
     const double2* C = A + (2 * L + 1);
-    const double2* Wa = sW;
-    const double2* Wb = sW + (M / 64 + 1);
-    const bool has_s = pm.has_s != 0;
+    for (int w = tid; w < nfb * n; w += nthr) {
+        const int fi = w / n, i = w - fi * n;
+        const int f = f0 + fi;
+        double xn = gp[f * npts + pm.rowN + i];
+        double xs = pm.has_s ? gp[f * npts + pm.rowS + i] : 0.;
+        if (f < nb_uv) {  // wind components enter the vor/div transform as u,v / (a cos(lat))
+            xn *= coslat[pair];
+            xs *= coslat[pair];
+        }
+        X[fi * PL + swz(i)] = cmulc(make_double2(xn, xs), C[i]);
+    }
+    __syncthreads();
+    fft_dif_g(X, nfb, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
+    fft_dit_g<true>(X, nfb, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
     const double wq = weights[pair];
     const double inv_n = 1.0 / n;
-    (void)ntw;
-    for (int g0 = 0; g0 < nfields; g0 += F) {
-        const int nfb = min(F, nfields - g0);
-        const int fbase = f0 + g0;
-        __syncthreads();
-        auto gen = [&](int sq, int e) -> double2 {
-            if (e >= n) return make_double2(0., 0.);
-            const int f = fbase + sq;
-            double xn = gp[f * npts + pm.rowN + e];
-            double xs = has_s ? gp[f * npts + pm.rowS + e] : 0.;
-            if (f < nb_uv) {  // wind components enter the vor/div transform as u,v / (a cos(lat))
-                xn *= uvscale[pair];
-                xs *= uvscale[pair];
-            }
-            return cmulc(make_double2(xn, xs), C[e]);
-        };
-        fft_dif_g_gen(X, nfb, M, sc, Wa, Wb, tid, nthr, gen);
-        fft_dif_g_rest(X, nfb, M, sc, Wa, Wb, tid, nthr);
-        fft_dit_g<true>(X, nfb, M, sc, Wa, Wb, filt + pm.filt_off, tid, nthr);
-        for (int w = tid; w < nfb * (L + 1); w += nthr) {
-            const int m = w / nfb, fi = w - m * nfb;
-            double2 Gp = cmulc(X[fi * M + swz(L + m)], A[L + m]);
-            double2 Gm = cmulc(X[fi * M + swz(L - m)], A[L - m]);
-            Gp.x *= inv_n; Gp.y *= inv_n; Gm.x *= inv_n; Gm.y *= inv_n;
-            // F_N = (G_m + conj(G_-m))/2 ; F_S = (G_m - conj(G_-m))/(2i)
-            const double2 FN = make_double2(0.5 * (Gp.x + Gm.x), 0.5 * (Gp.y - Gm.y));
-            const double2 FS = make_double2(0.5 * (Gp.y + Gm.y), -0.5 * (Gp.x - Gm.x));
-            double2 s, a;
-            if (has_s) {
-                s = make_double2((FN.x + FS.x) * wq, (FN.y + FS.y) * wq);
-                a = make_double2((FN.x - FS.x) * wq, (FN.y - FS.y) * wq);
-            }
-            else {
-                s = make_double2(FN.x * wq, FN.y * wq);
-                a = s;
-            }
-            const int n0 = nlat0[m];
-            const long long is = (fb_rowoff[m] + (pair - n0)) * nf + fbase + fi;
-            const long long ia = is + static_cast<long long>(nleg - n0) * nf;
-            fb[is] = s;
-            fb[ia] = a;
+    for (int w = tid; w < nfb * (L + 1); w += nthr) {
+        const int m = w / nfb, fi = w - m * nfb;
+        double2 Gp = cmulc(X[fi * PL + swz(L + m)], A[L + m]);
+        double2 Gm = cmulc(X[fi * PL + swz(L - m)], A[L - m]);
+        Gp.x *= inv_n; Gp.y *= inv_n; Gm.x *= inv_n; Gm.y *= inv_n;
+        // F_N = (G_m + conj(G_-m))/2 ; F_S = (G_m - conj(G_-m))/(2i)
+        const double2 FN = make_double2(0.5 * (Gp.x + Gm.x), 0.5 * (Gp.y - Gm.y));
+        const double2 FS = make_double2(0.5 * (Gp.y + Gm.y), -0.5 * (Gp.x - Gm.x));
+        double2 s, a;
+        if (pm.has_s) {
+            s = make_double2((FN.x + FS.x) * wq, (FN.y + FS.y) * wq);
+            a = make_double2((FN.x - FS.x) * wq, (FN.y - FS.y) * wq);
         }
+        else {
+            s = make_double2(FN.x * wq, FN.y * wq);
+            a = s;
+        }
+        const int n0 = nlat0[m];
+        const long long is = (fb_rowoff[m] + (pair - n0)) * nf + f0 + fi;
+        const long long ia = is + static_cast<long long>(nleg - n0) * nf;
+        fb[is] = s;
+        fb[ia] = a;
     }
 }
 
@@ -318,14 +276,6 @@ int fields_per_block(int M) {
 size_t block_smem_bytes(int M, int F) {
     return (static_cast<size_t>(F) * M + (M / 64 + 1 + 64)) * sizeof(double2);
 }
-size_t staging_bytes(int F, int L) { return static_cast<size_t>(F) * 2 * (L + 1) * sizeof(double2); }
-constexpr size_t kTwoBlocksSmem = 113 * 1024;  // at most this much per block for two resident blocks per SM
-constexpr size_t kMaxBlockSmem = 226 * 1024;
-// the inverse kernel prefetches the next fields' spectra through cp.async only where it costs no occupancy
-bool use_staging(int M, int F, int L) {
-    const size_t base = block_smem_bytes(M, F);
-    return base > kTwoBlocksSmem && base + staging_bytes(F, L) <= kMaxBlockSmem;
-}
 
 }  // namespace
 
@@ -334,7 +284,7 @@ struct FftGroups {
     std::vector<size_t> smem;              // dynamic shared memory of the group
     std::vector<std::vector<int>> pairs;   // pairs per group, costliest first
     int nf = -1;                           // block lists below are built for this number of fields
-    std::vector<int4*> d_blocks;
+    std::vector<int2*> d_blocks;
     std::vector<int> nblocks;
 };
 static std::map<Plan*, FftGroups> g_groups;
@@ -394,7 +344,7 @@ int build_fft_tables(Plan& p) {
     PairMeta* d_cls = nullptr;
     SPT_CUDA(cudaMalloc(&d_cls, classes.size() * sizeof(PairMeta)));
     SPT_CUDA(cudaMemcpyAsync(d_cls, classes.data(), classes.size() * sizeof(PairMeta), cudaMemcpyHostToDevice, p.stream));
-    const size_t smem_max = kMaxBlockSmem;
+    const size_t smem_max = block_smem_bytes(kMaxM, 1);
     SPT_CUDA(cudaFuncSetAttribute(chirp_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_dir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
@@ -407,14 +357,10 @@ int build_fft_tables(Plan& p) {
                              p.stream));
     // launch groups by shared-memory bucket over this rank's latitude band
     FftGroups grp;
-    const size_t buckets[] = {28 * 1024, 37 * 1024, 56 * 1024, 75 * 1024, kTwoBlocksSmem, kMaxBlockSmem};
+    const size_t buckets[] = {28 * 1024, 37 * 1024, 56 * 1024, 75 * 1024, 113 * 1024, smem_max};
     std::vector<std::vector<int>> by(6);
-    auto pair_smem = [&](int j) {
-        const int Luse = std::max(meta[j].L, 0);
-        return block_smem_bytes(meta[j].M, meta[j].F) + (use_staging(meta[j].M, meta[j].F, Luse) ? staging_bytes(meta[j].F, Luse) : 0);
-    };
     for (int j = g.pair_begin; j < g.pair_end; ++j) {
-        const size_t need = pair_smem(j);
+        const size_t need = block_smem_bytes(meta[j].M, meta[j].F);
         int b = 0;
         while (need > buckets[b]) ++b;
         by[b].push_back(j);
@@ -424,7 +370,7 @@ int build_fft_tables(Plan& p) {
         std::vector<int> v = by[b];
         std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return meta[x].M > meta[y].M; });
         size_t need = 0;
-        for (int j : v) need = std::max(need, pair_smem(j));
+        for (int j : v) need = std::max(need, block_smem_bytes(meta[j].M, meta[j].F));
         grp.smem.push_back(need);
         grp.pairs.push_back(v);
     }
@@ -438,7 +384,7 @@ int build_fft_tables(Plan& p) {
 void free_fft_tables(Plan& p) {
     auto it = g_groups.find(&p);
     if (it != g_groups.end()) {
-        for (int4* d : it->second.d_blocks) cudaFree(d);
+        for (int2* d : it->second.d_blocks) cudaFree(d);
         g_groups.erase(it);
     }
     g_meta.erase(&p);
@@ -447,22 +393,17 @@ void free_fft_tables(Plan& p) {
 static int ensure_block_lists(Plan& p, int nf) {
     FftGroups& grp = g_groups[&p];
     if (grp.nf == nf) return SPTRANS_OK;
-    for (int4* d : grp.d_blocks) cudaFree(d);
+    for (int2* d : grp.d_blocks) cudaFree(d);
     grp.d_blocks.clear();
     grp.nblocks.clear();
     const std::vector<PairMeta>& meta = g_meta[&p];
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
-        // a block owns a run of fields of one latitude pair (amortises its prologue, lets it prefetch the next fields)
-        std::vector<int4> blocks;
-        for (int j : grp.pairs[gi]) {
-            const int F = meta[j].F;
-            const int run = std::max(F, (8 / F) * F);  // ~8 fields per block, a multiple of F
-            const int stage = use_staging(meta[j].M, F, std::max(meta[j].L, 0)) ? 1 : 0;
-            for (int f0 = 0; f0 < nf; f0 += run) blocks.push_back(make_int4(j, f0, std::min(run, nf - f0), stage));
-        }
-        int4* d = nullptr;
-        SPT_CUDA(cudaMalloc(&d, std::max<size_t>(blocks.size(), 1) * sizeof(int4)));
-        SPT_CUDA(cudaMemcpyAsync(d, blocks.data(), blocks.size() * sizeof(int4), cudaMemcpyHostToDevice, p.stream));
+        std::vector<int2> blocks;
+        for (int j : grp.pairs[gi])
+            for (int f0 = 0; f0 < nf; f0 += meta[j].F) blocks.push_back(make_int2(j, f0));
+        int2* d = nullptr;
+        SPT_CUDA(cudaMalloc(&d, std::max<size_t>(blocks.size(), 1) * sizeof(int2)));
+        SPT_CUDA(cudaMemcpyAsync(d, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, p.stream));
         SPT_CUDA(cudaStreamSynchronize(p.stream));
         grp.d_blocks.push_back(d);
         grp.nblocks.push_back(static_cast<int>(blocks.size()));

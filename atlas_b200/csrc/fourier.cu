@@ -12,6 +12,7 @@
 // Algorithm and index algebra: fft_core.cuh (unit-tested on the CPU).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -31,7 +32,8 @@ struct PairMeta {
     int M;                // convolution length, 5-smooth, >= n + 2L
     int has_s;            // 0 for the equator row of a grid with an odd number of latitudes
     int F;                // fields transformed together by one block
-    int pad;
+    int mode;             // 0: north+south rows packed into one complex transform of length n
+                          // 1: every row on its own, even/odd samples packed, complex length n/2 (rows too long for mode 0)
 };
 
 namespace {
@@ -52,10 +54,19 @@ chirp_tables_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chir
                     double2* __restrict__ twid) {
     extern __shared__ double2 X[];
     const PairMeta pm = cls[blockIdx.x];
-    const int n = pm.n, L = pm.L, M = pm.M;
+    const int L = pm.L, M = pm.M;
+    const int n = pm.mode ? pm.n / 2 : pm.n;  // length of the complex chirp-z problem
     const int tid = threadIdx.x, nthr = blockDim.x;
     double2* A = chirp + pm.chirp_off;
     double2* C = A + (2 * L + 1);
+    if (pm.mode) {  // e^{2 pi i m / n_row}: recombines the even/odd sample transforms of a real row
+        double2* Wr = C + n;
+        for (int m = tid; m <= L; m += nthr) {
+            double s, c;
+            sincospi(2.0 * m / pm.n, &s, &c);
+            Wr[m] = make_double2(c, s);
+        }
+    }
     double2* Wa = twid + pm.tw_off;
     double2* Wb = Wa + (M / 64 + 1);
     for (int u = tid; u <= 2 * L; u += nthr) {
@@ -233,6 +244,121 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     }
 }
 
+// ---- row mode (mode 1): rows too long for the packed north/south transform (n + 2L > kMaxM, e.g. O2560) ----
+// A real row x_i, i < n, is transformed through z'_k = x_2k + i x_2k+1 (k < n/2):
+//   z'_k = sum_{m=-L..L} G_m e^{2 pi i m k/(n/2)},   G_m = F_m (1 + i w^m),  F_-m = conj(F_m),  w = e^{2 pi i/n}
+// i.e. the same chirp-z machinery with length n/2; the direct transform inverts the packing with
+//   F_m = 1/2 [ (H_m + conj H_-m)/2 + conj(w^m) (H_m - conj H_-m)/(2i) ],  H = chirp-z spectrum of z'.
+__global__ void __launch_bounds__(2 * kFftThreads, 1)
+fourier_inv_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf, int mlimit,
+                        int nb_uv, const double2* __restrict__ fb, const long long* __restrict__ fb_rowoff,
+                        const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
+                        const double2* __restrict__ chirp, const double2* __restrict__ filt,
+                        const double* __restrict__ coslatinv, double* __restrict__ gp, long long npts) {
+    extern __shared__ double2 X[];
+    const int2 bd = blocks[blockIdx.x];
+    const int pair = bd.x, f = bd.y;
+    const PairMeta pm = meta[pair];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int L = pm.L, M = pm.M, nh = pm.n / 2;
+    const int Lc = min(L, mlimit);
+    double2* sW = X + M;
+    const ScheduleG sc = make_schedule_g(M);
+    load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
+    const double2* A = chirp + pm.chirp_off;
+    const double2* C = A + (2 * L + 1);
+    const double2* Wr = C + nh;
+    const double scale = f < nb_uv ? coslatinv[pair] : 1.;
+    for (int row = 0; row < (pm.has_s ? 2 : 1); ++row) {
+        __syncthreads();
+        for (int e = tid; e < M; e += nthr) X[e] = make_double2(0., 0.);
+        __syncthreads();
+        for (int m = tid; m <= Lc; m += nthr) {
+            const int n0 = nlat0[m];
+            const long long is = (fb_rowoff[m] + (pair - n0)) * nf + f;
+            double2 cs = fb[is], ca = fb[is + static_cast<long long>(nleg - n0) * nf];
+            if (m == 0) cs.y = ca.y = 0.;
+            // northern row: sym + asym, southern: sym - asym; the single equator row: sym - asym (reference :1061-1070)
+            const bool minus = (row == 1) || !pm.has_s;
+            const double2 Fm = minus ? csub(cs, ca) : cadd(cs, ca);
+            const double2 w = Wr[m];
+            // G_m = F_m (1 + i w^m),  G_-m = conj(F_m) (1 + i conj(w^m))
+            const double2 gp1 = make_double2(1. - w.y, w.x);   // 1 + i w
+            const double2 gm1 = make_double2(1. + w.y, w.x);   // 1 + i conj(w)
+            X[swz(L + m)] = cmul(cmul(Fm, gp1), A[L + m]);
+            if (m > 0) X[swz(L - m)] = cmul(cmul(cconj(Fm), gm1), A[L - m]);
+        }
+        __syncthreads();
+        fft_dif_g(X, 1, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
+        fft_dit_g<false>(X, 1, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
+        double* out = gp + f * npts + (row == 0 ? pm.rowN : pm.rowS);
+        for (int k = tid; k < nh; k += nthr) {
+            const double2 z = cmul(X[swz(k)], C[k]);
+            *reinterpret_cast<double2*>(out + 2 * k) = make_double2(z.x * scale, z.y * scale);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(2 * kFftThreads, 1)
+fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf, int nb_uv,
+                        const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
+                        const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
+                        const double2* __restrict__ chirp, const double2* __restrict__ filt,
+                        const double* __restrict__ weights, const double* __restrict__ uvscale,
+                        double2* __restrict__ fb) {
+    extern __shared__ double2 X[];
+    const int2 bd = blocks[blockIdx.x];
+    const int pair = bd.x, f = bd.y;
+    const PairMeta pm = meta[pair];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int L = pm.L, M = pm.M, nh = pm.n / 2;
+    if (L < 0) return;
+    double2* sW = X + M;
+    const ScheduleG sc = make_schedule_g(M);
+    load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
+    const double2* A = chirp + pm.chirp_off;
+    const double2* C = A + (2 * L + 1);
+    const double2* Wr = C + nh;
+    const double wq = weights[pair];
+    const double scale = f < nb_uv ? uvscale[pair] : 1.;
+    const double inv_nh = 1.0 / nh;
+    for (int row = 0; row < (pm.has_s ? 2 : 1); ++row) {
+        __syncthreads();
+        for (int e = tid; e < M; e += nthr) X[e] = make_double2(0., 0.);
+        __syncthreads();
+        const double* in = gp + f * npts + (row == 0 ? pm.rowN : pm.rowS);
+        for (int k = tid; k < nh; k += nthr) {
+            const double2 x = *reinterpret_cast<const double2*>(in + 2 * k);
+            X[swz(k)] = cmulc(make_double2(x.x * scale, x.y * scale), C[k]);
+        }
+        __syncthreads();
+        fft_dif_g(X, 1, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
+        fft_dit_g<true>(X, 1, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
+        for (int m = tid; m <= L; m += nthr) {
+            double2 Hp = cmulc(X[swz(L + m)], A[L + m]);
+            double2 Hm = cmulc(X[swz(L - m)], A[L - m]);
+            Hp.x *= inv_nh; Hp.y *= inv_nh; Hm.x *= inv_nh; Hm.y *= inv_nh;
+            // E/n' = (H_m + conj H_-m)/2 ; O/n' = (H_m - conj H_-m)/(2i) ; F_m = (E + conj(w^m) O)/n
+            const double2 Ev = make_double2(0.5 * (Hp.x + Hm.x), 0.5 * (Hp.y - Hm.y));
+            const double2 Ov = make_double2(0.5 * (Hp.y + Hm.y), -0.5 * (Hp.x - Hm.x));
+            const double2 t = cmulc(Ov, Wr[m]);
+            const double2 Fm = make_double2(0.5 * (Ev.x + t.x) * wq, 0.5 * (Ev.y + t.y) * wq);
+            const int n0 = nlat0[m];
+            const long long is = (fb_rowoff[m] + (pair - n0)) * nf + f;
+            const long long ia = is + static_cast<long long>(nleg - n0) * nf;
+            if (row == 0) {        // northern row first: park w F_N in both slots
+                fb[is] = Fm;
+                fb[ia] = Fm;
+            }
+            else {                 // southern row (same thread, same m): sym = w (F_N + F_S), asym = w (F_N - F_S)
+                const double2 fnw = fb[is];
+                fb[is] = cadd(fnw, Fm);
+                fb[ia] = csub(fnw, Fm);
+            }
+        }
+    }
+}
+
 // Cost model used to pick the convolution length: every pass is one read+write sweep of shared memory;
 // larger radices do more arithmetic per point.
 double pass_cost(int R) {
@@ -246,12 +372,22 @@ double pass_cost(int R) {
         default: return 0.90;
     }
 }
+// SPTRANS_FFT_MAXM (testing only) lowers the single-CTA limit so that small grids exercise the row-mode kernels
+int max_conv_length() {
+    static int v = [] {
+        const char* e = std::getenv("SPTRANS_FFT_MAXM");
+        const int x = e ? std::atoi(e) : 0;
+        return (x >= 64 && x <= kMaxM) ? x : kMaxM;
+    }();
+    return v;
+}
 int choose_conv_length(int need) {
     int best = 0;
     double best_cost = 1e300;
-    for (long long p5 = 1; p5 <= kMaxM; p5 *= 5)
-        for (long long p3 = p5; p3 <= kMaxM; p3 *= 3)
-            for (long long p2 = p3 * 8; p2 <= kMaxM; p2 *= 2) {  // multiples of 8 (index swizzle)
+    const long long lim = max_conv_length();
+    for (long long p5 = 1; p5 <= lim; p5 *= 5)
+        for (long long p3 = p5; p3 <= lim; p3 *= 3)
+            for (long long p2 = p3 * 8; p2 <= lim; p2 *= 2) {  // multiples of 8 (index swizzle)
                 if (p2 < need) continue;
                 const ScheduleG s = fftc::make_schedule_g(static_cast<int>(p2));
                 double c = 0.4;  // load/store/pointwise sweeps
@@ -283,6 +419,7 @@ struct FftGroups {
     // launch groups by shared-memory footprint (so that small rows run several blocks per SM)
     std::vector<size_t> smem;              // dynamic shared memory of the group
     std::vector<std::vector<int>> pairs;   // pairs per group, costliest first
+    std::vector<int> mode;                 // 0: packed north/south kernels, 1: row kernels
     int nf = -1;                           // block lists below are built for this number of fields
     std::vector<int2*> d_blocks;
     std::vector<int> nblocks;
@@ -309,14 +446,19 @@ int build_fft_tables(Plan& p) {
             return SPTRANS_ERR_INVALID;
         }
         const int Luse = std::max(pm.L, 0);
-        const int M = choose_conv_length(pm.n + 2 * Luse);
+        int M = choose_conv_length(pm.n + 2 * Luse);
+        pm.mode = 0;
+        if (M == 0 && pm.n % 2 == 0) {  // too long for the packed transform: one row at a time, length n/2
+            M = choose_conv_length(pm.n / 2 + 2 * Luse);
+            pm.mode = 1;
+        }
         if (M == 0) {
-            set_error("sptrans_plan_create: row length + 2*truncation exceeds 8192 (grids beyond O1280 need the "
-                      "cluster Fourier kernel, not available yet)");
+            set_error("sptrans_plan_create: row length too large for the shared-memory Fourier kernels "
+                      "(n/2 + 2*truncation must not exceed 13824)");
             return SPTRANS_ERR_NOT_IMPLEMENTED;
         }
         pm.M = M;
-        pm.F = fields_per_block(M);
+        pm.F = pm.mode ? 1 : fields_per_block(M);
         auto key = std::make_pair(pm.n, Luse);
         auto it = cls_index.find(key);
         if (it == cls_index.end()) {
@@ -325,7 +467,7 @@ int build_fft_tables(Plan& p) {
             c.chirp_off = chirp_total;
             c.filt_off = filt_total;
             c.tw_off = tw_total;
-            chirp_total += 2LL * Luse + 1 + pm.n;
+            chirp_total += 2LL * Luse + 1 + (pm.mode ? pm.n / 2 + Luse + 1 : pm.n);
             filt_total += M;
             tw_total += M / 64 + 1 + 64;
             cls_index[key] = static_cast<int>(classes.size());
@@ -348,6 +490,8 @@ int build_fft_tables(Plan& p) {
     SPT_CUDA(cudaFuncSetAttribute(chirp_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_dir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    SPT_CUDA(cudaFuncSetAttribute(fourier_inv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    SPT_CUDA(cudaFuncSetAttribute(fourier_dir_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     chirp_tables_kernel<<<static_cast<int>(classes.size()), kFftThreads, smem_max, p.stream>>>(d_cls, p.d_chirp, p.d_filt,
                                                                                               p.d_twiddle);
     p.launches++;
@@ -359,11 +503,24 @@ int build_fft_tables(Plan& p) {
     FftGroups grp;
     const size_t buckets[] = {28 * 1024, 37 * 1024, 56 * 1024, 75 * 1024, 113 * 1024, smem_max};
     std::vector<std::vector<int>> by(6);
+    std::vector<int> rowmode;
     for (int j = g.pair_begin; j < g.pair_end; ++j) {
+        if (meta[j].mode) {
+            rowmode.push_back(j);
+            continue;
+        }
         const size_t need = block_smem_bytes(meta[j].M, meta[j].F);
         int b = 0;
         while (need > buckets[b]) ++b;
         by[b].push_back(j);
+    }
+    if (!rowmode.empty()) {
+        std::stable_sort(rowmode.begin(), rowmode.end(), [&](int x, int y) { return meta[x].M > meta[y].M; });
+        size_t need = 0;
+        for (int j : rowmode) need = std::max(need, block_smem_bytes(meta[j].M, 1));
+        grp.smem.push_back(need);
+        grp.pairs.push_back(rowmode);
+        grp.mode.push_back(1);
     }
     for (int b = 5; b >= 0; --b) {
         if (by[b].empty()) continue;
@@ -373,6 +530,7 @@ int build_fft_tables(Plan& p) {
         for (int j : v) need = std::max(need, block_smem_bytes(meta[j].M, meta[j].F));
         grp.smem.push_back(need);
         grp.pairs.push_back(v);
+        grp.mode.push_back(0);
     }
     SPT_CUDA(cudaStreamSynchronize(p.stream));
     cudaFree(d_cls);
@@ -419,6 +577,15 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         if (grp.nblocks[gi] == 0) continue;
         const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;  // one block per SM: 16 warps
+        if (grp.mode[gi]) {
+            fourier_inv_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
+                reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
+                reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp,
+                p.d_filt, p.d_coslatinv, d_gp, p.g.npts);
+            p.launches++;
+            SPT_CUDA(cudaGetLastError());
+            continue;
+        }
         fourier_inv_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
             reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp,
@@ -440,6 +607,15 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         if (grp.nblocks[gi] == 0) continue;
         const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;
+        if (grp.mode[gi]) {
+            fourier_dir_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
+                reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
+                p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
+                reinterpret_cast<double2*>(d_fourier));
+            p.launches++;
+            SPT_CUDA(cudaGetLastError());
+            continue;
+        }
         fourier_dir_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
             p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,

@@ -461,7 +461,8 @@ sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import helpers as H
 import atlas_b200
 from oracle import pyoracle as po
-for gridname, T, nf in (("O48", 47, 5), ("F24", 23, 3), ("L9", 17, 2)):
+gridname, T, nf = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+for _ in range(1):
     grid = atlas_b200.Grid(gridname)
     trans = atlas_b200.Trans(grid, T)
     plan = po.OraclePlan(grid.nx(), grid.y(), T, regular=grid.regular, weights=grid.weights())
@@ -479,10 +480,12 @@ for gridname, T, nf in (("O48", 47, 5), ("F24", 23, 3), ("L9", 17, 2)):
     assert e1 < 1e-12 and e2 < 1e-12, (gridname, e1, e2)
 print("ROWMODE_OK")
 '''
-    env = dict(os.environ, SPTRANS_FFT_MAXM="160")
-    r = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(__file__)), env=env,
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0 and "ROWMODE_OK" in r.stdout, r.stdout[-3000:]
+    # (grid, T, fields, limit): the limit is chosen so that the longest rows need row mode (n + 2L > limit >= n/2 + 2L)
+    for gridname, T, nf, maxm in (("O48", 47, 5, 256), ("L9", 17, 2, 64), ("F24", 23, 3, 96)):
+        env = dict(os.environ, SPTRANS_FFT_MAXM=str(maxm))
+        r = subprocess.run([sys.executable, "-c", code, gridname, str(T), str(nf)], cwd=os.path.dirname(os.path.dirname(__file__)),
+                           env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0 and "ROWMODE_OK" in r.stdout, r.stdout[-3000:]
 
 
 def test_config5_tco2559_inverse_sample():

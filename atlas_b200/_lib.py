@@ -55,6 +55,7 @@ def _load():
         "sptrans_invtrans": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp]),
         "sptrans_invtrans_vordiv2wind": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "sptrans_dirtrans_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_invtrans_adj_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_dirtrans_wind2vordiv": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "sptrans_invtrans_grad": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_vordiv_to_uv": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]),

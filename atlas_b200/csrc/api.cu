@@ -433,7 +433,7 @@ int sptrans_invtrans_vordiv2wind(sptrans_plan* plan, int nvd, const double* vor,
     return sptrans_invtrans(plan, 0, nullptr, nvd, vor, div, gp);  // reference :1488-1492
 }
 
-int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double* spectra) {
+static int dirtrans_scalar_impl(sptrans_plan* plan, int nf, const double* gp, double* spectra, int adjoint) {
     int rc = check_plan(plan);
     if (rc) return rc;
     Plan& p = plan->p;
@@ -446,7 +446,7 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double
         set_error("whole-transform entry points need an unsharded plan; use the stage-level API");
         return SPTRANS_ERR_INVALID;
     }
-    if (!p.d_weights) {
+    if (!p.d_weights && !adjoint) {
         set_error("sptrans_dirtrans_scalar: plan was created without quadrature weights");
         return SPTRANS_ERR_INVALID;
     }
@@ -472,7 +472,7 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double
     if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
     if ((rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nf)))) return rc;
     tm.mark(marks);
-    if ((rc = launch_fourier_dir(p, nf, d_gp, p.d_fourier, 0))) return rc;
+    if ((rc = launch_fourier_dir(p, nf, d_gp, p.d_fourier, 0, adjoint))) return rc;
     slots[marks++] = 2;
     tm.mark(marks);
     if (p.precision == SPTRANS_PREC_TC_SPLIT) {
@@ -483,7 +483,7 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double
     else if ((rc = launch_legendre_dir(p, nf, p.d_fourier, p.d_packed))) return rc;
     slots[marks++] = 1;
     tm.mark(marks);
-    if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spec))) return rc;
+    if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spec, adjoint))) return rc;
     slots[marks++] = 0;
     tm.mark(marks);
     if (spec_host) {
@@ -494,6 +494,14 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double
     tm.finish(marks + 1, slots);
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;
+}
+
+int sptrans_dirtrans_scalar(sptrans_plan* plan, int nf, const double* gp, double* spectra) {
+    return dirtrans_scalar_impl(plan, nf, gp, spectra, 0);
+}
+
+int sptrans_invtrans_adj_scalar(sptrans_plan* plan, int nf, const double* gp, double* spectra) {
+    return dirtrans_scalar_impl(plan, nf, gp, spectra, 1);
 }
 
 int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nf, const double* wind, double* vor, double* div) {

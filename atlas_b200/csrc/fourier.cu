@@ -186,7 +186,8 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
                    int nb_uv, const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
                    const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
                    const double2* __restrict__ chirp, const double2* __restrict__ filt,
-                   const double* __restrict__ weights, const double* __restrict__ coslat, double2* __restrict__ fb) {
+                   const double* __restrict__ weights, const double* __restrict__ coslat, double2* __restrict__ fb,
+                   int adjoint) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
     const int pair = bd.x, f0 = bd.y;
@@ -217,10 +218,13 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     __syncthreads();
     fft_dif_g(X, nfb, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
     fft_dit_g<true>(X, nfb, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
-    const double wq = weights[pair];
-    const double inv_n = 1.0 / n;
+    // direct transform: quadrature weight, 1/n normalisation.  Adjoint of the inverse (invtrans_adj): no weight,
+    // no normalisation, and the factor 2 of the m > 0 harmonics (f = sum_n X_n^0 P + 2 Re sum_{m>0} ...)
+    const double wq0 = adjoint ? 1.0 : weights[pair];
+    const double inv_n = adjoint ? 1.0 : 1.0 / n;
     for (int w = tid; w < nfb * (L + 1); w += nthr) {
         const int m = w / nfb, fi = w - m * nfb;
+        const double wq = (adjoint && m > 0) ? 2.0 * wq0 : wq0;
         double2 Gp = cmulc(X[fi * PL + swz(L + m)], A[L + m]);
         double2 Gm = cmulc(X[fi * PL + swz(L - m)], A[L - m]);
         Gp.x *= inv_n; Gp.y *= inv_n; Gm.x *= inv_n; Gm.y *= inv_n;
@@ -305,7 +309,7 @@ fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
                         const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
                         const double2* __restrict__ chirp, const double2* __restrict__ filt,
                         const double* __restrict__ weights, const double* __restrict__ uvscale,
-                        double2* __restrict__ fb) {
+                        double2* __restrict__ fb, int adjoint) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
     const int pair = bd.x, f = bd.y;
@@ -319,7 +323,7 @@ fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
     const double2* A = chirp + pm.chirp_off;
     const double2* C = A + (2 * L + 1);
     const double2* Wr = C + nh;
-    const double wq = weights[pair];
+    const double wq0 = adjoint ? static_cast<double>(pm.n) : weights[pair];  // adjoint: undo the 1/n of F_m below
     const double scale = f < nb_uv ? uvscale[pair] : 1.;
     const double inv_nh = 1.0 / nh;
     for (int row = 0; row < (pm.has_s ? 2 : 1); ++row) {
@@ -342,6 +346,7 @@ fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
             const double2 Ev = make_double2(0.5 * (Hp.x + Hm.x), 0.5 * (Hp.y - Hm.y));
             const double2 Ov = make_double2(0.5 * (Hp.y + Hm.y), -0.5 * (Hp.x - Hm.x));
             const double2 t = cmulc(Ov, Wr[m]);
+            const double wq = (adjoint && m > 0) ? 2.0 * wq0 : wq0;
             const double2 Fm = make_double2(0.5 * (Ev.x + t.x) * wq, 0.5 * (Ev.y + t.y) * wq);
             const int n0 = nlat0[m];
             const long long is = (fb_rowoff[m] + (pair - n0)) * nf + f;
@@ -596,8 +601,8 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
     return SPTRANS_OK;
 }
 
-int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv) {
-    if (!p.d_weights) {
+int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint) {
+    if (!p.d_weights && !adjoint) {
         set_error("dirtrans: plan was created without quadrature weights");
         return SPTRANS_ERR_INVALID;
     }
@@ -611,7 +616,7 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
             fourier_dir_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
                 reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
                 p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
-                reinterpret_cast<double2*>(d_fourier));
+                reinterpret_cast<double2*>(d_fourier), adjoint);
             p.launches++;
             SPT_CUDA(cudaGetLastError());
             continue;
@@ -619,7 +624,7 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
         fourier_dir_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
             p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
-            reinterpret_cast<double2*>(d_fourier));
+            reinterpret_cast<double2*>(d_fourier), adjoint);
         p.launches++;
         SPT_CUDA(cudaGetLastError());
     }

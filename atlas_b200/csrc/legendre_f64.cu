@@ -67,7 +67,8 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + kStages * kAStage;
-    __shared__ int s_tile;
+    __shared__ LegTile s_tl[2];   // current / next tile descriptor (fetched one tile ahead by thread 0)
+    __shared__ int s_ti[2];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -76,45 +77,63 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
     // blocks, so that a partial tile with <= 64 valid rows still keeps every sub-partition's FP64 pipe busy
     const int wm = warp / kWarpsN, wn = warp % kWarpsN;
 
-    for (;;) {
-        __syncthreads();  // previous tile fully consumed (smem + s_tile)
-        if (tid == 0) s_tile = atomicAdd(counter, 1);
-        __syncthreads();
-        const int ti = s_tile;
-        if (ti >= ntiles) break;
-        const LegTile tl = tiles[ti];
+    auto load_stage = [&](const LegTile& tl, int kb, int st) {
         const double* Ag = tab + tl.a_off;
         const double* Bg = B + tl.b_off;
+        double* as = As + st * kAStage;
+        double* bs = Bs + st * kBStage;
+        if (!kDirect) {
+            // kBK rows x kBM latitudes, 2 doubles per chunk
+            for (int c = tid; c < kBK * (kBM / 2); c += kLegThreads) {
+                const int kk = c / (kBM / 2), cc = (c % (kBM / 2)) * 2;
+                const bool ok = cc < tl.a_rows;  // a_rows: readable latitude columns (even)
+                const double* src = Ag + static_cast<long long>(kb * kBK + kk) * tl.a_pitch + (ok ? cc : 0);
+                cp_async16(as + kk * kAInvPitch + cc, src, ok);
+            }
+        }
+        else {
+            // kBM table rows x kBK latitudes
+            for (int c = tid; c < kBM * (kBK / 2); c += kLegThreads) {
+                const int rr = c / (kBK / 2), cc = (c % (kBK / 2)) * 2;
+                const bool ok = rr < tl.a_rows;  // a_rows: readable table rows
+                const double* src = Ag + static_cast<long long>(ok ? rr : 0) * tl.a_pitch + kb * kBK + cc;
+                cp_async16(as + rr * kADirPitch + cc, src, ok);
+            }
+        }
+        for (int c = tid; c < kBK * (kBN / 2); c += kLegThreads) {
+            const int kk = c / (kBN / 2), cc = (c % (kBN / 2)) * 2;
+            const int row = kb * kBK + kk;
+            const bool ok = (cc < tl.n_valid) && (row < tl.b_rows);
+            const double* src = Bg + static_cast<long long>(ok ? row : 0) * ldb + (ok ? cc : 0);
+            cp_async16(bs + kk * kBPitch + cc, src, ok);
+        }
+    };
+    // first kStages-1 stages of a tile (one commit group each, as the main loop expects)
+    auto prologue = [&](const LegTile& tl) {
+#pragma unroll
+        for (int s = 0; s < kStages - 1; ++s) {
+            if (s < tl.k_steps) load_stage(tl, s, s);
+            cp_async_commit();
+        }
+    };
 
-        auto load_stage = [&](int kb, int st) {
-            double* as = As + st * kAStage;
-            double* bs = Bs + st * kBStage;
-            if (!kDirect) {
-                // kBK rows x kBM latitudes, 2 doubles per chunk
-                for (int c = tid; c < kBK * (kBM / 2); c += kLegThreads) {
-                    const int kk = c / (kBM / 2), cc = (c % (kBM / 2)) * 2;
-                    const bool ok = cc < tl.a_rows;  // a_rows: readable latitude columns (even)
-                    const double* src = Ag + static_cast<long long>(kb * kBK + kk) * tl.a_pitch + (ok ? cc : 0);
-                    cp_async16(as + kk * kAInvPitch + cc, src, ok);
-                }
-            }
-            else {
-                // kBM table rows x kBK latitudes
-                for (int c = tid; c < kBM * (kBK / 2); c += kLegThreads) {
-                    const int rr = c / (kBK / 2), cc = (c % (kBK / 2)) * 2;
-                    const bool ok = rr < tl.a_rows;  // a_rows: readable table rows
-                    const double* src = Ag + static_cast<long long>(ok ? rr : 0) * tl.a_pitch + kb * kBK + cc;
-                    cp_async16(as + rr * kADirPitch + cc, src, ok);
-                }
-            }
-            for (int c = tid; c < kBK * (kBN / 2); c += kLegThreads) {
-                const int kk = c / (kBN / 2), cc = (c % (kBN / 2)) * 2;
-                const int row = kb * kBK + kk;
-                const bool ok = (cc < tl.n_valid) && (row < tl.b_rows);
-                const double* src = Bg + static_cast<long long>(ok ? row : 0) * ldb + (ok ? cc : 0);
-                cp_async16(bs + kk * kBPitch + cc, src, ok);
-            }
-        };
+    if (tid == 0) {
+        const int ti = atomicAdd(counter, 1);
+        s_ti[0] = ti;
+        if (ti < ntiles) s_tl[0] = tiles[ti];
+    }
+    __syncthreads();
+    if (s_ti[0] >= ntiles) return;
+    prologue(s_tl[0]);
+
+    for (int buf = 0;; buf ^= 1) {
+        const LegTile tl = s_tl[buf];
+        // claim the next tile and fetch its descriptor while this one computes
+        if (tid == 0) {
+            const int ti = atomicAdd(counter, 1);
+            s_ti[buf ^ 1] = ti;
+            if (ti < ntiles) s_tl[buf ^ 1] = tiles[ti];
+        }
 
         double acc[kMI][kNJ][2];
 #pragma unroll
@@ -123,11 +142,6 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
             for (int j = 0; j < kNJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
 
         const int ksteps = tl.k_steps;
-#pragma unroll
-        for (int s = 0; s < kStages - 1; ++s) {
-            if (s < ksteps) load_stage(s, s);
-            cp_async_commit();
-        }
         const int row_w = wm * (kMI * 8);   // warp's first row in the tile
         const int col_w = wn * (kNJ * 8);   // warp's first column
         const bool warp_active = (row_w < tl.m_valid) && (col_w < tl.n_valid);
@@ -137,7 +151,7 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
             __syncthreads();
             {
                 const int nk = kb + kStages - 1;
-                if (nk < ksteps) load_stage(nk, nk % kStages);
+                if (nk < ksteps) load_stage(tl, nk, nk % kStages);
                 cp_async_commit();
             }
             if (warp_active) {
@@ -147,14 +161,14 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
                 // DMMAs of step ks, so that the two warps of a sub-partition (which run in lock step between
                 // barriers) never wait on LDS latency with an idle FP64 pipe
                 double a[2][kMI], b[2][kNJ];
-                auto load_frag = [&](int ks, int buf) {
+                auto load_frag = [&](int ks, int fb) {
 #pragma unroll
                     for (int i = 0; i < kMI; ++i) {
-                        if (!kDirect) a[buf][i] = as[(ks * 4 + t) * kAInvPitch + row_w + 8 * i + g];
-                        else a[buf][i] = as[(row_w + 8 * i + g) * kADirPitch + ks * 4 + t];
+                        if (!kDirect) a[fb][i] = as[(ks * 4 + t) * kAInvPitch + row_w + 8 * i + g];
+                        else a[fb][i] = as[(row_w + 8 * i + g) * kADirPitch + ks * 4 + t];
                     }
 #pragma unroll
-                    for (int j = 0; j < kNJ; ++j) b[buf][j] = bs[(ks * 4 + t) * kBPitch + col_w + 8 * j + g];
+                    for (int j = 0; j < kNJ; ++j) b[fb][j] = bs[(ks * 4 + t) * kBPitch + col_w + 8 * j + g];
                 };
                 load_frag(0, 0);
 #pragma unroll
@@ -171,6 +185,10 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
             }
         }
         cp_async_wait<0>();
+        __syncthreads();  // every stage buffer is free again; the next descriptor written by thread 0 is visible
+        const int next_ti = s_ti[buf ^ 1];
+        // start streaming the next tile's operands before this tile's results are written out
+        if (next_ti < ntiles) prologue(s_tl[buf ^ 1]);
         // epilogue: thread holds C[row_w+8i+g][col_w+8j+2t .. +1] = (re, im) of one field
         if (warp_active) {
             double* Cg = C + tl.c_off;
@@ -189,6 +207,7 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
                 }
             }
         }
+        if (next_ti >= ntiles) break;
     }
 }
 
@@ -219,7 +238,7 @@ __global__ void pack_spectra_kernel(int T, int nf, int trunc, const long long* _
 // packed [m][p][k][2 fld + re/im] -> spectra [m][n][re/im][fld] for all n <= T
 __global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict__ sp_rowoff,
                                       const int* __restrict__ my_m, const double* __restrict__ packed,
-                                      double* __restrict__ spec) {
+                                      double* __restrict__ spec, int drop_mT) {
     const int m = my_m[blockIdx.x];
     const int p = blockIdx.y;
     const long long row0 = sp_rowoff[2 * m + p];
@@ -233,6 +252,7 @@ __global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict
         const int n = m + p + 2 * k;
         double v = packed[(row0 + k) * ld + 2 * f + imag];
         if (m == 0 && imag == 1) v = 0.;  // Im of the zonal-mean coefficients is identically zero
+        if (drop_mT && m >= T) v = 0.;     // adjoint of the scalar inverse, which ignores the m == T column (:982)
         spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f] = v;
     }
 }
@@ -332,11 +352,11 @@ int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double
     return SPTRANS_OK;
 }
 
-int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec) {
+int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec, int drop_mT) {
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
     dim3 grid(nm, 2);
-    unpack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, p.d_sp_rowoff, p.d_my_m, d_packed, d_spec);
+    unpack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, p.d_sp_rowoff, p.d_my_m, d_packed, d_spec, drop_mT);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;

@@ -17,10 +17,11 @@ namespace sptrans {
 
 namespace {
 
-constexpr int kLatsPerBlock = 4;
 constexpr int kGenThreads = 256;
 
-template <bool kCacheLayout>
+// kLatsPerBlock latitudes advance together (32-byte store runs); 4 normally, 2 when the three row buffers of a
+// very high truncation (T > ~2400) would not fit in shared memory
+template <bool kCacheLayout, int kLatsPerBlock>
 __global__ void __launch_bounds__(kGenThreads)
 legendre_gen_kernel(int trc,            // table truncation (T+1)
                     int Tm,             // highest m stored (T)
@@ -142,11 +143,22 @@ int generate_legendre_table(Plan& p) {
     SPT_CUDA(cudaMemcpyAsync(d_pitch, g.tab_pitch.data(), g.tab_pitch.size() * sizeof(int), cudaMemcpyHostToDevice,
                              p.stream));
 
-    const size_t smem = 3ull * W * kLatsPerBlock * sizeof(double);
-    SPT_CUDA(cudaFuncSetAttribute(legendre_gen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = (g.nleg + kLatsPerBlock - 1) / kLatsPerBlock;
-    legendre_gen_kernel<false><<<blocks, kGenThreads, smem, p.stream>>>(trc, g.T, g.nleg, d_x, d_c0, d_c1, d_dg, p.d_nlat0,
-                                                                  d_off, d_pitch, p.d_tab);
+    if (3ull * W * 4 * sizeof(double) <= 200 * 1024) {
+        const size_t smem = 3ull * W * 4 * sizeof(double);
+        SPT_CUDA(cudaFuncSetAttribute(legendre_gen_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        legendre_gen_kernel<false, 4><<<(g.nleg + 3) / 4, kGenThreads, smem, p.stream>>>(trc, g.T, g.nleg, d_x, d_c0, d_c1, d_dg,
+                                                                                       p.d_nlat0, d_off, d_pitch, p.d_tab);
+    }
+    else {
+        const size_t smem = 3ull * W * 2 * sizeof(double);
+        if (smem > 226 * 1024) {
+            set_error("sptrans_plan_create: truncation too high for the device Legendre generator");
+            return SPTRANS_ERR_NOT_IMPLEMENTED;
+        }
+        SPT_CUDA(cudaFuncSetAttribute(legendre_gen_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        legendre_gen_kernel<false, 2><<<(g.nleg + 1) / 2, kGenThreads, smem, p.stream>>>(trc, g.T, g.nleg, d_x, d_c0, d_c1, d_dg,
+                                                                                       p.d_nlat0, d_off, d_pitch, p.d_tab);
+    }
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     SPT_CUDA(cudaStreamSynchronize(p.stream));
@@ -208,11 +220,18 @@ int export_legendre_cache(const Plan& p, double* h_out) {
     SPT_CUDA(cudaMemcpy(d_dg, diag.data(), colb, cudaMemcpyHostToDevice));
     SPT_CUDA(cudaMemcpy(d_begin, begin.data(), begin.size() * sizeof(long long), cudaMemcpyHostToDevice));
     SPT_CUDA(cudaMemcpy(d_K, Ks.data(), Ks.size() * sizeof(int), cudaMemcpyHostToDevice));
-    const size_t smem = 3ull * W * kLatsPerBlock * sizeof(double);
-    SPT_CUDA(cudaFuncSetAttribute(legendre_gen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = (g.nleg + kLatsPerBlock - 1) / kLatsPerBlock;
-    legendre_gen_kernel<true><<<blocks, kGenThreads, smem, p.stream>>>(trc, trc, g.nleg, d_x, d_c0, d_c1, d_dg,
-                                                                       p.d_nlat0, d_begin, d_K, d_out);
+    if (3ull * W * 4 * sizeof(double) <= 200 * 1024) {
+        const size_t smem = 3ull * W * 4 * sizeof(double);
+        SPT_CUDA(cudaFuncSetAttribute(legendre_gen_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        legendre_gen_kernel<true, 4><<<(g.nleg + 3) / 4, kGenThreads, smem, p.stream>>>(trc, trc, g.nleg, d_x, d_c0, d_c1, d_dg,
+                                                                                      p.d_nlat0, d_begin, d_K, d_out);
+    }
+    else {
+        const size_t smem = 3ull * W * 2 * sizeof(double);
+        SPT_CUDA(cudaFuncSetAttribute(legendre_gen_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        legendre_gen_kernel<true, 2><<<(g.nleg + 1) / 2, kGenThreads, smem, p.stream>>>(trc, trc, g.nleg, d_x, d_c0, d_c1, d_dg,
+                                                                                      p.d_nlat0, d_begin, d_K, d_out);
+    }
     SPT_CUDA(cudaGetLastError());
     SPT_CUDA(cudaStreamSynchronize(p.stream));
     SPT_CUDA(cudaMemcpy(h_out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost));

@@ -186,7 +186,7 @@ size_t legendre_cache_doubles(const HostGeom& g);
 // ---- legendre_f64.cu ----
 int build_tiles(Plan& p, int nf, int trunc, int dir_trunc);
 int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed);
-int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec);
+int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec, int drop_mT = 0);
 int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier);
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed);
 
@@ -201,7 +201,7 @@ void tc_free(Plan& p);
 int build_fft_tables(Plan& p);
 void free_fft_tables(Plan& p);
 int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv);
-int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv);
+int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint = 0);
 
 // ---- exchange.cu ----
 int launch_exchange_copy(Plan& p, int nf, const ExSeg* d_segs, int nseg, double* d_fourier, double* d_buf, bool gather);

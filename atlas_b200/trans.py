@@ -147,6 +147,10 @@ class Trans:
         else:
             raise TypeError("dirtrans: wrong number of arguments")
 
+    def invtrans_adj(self, nb_fields, gp_fields, scalar_spectra):
+        """adjoint of invtrans(nb_fields, spectra, gp): <invtrans x, y> == <x, invtrans_adj y>  (TransImpl.h:155-157)"""
+        _lib.check(_lib.lib.sptrans_invtrans_adj_scalar(self._h, int(nb_fields), _ptr(gp_fields), _ptr(scalar_spectra)))
+
     def invtrans_grad(self, nb_fields, scalar_spectra, grad_fields):
         """grad_fields = [E-W_1..E-W_k | N-S_1..N-S_k][npts]  (TransIFS::__invtrans_grad, ifs/TransIFS.cc:2075-2142)"""
         _lib.check(_lib.lib.sptrans_invtrans_grad(self._h, int(nb_fields), _ptr(scalar_spectra), _ptr(grad_fields)))

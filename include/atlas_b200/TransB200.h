@@ -104,8 +104,9 @@ public:
                       const eckit::Configuration& = util::NoConfig()) const override {
         ATLAS_NOTIMPLEMENTED;
     }
-    void invtrans_adj(const int, const double[], double[], const eckit::Configuration& = util::NoConfig()) const override {
-        ATLAS_NOTIMPLEMENTED;
+    void invtrans_adj(const int nb_scalar_fields, const double gp_fields[], double scalar_spectra[],
+                      const eckit::Configuration& = util::NoConfig()) const override {
+        check(sptrans_invtrans_adj_scalar(plan_, nb_scalar_fields, gp_fields, scalar_spectra));
     }
     void invtrans_adj(const int, const double[], double[], double[],
                       const eckit::Configuration& = util::NoConfig()) const override {

@@ -142,6 +142,11 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nb_fields, const double* gp_
  * [E-W_1..E-W_k | N-S_1..N-S_k][npts], i.e. component 0 = (1/(a cos))d/dlambda, 1 = (1/a)d/dphi
  * (ifs/TransIFS.cc:2075-2142).  NotImplemented in TransLocal (TransLocal.cc:848-857).                          */
 
+/* TransImpl::invtrans_adj(nb_scalar_fields, gp_fields, scalar_spectra)            trans/detail/TransImpl.h:155-157
+ * adjoint of sptrans_invtrans_scalar w.r.t. the Euclidean inner products: <invtrans x, y> = <x, invtrans_adj y>.
+ * NotImplemented in TransLocal (TransLocal.cc:1599-1604); semantics of the adjoint tests test_transgeneral.cc:1591-1818. */
+int sptrans_invtrans_adj_scalar(sptrans_plan* plan, int nb_fields, const double* gp_fields, double* scalar_spectra);
+
 /* TransImpl::dirtrans(nb_fields, wind_fields, vorticity_spectra, divergence_spectra)   TransImpl.h:180-181
  * wind layout [u_1..u_k | v_1..v_k][npts] (what invtrans_vordiv2wind produces); NotImplemented in TransLocal
  * (TransLocal.cc:1680-1685).  Exact inverse of sptrans_invtrans_vordiv2wind up to quadrature error.          */

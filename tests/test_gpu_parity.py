@@ -532,3 +532,22 @@ def test_config5_tco2559_inverse_sample():
     assert abs(b[H.spec_index(T, m, m, 0, nf, 0)] - 1.0) < 1e-10
     b[H.spec_index(T, m, m, 0, nf, 0)] = 0.0
     assert np.abs(b).max() < 1e-10
+
+
+@pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("L9", 17, 1)])
+def test_invtrans_adjoint_identity(gridname, T, nf):
+    """<invtrans x, y> == <x, invtrans_adj y>  (the reference's adjoint test, test_transgeneral.cc:1591-1818, runs this
+    identity through TransIFS; TransLocal has no adjoint)."""
+    grid, trans, plan = make(gridname, T)
+    rng = np.random.default_rng(5)
+    x = H.synthetic_spectra(T, nf, seed=41)
+    y = rng.standard_normal(nf * grid.size())
+    ix = np.full(nf * grid.size(), np.nan)
+    trans.invtrans(nf, x, ix)
+    ay = np.full_like(x, np.nan)
+    trans.invtrans_adj(nf, y, ay)
+    lhs, rhs = float(ix @ y), float(x @ ay)
+    assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), np.linalg.norm(ix) * np.linalg.norm(y) * 1e-3)
+    # the adjoint annihilates what the inverse ignores: Im(m = 0) and the m == T column
+    ay3 = ay.reshape(-1, 2, nf)
+    assert np.all(ay3[: T + 1, 1, :] == 0.0) and np.all(ay3[-1] == 0.0)

@@ -367,14 +367,16 @@ fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
 // Cost model used to pick the convolution length: every pass is one read+write sweep of shared memory;
 // larger radices do more arithmetic per point.
 double pass_cost(int R) {
+    // measured (profiles/ncu_summary_r01.md): the kernels are issue/latency bound with a barrier per pass, so a pass
+    // costs about the same whatever its radix; the radix only adds arithmetic
     switch (R) {
-        case 16: return 1.25;
-        case 9: return 1.10;
-        case 8: return 1.05;
-        case 5: return 1.05;
-        case 4: return 0.95;
-        case 3: return 0.95;
-        default: return 0.90;
+        case 16: return 1.32;
+        case 9: return 1.25;
+        case 8: return 1.24;
+        case 5: return 1.19;
+        case 4: return 1.16;
+        case 3: return 1.13;
+        default: return 1.08;
     }
 }
 // SPTRANS_FFT_MAXM (testing only) lowers the single-CTA limit so that small grids exercise the row-mode kernels

@@ -32,6 +32,8 @@ struct PairMeta {
     int M;                // convolution length, 5-smooth, >= n + 2L
     int has_s;            // 0 for the equator row of a grid with an odd number of latitudes
     int F;                // fields transformed together by one block
+    int sched;            // index into the per-class pass schedules (precomputed on the host)
+    int pad_;
     int mode;             // 0: north+south rows packed into one complex transform of length n
                           // 1: every row on its own, even/odd samples packed, complex length n/2 (rows too long for mode 0)
 };
@@ -42,6 +44,13 @@ using namespace fftc;
 
 constexpr int kMaxM = 13824;     // largest convolution length a single CTA can hold in shared memory (221 KB)
 constexpr int kFftThreads = 256;
+
+// the pass schedule (radices, reciprocals for index arithmetic) is computed once per class on the host: deriving it
+// in every thread cost ~2 us per block in 64-bit divisions
+__device__ __forceinline__ void load_schedule(const ScheduleG* __restrict__ g, ScheduleG* s, int tid) {
+    const int nw = sizeof(ScheduleG) / 4;
+    if (tid < nw) reinterpret_cast<int*>(s)[tid] = reinterpret_cast<const int*>(g)[tid];
+}
 
 __device__ __forceinline__ void load_twiddles(const double2* __restrict__ g, double2* s, int M, int tid, int nthr) {
     const int ntw = M / 64 + 1 + 64;
@@ -114,7 +123,7 @@ chirp_tables_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chir
 __global__ void __launch_bounds__(2 * kFftThreads, 1)
 fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
                    int mlimit, int nb_uv, const double2* __restrict__ fb, const long long* __restrict__ fb_rowoff,
-                   const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
+                   const int* __restrict__ nlat0, int nleg, const ScheduleG* __restrict__ scheds, const double2* __restrict__ twid,
                    const double2* __restrict__ chirp, const double2* __restrict__ filt,
                    const double* __restrict__ coslatinv, double* __restrict__ gp, long long npts) {
     extern __shared__ double2 X[];
@@ -135,7 +144,8 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
         return;
     }
     double2* sW = X + pm.F * PL;
-    const ScheduleG sc = make_schedule_g(M);
+    __shared__ ScheduleG sc;
+    load_schedule(scheds + pm.sched, &sc, tid);
     for (int e = tid; e < nfb * PL; e += nthr) X[e] = make_double2(0., 0.);
     load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
     __syncthreads();
@@ -184,7 +194,7 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
 __global__ void __launch_bounds__(2 * kFftThreads, 1)
 fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
                    int nb_uv, const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
-                   const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
+                   const int* __restrict__ nlat0, int nleg, const ScheduleG* __restrict__ scheds, const double2* __restrict__ twid,
                    const double2* __restrict__ chirp, const double2* __restrict__ filt,
                    const double* __restrict__ weights, const double* __restrict__ coslat, double2* __restrict__ fb,
                    int adjoint) {
@@ -198,7 +208,8 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     if (L < 0) return;
     const int M = pm.M, PL = M;
     double2* sW = X + pm.F * PL;
-    const ScheduleG sc = make_schedule_g(M);
+    __shared__ ScheduleG sc;
+    load_schedule(scheds + pm.sched, &sc, tid);
     for (int e = tid; e < nfb * PL; e += nthr) X[e] = make_double2(0., 0.);
     load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
     __syncthreads();
@@ -256,7 +267,7 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
 __global__ void __launch_bounds__(2 * kFftThreads, 1)
 fourier_inv_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf, int mlimit,
                         int nb_uv, const double2* __restrict__ fb, const long long* __restrict__ fb_rowoff,
-                        const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
+                        const int* __restrict__ nlat0, int nleg, const ScheduleG* __restrict__ scheds, const double2* __restrict__ twid,
                         const double2* __restrict__ chirp, const double2* __restrict__ filt,
                         const double* __restrict__ coslatinv, double* __restrict__ gp, long long npts) {
     extern __shared__ double2 X[];
@@ -267,7 +278,8 @@ fourier_inv_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
     const int L = pm.L, M = pm.M, nh = pm.n / 2;
     const int Lc = min(L, mlimit);
     double2* sW = X + M;
-    const ScheduleG sc = make_schedule_g(M);
+    __shared__ ScheduleG sc;
+    load_schedule(scheds + pm.sched, &sc, tid);
     load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
     const double2* A = chirp + pm.chirp_off;
     const double2* C = A + (2 * L + 1);
@@ -306,7 +318,7 @@ fourier_inv_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
 __global__ void __launch_bounds__(2 * kFftThreads, 1)
 fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf, int nb_uv,
                         const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
-                        const int* __restrict__ nlat0, int nleg, const double2* __restrict__ twid,
+                        const int* __restrict__ nlat0, int nleg, const ScheduleG* __restrict__ scheds, const double2* __restrict__ twid,
                         const double2* __restrict__ chirp, const double2* __restrict__ filt,
                         const double* __restrict__ weights, const double* __restrict__ uvscale,
                         double2* __restrict__ fb, int adjoint) {
@@ -318,7 +330,8 @@ fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
     const int L = pm.L, M = pm.M, nh = pm.n / 2;
     if (L < 0) return;
     double2* sW = X + M;
-    const ScheduleG sc = make_schedule_g(M);
+    __shared__ ScheduleG sc;
+    load_schedule(scheds + pm.sched, &sc, tid);
     load_twiddles(twid + pm.tw_off, sW, M, tid, nthr);
     const double2* A = chirp + pm.chirp_off;
     const double2* C = A + (2 * L + 1);
@@ -474,6 +487,7 @@ int build_fft_tables(Plan& p) {
             c.chirp_off = chirp_total;
             c.filt_off = filt_total;
             c.tw_off = tw_total;
+            c.sched = static_cast<int>(classes.size());
             chirp_total += 2LL * Luse + 1 + (pm.mode ? pm.n / 2 + Luse + 1 : pm.n);
             filt_total += M;
             tw_total += M / 64 + 1 + 64;
@@ -484,12 +498,22 @@ int build_fft_tables(Plan& p) {
         pm.chirp_off = classes[it->second].chirp_off;
         pm.filt_off = classes[it->second].filt_off;
         pm.tw_off = classes[it->second].tw_off;
+        pm.sched = classes[it->second].sched;
         meta[j] = pm;
     }
     SPT_CUDA(cudaMalloc(&p.d_chirp, std::max<long long>(chirp_total, 1) * sizeof(double2)));
     SPT_CUDA(cudaMalloc(&p.d_filt, std::max<long long>(filt_total, 1) * sizeof(double2)));
     SPT_CUDA(cudaMalloc(&p.d_twiddle, std::max<long long>(tw_total, 1) * sizeof(double2)));
     p.bytes_tables += (chirp_total + filt_total + tw_total) * sizeof(double2);
+    {
+        std::vector<ScheduleG> sch(classes.size());
+        for (size_t c = 0; c < classes.size(); ++c) sch[c] = fftc::make_schedule_g(classes[c].M);
+        ScheduleG* d_s = nullptr;
+        SPT_CUDA(cudaMalloc(&d_s, std::max<size_t>(sch.size(), 1) * sizeof(ScheduleG)));
+        SPT_CUDA(cudaMemcpyAsync(d_s, sch.data(), sch.size() * sizeof(ScheduleG), cudaMemcpyHostToDevice, p.stream));
+        SPT_CUDA(cudaStreamSynchronize(p.stream));
+        p.d_fft_order = reinterpret_cast<int*>(d_s);  // owned by the plan (freed with it)
+    }
     PairMeta* d_cls = nullptr;
     SPT_CUDA(cudaMalloc(&d_cls, classes.size() * sizeof(PairMeta)));
     SPT_CUDA(cudaMemcpyAsync(d_cls, classes.data(), classes.size() * sizeof(PairMeta), cudaMemcpyHostToDevice, p.stream));
@@ -587,7 +611,7 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
         if (grp.mode[gi]) {
             fourier_inv_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
                 reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
-                reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp,
+                reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp,
                 p.d_filt, p.d_coslatinv, d_gp, p.g.npts);
             p.launches++;
             SPT_CUDA(cudaGetLastError());
@@ -595,7 +619,7 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
         }
         fourier_inv_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
-            reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp,
+            reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp,
             p.d_filt, p.d_coslatinv, d_gp, p.g.npts);
         p.launches++;
         SPT_CUDA(cudaGetLastError());
@@ -617,7 +641,7 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
         if (grp.mode[gi]) {
             fourier_dir_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
                 reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
-                p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
+                p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
                 reinterpret_cast<double2*>(d_fourier), adjoint);
             p.launches++;
             SPT_CUDA(cudaGetLastError());
@@ -625,7 +649,7 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
         }
         fourier_dir_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
-            p.d_fb_rowoff, p.d_nlat0, p.g.nleg, p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
+            p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
             reinterpret_cast<double2*>(d_fourier), adjoint);
         p.launches++;
         SPT_CUDA(cudaGetLastError());

@@ -178,7 +178,9 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
                     for (int i = 0; i < kMI; ++i) {
                         if (row_w + 8 * i < tl.m_valid) {
 #pragma unroll
-                            for (int j = 0; j < kNJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[ks & 1][i], b[ks & 1][j]);
+                            for (int j = 0; j < kNJ; ++j)
+                                if (col_w + 8 * j < tl.n_valid)  // warp-uniform: skip 8-column groups past the last field
+                                    dmma884(acc[i][j][0], acc[i][j][1], a[ks & 1][i], b[ks & 1][j]);
                         }
                     }
                 }

@@ -71,6 +71,18 @@ def _load():
         "sptrans_exchange_rows": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
         "sptrans_exchange_pack": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
         "sptrans_exchange_unpack": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+        "sptrans_peer_alloc": (C.c_int, [vp, C.c_int, C.c_char_p]),
+        "sptrans_peer_attach_ipc": (C.c_int, [vp, C.c_int, C.c_char_p]),
+        "sptrans_peer_attach_ptrs": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+        "sptrans_peer_region": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "sptrans_peer_buffer": (C.c_int, [vp, C.POINTER(vp)]),
+        "sptrans_peer_free": (C.c_int, [vp]),
+        "sptrans_invtrans_sharded": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_dirtrans_sharded": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_invtrans_legendre_peers": (C.c_int, [vp, C.c_int, vp]),
+        "sptrans_dirtrans_fourier_peers": (C.c_int, [vp, C.c_int, vp]),
+        "sptrans_peer_barrier": (C.c_int, [vp]),
+        "sptrans_peer_advance": (C.c_int, [vp]),
         "sptrans_last_timings": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "sptrans_kernel_launches": (C.c_uint64, [vp]),
     }

@@ -72,6 +72,17 @@ struct StageTimer {
     }
 };
 
+void peer_release(Plan& p) {
+    PeerState& ps = p.peer;
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (ps.ipc_opened[r] && ps.peer_region[r]) cudaIpcCloseMemHandle(ps.peer_region[r]);
+        ps.ipc_opened[r] = false;
+        ps.peer_region[r] = nullptr;
+    }
+    if (ps.region) cudaFree(ps.region);
+    ps = PeerState{};
+}
+
 int check_plan(sptrans_plan* plan) {
     if (!plan) {
         set_error("null plan");
@@ -260,6 +271,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     if (p.stream) cudaStreamSynchronize(p.stream);
     free_fft_tables(p);
     tc_free(p);
+    peer_release(p);
     void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_weights,
                     p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
                     p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
@@ -787,8 +799,221 @@ int sptrans_exchange_unpack(sptrans_plan* plan, int nf, int side, const double* 
     return SPTRANS_OK;
 }
 
+// ---- peer-memory exchange of a sharded plan (NVLink / NVSwitch node, one process per GPU) ----------------------
+
+static int peer_ready(Plan& p, int nf, const char* who) {
+    const PeerState& ps = p.peer;
+    if (!ps.region || ps.nranks != p.g.nranks || ps.nf != nf) {
+        set_error(std::string(who) + ": peer buffers are not allocated/attached for this number of fields");
+        return SPTRANS_ERR_INVALID;
+    }
+    for (int r = 0; r < ps.nranks; ++r)
+        if (!ps.peer_region[r]) {
+            set_error(std::string(who) + ": peer region of rank " + std::to_string(r) + " is not attached");
+            return SPTRANS_ERR_INVALID;
+        }
+    if (p.precision != SPTRANS_PREC_FP64) {
+        set_error(std::string(who) + ": the peer-memory exchange is implemented for the fp64 Legendre kernel");
+        return SPTRANS_ERR_NOT_IMPLEMENTED;
+    }
+    return SPTRANS_OK;
+}
+
+int sptrans_peer_alloc(sptrans_plan* plan, int nf, unsigned char* ipc_handle_out) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf <= 0 || p.g.nranks > kMaxPeers) {
+        set_error("sptrans_peer_alloc: invalid arguments (at most 8 ranks: one NVSwitch node)");
+        return SPTRANS_ERR_INVALID;
+    }
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    peer_release(p);
+    PeerState& ps = p.peer;
+    ps.nranks = p.g.nranks;
+    ps.nf = nf;
+    ps.buf_doubles = fourier_doubles(p, nf);
+    const size_t bytes = kPeerFlagBytes + 2 * ps.buf_doubles * sizeof(double);
+    SPT_CUDA(cudaMalloc(&ps.region, bytes));
+    SPT_CUDA(cudaMemset(ps.region, 0, bytes));
+    SPT_CUDA(cudaDeviceSynchronize());
+    ps.peer_region[p.g.rank] = ps.region;
+    if (ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == SPTRANS_IPC_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        SPT_CUDA(cudaIpcGetMemHandle(&h, ps.region));
+        std::memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    return SPTRANS_OK;
+}
+
+int sptrans_peer_attach_ipc(sptrans_plan* plan, int nranks, const unsigned char* handles) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    PeerState& ps = p.peer;
+    if (!ps.region || nranks != p.g.nranks || !handles) {
+        set_error("sptrans_peer_attach_ipc: call sptrans_peer_alloc first; nranks must match the plan");
+        return SPTRANS_ERR_INVALID;
+    }
+    for (int r = 0; r < nranks; ++r) {
+        if (r == p.g.rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + static_cast<size_t>(r) * SPTRANS_IPC_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        SPT_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ps.peer_region[r] = ptr;
+        ps.ipc_opened[r] = true;
+    }
+    return SPTRANS_OK;
+}
+
+int sptrans_peer_attach_ptrs(sptrans_plan* plan, int nranks, void* const* regions) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    PeerState& ps = p.peer;
+    if (!ps.region || nranks != p.g.nranks || !regions) {
+        set_error("sptrans_peer_attach_ptrs: call sptrans_peer_alloc first; nranks must match the plan");
+        return SPTRANS_ERR_INVALID;
+    }
+    for (int r = 0; r < nranks; ++r)
+        if (r != p.g.rank) ps.peer_region[r] = regions[r];
+    return SPTRANS_OK;
+}
+
+int sptrans_peer_region(const sptrans_plan* plan, void** region, size_t* bytes) {
+    if (!plan || !plan->p.peer.region) {
+        set_error("sptrans_peer_region: no peer region allocated");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (region) *region = plan->p.peer.region;
+    if (bytes) *bytes = kPeerFlagBytes + 2 * plan->p.peer.buf_doubles * sizeof(double);
+    return SPTRANS_OK;
+}
+
+int sptrans_peer_buffer(const sptrans_plan* plan, double** d_fourier) {
+    if (!plan || !plan->p.peer.region || !d_fourier) {
+        set_error("sptrans_peer_buffer: no peer region allocated");
+        return SPTRANS_ERR_INVALID;
+    }
+    *d_fourier = make_peer_dst(plan->p).base[plan->p.g.rank];
+    return SPTRANS_OK;
+}
+
+int sptrans_peer_free(sptrans_plan* plan) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    SPT_CUDA(cudaStreamSynchronize(plan->p.stream));
+    peer_release(plan->p);
+    return SPTRANS_OK;
+}
+
+int sptrans_peer_barrier(sptrans_plan* plan) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    if ((rc = peer_ready(plan->p, plan->p.peer.nf, "sptrans_peer_barrier"))) return rc;
+    return launch_peer_barrier(plan->p);
+}
+
+int sptrans_peer_advance(sptrans_plan* plan) {
+    if (!plan) return SPTRANS_ERR_INVALID;
+    plan->p.peer.parity ^= 1;
+    return SPTRANS_OK;
+}
+
+// The four stream-ordered halves of the sharded transforms (no host synchronisation; the caller synchronises
+// the stream).  sptrans_invtrans_sharded / sptrans_dirtrans_sharded chain them with the barrier.
+int sptrans_invtrans_legendre_peers(sptrans_plan* plan, int nf, const double* d_spectra) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if ((rc = peer_ready(p, nf, "sptrans_invtrans_legendre_peers"))) return rc;
+    if (!d_spectra) {
+        set_error("sptrans_invtrans_legendre_peers: null spectra");
+        return SPTRANS_ERR_INVALID;
+    }
+    if ((rc = build_tiles(p, nf, p.g.T, p.g.T))) return rc;
+    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
+    if ((rc = launch_pack_spectra(p, nf, p.g.T, d_spectra, p.d_packed))) return rc;
+    return launch_legendre_inv_peers(p, nf, p.d_packed, make_peer_dst(p));
+}
+
+int sptrans_dirtrans_fourier_peers(sptrans_plan* plan, int nf, const double* d_gp) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if ((rc = peer_ready(p, nf, "sptrans_dirtrans_fourier_peers"))) return rc;
+    if (!d_gp) {
+        set_error("sptrans_dirtrans_fourier_peers: null grid-point array");
+        return SPTRANS_ERR_INVALID;
+    }
+    double* local = make_peer_dst(p).base[p.g.rank];
+    if ((rc = launch_fourier_dir(p, nf, d_gp, local, 0))) return rc;
+    cudaEventRecord(p.ev[6], p.stream);
+    return launch_exchange_push(p, nf);
+}
+
+int sptrans_invtrans_sharded(sptrans_plan* plan, int nf, const double* d_spectra, double* d_gp) {
+    if (!plan || !d_gp) {
+        set_error("sptrans_invtrans_sharded: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    Plan& p = plan->p;
+    int rc;
+    cudaEventRecord(p.ev[0], p.stream);
+    if ((rc = sptrans_invtrans_legendre_peers(plan, nf, d_spectra))) return rc;
+    cudaEventRecord(p.ev[1], p.stream);
+    if ((rc = launch_peer_barrier(p))) return rc;
+    cudaEventRecord(p.ev[2], p.stream);
+    double* local = make_peer_dst(p).base[p.g.rank];
+    if ((rc = launch_fourier_inv(p, nf, p.g.T - 1, local, d_gp, 0))) return rc;
+    cudaEventRecord(p.ev[3], p.stream);
+    p.pending_marks = 4;
+    const int slots[3] = {1, 5, 2};  // legendre (incl. pack), exchange wait, fourier
+    std::memcpy(p.pending_slots, slots, sizeof(slots));
+    p.peer.parity ^= 1;
+    return SPTRANS_OK;
+}
+
+int sptrans_dirtrans_sharded(sptrans_plan* plan, int nf, const double* d_gp, double* d_spectra) {
+    if (!plan || !d_spectra) {
+        set_error("sptrans_dirtrans_sharded: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    Plan& p = plan->p;
+    int rc;
+    cudaEventRecord(p.ev[0], p.stream);
+    if ((rc = sptrans_dirtrans_fourier_peers(plan, nf, d_gp))) return rc;   // records ev[6] between fourier and push
+    cudaEventRecord(p.ev[1], p.stream);
+    if ((rc = launch_peer_barrier(p))) return rc;
+    cudaEventRecord(p.ev[2], p.stream);
+    double* local = make_peer_dst(p).base[p.g.rank];
+    if ((rc = build_tiles(p, nf, p.g.T, p.g.T))) return rc;
+    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
+    if ((rc = launch_legendre_dir(p, nf, local, p.d_packed))) return rc;
+    if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spectra))) return rc;
+    cudaEventRecord(p.ev[3], p.stream);
+    p.pending_marks = 4;
+    const int slots[3] = {2, 5, 1};  // fourier + push, exchange wait, legendre (incl. unpack)
+    std::memcpy(p.pending_slots, slots, sizeof(slots));
+    p.peer.parity ^= 1;
+    return SPTRANS_OK;
+}
+
 int sptrans_last_timings(const sptrans_plan* plan, float out_ms[8]) {
     if (!plan || !out_ms) return SPTRANS_ERR_INVALID;
+    if (plan->p.pending_marks > 0) {   // stream-ordered sharded call: read the events now
+        Plan& p = const_cast<Plan&>(plan->p);
+        cudaStreamSynchronize(p.stream);
+        for (float& t : p.t_ms) t = 0.f;
+        for (int i = 0; i + 1 < p.pending_marks; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
+            p.t_ms[p.pending_slots[i]] += ms;
+        }
+        p.pending_marks = 0;
+    }
     std::memcpy(out_ms, plan->p.t_ms, 8 * sizeof(float));
     return SPTRANS_OK;
 }

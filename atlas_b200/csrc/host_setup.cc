@@ -132,7 +132,7 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
     for (int j = 0; j < g.nleg; ++j)
         for (int m = 0; m <= T; ++m)
             if (g.nlat0[m] <= j) g.mmax[j] = m;
-    // sharding: zonal wavenumbers by cost-balanced greedy assignment, latitude pairs by sum(nx) bands
+    // sharding: zonal wavenumbers by cost-balanced greedy assignment, latitude pairs by cost-balanced contiguous bands
     g.rank = rank;
     g.nranks = nranks;
     g.my_m.clear();
@@ -159,15 +159,20 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
             if (best == rank) g.my_m.push_back(m);
         }
         std::sort(g.my_m.begin(), g.my_m.end());
-        // contiguous bands of latitude pairs with ~equal number of grid points
-        long long total = 0;
-        for (int j = 0; j < g.nleg; ++j) total += nx[j];
+        // contiguous bands of latitude pairs with ~equal Fourier-stage cost: a row pair of length n with zonal
+        // wavenumbers up to L is one chirp-z transform of length ~ n + 2L (fourier.cu), i.e. ~ M log M work
+        auto fcost = [&](int j) {
+            const double M = nx[j] + 2.0 * std::max(0, g.mmax[j]);
+            return M * std::log2(M + 2.0);
+        };
+        double total = 0;
+        for (int j = 0; j < g.nleg; ++j) total += fcost(j);
         std::vector<int> bound(nranks + 1, g.nleg);
         bound[0] = 0;
-        long long acc = 0;
+        double acc = 0;
         int r = 1;
         for (int j = 0; j < g.nleg && r < nranks; ++j) {
-            acc += nx[j];
+            acc += fcost(j);
             while (r < nranks && acc * nranks >= total * r) bound[r++] = j + 1;
         }
         g.band = bound;
@@ -208,7 +213,7 @@ void build_exchange(const HostGeom& g, ExchangeLayout& ex) {
     ex.band_side.clear();
     ex.m_side_rows.assign(R, 0);
     ex.band_side_rows.assign(R, 0);
-    auto add = [&](std::vector<ExSeg>& v, long long& cursor, int m, int b0, int b1) -> long long {
+    auto add = [&](std::vector<ExSeg>& v, long long& cursor, int m, int b0, int b1, int peer) -> long long {
         const int n0 = g.nlat0[m];
         const int ncol = g.nleg - n0;
         const int lo = std::max(b0, n0), hi = b1;
@@ -219,6 +224,7 @@ void build_exchange(const HostGeom& g, ExchangeLayout& ex) {
             s.fb_row = g.fb_rowoff[m] + static_cast<long long>(p) * ncol + (lo - n0);
             s.buf_row = cursor;
             s.nrows = hi - lo;
+            s.peer = peer;
             v.push_back(s);
             cursor += s.nrows;
             rows += s.nrows;
@@ -227,11 +233,11 @@ void build_exchange(const HostGeom& g, ExchangeLayout& ex) {
     };
     long long cur = 0;
     for (int d = 0; d < R; ++d)           // my zonal wavenumbers, restricted to rank d's latitude band
-        for (int m : g.my_m) ex.m_side_rows[d] += add(ex.m_side, cur, m, g.band[d], g.band[d + 1]);
+        for (int m : g.my_m) ex.m_side_rows[d] += add(ex.m_side, cur, m, g.band[d], g.band[d + 1], d);
     cur = 0;
     for (int s = 0; s < R; ++s)           // rank s's zonal wavenumbers, restricted to my latitude band
         for (int m = 0; m <= g.T; ++m)
-            if (g.owner[m] == s) ex.band_side_rows[s] += add(ex.band_side, cur, m, g.band[me], g.band[me + 1]);
+            if (g.owner[m] == s) ex.band_side_rows[s] += add(ex.band_side, cur, m, g.band[me], g.band[me + 1], s);
 }
 
 // Seeds of the Legendre recurrence for each latitude: cos(theta), the m=0 and m=1 columns (cosine /

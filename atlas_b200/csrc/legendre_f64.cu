@@ -60,10 +60,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // kDirect == false : A tile is [kBK][kBM] (k rows, latitude contiguous)   -> C rows are latitudes
 // kDirect == true  : A tile is [kBM][kBK] (table rows, latitude contiguous) -> C rows are table rows (n)
-template <bool kDirect>
+template <bool kDirect, bool kPeers>
 __global__ void __launch_bounds__(kLegThreads, 1)
 legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
-                     const double* __restrict__ tab, const double* __restrict__ B, double* __restrict__ C, int ldb) {
+                     const double* __restrict__ tab, const double* __restrict__ B, double* __restrict__ C, int ldb,
+                     const __grid_constant__ PeerDst dst) {
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + kStages * kAStage;
@@ -193,11 +194,20 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
         if (next_ti < ntiles) prologue(s_tl[buf ^ 1]);
         // epilogue: thread holds C[row_w+8i+g][col_w+8j+2t .. +1] = (re, im) of one field
         if (warp_active) {
-            double* Cg = C + tl.c_off;
 #pragma unroll
             for (int i = 0; i < kMI; ++i) {
                 const int row = row_w + 8 * i + g;
                 if (row < tl.m_valid) {
+                    double* Cg;
+                    if (!kPeers) Cg = C + tl.c_off;
+                    else {
+                        // fused exchange: the row goes straight into the Fourier-side buffer of the rank whose
+                        // latitude band contains it (NVLink store; same layout on every rank)
+                        const int lat = tl.lat0 + row;
+                        int d = 0;
+                        while (d + 1 < dst.nranks && lat >= dst.band[d + 1]) ++d;
+                        Cg = dst.base[d] + tl.c_off;
+                    }
 #pragma unroll
                     for (int j = 0; j < kNJ; ++j) {
                         const int col = col_w + 8 * j + 2 * t;
@@ -211,6 +221,7 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
         }
         if (next_ti >= ntiles) break;
     }
+    if (kPeers) __threadfence_system();  // remote rows are visible to the peers before this kernel completes
 }
 
 // spectra [m][n][re/im][fld]  ->  packed [m][p][k][2 fld + re/im], rows k >= K_eff (and whole blocks with
@@ -292,6 +303,7 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
                         t.b_off = g.sp_rowoff[2 * m + par] * ld + n0;
                         t.b_rows = ksteps * kBK;
                         t.c_off = (fb_row0 + l0) * ld + n0;
+                        t.lat0 = g.nlat0[m] + l0;
                         t.m_valid = std::min(kBM, ncol - l0);
                         t.n_valid = std::min(kBN, ld - n0);
                         t.k_steps = ksteps;
@@ -364,29 +376,33 @@ int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spe
     return SPTRANS_OK;
 }
 
-template <bool kDirect>
-static int launch_gemm(Plan& p, int nf, const LegTile* tiles, int ntiles, const double* B, double* C) {
+template <bool kDirect, bool kPeers>
+static int launch_gemm(Plan& p, int nf, const LegTile* tiles, int ntiles, const double* B, double* C,
+                       const PeerDst& dst) {
     if (ntiles == 0) return SPTRANS_OK;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[kDirect]) {
-        SPT_CUDA(cudaFuncSetAttribute(legendre_dmma_kernel<kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static bool attr_set[4] = {false, false, false, false};
+    if (!attr_set[2 * kDirect + kPeers]) {
+        SPT_CUDA(cudaFuncSetAttribute(legendre_dmma_kernel<kDirect, kPeers>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(kLegSmemBytes)));
-        attr_set[kDirect] = true;
+        attr_set[2 * kDirect + kPeers] = true;
     }
     SPT_CUDA(cudaMemsetAsync(p.d_tile_counter, 0, sizeof(int), p.stream));
     const int grid = std::min(ntiles, p.num_sms);
-    legendre_dmma_kernel<kDirect><<<grid, kLegThreads, kLegSmemBytes, p.stream>>>(tiles, ntiles, p.d_tile_counter,
-                                                                                 p.d_tab, B, C, 2 * nf);
+    legendre_dmma_kernel<kDirect, kPeers><<<grid, kLegThreads, kLegSmemBytes, p.stream>>>(
+        tiles, ntiles, p.d_tile_counter, p.d_tab, B, C, 2 * nf, dst);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;
 }
 
 int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier) {
-    return launch_gemm<false>(p, nf, p.d_tiles_inv, p.n_tiles_inv, d_packed, d_fourier);
+    return launch_gemm<false, false>(p, nf, p.d_tiles_inv, p.n_tiles_inv, d_packed, d_fourier, PeerDst{});
+}
+int launch_legendre_inv_peers(Plan& p, int nf, const double* d_packed, const PeerDst& dst) {
+    return launch_gemm<false, true>(p, nf, p.d_tiles_inv, p.n_tiles_inv, d_packed, nullptr, dst);
 }
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed) {
-    return launch_gemm<true>(p, nf, p.d_tiles_dir, p.n_tiles_dir, d_fourier, d_packed);
+    return launch_gemm<true, false>(p, nf, p.d_tiles_dir, p.n_tiles_dir, d_fourier, d_packed, PeerDst{});
 }
 
 }  // namespace sptrans

@@ -35,7 +35,8 @@ struct alignas(16) LegTile {
     int k_steps;      // number of kBK steps
     int a_rows;       // inverse: #lat columns readable from a_off (pitch - lat0); direct: #table rows readable
     int b_rows;       // rows of B that may be read (rest zero-filled)
-    int pad0, pad1;
+    int lat0;         // inverse: latitude-pair index of tile row 0 (selects the destination rank of a sharded plan)
+    int pad1;
 };
 
 struct HostGeom {
@@ -81,7 +82,7 @@ struct ExSeg {
     long long fb_row;
     long long buf_row;
     int nrows;
-    int pad;
+    int peer;   // rank at the other end of this run
 };
 // Exchange plan between the m-sharded Legendre stage and the latitude-band-sharded Fourier stage.
 // m_side: segments of the rows this rank owns as m-owner, grouped by the band owner they travel to/from;
@@ -89,6 +90,29 @@ struct ExSeg {
 struct ExchangeLayout {
     std::vector<ExSeg> m_side, band_side;
     std::vector<long long> m_side_rows, band_side_rows;  // [nranks] rows per peer
+};
+// Peer-memory exchange of a sharded plan (one GPU per process on an NVLink/NVSwitch node): every rank owns a region
+//   [ flags: kPeerFlagBytes | exchange buffer 0 | exchange buffer 1 ]
+// mapped into all peers (CUDA IPC or pointers supplied by the host).  Producers store rows straight into the
+// consumer's buffer; exchanges alternate between the two buffers, so that one device-side barrier per
+// exchange is enough (a rank can only overwrite buffer b after every peer has passed the barrier of the
+// following exchange, i.e. has finished reading b).
+constexpr int kMaxPeers = 8;
+constexpr size_t kPeerFlagBytes = 4096;
+struct PeerDst {            // kernel argument: where rows of the exchange buffer go
+    double* base[kMaxPeers];
+    int band[kMaxPeers + 1];
+    int nranks;
+};
+struct PeerState {
+    int nranks = 0;
+    int nf = 0;
+    size_t buf_doubles = 0;
+    void* region = nullptr;                 // local allocation
+    void* peer_region[kMaxPeers] = {};      // mapped regions, [me] == region
+    bool ipc_opened[kMaxPeers] = {};
+    int parity = 0;
+    unsigned long long epoch = 0;
 };
 // per distinct row length: Bluestein / chirp-z tables on the device
 struct FftLen {
@@ -147,11 +171,14 @@ struct Plan {
     ExchangeLayout ex;
     ExSeg* d_ex_m = nullptr;
     ExSeg* d_ex_band = nullptr;
+    PeerState peer;
     size_t bytes_tables = 0;
     // stats
     uint64_t launches = 0;
     float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8] = {};
+    int pending_marks = 0;      // stream-ordered (sharded) calls: events recorded, elapsed times read lazily
+    int pending_slots[8] = {};
 };
 
 // ---- error handling ----
@@ -188,6 +215,8 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc);
 int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed);
 int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec, int drop_mT = 0);
 int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier);
+// same, every output row stored into the exchange buffer of the rank that owns its latitude band
+int launch_legendre_inv_peers(Plan& p, int nf, const double* d_packed, const PeerDst& dst);
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed);
 
 // ---- legendre_tc.cu (tcgen05 split-TF32 path) ----
@@ -205,6 +234,9 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
 
 // ---- exchange.cu ----
 int launch_exchange_copy(Plan& p, int nf, const ExSeg* d_segs, int nseg, double* d_fourier, double* d_buf, bool gather);
+PeerDst make_peer_dst(const Plan& p);      // exchange buffers of the current parity on every rank
+int launch_exchange_push(Plan& p, int nf);  // band-side rows of the local buffer -> owners of their zonal wavenumber
+int launch_peer_barrier(Plan& p);
 
 // ---- vordiv.cu ----
 int launch_grad_spectra(cudaStream_t s, int T, int nf, const double* d_sp, double* d_all, uint64_t* launches);

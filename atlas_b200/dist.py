@@ -3,8 +3,17 @@
 Sharding: the Legendre stage is independent per zonal wavenumber m, the Fourier stage per latitude
 pair, so rank r owns a cost-balanced set of m (and only those blocks of the Legendre table) and a band of
 latitude pairs.  Between the two stages there is exactly one exchange -- the classic spectral-transform
-transposition -- done as ONE all-to-all of the (my m) x (your latitudes) blocks of the Legendre<->Fourier
-buffer; the grid-point fields stay latitude-band distributed (atlas's StructuredColumns distribution) unless
+transposition of the (my m) x (your latitudes) blocks of the Legendre<->Fourier buffer.  Two implementations:
+
+* exchange="peer" (default): the exchange buffers of all ranks are mapped into every process (CUDA IPC over
+  NVLink/NVSwitch; this module only ships the 64-byte handles through torch.distributed once).  The inverse
+  Legendre GEMM stores its rows straight into the consumer's buffer from its epilogue, the direct transform
+  pushes its rows with one copy kernel, and a device-side flag barrier is the only synchronisation: one
+  stream-ordered library call per transform, no collective library on the data path.
+* exchange="nccl": pack -> ONE all_to_all_single -> unpack (kept as the portable fallback and as the baseline
+  the fused path is measured against).
+
+The grid-point fields stay latitude-band distributed (atlas's StructuredColumns distribution) unless
 `gather_grid()` is called, which is the single all-gather the north star mentions.
 
 The reference has no counterpart: TransLocal throws for mpi::size() > 1 (trans/local/TransLocal.cc:338-340).
@@ -53,7 +62,7 @@ def shard_segments(grid, truncation, rank, nranks, side):
 class ShardedTrans:
     """m-sharded / latitude-band-sharded transform over an initialised torch.distributed process group."""
 
-    def __init__(self, grid, truncation, device, group=None):
+    def __init__(self, grid, truncation, device, group=None, exchange="peer"):
         import torch
         import torch.distributed as dist
 
@@ -70,13 +79,30 @@ class ShardedTrans:
         self.m_rows, self.band_rows = ms, bs
         self.device = torch.device("cuda", device)
         self._nf = None
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.exchange = exchange
         # run the library on torch's current stream: the NCCL collective is ordered against that stream, so the
         # pack -> all_to_all -> unpack chain needs no extra synchronisation
         with torch.cuda.device(self.device):
             self.trans.set_stream(torch.cuda.current_stream().cuda_stream)
 
+    def _attach_peers(self, nf):
+        """Allocate this rank's exchange region and map every peer's (collective)."""
+        h = self.trans._h
+        handle = C.create_string_buffer(64)
+        _lib.check(_lib.lib.sptrans_peer_alloc(h, int(nf), handle))
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle.raw, group=self.group)
+        _lib.check(_lib.lib.sptrans_peer_attach_ipc(h, self.world, b"".join(handles)))
+        self.dist.barrier(group=self.group)   # nobody stores into a region before everybody has mapped it
+
     def _buffers(self, nf):
         if self._nf == nf:
+            return
+        if self.exchange == "peer":
+            self._attach_peers(nf)
+            self._nf = nf
             return
         t = self.torch
         self.fb = t.zeros(self.trans.fourier_elems_per_field() * 2 * nf, dtype=t.float64, device=self.device)
@@ -89,6 +115,9 @@ class ShardedTrans:
         d_gp: full-size grid array (only this rank's latitude rows are written)."""
         self._buffers(nf)
         tr, h = self.trans, self.trans._h
+        if self.exchange == "peer":
+            _lib.check(_lib.lib.sptrans_invtrans_sharded(h, int(nf), _ptr(d_spec), _ptr(d_gp)))
+            return
         tr.invtrans_legendre(nf, self.T, d_spec, self.fb)
         _lib.check(_lib.lib.sptrans_exchange_pack(h, nf, 0, _ptr(self.fb), _ptr(self.buf_m)))
         k = 2 * nf
@@ -101,6 +130,9 @@ class ShardedTrans:
         """d_gp: grid array whose rows of this rank's band are valid; d_spec: spectral array, this rank's m written."""
         self._buffers(nf)
         tr, h = self.trans, self.trans._h
+        if self.exchange == "peer":
+            _lib.check(_lib.lib.sptrans_dirtrans_sharded(h, int(nf), _ptr(d_gp), _ptr(d_spec)))
+            return
         tr.dirtrans_fourier(nf, d_gp, self.fb)
         _lib.check(_lib.lib.sptrans_exchange_pack(h, nf, 1, _ptr(self.fb), _ptr(self.buf_b)))
         k = 2 * nf
@@ -129,7 +161,7 @@ def bench_sharded(args, rank, world, local_rank, metric, unit, fp64_peak):
 
     gridname, T, nf = B.workload(args.workload)
     grid = Grid(gridname)
-    st = ShardedTrans(grid, T, local_rank)
+    st = ShardedTrans(grid, T, local_rank, exchange=args.exchange)
     npts = grid.size()
     d_sp = torch.from_numpy(H.synthetic_spectra(T, nf)).to(st.device)
     d_gp = torch.zeros(nf * npts, dtype=torch.float64, device=st.device)
@@ -156,6 +188,17 @@ def bench_sharded(args, rank, world, local_rank, metric, unit, fp64_peak):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = torch.tensor([st.trans.kernel_launches() - launches0], device=st.device, dtype=torch.float64)
     dist.all_reduce(launches)
+    # stage times of the last inverse + direct pair on every rank (outside the timed region)
+    stage = torch.zeros(6, device=st.device, dtype=torch.float64)
+    if args.exchange == "peer":
+        st.invtrans(nf, d_sp, d_gp)
+        ti = st.trans.last_timings()
+        st.dirtrans(nf, d_gp, d_sp2)
+        td = st.trans.last_timings()
+        stage = torch.tensor([ti["legendre"], ti["exchange_wait"], ti["fourier"], td["fourier"], td["exchange_wait"], td["legendre"]],
+                             device=st.device, dtype=torch.float64)
+    stage_all = [torch.zeros_like(stage) for _ in range(world)]
+    dist.all_gather(stage_all, stage)
     # correctness of the sharded round trip: every rank owns some m; gather spectra and compare on rank 0
     owner, band, _, _ = shard_layout(grid, T, rank, world)
     if rank == 0:
@@ -166,11 +209,15 @@ def bench_sharded(args, rank, world, local_rank, metric, unit, fp64_peak):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload} L{nf} invtrans+dirtrans fp64 (grid {gridname}, T{T})",
-                       "parallelism": f"zonal-wavenumber sharded Legendre x latitude-band sharded Fourier over {world} GPUs, "
-                                      "one NCCL all-to-all per direction; grid fields stay band-distributed",
+                       "parallelism": f"zonal-wavenumber sharded Legendre x latitude-band sharded Fourier over {world} GPUs; "
+                                      + ("exchange fused into the kernels over NVLink peer memory (Legendre epilogue stores / "
+                                         "push kernel, device-side barrier)" if args.exchange == "peer"
+                                         else "one NCCL all-to-all per direction") + "; grid fields stay band-distributed",
                        "l2": "inputs larger than L2"},
             "clocks": clocks, "gpu_launches": int(launches.item()),
             "e2e": None, "roofline": None, "cpu_baseline": None,
+            "stage_ms_per_rank": {k: [round(float(x[i]), 3) for x in stage_all] for i, k in enumerate(
+                ["inv_legendre", "inv_exchange_wait", "inv_fourier", "dir_fourier_push", "dir_exchange_wait", "dir_legendre"])},
         }
         print(json.dumps(out))
     dist.destroy_process_group()

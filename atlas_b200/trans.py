@@ -102,7 +102,7 @@ class Trans:
         out = (C.c_float * 8)()
         _lib.check(_lib.lib.sptrans_last_timings(self._h, out))
         t = list(out)
-        return {"pack": t[0], "legendre": t[1], "fourier": t[2], "h2d": t[3], "d2h": t[4]}
+        return {"pack": t[0], "legendre": t[1], "fourier": t[2], "h2d": t[3], "d2h": t[4], "exchange_wait": t[5]}
 
     def set_precision(self, name):
         """'fp64' (default, DMMA) or 'tc' (tcgen05 split-TF32 Legendre stage, fp32-level accuracy)."""

@@ -57,14 +57,33 @@ def legendre_flops(nlat0, T, nleg, nf, trunc):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line): NVML polled
+    every 10 ms from a thread of this process (nvidia_ml_py), nvidia-smi -lms as the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.bits = [], [], 0
         self.proc = None
+        self.nvml = None
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self._poll_once()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
@@ -75,24 +94,51 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_once(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            self.bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+
+    def _poll(self):
+        while not self._stop.wait(0.01):
+            try:
+                self._poll_once()
+            except Exception:
+                break
+
     def _read(self):
+        names = {3: 0x8, 4: 0x40, 5: 0x20, 6: 0x4}
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 7 and r[0].replace(".", "").isdigit():
+                self.sm.append(float(r[0]))
+                self.mx.append(float(r[1]))
+                for i, bit in names.items():
+                    if r[i].lower().startswith("active"):
+                        self.bits |= bit
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        self._stop.set()
+        if self.nvml is not None:
+            try:
+                self._poll_once()
+            except Exception:
+                pass
+            self.thread.join(timeout=1)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": reasons, "samples": len(self.sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def run_reference(args, rank, world):
@@ -144,6 +190,8 @@ def main():
     ap.add_argument("--cpu-fields", type=int, default=16, help="fields in the bounded CPU sample")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "tc"],
                     help="Legendre arithmetic: fp64 DMMA (headline) or tcgen05 split-TF32 (BASELINE config 4; fp32-level accuracy)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer-memory exchange fused into the kernels (default) or one NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

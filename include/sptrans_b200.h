@@ -194,8 +194,37 @@ int sptrans_exchange_rows(const sptrans_plan* plan, long long* m_side_rows, long
 int sptrans_exchange_pack(sptrans_plan* plan, int nb_fields, int side, const double* d_fourier, double* d_buf);
 int sptrans_exchange_unpack(sptrans_plan* plan, int nb_fields, int side, const double* d_buf, double* d_fourier);
 
+
+/* ---- peer-memory exchange (default multi-GPU path on one NVLink / NVSwitch node, <= 8 ranks) ----------------
+ * Every rank allocates one region [flags | exchange buffer 0 | exchange buffer 1] and maps the regions of all
+ * peers (CUDA IPC: the 64-byte handles travel over whatever the host uses -- MPI in atlas, torch.distributed
+ * here; or plain device pointers when the host already shares memory).  After that a sharded transform is ONE
+ * stream-ordered call per rank, with no host synchronisation and no collective library:
+ *   inverse: the Legendre GEMM stores every output row straight into the Fourier-side buffer of the rank that
+ *            owns its latitude band (NVLink stores from the GEMM epilogue) -> device-side barrier -> Fourier;
+ *   direct : Fourier -> rows pushed to the owners of their zonal wavenumber -> device-side barrier -> Legendre.
+ * Calls are collective: every rank must issue the same sequence.  d_* are device pointers; the grid-point
+ * array is full size, only the rows of this rank's latitude band are read/written; the spectral array is full
+ * size, only this rank's zonal wavenumbers are read/written. */
+#define SPTRANS_IPC_HANDLE_BYTES 64
+int sptrans_peer_alloc(sptrans_plan* plan, int nb_fields, unsigned char* ipc_handle_out /* 64 bytes or NULL */);
+int sptrans_peer_attach_ipc(sptrans_plan* plan, int nranks, const unsigned char* handles /* nranks x 64 bytes */);
+int sptrans_peer_attach_ptrs(sptrans_plan* plan, int nranks, void* const* regions /* from sptrans_peer_region */);
+int sptrans_peer_region(const sptrans_plan* plan, void** region, size_t* bytes);
+int sptrans_peer_buffer(const sptrans_plan* plan, double** d_fourier);   /* local exchange buffer in use */
+int sptrans_peer_free(sptrans_plan* plan);
+int sptrans_invtrans_sharded(sptrans_plan* plan, int nb_fields, const double* d_spectra, double* d_gp);
+int sptrans_dirtrans_sharded(sptrans_plan* plan, int nb_fields, const double* d_gp, double* d_spectra);
+/* the halves of the two calls above, for hosts that sequence the stages themselves (tests emulate N ranks on
+ * one GPU this way): produce into the peers' buffers / barrier kernel / flip to the other buffer pair */
+int sptrans_invtrans_legendre_peers(sptrans_plan* plan, int nb_fields, const double* d_spectra);
+int sptrans_dirtrans_fourier_peers(sptrans_plan* plan, int nb_fields, const double* d_gp);
+int sptrans_peer_barrier(sptrans_plan* plan);
+int sptrans_peer_advance(sptrans_plan* plan);
+
 /* kernel time of the last call's stages in milliseconds (CUDA events on the plan's stream):
- * out[0]=pack/unpack+vd2uv, out[1]=Legendre GEMM, out[2]=Fourier, out[3]=H2D, out[4]=D2H */
+ * out[0]=pack/unpack+vd2uv, out[1]=Legendre GEMM, out[2]=Fourier, out[3]=H2D, out[4]=D2H,
+ * out[5]=wait at the exchange barrier (sharded calls; these read their events lazily here) */
 int sptrans_last_timings(const sptrans_plan* plan, float out_ms[8]);
 /* number of kernels this library launched on behalf of the plan since creation */
 uint64_t sptrans_kernel_launches(const sptrans_plan* plan);

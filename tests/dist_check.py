@@ -19,14 +19,23 @@ from atlas_b200.dist import ShardedTrans  # noqa: E402
 
 def main():
     gridname, T, nf = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    exchange = sys.argv[4] if len(sys.argv) > 4 else "peer"
     rank = int(os.environ["RANK"])
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     grid = atlas_b200.Grid(gridname)
-    st = ShardedTrans(grid, T, local)
+    st = ShardedTrans(grid, T, local, exchange=exchange)
     sp = H.synthetic_spectra(T, nf)
     d_sp = torch.from_numpy(sp).cuda()
+    # three back-to-back round trips without host synchronisation in between: exercises the alternation of the
+    # two exchange buffers and the barrier epochs of the peer-memory path; the last one is checked
+    for it in range(3):
+        d_gp = torch.zeros(nf * grid.size(), dtype=torch.float64, device="cuda")
+        st.invtrans(nf, d_sp, d_gp)
+        d_tmp = torch.zeros_like(d_sp)
+        st.dirtrans(nf, d_gp, d_tmp)
+    torch.cuda.synchronize()
     d_gp = torch.zeros(nf * grid.size(), dtype=torch.float64, device="cuda")
     st.invtrans(nf, d_sp, d_gp)
     st.gather_grid(nf, d_gp)  # disjoint rows summed with zeros elsewhere
@@ -43,7 +52,7 @@ def main():
         want_sp = plan.dirtrans(nf, want)
         e2 = H.rel_max(d_sp2.cpu().numpy(), want_sp)
         ok = e1 < 1e-12 and e2 < 1e-12
-        print(f"DIST_CHECK world={dist.get_world_size()} {gridname} T{T} nf={nf}: invtrans rel err {e1:.2e}, dirtrans rel err {e2:.2e} -> {'OK' if ok else 'FAIL'}")
+        print(f"DIST_CHECK world={dist.get_world_size()} exchange={exchange} {gridname} T{T} nf={nf}: invtrans rel err {e1:.2e}, dirtrans rel err {e2:.2e} -> {'OK' if ok else 'FAIL'}")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

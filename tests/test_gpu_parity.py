@@ -425,6 +425,74 @@ def test_sharded_path_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
     assert H.rel_max(d_back.cpu().numpy(), plan.dirtrans(nf, want)) < TOL_MAX
 
 
+@pytest.mark.parametrize("gridname,T,nf,R", [("O48", 47, 5, 2), ("O80", 79, 4, 3), ("F24", 23, 3, 1), ("O48", 47, 137, 4)])
+def test_peer_memory_exchange_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
+    """The peer-memory exchange with all R ranks living on one device: every plan's exchange region is handed to the
+    others as plain pointers (sptrans_peer_attach_ptrs), the inverse Legendre kernel stores each row into the buffer of
+    the rank that owns its latitude band, the direct transform pushes rows to the owner of their zonal wavenumber.
+    The stages of the R ranks are sequenced on one stream here (the cross-GPU barrier is covered by test_gpu_dist)."""
+    import ctypes as C
+
+    import atlas_b200
+    from atlas_b200 import _lib
+    from atlas_b200.trans import _ptr
+    from oracle import pyoracle as po
+
+    torch = torch_cuda
+    lib = _lib.lib
+    grid = atlas_b200.Grid(gridname)
+    plans = [atlas_b200.Trans(grid, T, rank=r, nranks=R) for r in range(R)]
+    stream = torch.cuda.current_stream().cuda_stream
+    regions = (C.c_void_p * R)()
+    for r, t in enumerate(plans):
+        t.set_stream(stream)
+        _lib.check(lib.sptrans_peer_alloc(t._h, nf, None))
+        reg = C.c_void_p()
+        _lib.check(lib.sptrans_peer_region(t._h, C.byref(reg), None))
+        regions[r] = reg
+    for t in plans:
+        _lib.check(lib.sptrans_peer_attach_ptrs(t._h, R, regions))
+    sp = H.synthetic_spectra(T, nf)
+    d_sp = torch.from_numpy(sp).cuda()
+    kw = dict(dtype=torch.float64, device="cuda")
+    plan = po.OraclePlan(grid.nx(), grid.y(), T, regular=grid.regular, weights=grid.weights())
+    want = plan.invtrans(nf, sp, mode=2)
+    want_sp = plan.dirtrans(nf, want)
+
+    def local_buffer(t):
+        b = C.c_void_p()
+        _lib.check(lib.sptrans_peer_buffer(t._h, C.byref(b)))
+        return b
+
+    for it in range(3):  # both exchange buffers are used, and reused
+        d_gp = torch.full((nf * grid.size(),), float("nan"), **kw)
+        for t in plans:
+            _lib.check(lib.sptrans_invtrans_legendre_peers(t._h, nf, _ptr(d_sp)))
+        for t in plans:
+            _lib.check(lib.sptrans_invtrans_fourier(t._h, nf, T - 1, local_buffer(t), _ptr(d_gp), 0))
+            _lib.check(lib.sptrans_peer_advance(t._h))
+        assert H.rel_max(d_gp.cpu().numpy(), want) < TOL_MAX
+        d_back = torch.full_like(d_sp, float("nan"))
+        for t in plans:
+            _lib.check(lib.sptrans_dirtrans_fourier_peers(t._h, nf, _ptr(d_gp)))
+        for t in plans:
+            _lib.check(lib.sptrans_dirtrans_legendre(t._h, nf, local_buffer(t), _ptr(d_back)))
+            _lib.check(lib.sptrans_peer_advance(t._h))
+        assert H.rel_max(d_back.cpu().numpy(), want_sp) < TOL_MAX
+    if R == 1:  # the whole stream-ordered call, barrier kernel included (trivial with one rank)
+        d_gp = torch.full((nf * grid.size(),), float("nan"), **kw)
+        d_back = torch.full_like(d_sp, float("nan"))
+        _lib.check(lib.sptrans_invtrans_sharded(plans[0]._h, nf, _ptr(d_sp), _ptr(d_gp)))
+        _lib.check(lib.sptrans_dirtrans_sharded(plans[0]._h, nf, _ptr(d_gp), _ptr(d_back)))
+        torch.cuda.synchronize()
+        assert H.rel_max(d_gp.cpu().numpy(), want) < TOL_MAX
+        assert H.rel_max(d_back.cpu().numpy(), want_sp) < TOL_MAX
+        tm = plans[0].last_timings()
+        assert tm["legendre"] > 0 and tm["fourier"] > 0
+    for t in plans:
+        _lib.check(lib.sptrans_peer_free(t._h))
+
+
 @pytest.mark.parametrize("gridname,T,nf", [("O32", 31, 4), ("O48", 47, 137), ("O160", 159, 20), ("F24", 23, 3)])
 def test_tensor_core_split_tf32_legendre(gridname, T, nf):
     """BASELINE config 4: Legendre stage on tcgen05 (kind::tf32, operands split hi+lo, fp32 accumulation in TMEM).

@@ -220,6 +220,8 @@ int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, con
     if ((rc = upload(p.d_rowoff, g.rowoff, p.stream))) return fail(rc);
     if ((rc = upload(p.d_nx, g.nx, p.stream))) return fail(rc);
     if ((rc = upload(p.d_my_m, g.my_m, p.stream))) return fail(rc);
+    if ((rc = upload(p.d_owner, g.owner, p.stream))) return fail(rc);
+    if ((rc = upload(p.d_pair_done, std::vector<int>(std::max(g.nleg, 1), 0), p.stream))) return fail(rc);
     {
         std::vector<double> ci(g.nleg), c(g.nleg);
         for (int j = 0; j < g.nleg; ++j) {
@@ -272,7 +274,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     free_fft_tables(p);
     tc_free(p);
     peer_release(p);
-    void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_weights,
+    void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_owner, p.d_pair_done, p.d_weights,
                     p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
                     p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
                     p.d_gp};
@@ -948,10 +950,9 @@ int sptrans_dirtrans_fourier_peers(sptrans_plan* plan, int nf, const double* d_g
         set_error("sptrans_dirtrans_fourier_peers: null grid-point array");
         return SPTRANS_ERR_INVALID;
     }
-    double* local = make_peer_dst(p).base[p.g.rank];
-    if ((rc = launch_fourier_dir(p, nf, d_gp, local, 0))) return rc;
-    cudaEventRecord(p.ev[6], p.stream);
-    return launch_exchange_push(p, nf);
+    bool fused = false;
+    if ((rc = launch_fourier_dir_peers(p, nf, d_gp, make_peer_dst(p), &fused))) return rc;
+    return fused ? SPTRANS_OK : launch_exchange_push(p, nf);
 }
 
 int sptrans_invtrans_sharded(sptrans_plan* plan, int nf, const double* d_spectra, double* d_gp) {
@@ -984,7 +985,7 @@ int sptrans_dirtrans_sharded(sptrans_plan* plan, int nf, const double* d_gp, dou
     Plan& p = plan->p;
     int rc;
     cudaEventRecord(p.ev[0], p.stream);
-    if ((rc = sptrans_dirtrans_fourier_peers(plan, nf, d_gp))) return rc;   // records ev[6] between fourier and push
+    if ((rc = sptrans_dirtrans_fourier_peers(plan, nf, d_gp))) return rc;
     cudaEventRecord(p.ev[1], p.stream);
     if ((rc = launch_peer_barrier(p))) return rc;
     cudaEventRecord(p.ev[2], p.stream);

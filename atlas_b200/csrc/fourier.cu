@@ -191,13 +191,42 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     }
 }
 
+// Rows (m <= L, parity) of one latitude pair: local exchange buffer -> buffer of the rank that owns m.
+// One warp per row, up to 5 x 16 B per lane in flight; the rows were written by other blocks, so they are read
+// through L2 (ld.cg).
+__device__ __forceinline__ void push_pair_rows(int pair, int L, int nf, const double2* __restrict__ fb,
+                                               const long long* __restrict__ fb_rowoff, const int* __restrict__ nlat0,
+                                               int nleg, const int* __restrict__ owner, const PeerDst& dst, int me) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    constexpr int kU = 5;
+    for (int r = warp; r < 2 * (L + 1); r += nw) {
+        const int m = r >> 1, par = r & 1;
+        const int o = owner[m];
+        if (o == me) continue;
+        const int n0 = nlat0[m];
+        const long long row = fb_rowoff[m] + static_cast<long long>(par) * (nleg - n0) + (pair - n0);
+        const double2* src = fb + row * nf;
+        double2* out = reinterpret_cast<double2*>(dst.base[o]) + row * nf;
+        for (int i0 = lane; i0 < nf; i0 += 32 * kU) {
+            double2 v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (i0 + 32 * u < nf) v[u] = __ldcg(src + i0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (i0 + 32 * u < nf) out[i0 + 32 * u] = v[u];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(2 * kFftThreads, 1)
 fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ blocks, int nf,
                    int nb_uv, const double* __restrict__ gp, long long npts, const long long* __restrict__ fb_rowoff,
                    const int* __restrict__ nlat0, int nleg, const ScheduleG* __restrict__ scheds, const double2* __restrict__ twid,
                    const double2* __restrict__ chirp, const double2* __restrict__ filt,
                    const double* __restrict__ weights, const double* __restrict__ coslat, double2* __restrict__ fb,
-                   int adjoint) {
+                   int adjoint, const int* __restrict__ owner, const __grid_constant__ PeerDst dst, int me,
+                   int* __restrict__ pair_done) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
     const int pair = bd.x, f0 = bd.y;
@@ -256,6 +285,26 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
         const long long ia = is + static_cast<long long>(nleg - n0) * nf;
         fb[is] = s;
         fb[ia] = a;
+    }
+    if (owner) {
+        // sharded plan: every row belongs to the rank that owns its zonal wavenumber.  The block that completes a
+        // latitude pair (all field groups done) ships the pair's rows -- nf double2 = whole rows, so the NVLink
+        // stores are long and coalesced -- while the other SMs keep transforming: the exchange hides behind the FFTs.
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int nblk = (nf + pm.F - 1) / pm.F;
+            const int done = atomicAdd(pair_done + pair, 1);
+            s_last = (done == nblk - 1);
+            if (s_last) pair_done[pair] = 0;  // ready for the next call
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            push_pair_rows(pair, L, nf, fb, fb_rowoff, nlat0, nleg, owner, dst, me);
+            __threadfence_system();  // remote rows are visible to the peers before this kernel completes
+        }
     }
 }
 
@@ -627,7 +676,8 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
     return SPTRANS_OK;
 }
 
-int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint) {
+static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint,
+                                   const int* d_owner, const PeerDst& dst) {
     if (!p.d_weights && !adjoint) {
         set_error("dirtrans: plan was created without quadrature weights");
         return SPTRANS_ERR_INVALID;
@@ -650,11 +700,25 @@ int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, i
         fourier_dir_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
             p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
-            reinterpret_cast<double2*>(d_fourier), adjoint);
+            reinterpret_cast<double2*>(d_fourier), adjoint, d_owner, dst, p.g.rank, p.d_pair_done);
         p.launches++;
         SPT_CUDA(cudaGetLastError());
     }
     return SPTRANS_OK;
+}
+
+int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint) {
+    return launch_fourier_dir_impl(p, nf, d_gp, d_fourier, nb_uv, adjoint, nullptr, PeerDst{});
+}
+
+int launch_fourier_dir_peers(Plan& p, int nf, const double* d_gp, const PeerDst& dst, bool* fused) {
+    int rc = ensure_block_lists(p, nf);
+    if (rc) return rc;
+    const FftGroups& grp = g_groups[&p];
+    bool rows = false;
+    for (size_t gi = 0; gi < grp.pairs.size(); ++gi) rows = rows || (grp.mode[gi] && grp.nblocks[gi] > 0);
+    *fused = !rows;
+    return launch_fourier_dir_impl(p, nf, d_gp, dst.base[p.g.rank], 0, 0, rows ? nullptr : p.d_owner, dst);
 }
 
 }  // namespace sptrans

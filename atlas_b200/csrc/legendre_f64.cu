@@ -179,9 +179,7 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
                     for (int i = 0; i < kMI; ++i) {
                         if (row_w + 8 * i < tl.m_valid) {
 #pragma unroll
-                            for (int j = 0; j < kNJ; ++j)
-                                if (col_w + 8 * j < tl.n_valid)  // warp-uniform: skip 8-column groups past the last field
-                                    dmma884(acc[i][j][0], acc[i][j][1], a[ks & 1][i], b[ks & 1][j]);
+                            for (int j = 0; j < kNJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[ks & 1][i], b[ks & 1][j]);
                         }
                     }
                 }
@@ -227,18 +225,23 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
 // spectra [m][n][re/im][fld]  ->  packed [m][p][k][2 fld + re/im], rows k >= K_eff (and whole blocks with
 // m >= trunc) are zero: this is the split + zero padding of TransLocal.cc:970-1003, including the
 // `jn <= truncation && jm < truncation` rule (:982) that drops the m == truncation column.
-__global__ void pack_spectra_kernel(int T, int nf, int trunc, const long long* __restrict__ sp_rowoff,
+constexpr int kPackRows = 16;  // rows of one (m, parity) block per CTA: keeps the m = 0 blocks from being the long pole
+
+__global__ void pack_spectra_kernel(int /*T*/, int nf, int trunc, const long long* __restrict__ sp_rowoff,
                                     const int* __restrict__ my_m, const double* __restrict__ spec,
                                     double* __restrict__ packed) {
     const int m = my_m[blockIdx.x];
     const int p = blockIdx.y;
     const long long row0 = sp_rowoff[2 * m + p];
     const int rows = static_cast<int>(sp_rowoff[2 * m + p + 1] - row0);
+    const int k0 = blockIdx.z * kPackRows;
+    if (k0 >= rows) return;
+    const int kn = min(kPackRows, rows - k0);
     const int ld = 2 * nf;
     const long long ioff = static_cast<long long>(2 * trunc + 3 - m) * m / 2 * nf * 2;  // reference :970
-    for (long long e = threadIdx.x; e < static_cast<long long>(rows) * ld; e += blockDim.x) {
-        const int k = static_cast<int>(e / ld);
-        const int r = static_cast<int>(e % ld);
+    for (int e = threadIdx.x; e < kn * ld; e += blockDim.x) {
+        const int k = k0 + e / ld;
+        const int r = e % ld;
         // read order: field fastest within (k, imag) so that global loads coalesce
         const int imag = r / nf, f = r % nf;
         const int n = m + p + 2 * k;
@@ -256,11 +259,14 @@ __global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict
     const int p = blockIdx.y;
     const long long row0 = sp_rowoff[2 * m + p];
     const int K = (T - m + (p ? 1 : 2)) / 2;  // n <= T
+    const int k0 = blockIdx.z * kPackRows;
+    if (k0 >= K) return;
+    const int kn = min(kPackRows, K - k0);
     const int ld = 2 * nf;
     const long long ioff = static_cast<long long>(2 * T + 3 - m) * m / 2 * nf * 2;
-    for (long long e = threadIdx.x; e < static_cast<long long>(K) * ld; e += blockDim.x) {
-        const int k = static_cast<int>(e / ld);
-        const int r = static_cast<int>(e % ld);
+    for (int e = threadIdx.x; e < kn * ld; e += blockDim.x) {
+        const int k = k0 + e / ld;
+        const int r = e % ld;
         const int imag = r / nf, f = r % nf;
         const int n = m + p + 2 * k;
         double v = packed[(row0 + k) * ld + 2 * f + imag];
@@ -276,7 +282,6 @@ __global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict
 int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
     if (p.tiles_nf == nf && p.tiles_trunc == trunc && p.tiles_dir_trunc == dir_trunc) return SPTRANS_OK;
     const HostGeom& g = p.g;
-    const int T = g.T;
     const int ld = 2 * nf;
     struct Keyed {
         double cost;
@@ -359,7 +364,7 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
 int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed) {
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
-    dim3 grid(nm, 2);
+    dim3 grid(nm, 2, (round_up(p.g.T / 2 + 2, kBK) + kPackRows - 1) / kPackRows);
     pack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, trunc, p.d_sp_rowoff, p.d_my_m, d_spec, d_packed);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
@@ -369,7 +374,7 @@ int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double
 int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec, int drop_mT) {
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
-    dim3 grid(nm, 2);
+    dim3 grid(nm, 2, (p.g.T / 2 + 1 + kPackRows - 1) / kPackRows);
     unpack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, p.d_sp_rowoff, p.d_my_m, d_packed, d_spec, drop_mT);
     p.launches++;
     SPT_CUDA(cudaGetLastError());

@@ -472,7 +472,6 @@ int tc_build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
     TcState* s = tc_state(p);
     if (s->nf == nf && s->trunc == trunc && s->dir_trunc == dir_trunc) return SPTRANS_OK;
     const HostGeom& g = p.g;
-    const int T = g.T;
     const int n_tot = n_total_cols(nf);
     if (n_tot > kTcMaxN) {
         set_error("tensor-core Legendre path: at most 256 fields per call (512 TMEM columns)");

@@ -143,6 +143,8 @@ struct Plan {
     double* d_uvscale = nullptr;       // [nleg] 1/(a cos(lat)): wind -> scaled wind of the direct vor/div transform
     long long* d_sp_rowoff = nullptr;  // [2(T+1)+1]
     int* d_my_m = nullptr;             // [my_m.size()]
+    int* d_owner = nullptr;            // [T+1] rank that owns zonal wavenumber m
+    int* d_pair_done = nullptr;        // [nleg] field-group blocks finished per latitude pair (sharded direct Fourier)
     // FFT tables
     std::vector<FftLen> fft_len;       // distinct lengths
     std::vector<int> pair_len_idx;     // [nleg] -> index into fft_len
@@ -231,6 +233,10 @@ int build_fft_tables(Plan& p);
 void free_fft_tables(Plan& p);
 int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv);
 int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint = 0);
+// sharded direct transform: every output row is stored into the exchange buffer of the rank that owns its zonal
+// wavenumber (NVLink stores).  *fused = false if the plan has row-mode groups, which write the local buffer only
+// (the caller then pushes the rows with launch_exchange_push)
+int launch_fourier_dir_peers(Plan& p, int nf, const double* d_gp, const PeerDst& dst, bool* fused);
 
 // ---- exchange.cu ----
 int launch_exchange_copy(Plan& p, int nf, const ExSeg* d_segs, int nseg, double* d_fourier, double* d_buf, bool gather);

@@ -199,11 +199,86 @@ def bench_sharded(args, rank, world, local_rank, metric, unit, fp64_peak):
                              device=st.device, dtype=torch.float64)
     stage_all = [torch.zeros_like(stage) for _ in range(world)]
     dist.all_gather(stage_all, stage)
-    # correctness of the sharded round trip: every rank owns some m; gather spectra and compare on rank 0
+    # steady-state duration of the two calls on every rank (back to back, no host synchronisation), again untimed
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    dist.barrier()
+    for e in evs:
+        e[0].record()
+        st.invtrans(nf, d_sp, d_gp)
+        e[1].record()
+        st.dirtrans(nf, d_gp, d_sp2)
+        e[2].record()
+    torch.cuda.synchronize()
+    calls = torch.tensor([float(np.median([e[0].elapsed_time(e[1]) for e in evs])), float(np.median([e[1].elapsed_time(e[2]) for e in evs]))],
+                         device=st.device, dtype=torch.float64)
+    calls_all = [torch.zeros_like(calls) for _ in range(world)]
+    dist.all_gather(calls_all, calls)
     owner, band, _, _ = shard_layout(grid, T, rank, world)
+    # ---- end to end with pinned HOST buffers: every rank moves its own share (the spectra of its zonal wavenumbers,
+    # the grid rows of its latitude band) over its own PCIe link, inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        rowoff = np.concatenate([[0], np.cumsum(grid.nx(), dtype=np.int64)])
+        nlat = grid.ny()
+        j0, j1 = int(band[rank]), int(band[rank + 1])
+        spans = [(int(rowoff[j0]), int(rowoff[j1])), (int(rowoff[nlat - j1]), int(rowoff[nlat - j0]))]
+        if spans[0][1] > spans[1][0]:   # band contains the equator row of an odd grid: one span
+            spans = [(spans[0][0], spans[1][1])]
+        my_m = [m for m in range(T + 1) if owner[m] == rank]
+        chunks = [((2 * T + 3 - m) * m // 2 * nf * 2, (T - m + 1) * 2 * nf) for m in my_m]
+        h_sp = torch.from_numpy(H.synthetic_spectra(T, nf)).pin_memory()
+        h_sp2 = torch.zeros_like(h_sp).pin_memory()
+        h_gp = [torch.zeros(nf, b - a, dtype=torch.float64).pin_memory() for a, b in spans]
+        gp2d = d_gp.view(nf, npts)
+
+        def e2e_step():
+            for off, n in chunks:
+                d_sp[off:off + n].copy_(h_sp[off:off + n], non_blocking=True)
+            st.invtrans(nf, d_sp, d_gp)
+            for (a, b), h in zip(spans, h_gp):
+                h.copy_(gp2d[:, a:b], non_blocking=True)
+            for (a, b), h in zip(spans, h_gp):
+                gp2d[:, a:b].copy_(h, non_blocking=True)
+            st.dirtrans(nf, d_gp, d_sp2)
+            for off, n in chunks:
+                h_sp2[off:off + n].copy_(d_sp2[off:off + n], non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        g1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ems = torch.tensor([g0.elapsed_time(g1)], device=st.device, dtype=torch.float64)
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        nbytes = torch.tensor([8.0 * (sum(n for _, n in chunks) + nf * sum(b - a for a, b in spans))], device=st.device, dtype=torch.float64)
+        dist.all_reduce(nbytes)
+        e2e_ms = float(ems.item()) / args.steps
+        e2e = {"value": 1e3 / e2e_ms, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(nbytes.item()),
+               "d2h_bytes_per_step": int(nbytes.item()),
+               "note": "bytes summed over ranks; every rank copies its own shard from/to pinned host memory"}
     if rank == 0:
         clocks = sampler.stop()
         ms_per_step = float(ms.item()) / args.steps
+        roofline = None
+        if args.exchange == "peer":
+            nlat0 = st.trans.nlat0()
+            nleg = (grid.ny() + 1) // 2
+            fl = [B.legendre_flops(nlat0, T, nleg, nf, T, [m for m in range(T + 1) if owner[m] == 0]),
+                  sum(2.0 * nf * (1 if m == 0 else 2) * (T - m + 1) * max(0, nleg - int(nlat0[m])) for m in range(T + 1) if owner[m] == 0)]
+            leg = [float(stage_all[0][0]), float(stage_all[0][5])]
+            ach = (fl[0] + fl[1]) / ((leg[0] + leg[1]) * 1e-3) / 1e12
+            roofline = {"kernel": "legendre_dmma_kernel<inverse + peer stores | direct> on rank 0 (its share of the zonal wavenumbers; "
+                                  "launch time includes the spectra pack / unpack kernel)",
+                        "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                        "traffic": None, "flops_per_launch": {"inverse": fl[0], "direct": fl[1]},
+                        "ms_per_launch": {"inverse": leg[0], "direct": leg[1]}, "share_of_step": (leg[0] + leg[1]) / ms_per_step,
+                        "peak_source": "fp64 DMMA/DFMA microbenchmark on this pool's B200 (profiles/microbench_f64_r01.txt)"}
         out = {
             "metric": metric, "value": 1e3 / ms_per_step, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -215,9 +290,10 @@ def bench_sharded(args, rank, world, local_rank, metric, unit, fp64_peak):
                                          else "one NCCL all-to-all per direction") + "; grid fields stay band-distributed",
                        "l2": "inputs larger than L2"},
             "clocks": clocks, "gpu_launches": int(launches.item()),
-            "e2e": None, "roofline": None, "cpu_baseline": None,
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": None,
             "stage_ms_per_rank": {k: [round(float(x[i]), 3) for x in stage_all] for i, k in enumerate(
                 ["inv_legendre", "inv_exchange_wait", "inv_fourier", "dir_fourier_push", "dir_exchange_wait", "dir_legendre"])},
+            "call_ms_per_rank": {"invtrans": [round(float(x[0]), 3) for x in calls_all], "dirtrans": [round(float(x[1]), 3) for x in calls_all]},
         }
-        print(json.dumps(out))
     dist.destroy_process_group()
+    return out if rank == 0 else None

@@ -43,11 +43,12 @@ def workload(name):
     return table[name]
 
 
-def legendre_flops(nlat0, T, nleg, nf, trunc):
+def legendre_flops(nlat0, T, nleg, nf, trunc, ms=None):
     """Algorithmic (pruned) Legendre flops of one direction, SURVEY 8(d):
-    sum_m 2 * (nf * nimag(m)) * (K_s + K_a) * (nleg - nlat0[m]) with K counted up to `trunc`."""
+    sum_m 2 * (nf * nimag(m)) * (K_s + K_a) * (nleg - nlat0[m]) with K counted up to `trunc`
+    (over the zonal wavenumbers `ms` of one rank, all by default)."""
     tot = 0.0
-    for m in range(T + 1):
+    for m in (range(T + 1) if ms is None else ms):
         if m >= trunc and trunc == T:  # scalar inverse drops m == T (TransLocal.cc:982)
             continue
         nimag = 1 if m == 0 else 2
@@ -177,10 +178,28 @@ def run_reference(args, rank, world):
                          "sample": f"{nfs} of {nf} fields, full grid, inv+dir, time scaled x{nf}/{nfs}; plan setup {setup_s:.1f}s untimed"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit_json(out)
+
+
+_JSON_FD = None
+
+
+def emit_json(obj):
+    """The ONE JSON line of the contract, on the real stdout (libraries that chat on fd 1, e.g. NCCL's version
+    banner, are diverted to stderr by main())."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -216,7 +235,10 @@ def main():
 
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        return spdist.bench_sharded(args, rank, world, local_rank, METRIC, UNIT, FP64_DMMA_PEAK_TFLOPS)
+        out = spdist.bench_sharded(args, rank, world, local_rank, METRIC, UNIT, FP64_DMMA_PEAK_TFLOPS)
+        if out is not None:
+            emit_json(out)
+        return
 
     torch.cuda.set_device(0)
     gridname, T, nf = workload(args.workload)
@@ -373,7 +395,7 @@ def main():
         "stage_ms": {"pack_inv": float(np.mean([a for a, _ in pack_ms])), "unpack_dir": float(np.mean([b for _, b in pack_ms])),
                      "legendre_inv": leg_inv, "legendre_dir": leg_dir, "fourier_inv": f_inv, "fourier_dir": f_dir},
     }
-    print(json.dumps(out))
+    emit_json(out)
 
 
 if __name__ == "__main__":

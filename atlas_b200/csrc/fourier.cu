@@ -16,27 +16,12 @@
 #include <map>
 #include <vector>
 
+#include "fft2_core.cuh"
 #include "fft_core.cuh"
+#include "fourier_types.hpp"
 #include "plan.hpp"
 
 namespace sptrans {
-
-struct PairMeta {
-    long long chirp_off;  // A_u (2L+1 entries) then C_i (n entries), double2 units
-    long long filt_off;   // Bhat, M entries, digit-reversed order, scaled by 1/M
-    long long rowN;       // grid offset of the northern row
-    long long rowS;       // grid offset of the southern row
-    long long tw_off;     // two-level twiddle table: Wa (M/64+1 entries) then Wb (64 entries), double2 units
-    int n;                // row length
-    int L;                // zonal truncation at this latitude (mmax[j]); -1: nothing resolved
-    int M;                // convolution length, 5-smooth, >= n + 2L
-    int has_s;            // 0 for the equator row of a grid with an odd number of latitudes
-    int F;                // fields transformed together by one block
-    int sched;            // index into the per-class pass schedules (precomputed on the host)
-    int pad_;
-    int mode;             // 0: north+south rows packed into one complex transform of length n
-                          // 1: every row on its own, even/odd samples packed, complex length n/2 (rows too long for mode 0)
-};
 
 namespace {
 
@@ -426,6 +411,97 @@ fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
     }
 }
 
+// ---- v2 kernels: register-tiled chirp-z (fft2_core.cuh) ---------------------------------------------------------------
+// One block = one latitude pair x a run of fields (transformed one after the other, the next field's inputs staged by
+// cp.async behind the current transforms).  256 threads and one block per SM for M1 >= 18 (a radix-M1 butterfly
+// needs 4 M1 registers for its data alone); 128 threads and two blocks per SM for M1 <= 16.
+__host__ __device__ constexpr int v2_threads(int M1) { return M1 <= 16 ? 128 : 256; }
+__host__ __device__ constexpr int v2_min_blocks(int M1) { return M1 <= 16 ? 2 : 1; }
+
+// per class: chirps A_u, C_i and W1[t] = e^{-2 pi i t/M}; block 0 also writes the shared T256 table
+__global__ void __launch_bounds__(256)
+chirp_tables2_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chirp, double2* __restrict__ twid,
+                     double2* __restrict__ t256) {
+    const PairMeta pm = cls[blockIdx.x];
+    const int L = pm.L, n = pm.n, M = pm.M;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    double2* A = chirp + pm.chirp_off;
+    double2* C = A + (2 * L + 1);
+    for (int u = tid; u <= 2 * L; u += nthr) {
+        double s, c;
+        sincospi(static_cast<double>(chirp_residue(u, 0, n)) / n, &s, &c);
+        A[u] = make_double2(c, s);
+    }
+    for (int i = tid; i < n; i += nthr) {
+        double s, c;
+        sincospi(static_cast<double>(chirp_residue(i, -2LL * L, n)) / n, &s, &c);
+        C[i] = make_double2(c, s);
+    }
+    for (int t = tid; t < fft2::kM2; t += nthr) {
+        double s, c;
+        sincospi(-2.0 * t / M, &s, &c);
+        twid[pm.tw_off + t] = make_double2(c, s);
+    }
+    if (blockIdx.x == 0)
+        for (int e = tid; e < 256; e += nthr) {
+            double s, c;
+            sincospi(-2.0 * ((e >> 4) * (e & 15)) / 256.0, &s, &c);
+            t256[e] = make_double2(c, s);
+        }
+}
+
+// filter spectrum of one class, in the register order of the forward machinery (runs after chirp_tables2_kernel)
+__global__ void __launch_bounds__(256, 1)
+filter_tables2_kernel(const PairMeta* __restrict__ cls, const double2* __restrict__ twid,
+                      const double2* __restrict__ t256, double2* __restrict__ filt) {
+    extern __shared__ double2 X[];
+    const PairMeta pm = cls[blockIdx.x];
+    const double2* W1 = twid + pm.tw_off;
+    double2* out = filt + pm.filt_off;
+    const int tid = threadIdx.x;
+    switch (pm.m1) {
+#define SPT_CASE(R) case R: fft2::filter_table_body<R, 256>(pm, tid, X, W1, t256, out); break;
+        SPT_CASE(8) SPT_CASE(9) SPT_CASE(10) SPT_CASE(12) SPT_CASE(15) SPT_CASE(16) SPT_CASE(18) SPT_CASE(20)
+        SPT_CASE(24) SPT_CASE(25) SPT_CASE(27) SPT_CASE(30) SPT_CASE(32)
+#undef SPT_CASE
+        default: break;
+    }
+}
+
+template <int M1>
+__global__ void __launch_bounds__(v2_threads(M1), v2_min_blocks(M1))
+fourier2_inv_kernel(const __grid_constant__ Fft2Args a, const int2* __restrict__ blocks) {
+    extern __shared__ double2 X[];
+    const int2 bd = blocks[blockIdx.x];
+    fft2::fourier2_inv_body<M1, v2_threads(M1)>(a, bd.x, bd.y, threadIdx.x, X);
+}
+
+template <int M1>
+__global__ void __launch_bounds__(v2_threads(M1), v2_min_blocks(M1))
+fourier2_dir_kernel(const __grid_constant__ Fft2Args a, const int2* __restrict__ blocks, const int* __restrict__ owner,
+                    const __grid_constant__ PeerDst dst, int me, int* __restrict__ pair_done) {
+    extern __shared__ double2 X[];
+    const int2 bd = blocks[blockIdx.x];
+    fft2::fourier2_dir_body<M1, v2_threads(M1)>(a, bd.x, bd.y, threadIdx.x, X);
+    if (owner) {  // sharded plan: the block that completes a latitude pair ships its rows to their owners (see v1)
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nblk = (a.nf + a.F - 1) / a.F;
+            const int done = atomicAdd(pair_done + bd.x, 1);
+            s_last = (done == nblk - 1);
+            if (s_last) pair_done[bd.x] = 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            push_pair_rows(bd.x, a.meta[bd.x].L, a.nf, a.fb, a.fb_rowoff, a.nlat0, a.nleg, owner, dst, me);
+            __threadfence_system();
+        }
+    }
+}
+
 // Cost model used to pick the convolution length: every pass is one read+write sweep of shared memory;
 // larger radices do more arithmetic per point.
 double pass_cost(int R) {
@@ -485,16 +561,39 @@ size_t block_smem_bytes(int M, int F) {
 }  // namespace
 
 struct FftGroups {
-    // launch groups by shared-memory footprint (so that small rows run several blocks per SM)
-    std::vector<size_t> smem;              // dynamic shared memory of the group
+    // launch groups: v1 by shared-memory footprint (so that small rows run several blocks per SM), v2 by radix
+    std::vector<size_t> smem;              // dynamic shared memory of the group (v2: inverse kernel)
+    std::vector<size_t> smem_dir;          // v2: direct kernel (its staging area holds two grid rows)
     std::vector<std::vector<int>> pairs;   // pairs per group, costliest first
-    std::vector<int> mode;                 // 0: packed north/south kernels, 1: row kernels
+    std::vector<int> mode;                 // 0: packed north/south kernels, 1: row kernels, 2: v2 kernels
+    std::vector<int> m1;                   // v2: block-level radix of the group
     int nf = -1;                           // block lists below are built for this number of fields
+    int F2 = 1;                            // v2: fields per block for this nf
     std::vector<int2*> d_blocks;
     std::vector<int> nblocks;
 };
 static std::map<Plan*, FftGroups> g_groups;
 static std::map<Plan*, std::vector<PairMeta>> g_meta;
+static std::map<Plan*, double2*> g_t256;
+
+namespace {
+int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+size_t v2_smem_inv(int M, int L) { return (static_cast<size_t>(M) + 2 * (L + 1)) * sizeof(double2); }
+size_t v2_smem_dir(int M, int n) { return static_cast<size_t>(M) * sizeof(double2) + 2 * static_cast<size_t>(n) * sizeof(double); }
+constexpr size_t kSmemLimit = 227 * 1024;
+
+template <int M1>
+int v2_set_attributes() {
+    SPT_CUDA(cudaFuncSetAttribute(fourier2_inv_kernel<M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    SPT_CUDA(cudaFuncSetAttribute(fourier2_dir_kernel<M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    return SPTRANS_OK;
+}
+}  // namespace
+
+#define SPT_V2_RADICES(X) X(8) X(9) X(10) X(12) X(15) X(16) X(18) X(20) X(24) X(25) X(27) X(30) X(32)
 
 int build_fft_tables(Plan& p) {
     HostGeom& g = p.g;
@@ -502,7 +601,13 @@ int build_fft_tables(Plan& p) {
     std::vector<PairMeta> meta(nleg);
     std::map<std::pair<int, int>, int> cls_index;
     std::vector<PairMeta> classes;
-    long long chirp_total = 0, filt_total = 0, tw_total = 0;
+    long long chirp_total = 0, filt_total = 0, tw_total = 256;  // twiddle slot 0..255: the shared T256 table of v2
+    // v2 (register-tiled) kernels: rows of even length (16-byte row starts for the cp.async staging) whose
+    // convolution fits M1 * 256; everything else (short rows, rows beyond 8192) stays on the v1 kernels
+    bool all_even = true;
+    for (int j = 0; j < g.nlat; ++j) all_even = all_even && (g.nx[j] % 2 == 0);
+    const bool use_v2 = env_int("SPTRANS_FFT_V2", 1) != 0 && all_even;
+    const int v2_min_need = env_int("SPTRANS_FFT2_MIN", 1281);
     for (int j = 0; j < nleg; ++j) {
         PairMeta pm{};
         pm.n = g.nx[j];
@@ -515,8 +620,18 @@ int build_fft_tables(Plan& p) {
             return SPTRANS_ERR_INVALID;
         }
         const int Luse = std::max(pm.L, 0);
-        int M = choose_conv_length(pm.n + 2 * Luse);
+        int M = 0;
         pm.mode = 0;
+        pm.m1 = 0;
+        if (use_v2 && pm.L >= 0 && pm.n + 2 * Luse >= v2_min_need) {
+            int m1 = 0;
+            const int M2 = fft2::conv_length_v2(pm.n + 2 * Luse, &m1);
+            if (M2 && v2_smem_inv(M2, Luse) <= kSmemLimit && v2_smem_dir(M2, pm.n) <= kSmemLimit) {
+                M = M2;
+                pm.m1 = m1;
+            }
+        }
+        if (M == 0) M = choose_conv_length(pm.n + 2 * Luse);
         if (M == 0 && pm.n % 2 == 0) {  // too long for the packed transform: one row at a time, length n/2
             M = choose_conv_length(pm.n / 2 + 2 * Luse);
             pm.mode = 1;
@@ -527,7 +642,7 @@ int build_fft_tables(Plan& p) {
             return SPTRANS_ERR_NOT_IMPLEMENTED;
         }
         pm.M = M;
-        pm.F = pm.mode ? 1 : fields_per_block(M);
+        pm.F = (pm.mode || pm.m1) ? 1 : fields_per_block(M);
         auto key = std::make_pair(pm.n, Luse);
         auto it = cls_index.find(key);
         if (it == cls_index.end()) {
@@ -539,7 +654,7 @@ int build_fft_tables(Plan& p) {
             c.sched = static_cast<int>(classes.size());
             chirp_total += 2LL * Luse + 1 + (pm.mode ? pm.n / 2 + Luse + 1 : pm.n);
             filt_total += M;
-            tw_total += M / 64 + 1 + 64;
+            tw_total += pm.m1 ? fft2::kM2 : M / 64 + 1 + 64;
             cls_index[key] = static_cast<int>(classes.size());
             classes.push_back(c);
             it = cls_index.find(key);
@@ -554,37 +669,65 @@ int build_fft_tables(Plan& p) {
     SPT_CUDA(cudaMalloc(&p.d_filt, std::max<long long>(filt_total, 1) * sizeof(double2)));
     SPT_CUDA(cudaMalloc(&p.d_twiddle, std::max<long long>(tw_total, 1) * sizeof(double2)));
     p.bytes_tables += (chirp_total + filt_total + tw_total) * sizeof(double2);
+    g_t256[&p] = p.d_twiddle;
     {
         std::vector<ScheduleG> sch(classes.size());
-        for (size_t c = 0; c < classes.size(); ++c) sch[c] = fftc::make_schedule_g(classes[c].M);
+        for (size_t c = 0; c < classes.size(); ++c)
+            if (!classes[c].m1) sch[c] = fftc::make_schedule_g(classes[c].M);
         ScheduleG* d_s = nullptr;
         SPT_CUDA(cudaMalloc(&d_s, std::max<size_t>(sch.size(), 1) * sizeof(ScheduleG)));
         SPT_CUDA(cudaMemcpyAsync(d_s, sch.data(), sch.size() * sizeof(ScheduleG), cudaMemcpyHostToDevice, p.stream));
         SPT_CUDA(cudaStreamSynchronize(p.stream));
         p.d_fft_order = reinterpret_cast<int*>(d_s);  // owned by the plan (freed with it)
     }
-    PairMeta* d_cls = nullptr;
-    SPT_CUDA(cudaMalloc(&d_cls, classes.size() * sizeof(PairMeta)));
-    SPT_CUDA(cudaMemcpyAsync(d_cls, classes.data(), classes.size() * sizeof(PairMeta), cudaMemcpyHostToDevice, p.stream));
+    std::vector<PairMeta> cls1, cls2;
+    for (const PairMeta& c : classes) (c.m1 ? cls2 : cls1).push_back(c);
+    PairMeta *d_cls1 = nullptr, *d_cls2 = nullptr;
     const size_t smem_max = block_smem_bytes(kMaxM, 1);
     SPT_CUDA(cudaFuncSetAttribute(chirp_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_dir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_inv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_dir_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    chirp_tables_kernel<<<static_cast<int>(classes.size()), kFftThreads, smem_max, p.stream>>>(d_cls, p.d_chirp, p.d_filt,
-                                                                                              p.d_twiddle);
-    p.launches++;
-    SPT_CUDA(cudaGetLastError());
+    if (!cls1.empty()) {
+        SPT_CUDA(cudaMalloc(&d_cls1, cls1.size() * sizeof(PairMeta)));
+        SPT_CUDA(cudaMemcpyAsync(d_cls1, cls1.data(), cls1.size() * sizeof(PairMeta), cudaMemcpyHostToDevice, p.stream));
+        chirp_tables_kernel<<<static_cast<int>(cls1.size()), kFftThreads, smem_max, p.stream>>>(d_cls1, p.d_chirp, p.d_filt,
+                                                                                             p.d_twiddle);
+        p.launches++;
+        SPT_CUDA(cudaGetLastError());
+    }
+    if (!cls2.empty()) {
+        int rc = SPTRANS_OK;
+#define SPT_ATTR(R) if (rc == SPTRANS_OK) rc = v2_set_attributes<R>();
+        SPT_V2_RADICES(SPT_ATTR)
+#undef SPT_ATTR
+        if (rc) return rc;
+        const size_t smem_f = static_cast<size_t>(32) * fft2::kM2 * sizeof(double2);
+        SPT_CUDA(cudaFuncSetAttribute(filter_tables2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        SPT_CUDA(cudaMalloc(&d_cls2, cls2.size() * sizeof(PairMeta)));
+        SPT_CUDA(cudaMemcpyAsync(d_cls2, cls2.data(), cls2.size() * sizeof(PairMeta), cudaMemcpyHostToDevice, p.stream));
+        chirp_tables2_kernel<<<static_cast<int>(cls2.size()), 256, 0, p.stream>>>(d_cls2, p.d_chirp, p.d_twiddle, p.d_twiddle);
+        SPT_CUDA(cudaGetLastError());
+        filter_tables2_kernel<<<static_cast<int>(cls2.size()), 256, smem_f, p.stream>>>(d_cls2, p.d_twiddle, p.d_twiddle,
+                                                                                       p.d_filt);
+        SPT_CUDA(cudaGetLastError());
+        p.launches += 2;
+    }
     SPT_CUDA(cudaMalloc(&p.d_pair_meta, meta.size() * sizeof(PairMeta)));
     SPT_CUDA(cudaMemcpyAsync(p.d_pair_meta, meta.data(), meta.size() * sizeof(PairMeta), cudaMemcpyHostToDevice,
                              p.stream));
-    // launch groups by shared-memory bucket over this rank's latitude band
+    // launch groups over this rank's latitude band
     FftGroups grp;
     const size_t buckets[] = {28 * 1024, 37 * 1024, 56 * 1024, 75 * 1024, 113 * 1024, smem_max};
     std::vector<std::vector<int>> by(6);
+    std::map<int, std::vector<int>> by_m1;
     std::vector<int> rowmode;
     for (int j = g.pair_begin; j < g.pair_end; ++j) {
+        if (meta[j].m1) {
+            by_m1[meta[j].m1].push_back(j);
+            continue;
+        }
         if (meta[j].mode) {
             rowmode.push_back(j);
             continue;
@@ -594,26 +737,31 @@ int build_fft_tables(Plan& p) {
         while (need > buckets[b]) ++b;
         by[b].push_back(j);
     }
-    if (!rowmode.empty()) {
-        std::stable_sort(rowmode.begin(), rowmode.end(), [&](int x, int y) { return meta[x].M > meta[y].M; });
-        size_t need = 0;
-        for (int j : rowmode) need = std::max(need, block_smem_bytes(meta[j].M, 1));
+    auto add_group = [&](std::vector<int> v, int mode, int m1) {
+        std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
+            return meta[x].M != meta[y].M ? meta[x].M > meta[y].M : meta[x].n > meta[y].n;
+        });
+        size_t need = 0, need_dir = 0;
+        for (int j : v) {
+            if (mode == 2) {
+                need = std::max(need, v2_smem_inv(meta[j].M, std::max(meta[j].L, 0)));
+                need_dir = std::max(need_dir, v2_smem_dir(meta[j].M, meta[j].n));
+            }
+            else need = std::max(need, block_smem_bytes(meta[j].M, mode == 1 ? 1 : meta[j].F));
+        }
         grp.smem.push_back(need);
-        grp.pairs.push_back(rowmode);
-        grp.mode.push_back(1);
-    }
-    for (int b = 5; b >= 0; --b) {
-        if (by[b].empty()) continue;
-        std::vector<int> v = by[b];
-        std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return meta[x].M > meta[y].M; });
-        size_t need = 0;
-        for (int j : v) need = std::max(need, block_smem_bytes(meta[j].M, meta[j].F));
-        grp.smem.push_back(need);
+        grp.smem_dir.push_back(mode == 2 ? need_dir : need);
         grp.pairs.push_back(v);
-        grp.mode.push_back(0);
-    }
+        grp.mode.push_back(mode);
+        grp.m1.push_back(m1);
+    };
+    for (auto it = by_m1.rbegin(); it != by_m1.rend(); ++it) add_group(it->second, 2, it->first);
+    if (!rowmode.empty()) add_group(rowmode, 1, 0);
+    for (int b = 5; b >= 0; --b)
+        if (!by[b].empty()) add_group(by[b], 0, 0);
     SPT_CUDA(cudaStreamSynchronize(p.stream));
-    cudaFree(d_cls);
+    cudaFree(d_cls1);
+    cudaFree(d_cls2);
     g_groups[&p] = grp;
     g_meta[&p] = meta;
     return SPTRANS_OK;
@@ -626,6 +774,7 @@ void free_fft_tables(Plan& p) {
         g_groups.erase(it);
     }
     g_meta.erase(&p);
+    g_t256.erase(&p);
 }
 
 static int ensure_block_lists(Plan& p, int nf) {
@@ -635,10 +784,16 @@ static int ensure_block_lists(Plan& p, int nf) {
     grp.d_blocks.clear();
     grp.nblocks.clear();
     const std::vector<PairMeta>& meta = g_meta[&p];
+    // v2: fields per block, chosen so that the blocks of a pair carry (almost) equal numbers of fields
+    const int ft = std::max(1, env_int("SPTRANS_FFT2_F", 6));
+    const int nblk = (nf + ft - 1) / ft;
+    grp.F2 = (nf + nblk - 1) / std::max(nblk, 1);
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         std::vector<int2> blocks;
-        for (int j : grp.pairs[gi])
-            for (int f0 = 0; f0 < nf; f0 += meta[j].F) blocks.push_back(make_int2(j, f0));
+        for (int j : grp.pairs[gi]) {
+            const int step = grp.mode[gi] == 2 ? grp.F2 : meta[j].F;
+            for (int f0 = 0; f0 < nf; f0 += step) blocks.push_back(make_int2(j, f0));
+        }
         int2* d = nullptr;
         SPT_CUDA(cudaMalloc(&d, std::max<size_t>(blocks.size(), 1) * sizeof(int2)));
         SPT_CUDA(cudaMemcpyAsync(d, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, p.stream));
@@ -650,12 +805,48 @@ static int ensure_block_lists(Plan& p, int nf) {
     return SPTRANS_OK;
 }
 
+static Fft2Args make_v2_args(Plan& p, const FftGroups& grp, int nf) {
+    Fft2Args a{};
+    a.meta = reinterpret_cast<const PairMeta*>(p.d_pair_meta);
+    a.nf = nf;
+    a.F = grp.F2;
+    a.fb_rowoff = p.d_fb_rowoff;
+    a.nlat0 = p.d_nlat0;
+    a.nleg = p.g.nleg;
+    a.twid = p.d_twiddle;
+    a.t256 = g_t256[&p];
+    a.chirp = p.d_chirp;
+    a.filt = p.d_filt;
+    a.npts = p.g.npts;
+    return a;
+}
+
 int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv) {
     int rc = ensure_block_lists(p, nf);
     if (rc) return rc;
     const FftGroups& grp = g_groups[&p];
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         if (grp.nblocks[gi] == 0) continue;
+        if (grp.mode[gi] == 2) {
+            Fft2Args a = make_v2_args(p, grp, nf);
+            a.mlimit = mlimit;
+            a.nb_uv = nb_uv;
+            a.scale_lat = p.d_coslatinv;
+            a.fb = const_cast<double2*>(reinterpret_cast<const double2*>(d_fourier));
+            a.gp = d_gp;
+            switch (grp.m1[gi]) {
+#define SPT_LAUNCH(R)                                                                                                 \
+    case R:                                                                                                           \
+        fourier2_inv_kernel<R><<<grp.nblocks[gi], v2_threads(R), grp.smem[gi], p.stream>>>(a, grp.d_blocks[gi]);      \
+        break;
+                SPT_V2_RADICES(SPT_LAUNCH)
+#undef SPT_LAUNCH
+                default: set_error("fourier: unsupported v2 radix"); return SPTRANS_ERR_INVALID;
+            }
+            p.launches++;
+            SPT_CUDA(cudaGetLastError());
+            continue;
+        }
         const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;  // one block per SM: 16 warps
         if (grp.mode[gi]) {
             fourier_inv_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
@@ -687,6 +878,29 @@ static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* 
     const FftGroups& grp = g_groups[&p];
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         if (grp.nblocks[gi] == 0) continue;
+        if (grp.mode[gi] == 2) {
+            Fft2Args a = make_v2_args(p, grp, nf);
+            a.nb_uv = nb_uv;
+            a.scale_lat = p.d_uvscale;
+            a.weights = p.d_weights;
+            a.fb = reinterpret_cast<double2*>(d_fourier);
+            a.gp = const_cast<double*>(d_gp);
+            a.adjoint = adjoint;
+            a.gp_aligned16 = (reinterpret_cast<uintptr_t>(d_gp) % 16 == 0) ? 1 : 0;
+            switch (grp.m1[gi]) {
+#define SPT_LAUNCH(R)                                                                                                 \
+    case R:                                                                                                           \
+        fourier2_dir_kernel<R><<<grp.nblocks[gi], v2_threads(R), grp.smem_dir[gi], p.stream>>>(                       \
+            a, grp.d_blocks[gi], d_owner, dst, p.g.rank, p.d_pair_done);                                              \
+        break;
+                SPT_V2_RADICES(SPT_LAUNCH)
+#undef SPT_LAUNCH
+                default: set_error("fourier: unsupported v2 radix"); return SPTRANS_ERR_INVALID;
+            }
+            p.launches++;
+            SPT_CUDA(cudaGetLastError());
+            continue;
+        }
         const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;
         if (grp.mode[gi]) {
             fourier_dir_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
@@ -716,7 +930,7 @@ int launch_fourier_dir_peers(Plan& p, int nf, const double* d_gp, const PeerDst&
     if (rc) return rc;
     const FftGroups& grp = g_groups[&p];
     bool rows = false;
-    for (size_t gi = 0; gi < grp.pairs.size(); ++gi) rows = rows || (grp.mode[gi] && grp.nblocks[gi] > 0);
+    for (size_t gi = 0; gi < grp.pairs.size(); ++gi) rows = rows || (grp.mode[gi] == 1 && grp.nblocks[gi] > 0);
     *fused = !rows;
     return launch_fourier_dir_impl(p, nf, d_gp, dst.base[p.g.rank], 0, 0, rows ? nullptr : p.d_owner, dst);
 }

@@ -15,3 +15,16 @@ def test_fft_core_on_cpu():
         r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
         assert r.returncode == 0, r.stdout
         assert "ALL OK" in r.stdout
+
+
+def test_fft2_kernel_bodies_under_thread_emulation():
+    """The v2 (register-tiled) Fourier kernel bodies of atlas_b200/csrc/fft2_core.cuh, compiled for the host and run
+    with one OS thread per CUDA thread (tests/cpu/test_fft2_emul.cc): every block-level radix, both directions,
+    the filter-table construction, against a naive DFT."""
+    src = os.path.join(REPO, "tests", "cpu", "test_fft2_emul.cc")
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "t2")
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++20", "-pthread", "-o", exe, src], check=True)
+        r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stdout
+        assert "ALL OK" in r.stdout

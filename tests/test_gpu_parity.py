@@ -619,3 +619,40 @@ def test_invtrans_adjoint_identity(gridname, T, nf):
     # the adjoint annihilates what the inverse ignores: Im(m = 0) and the m == T column
     ay3 = ay.reshape(-1, 2, nf)
     assert np.all(ay3[: T + 1, 1, :] == 0.0) and np.all(ay3[-1] == 0.0)
+
+
+@pytest.mark.parametrize("gridname,T,nf,nb_uv", [("O1280", 1279, 7, 2), ("O400", 399, 13, 0), ("O640", 639, 3, 0)])
+def test_fourier_v2_kernels_match_v1_kernels(torch_cuda, monkeypatch, gridname, T, nf, nb_uv):
+    """The register-tiled (v2) Fourier kernels against the shared-memory-pass (v1) kernels on the same random exchange
+    buffer / grid fields, whole grid (every block-level radix M1 occurs at O1280), both directions.  Both are chirp-z
+    evaluations of the same sums, so they agree to rounding: <= 1e-12 of the field maximum."""
+    import atlas_b200
+
+    torch = torch_cuda
+    grid = atlas_b200.Grid(gridname)
+    monkeypatch.setenv("SPTRANS_FFT_V2", "0")
+    t1 = atlas_b200.Trans(grid, T, atlas_b200.option.type("b200"))
+    monkeypatch.setenv("SPTRANS_FFT_V2", "1")
+    monkeypatch.setenv("SPTRANS_FFT2_F", "3")
+    t2 = atlas_b200.Trans(grid, T, atlas_b200.option.type("b200"))
+    kw = dict(dtype=torch.float64, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    nfb = t1.fourier_elems_per_field() * 2 * nf
+    fb = torch.rand(nfb, generator=g, **kw) - 0.5
+    gp1 = torch.full((nf * grid.size(),), 7.0, **kw)
+    gp2 = torch.full((nf * grid.size(),), -7.0, **kw)
+    t1.invtrans_fourier(nf, T - 1, fb, gp1, nb_uv)
+    t2.invtrans_fourier(nf, T - 1, fb, gp2, nb_uv)
+    torch.cuda.synchronize()
+    scale = gp1.abs().max().item()
+    err = (gp1 - gp2).abs().max().item()
+    assert scale > 1.0 and err <= 1e-12 * scale, (err, scale)
+    gp = torch.rand(nf * grid.size(), generator=g, **kw) - 0.5
+    fb1 = torch.zeros(nfb, **kw)
+    fb2 = torch.zeros(nfb, **kw)
+    t1.dirtrans_fourier(nf, gp, fb1, nb_uv)
+    t2.dirtrans_fourier(nf, gp, fb2, nb_uv)
+    torch.cuda.synchronize()
+    scale = fb1.abs().max().item()
+    err = (fb1 - fb2).abs().max().item()
+    assert scale > 0 and err <= 1e-12 * scale, (err, scale)

@@ -207,17 +207,24 @@ SPT2_DEV void passA_inv_load(double2* v, const double2* X, int t, double2 w1) {
 // ---- half-warp-local 256-point transforms -------------------------------------------------------------------------
 // `base`: the 256 contiguous elements of sub-transform s; l = lane within the half-warp.  The 16x16 transpose uses a
 // rotation (row a', slot (l + a') & 15) so that both the row-wise and the column-wise accesses are conflict free.
-// MODE 0: forward, multiply by filt (or its conjugate), inverse, back in place (natural order)
+// T256 = e^{-2 pi i q l/256} at [q*16 + l] (shared memory in the transform kernels).
+// MODE 0: forward, multiply by filt (or its conjugate), inverse, back in place (natural order).  The 16 filter values
+//         of this lane are requested first so that their L2 latency hides behind the forward transform.
 // MODE 1: forward only, registers * scale written to out[q*16 + l]  (filter-table construction)
 template <int MODE, bool CONJ_FILT>
 SPT2_DEV void local256(double2* base, int l, int tid, const double2* __restrict__ T256,
                        const double2* __restrict__ filt, double2* __restrict__ out, double scale) {
     double2 e[16];
+    double2 fl[MODE == 0 ? 16 : 1];
+    if constexpr (MODE == 0) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) fl[q] = SPT2_LDG(filt + q * 16 + l);
+    }
 #pragma unroll
     for (int a = 0; a < 16; ++a) e[a] = base[l + 16 * a];
     dft16<true>(e);
 #pragma unroll
-    for (int q = 1; q < 16; ++q) e[q] = cmul(e[q], SPT2_LDG(T256 + q * 16 + l));
+    for (int q = 1; q < 16; ++q) e[q] = cmul(e[q], T256[q * 16 + l]);
     SPT2_SYNC_HALFWARP(tid);  // every lane has read its column before rows are overwritten
 #pragma unroll
     for (int q = 0; q < 16; ++q) base[16 * q + ((l + q) & 15)] = e[q];
@@ -231,22 +238,19 @@ SPT2_DEV void local256(double2* base, int l, int tid, const double2* __restrict_
     }
     else {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const double2 f = SPT2_LDG(filt + q * 16 + l);
-        e[q] = CONJ_FILT ? cmulc(e[q], f) : cmul(e[q], f);
-    }
-    dft16<false>(e);
+        for (int q = 0; q < 16; ++q) e[q] = CONJ_FILT ? cmulc(e[q], fl[q]) : cmul(e[q], fl[q]);
+        dft16<false>(e);
 #pragma unroll
-    for (int q = 1; q < 16; ++q) e[q] = cmulc(e[q], SPT2_LDG(T256 + q * 16 + l));
+        for (int q = 1; q < 16; ++q) e[q] = cmulc(e[q], T256[q * 16 + l]);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) base[16 * l + ((q + l) & 15)] = e[q];  // own row
-    SPT2_SYNC_HALFWARP(tid);
+        for (int q = 0; q < 16; ++q) base[16 * l + ((q + l) & 15)] = e[q];  // own row
+        SPT2_SYNC_HALFWARP(tid);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) e[q] = base[16 * q + ((l + q) & 15)];
-    dft16<false>(e);
-    SPT2_SYNC_HALFWARP(tid);  // all rows read before columns are written
+        for (int q = 0; q < 16; ++q) e[q] = base[16 * q + ((l + q) & 15)];
+        dft16<false>(e);
+        SPT2_SYNC_HALFWARP(tid);  // all rows read before columns are written
 #pragma unroll
-    for (int a = 0; a < 16; ++a) base[l + 16 * a] = e[a];
+        for (int a = 0; a < 16; ++a) base[l + 16 * a] = e[a];
     }
 }
 
@@ -298,79 +302,117 @@ SPT2_DEV void filter_table_body(const PairMeta& pm, int tid, double2* X, const d
         local256<1, false>(X + kM2 * s, l, tid, T256, nullptr, filt_out + kM2 * s, 1.0 / M);
 }
 
-// ---- inverse Fourier stage (spectral -> grid) of one latitude pair, fields f0 .. f0+nfb-1 ------------------------------
-// Shared memory: X[M] double2, then S[2 (L+1)] double2 (raw sym / asym parts of the field being staged).
-template <int M1, int NT>
-SPT2_DEV void stage_inv_inputs(const Fft2Args& a, const PairMeta& pm, int pair, int f, int Lc, int tid, double2* S) {
-    for (int e = tid; e < 2 * (Lc + 1); e += NT) {
-        const int m = e >> 1, par = e & 1;
-        const int n0 = a.nlat0[m];
-        const long long row = a.fb_rowoff[m] + static_cast<long long>(par) * (a.nleg - n0) + (pair - n0);
-        cp_async16(S + e, a.fb + row * a.nf + f);
+// ---- transform kernels ------------------------------------------------------------------------------------------------
+// Shared memory (double2 units): X[M] | T256[256] | S (staging area of the field being fetched).
+// Loads from the L2-resident class tables (chirps, filter) are requested in batches ahead of the arithmetic that hides
+// them: with 8 warps per SM all at the same phase, a load issued next to its use stalls the whole SM for an L2 round trip
+// (first ncu capture: 43 % of the stall samples were long-scoreboard waits on exactly these loads).
+template <int M1>
+struct V2Counts {
+    static constexpr int NA = (M1 + 1) / 2;        // 256 j <= 2L < M/2: inputs of the inverse / outputs of the direct kernel
+    static constexpr int NJ = (7 * M1 + 9) / 10;   // chirp values C requested ahead of the butterfly (rows up to 0.7 M)
+};
+
+template <int NT>
+SPT2_DEV void load_t256(double2* Tsm, const double2* __restrict__ t256, int tid) {
+    for (int e = tid; e < 256; e += NT) Tsm[e] = SPT2_LDG(t256 + e);
+}
+
+// inverse: raw sym / asym parts of field f, S[2 m + par], m <= Lc; four independent address chains per thread in flight
+template <int NT>
+SPT2_DEV void stage_inv_inputs(const Fft2Args& a, int pair, int f, int Lc, int tid, double2* S) {
+    const int cnt = 2 * (Lc + 1);
+    for (int e0 = tid; e0 < cnt; e0 += 4 * NT) {
+        const double2* src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = min(e0 + u * NT, cnt - 1);
+            const int m = e >> 1, par = e & 1;
+            const int n0 = SPT2_LDG(a.nlat0 + m);
+            const long long row = SPT2_LDG(a.fb_rowoff + m) + static_cast<long long>(par) * (a.nleg - n0) + (pair - n0);
+            src[u] = a.fb + row * a.nf + f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (e0 + u * NT < cnt) cp_async16(S + e0 + u * NT, src[u]);
     }
 }
 
 template <int M1, int NT>
 SPT2_DEV void fourier2_inv_body(const Fft2Args& a, int pair, int f0, int tid, double2* X) {
+    using CN = V2Counts<M1>;
     const PairMeta pm = a.meta[pair];
     const int nfb = min(a.F, a.nf - f0);
     const int n = pm.n, L = pm.L;
     const int Lc = min(L, a.mlimit);
-    double2* S = X + M1 * kM2;
+    double2* Tsm = X + M1 * kM2;
+    double2* S = Tsm + 256;
     const double2* __restrict__ A = a.chirp + pm.chirp_off;
     const double2* __restrict__ C = A + (2 * L + 1);
     const double2* __restrict__ W1 = a.twid + pm.tw_off;
     const double2* __restrict__ F2 = a.filt + pm.filt_off;
-    stage_inv_inputs<M1, NT>(a, pm, pair, f0, Lc, tid, S);
+    stage_inv_inputs<NT>(a, pair, f0, Lc, tid, S);
+    load_t256<NT>(Tsm, a.t256, tid);
     for (int fi = 0; fi < nfb; ++fi) {
         const int f = f0 + fi;
         cp_async_commit_wait_all();
         SPT2_SYNC_BLOCK();  // S holds field f; X is free (previous field's outputs are in registers / stored)
         for (int t = tid; t < kM2; t += NT) {
+            double2 ach[CN::NA];
+#pragma unroll
+            for (int j = 0; j < CN::NA; ++j)
+                ach[j] = (kM2 * j <= 2 * L) ? SPT2_LDG(A + min(t + kM2 * j, 2 * L)) : make_double2(0., 0.);
+            const double2 w1 = SPT2_LDG(W1 + t);
             double2 v[M1];
 #pragma unroll
             for (int j = 0; j < M1; ++j) {
                 double2 val = make_double2(0., 0.);
-                if (kM2 * j <= 2 * L) {  // block-uniform: elements beyond 2L are zero padding
+                if (j < CN::NA && kM2 * j <= 2 * L) {  // block-uniform: elements beyond 2L are zero padding
                     const int i = t + kM2 * j;
                     const int m = i - L, am = m < 0 ? -m : m;
-                    if (am <= Lc) {
-                        double2 cs = S[2 * am], ca = S[2 * am + 1];
-                        if (am == 0) cs.y = ca.y = 0.;  // only Re of m = 0 enters (reference :1165)
-                        double2 FN, FS;
-                        if (pm.has_s) {
-                            FN = cadd(cs, ca);
-                            FS = csub(cs, ca);
-                        }
-                        else {  // equator row: the reference's southern loop overwrites it with sym - asym (:1061-1070)
-                            FN = csub(cs, ca);
-                            FS = make_double2(0., 0.);
-                        }
-                        // Z_m = F_N + i F_S ;  Z_{-m} = conj(F_N) + i conj(F_S)
-                        const double2 Z = m >= 0 ? make_double2(FN.x - FS.y, FN.y + FS.x)
-                                                 : make_double2(FN.x + FS.y, FS.x - FN.y);
-                        val = cmul(Z, SPT2_LDG(A + i));
+                    const int ar = min(am, Lc);
+                    double2 cs = S[2 * ar], ca = S[2 * ar + 1];
+                    if (am == 0) cs.y = ca.y = 0.;  // only Re of m = 0 enters (reference :1165)
+                    double2 FN, FS;
+                    if (pm.has_s) {
+                        FN = cadd(cs, ca);
+                        FS = csub(cs, ca);
                     }
+                    else {  // equator row: the reference's southern loop overwrites it with sym - asym (:1061-1070)
+                        FN = csub(cs, ca);
+                        FS = make_double2(0., 0.);
+                    }
+                    // Z_m = F_N + i F_S ;  Z_{-m} = conj(F_N) + i conj(F_S)
+                    const double2 Z = m >= 0 ? make_double2(FN.x - FS.y, FN.y + FS.x)
+                                             : make_double2(FN.x + FS.y, FS.x - FN.y);
+                    const double2 za = cmul(Z, ach[j < CN::NA ? j : 0]);
+                    if (am <= Lc) val = za;
                 }
                 v[j] = val;
             }
-            passA_fwd_store<M1>(v, X, t, SPT2_LDG(W1 + t));
+            passA_fwd_store<M1>(v, X, t, w1);
         }
         SPT2_SYNC_BLOCK();  // S consumed, X complete
-        if (fi + 1 < nfb) stage_inv_inputs<M1, NT>(a, pm, pair, f + 1, Lc, tid, S);  // lands behind the transforms
-        local_phase<M1, NT, false>(X, tid, a.t256, F2);
+        if (fi + 1 < nfb) stage_inv_inputs<NT>(a, pair, f + 1, Lc, tid, S);  // lands behind the transforms
+        local_phase<M1, NT, false>(X, tid, Tsm, F2);
         SPT2_SYNC_BLOCK();
         const double sc = (f < a.nb_uv) ? a.scale_lat[pair] : 1.0;  // u,v = U,V / cos(lat)  (reference :1443-1469)
         double* __restrict__ gN = a.gp + f * a.npts + pm.rowN;
         double* __restrict__ gS = a.gp + f * a.npts + pm.rowS;
         for (int t = tid; t < kM2; t += NT) {
+            double2 c[CN::NJ];
+#pragma unroll
+            for (int j = 0; j < CN::NJ; ++j)
+                c[j] = (kM2 * j < n) ? SPT2_LDG(C + min(t + kM2 * j, n - 1)) : make_double2(0., 0.);
+            const double2 w1 = SPT2_LDG(W1 + t);
             double2 v[M1];
-            passA_inv_load<M1>(v, X, t, SPT2_LDG(W1 + t));
+            passA_inv_load<M1>(v, X, t, w1);
 #pragma unroll
             for (int j = 0; j < M1; ++j) {
                 const int i = t + kM2 * j;
                 if (i < n) {
-                    const double2 z = cmul(v[j], SPT2_LDG(C + i));
+                    const double2 cc = j < CN::NJ ? c[j < CN::NJ ? j : 0] : SPT2_LDG(C + i);
+                    const double2 z = cmul(v[j], cc);
                     gN[i] = z.x * sc;
                     if (pm.has_s) gS[i] = z.y * sc;
                 }
@@ -380,10 +422,10 @@ SPT2_DEV void fourier2_inv_body(const Fft2Args& a, int pair, int f0, int tid, do
 }
 
 // ---- direct Fourier stage (grid -> spectral) ------------------------------------------------------------------------------
-// Shared memory: X[M] double2, then S: northern row (n doubles) and southern row (n doubles) of the field being staged.
+// Staging area: northern row (n doubles) and southern row (n doubles) of the field being fetched.
 template <int NT>
 SPT2_DEV void stage_dir_inputs(const Fft2Args& a, const PairMeta& pm, int f, int tid, double* S) {
-    const int n = pm.n, q = n / 2;  // n % 4 == 0 for v2 classes: rows are 16-byte multiples, 16-byte aligned
+    const int n = pm.n, q = n / 2;  // v2 classes have even n: rows are 16-byte multiples
     const double* gN = a.gp + f * a.npts + pm.rowN;
     const double* gS = a.gp + f * a.npts + pm.rowS;
     if (a.gp_aligned16) {
@@ -400,10 +442,12 @@ SPT2_DEV void stage_dir_inputs(const Fft2Args& a, const PairMeta& pm, int f, int
 
 template <int M1, int NT>
 SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, double2* X) {
+    using CN = V2Counts<M1>;
     const PairMeta pm = a.meta[pair];
     const int nfb = min(a.F, a.nf - f0);
     const int n = pm.n, L = pm.L;
-    double* S = reinterpret_cast<double*>(X + M1 * kM2);
+    double2* Tsm = X + M1 * kM2;
+    double* S = reinterpret_cast<double*>(Tsm + 256);
     const double2* __restrict__ A = a.chirp + pm.chirp_off;
     const double2* __restrict__ C = A + (2 * L + 1);
     const double2* __restrict__ W1 = a.twid + pm.tw_off;
@@ -413,12 +457,18 @@ SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, do
     const double wq0 = a.adjoint ? 1.0 : a.weights[pair];
     const double inv_n = a.adjoint ? 1.0 : 1.0 / n;
     stage_dir_inputs<NT>(a, pm, f0, tid, S);
+    load_t256<NT>(Tsm, a.t256, tid);
     for (int fi = 0; fi < nfb; ++fi) {
         const int f = f0 + fi;
         cp_async_commit_wait_all();
         SPT2_SYNC_BLOCK();  // S holds field f; the previous field's spectrum has been read out of X
         const double sc = (f < a.nb_uv) ? a.scale_lat[pair] : 1.0;  // wind components enter as u,v * scale(lat)
         for (int t = tid; t < kM2; t += NT) {
+            double2 c[CN::NJ];
+#pragma unroll
+            for (int j = 0; j < CN::NJ; ++j)
+                c[j] = (kM2 * j < n) ? SPT2_LDG(C + min(t + kM2 * j, n - 1)) : make_double2(0., 0.);
+            const double2 w1 = SPT2_LDG(W1 + t);
             double2 v[M1];
 #pragma unroll
             for (int j = 0; j < M1; ++j) {
@@ -428,47 +478,65 @@ SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, do
                     if (i < n) {
                         const double xn = S[i] * sc;
                         const double xs = pm.has_s ? S[n + i] * sc : 0.;
-                        val = cmulc(make_double2(xn, xs), SPT2_LDG(C + i));
+                        const double2 cc = j < CN::NJ ? c[j < CN::NJ ? j : 0] : SPT2_LDG(C + i);
+                        val = cmulc(make_double2(xn, xs), cc);
                     }
                 }
                 v[j] = val;
             }
-            passA_fwd_store<M1>(v, X, t, SPT2_LDG(W1 + t));
+            passA_fwd_store<M1>(v, X, t, w1);
         }
         SPT2_SYNC_BLOCK();
         if (fi + 1 < nfb) stage_dir_inputs<NT>(a, pm, f + 1, tid, S);
-        local_phase<M1, NT, true>(X, tid, a.t256, F2);
+        local_phase<M1, NT, true>(X, tid, Tsm, F2);
         SPT2_SYNC_BLOCK();
         for (int t = tid; t < kM2; t += NT) {
+            const double2 w1 = SPT2_LDG(W1 + t);
             double2 v[M1];
-            passA_inv_load<M1>(v, X, t, SPT2_LDG(W1 + t));
+            passA_inv_load<M1>(v, X, t, w1);
 #pragma unroll
-            for (int j = 0; j < M1; ++j)
+            for (int j = 0; j < CN::NA; ++j)
                 if (kM2 * j <= 2 * L) X[kM2 * j + t] = v[j];  // same addresses this thread has just read: in place
         }
         SPT2_SYNC_BLOCK();
-        for (int m = tid; m <= L; m += NT) {
-            const double wq = (a.adjoint && m > 0) ? 2.0 * wq0 : wq0;
-            double2 Gp = cmulc(X[L + m], SPT2_LDG(A + L + m));
-            double2 Gm = cmulc(X[L - m], SPT2_LDG(A + L - m));
-            Gp.x *= inv_n; Gp.y *= inv_n; Gm.x *= inv_n; Gm.y *= inv_n;
-            // F_N = (G_m + conj(G_-m))/2 ; F_S = (G_m - conj(G_-m))/(2i)
-            const double2 FN = make_double2(0.5 * (Gp.x + Gm.x), 0.5 * (Gp.y - Gm.y));
-            const double2 FS = make_double2(0.5 * (Gp.y + Gm.y), -0.5 * (Gp.x - Gm.x));
-            double2 s, as;
-            if (pm.has_s) {
-                s = make_double2((FN.x + FS.x) * wq, (FN.y + FS.y) * wq);
-                as = make_double2((FN.x - FS.x) * wq, (FN.y - FS.y) * wq);
+        for (int m0 = tid; m0 <= L; m0 += 4 * NT) {  // four zonal wavenumbers per thread and sweep, loads batched
+            double2 ap[4], am_[4];
+            int n0[4];
+            long long ro[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int m = min(m0 + u * NT, L);
+                ap[u] = SPT2_LDG(A + L + m);
+                am_[u] = SPT2_LDG(A + L - m);
+                n0[u] = SPT2_LDG(a.nlat0 + m);
+                ro[u] = SPT2_LDG(a.fb_rowoff + m);
             }
-            else {
-                s = make_double2(FN.x * wq, FN.y * wq);
-                as = s;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int m = m0 + u * NT;
+                if (m <= L) {
+                    const double wq = (a.adjoint && m > 0) ? 2.0 * wq0 : wq0;
+                    double2 Gp = cmulc(X[L + m], ap[u]);
+                    double2 Gm = cmulc(X[L - m], am_[u]);
+                    Gp.x *= inv_n; Gp.y *= inv_n; Gm.x *= inv_n; Gm.y *= inv_n;
+                    // F_N = (G_m + conj(G_-m))/2 ; F_S = (G_m - conj(G_-m))/(2i)
+                    const double2 FN = make_double2(0.5 * (Gp.x + Gm.x), 0.5 * (Gp.y - Gm.y));
+                    const double2 FS = make_double2(0.5 * (Gp.y + Gm.y), -0.5 * (Gp.x - Gm.x));
+                    double2 s, as;
+                    if (pm.has_s) {
+                        s = make_double2((FN.x + FS.x) * wq, (FN.y + FS.y) * wq);
+                        as = make_double2((FN.x - FS.x) * wq, (FN.y - FS.y) * wq);
+                    }
+                    else {
+                        s = make_double2(FN.x * wq, FN.y * wq);
+                        as = s;
+                    }
+                    const long long is = (ro[u] + (pair - n0[u])) * a.nf + f;
+                    const long long ia = is + static_cast<long long>(a.nleg - n0[u]) * a.nf;
+                    a.fb[is] = s;
+                    a.fb[ia] = as;
+                }
             }
-            const int n0 = a.nlat0[m];
-            const long long is = (a.fb_rowoff[m] + (pair - n0)) * a.nf + f;
-            const long long ia = is + static_cast<long long>(a.nleg - n0) * a.nf;
-            a.fb[is] = s;
-            a.fb[ia] = as;
         }
     }
 }

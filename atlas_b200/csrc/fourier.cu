@@ -581,9 +581,9 @@ int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
 }
-size_t v2_smem_inv(int M, int L) { return (static_cast<size_t>(M) + 2 * (L + 1)) * sizeof(double2); }
-size_t v2_smem_dir(int M, int n) { return static_cast<size_t>(M) * sizeof(double2) + 2 * static_cast<size_t>(n) * sizeof(double); }
-constexpr size_t kSmemLimit = 227 * 1024;
+size_t v2_smem_inv(int M, int L) { return (static_cast<size_t>(M) + 256 + 2 * (L + 1)) * sizeof(double2); }
+size_t v2_smem_dir(int M, int n) { return (static_cast<size_t>(M) + 256) * sizeof(double2) + 2 * static_cast<size_t>(n) * sizeof(double); }
+constexpr size_t kSmemLimit = 226 * 1024;  // 227 KB opt-in maximum minus the kernels' few bytes of static shared memory
 
 template <int M1>
 int v2_set_attributes() {

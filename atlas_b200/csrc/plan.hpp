@@ -167,6 +167,7 @@ struct Plan {
     double* d_spec = nullptr;     size_t spec_cap = 0;     // device copy of spectra (host-pointer mode)
     double* d_spec2 = nullptr;    size_t spec2_cap = 0;
     double* d_gp = nullptr;       size_t gp_cap = 0;       // device copy of grid fields (host-pointer mode)
+    double* d_rows = nullptr;     size_t rows_cap = 0;     // row-layout image of a Field-layout grid buffer
     void* h_pinned = nullptr;     size_t pinned_cap = 0;
     int precision = 0;           // SPTRANS_PREC_FP64 | SPTRANS_PREC_TC_SPLIT
     void* tc = nullptr;          // TcState (legendre_tc.cu)
@@ -243,6 +244,10 @@ int launch_exchange_copy(Plan& p, int nf, const ExSeg* d_segs, int nseg, double*
 PeerDst make_peer_dst(const Plan& p);      // exchange buffers of the current parity on every rank
 int launch_exchange_push(Plan& p, int nf);  // band-side rows of the local buffer -> owners of their zonal wavenumber
 int launch_peer_barrier(Plan& p);
+
+// ---- fields.cu ----
+// atlas Field layout (node, level, component) <-> transform rows [component * nlev + level][node]
+int launch_gp_repack(Plan& p, int nlev, int ncomp, const double* d_in, double* d_out, bool to_rows);
 
 // ---- vordiv.cu ----
 int launch_grad_spectra(cudaStream_t s, int T, int nf, const double* d_sp, double* d_all, uint64_t* launches);

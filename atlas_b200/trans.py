@@ -39,6 +39,18 @@ def _ptr(a):
     raise TypeError(f"unsupported array type {type(a)}")
 
 
+def _wait_for_producers(*arrays):
+    """The plan runs on its own (non-blocking) CUDA stream and the calls are blocking like the reference's; device
+    buffers handed in as torch tensors may still be being written by kernels queued on torch's current stream, so
+    that stream is drained first (one host synchronisation, only when a CUDA tensor is passed)."""
+    for a in arrays:
+        if a is not None and hasattr(a, "data_ptr") and getattr(a, "is_cuda", False):
+            import torch
+
+            torch.cuda.current_stream(a.device).synchronize()
+            return
+
+
 class Trans:
     """`trans::Trans(grid, truncation, option::type("b200"))`."""
 
@@ -110,6 +122,7 @@ class Trans:
         _lib.check(_lib.lib.sptrans_set_precision(self._h, code))
 
     def set_stream(self, cuda_stream_ptr):
+        self._external_stream = True  # stream-ordered use (dist.py): the caller orders producers on that stream
         _lib.check(_lib.lib.sptrans_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
     def export_legendre_cache(self):
@@ -118,11 +131,16 @@ class Trans:
         _lib.check(_lib.lib.sptrans_export_legendre_cache(self._h, C.c_void_p(out.ctypes.data)))
         return out
 
+    def _sync(self, *arrays):
+        if not getattr(self, "_external_stream", False):
+            _wait_for_producers(*arrays)
+
     # --- transforms, IFS-style buffers (TransImpl.h:116-181) ---
     def invtrans(self, *args):
         """invtrans(nb_scalar, scalar_spectra, gp)
         invtrans(nb_vordiv, vor, div, gp)
         invtrans(nb_scalar, scalar_spectra, nb_vordiv, vor, div, gp)"""
+        self._sync(*args)
         if len(args) == 3:
             n, sp, gp = args
             _lib.check(_lib.lib.sptrans_invtrans_scalar(self._h, int(n), _ptr(sp), _ptr(gp)))
@@ -138,6 +156,7 @@ class Trans:
     def dirtrans(self, *args):
         """dirtrans(nb_fields, scalar_fields, scalar_spectra)
         dirtrans(nb_fields, wind_fields, vorticity_spectra, divergence_spectra)"""
+        self._sync(*args)
         if len(args) == 3:
             n, gp, sp = args
             _lib.check(_lib.lib.sptrans_dirtrans_scalar(self._h, int(n), _ptr(gp), _ptr(sp)))
@@ -149,10 +168,12 @@ class Trans:
 
     def invtrans_adj(self, nb_fields, gp_fields, scalar_spectra):
         """adjoint of invtrans(nb_fields, spectra, gp): <invtrans x, y> == <x, invtrans_adj y>  (TransImpl.h:155-157)"""
+        self._sync(gp_fields, scalar_spectra)
         _lib.check(_lib.lib.sptrans_invtrans_adj_scalar(self._h, int(nb_fields), _ptr(gp_fields), _ptr(scalar_spectra)))
 
     def invtrans_grad(self, nb_fields, scalar_spectra, grad_fields):
         """grad_fields = [E-W_1..E-W_k | N-S_1..N-S_k][npts]  (TransIFS::__invtrans_grad, ifs/TransIFS.cc:2075-2142)"""
+        self._sync(scalar_spectra, grad_fields)
         _lib.check(_lib.lib.sptrans_invtrans_grad(self._h, int(nb_fields), _ptr(scalar_spectra), _ptr(grad_fields)))
 
     # --- stage level (device pointers only) ---
@@ -160,15 +181,19 @@ class Trans:
         return int(_lib.lib.sptrans_fourier_elems_per_field(self._h))
 
     def invtrans_legendre(self, nf, trunc, d_spec, d_fourier):
+        self._sync(d_spec, d_fourier)
         _lib.check(_lib.lib.sptrans_invtrans_legendre(self._h, int(nf), int(trunc), _ptr(d_spec), _ptr(d_fourier)))
 
     def invtrans_fourier(self, nf, mlimit, d_fourier, d_gp, nb_uv=0):
+        self._sync(d_fourier, d_gp)
         _lib.check(_lib.lib.sptrans_invtrans_fourier(self._h, int(nf), int(mlimit), _ptr(d_fourier), _ptr(d_gp), int(nb_uv)))
 
     def dirtrans_fourier(self, nf, d_gp, d_fourier, nb_uv=0):
+        self._sync(d_gp, d_fourier)
         _lib.check(_lib.lib.sptrans_dirtrans_fourier(self._h, int(nf), _ptr(d_gp), _ptr(d_fourier), int(nb_uv)))
 
     def dirtrans_legendre(self, nf, d_fourier, d_spec):
+        self._sync(d_fourier, d_spec)
         _lib.check(_lib.lib.sptrans_dirtrans_legendre(self._h, int(nf), _ptr(d_fourier), _ptr(d_spec)))
 
 

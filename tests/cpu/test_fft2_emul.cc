@@ -91,7 +91,7 @@ static int run_case(const Case& c) {
     for (int t = 0; t < kM2; ++t) W1[t] = make_double2(std::cos(-2 * M_PI * t / M), std::sin(-2 * M_PI * t / M));
     for (int q = 0; q < 16; ++q)
         for (int l = 0; l < 16; ++l) T[q * 16 + l] = make_double2(std::cos(-2 * M_PI * q * l / 256), std::sin(-2 * M_PI * q * l / 256));
-    const size_t smem = (size_t)M + 2 * (L + 1) + n + 16;  // double2 units: X, then the larger of the two staging areas
+    const size_t smem = (size_t)M + 256 + 2 * (L + 1) + n + 16;  // double2 units: X, then the larger of the two staging areas
     std::vector<double2> X(smem);
     emu::run_block(NT, [&](int tid) { filter_table_body<M1, NT>(pm, tid, X.data(), W1.data(), T.data(), filt.data()); });
 
@@ -189,6 +189,8 @@ int main() {
     bad += run_case<30, 256>({5120, 1279, 3, 3, 1, 1279, 0, 0});
     bad += run_case<32, 256>({5136, 1500, 1, 1, 1, 1500, 0, 0});
     bad += run_case<30, 128>({5000, 1279, 2, 2, 1, 1279, 0, 0});
+    bad += run_case<24, 256>({5000, 500, 2, 2, 1, 500, 0, 0});  // long rows, low truncation: n > 0.7 M (late chirp loads)
+    bad += run_case<16, 128>({3700, 190, 2, 2, 1, 190, 0, 0});
     std::printf(bad ? "FAILED (%d)\n" : "ALL OK\n", bad);
     return bad ? 1 : 0;
 }

@@ -641,6 +641,7 @@ def test_fourier_v2_kernels_match_v1_kernels(torch_cuda, monkeypatch, gridname, 
     fb = torch.rand(nfb, generator=g, **kw) - 0.5
     gp1 = torch.full((nf * grid.size(),), 7.0, **kw)
     gp2 = torch.full((nf * grid.size(),), -7.0, **kw)
+    torch.cuda.synchronize()
     t1.invtrans_fourier(nf, T - 1, fb, gp1, nb_uv)
     t2.invtrans_fourier(nf, T - 1, fb, gp2, nb_uv)
     torch.cuda.synchronize()
@@ -650,6 +651,7 @@ def test_fourier_v2_kernels_match_v1_kernels(torch_cuda, monkeypatch, gridname, 
     gp = torch.rand(nf * grid.size(), generator=g, **kw) - 0.5
     fb1 = torch.zeros(nfb, **kw)
     fb2 = torch.zeros(nfb, **kw)
+    torch.cuda.synchronize()
     t1.dirtrans_fourier(nf, gp, fb1, nb_uv)
     t2.dirtrans_fourier(nf, gp, fb2, nb_uv)
     torch.cuda.synchronize()

@@ -318,9 +318,25 @@ SPT2_DEV void load_t256(double2* Tsm, const double2* __restrict__ t256, int tid)
     for (int e = tid; e < 256; e += NT) Tsm[e] = SPT2_LDG(t256 + e);
 }
 
-// inverse: raw sym / asym parts of field f, S[2 m + par], m <= Lc; four independent address chains per thread in flight
+// Row table of one latitude pair (shared memory, built once per block): rowtab[2 m + par] = row of (m, par, pair) in
+// the exchange buffer.  The per-field staging / store loops then need no dependent global loads.
 template <int NT>
-SPT2_DEV void stage_inv_inputs(const Fft2Args& a, int pair, int f, int Lc, int tid, double2* S) {
+SPT2_DEV void build_rowtab(const Fft2Args& a, int pair, int L, int tid, int* rowtab) {
+    for (int e = tid; e < 2 * (L + 1); e += NT) {
+        const int m = e >> 1, par = e & 1;
+        const int n0 = SPT2_LDG(a.nlat0 + m);
+        rowtab[e] = static_cast<int>(SPT2_LDG(a.fb_rowoff + m) + static_cast<long long>(par) * (a.nleg - n0) + (pair - n0));
+    }
+}
+// inverse: raw sym / asym parts of field f, S[2 m + par], m <= Lc
+template <int NT>
+SPT2_DEV void stage_inv_inputs(const Fft2Args& a, int f, int Lc, int tid, double2* S, const int* rowtab) {
+    const int cnt = 2 * (Lc + 1);
+    for (int e = tid; e < cnt; e += NT) cp_async16(S + e, a.fb + static_cast<long long>(rowtab[e]) * a.nf + f);
+}
+// the same for the first field of a block, before the row table exists: four independent address chains per thread
+template <int NT>
+SPT2_DEV void stage_inv_inputs_first(const Fft2Args& a, int pair, int f, int Lc, int tid, double2* S) {
     const int cnt = 2 * (Lc + 1);
     for (int e0 = tid; e0 < cnt; e0 += 4 * NT) {
         const double2* src[4];
@@ -347,11 +363,13 @@ SPT2_DEV void fourier2_inv_body(const Fft2Args& a, int pair, int f0, int tid, do
     const int Lc = min(L, a.mlimit);
     double2* Tsm = X + M1 * kM2;
     double2* S = Tsm + 256;
+    int* rowtab = reinterpret_cast<int*>(S + 2 * (L + 1));
     const double2* __restrict__ A = a.chirp + pm.chirp_off;
     const double2* __restrict__ C = A + (2 * L + 1);
     const double2* __restrict__ W1 = a.twid + pm.tw_off;
     const double2* __restrict__ F2 = a.filt + pm.filt_off;
-    stage_inv_inputs<NT>(a, pair, f0, Lc, tid, S);
+    stage_inv_inputs_first<NT>(a, pair, f0, Lc, tid, S);
+    if (nfb > 1) build_rowtab<NT>(a, pair, L, tid, rowtab);  // first read after the block barriers of field f0
     load_t256<NT>(Tsm, a.t256, tid);
     for (int fi = 0; fi < nfb; ++fi) {
         const int f = f0 + fi;
@@ -393,7 +411,7 @@ SPT2_DEV void fourier2_inv_body(const Fft2Args& a, int pair, int f0, int tid, do
             passA_fwd_store<M1>(v, X, t, w1);
         }
         SPT2_SYNC_BLOCK();  // S consumed, X complete
-        if (fi + 1 < nfb) stage_inv_inputs<NT>(a, pair, f + 1, Lc, tid, S);  // lands behind the transforms
+        if (fi + 1 < nfb) stage_inv_inputs<NT>(a, f + 1, Lc, tid, S, rowtab);  // lands behind the transforms
         local_phase<M1, NT, false>(X, tid, Tsm, F2);
         SPT2_SYNC_BLOCK();
         const double sc = (f < a.nb_uv) ? a.scale_lat[pair] : 1.0;  // u,v = U,V / cos(lat)  (reference :1443-1469)
@@ -448,6 +466,7 @@ SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, do
     const int n = pm.n, L = pm.L;
     double2* Tsm = X + M1 * kM2;
     double* S = reinterpret_cast<double*>(Tsm + 256);
+    int* rowtab = reinterpret_cast<int*>(S + 2 * n);
     const double2* __restrict__ A = a.chirp + pm.chirp_off;
     const double2* __restrict__ C = A + (2 * L + 1);
     const double2* __restrict__ W1 = a.twid + pm.tw_off;
@@ -458,6 +477,7 @@ SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, do
     const double inv_n = a.adjoint ? 1.0 : 1.0 / n;
     stage_dir_inputs<NT>(a, pm, f0, tid, S);
     load_t256<NT>(Tsm, a.t256, tid);
+    build_rowtab<NT>(a, pair, L, tid, rowtab);  // first read after several block barriers
     for (int fi = 0; fi < nfb; ++fi) {
         const int f = f0 + fi;
         cp_async_commit_wait_all();
@@ -499,17 +519,13 @@ SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, do
                 if (kM2 * j <= 2 * L) X[kM2 * j + t] = v[j];  // same addresses this thread has just read: in place
         }
         SPT2_SYNC_BLOCK();
-        for (int m0 = tid; m0 <= L; m0 += 4 * NT) {  // four zonal wavenumbers per thread and sweep, loads batched
+        for (int m0 = tid; m0 <= L; m0 += 4 * NT) {  // four zonal wavenumbers per thread and sweep, chirp loads batched
             double2 ap[4], am_[4];
-            int n0[4];
-            long long ro[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int m = min(m0 + u * NT, L);
                 ap[u] = SPT2_LDG(A + L + m);
                 am_[u] = SPT2_LDG(A + L - m);
-                n0[u] = SPT2_LDG(a.nlat0 + m);
-                ro[u] = SPT2_LDG(a.fb_rowoff + m);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -531,10 +547,8 @@ SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, do
                         s = make_double2(FN.x * wq, FN.y * wq);
                         as = s;
                     }
-                    const long long is = (ro[u] + (pair - n0[u])) * a.nf + f;
-                    const long long ia = is + static_cast<long long>(a.nleg - n0[u]) * a.nf;
-                    a.fb[is] = s;
-                    a.fb[ia] = as;
+                    a.fb[static_cast<long long>(rowtab[2 * m]) * a.nf + f] = s;
+                    a.fb[static_cast<long long>(rowtab[2 * m + 1]) * a.nf + f] = as;
                 }
             }
         }

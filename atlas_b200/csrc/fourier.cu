@@ -581,8 +581,13 @@ int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
 }
-size_t v2_smem_inv(int M, int L) { return (static_cast<size_t>(M) + 256 + 2 * (L + 1)) * sizeof(double2); }
-size_t v2_smem_dir(int M, int n) { return (static_cast<size_t>(M) + 256) * sizeof(double2) + 2 * static_cast<size_t>(n) * sizeof(double); }
+// X | T256 | S | row table (int per exchange-buffer row of the pair)
+size_t v2_smem_inv(int M, int L) {
+    return (static_cast<size_t>(M) + 256 + 2 * (L + 1)) * sizeof(double2) + 2 * (L + 1) * sizeof(int);
+}
+size_t v2_smem_dir(int M, int n, int L) {
+    return (static_cast<size_t>(M) + 256) * sizeof(double2) + 2 * static_cast<size_t>(n) * sizeof(double) + 2 * (L + 1) * sizeof(int);
+}
 constexpr size_t kSmemLimit = 226 * 1024;  // 227 KB opt-in maximum minus the kernels' few bytes of static shared memory
 
 template <int M1>
@@ -606,7 +611,8 @@ int build_fft_tables(Plan& p) {
     // convolution fits M1 * 256; everything else (short rows, rows beyond 8192) stays on the v1 kernels
     bool all_even = true;
     for (int j = 0; j < g.nlat; ++j) all_even = all_even && (g.nx[j] % 2 == 0);
-    const bool use_v2 = env_int("SPTRANS_FFT_V2", 1) != 0 && all_even;
+    // (the kernels keep exchange-buffer row indices as 32-bit integers)
+    const bool use_v2 = env_int("SPTRANS_FFT_V2", 1) != 0 && all_even && g.fb_rowoff.back() < 2147483647LL;
     const int v2_min_need = env_int("SPTRANS_FFT2_MIN", 1281);
     for (int j = 0; j < nleg; ++j) {
         PairMeta pm{};
@@ -626,7 +632,7 @@ int build_fft_tables(Plan& p) {
         if (use_v2 && pm.L >= 0 && pm.n + 2 * Luse >= v2_min_need) {
             int m1 = 0;
             const int M2 = fft2::conv_length_v2(pm.n + 2 * Luse, &m1);
-            if (M2 && v2_smem_inv(M2, Luse) <= kSmemLimit && v2_smem_dir(M2, pm.n) <= kSmemLimit) {
+            if (M2 && v2_smem_inv(M2, Luse) <= kSmemLimit && v2_smem_dir(M2, pm.n, Luse) <= kSmemLimit) {
                 M = M2;
                 pm.m1 = m1;
             }
@@ -745,7 +751,7 @@ int build_fft_tables(Plan& p) {
         for (int j : v) {
             if (mode == 2) {
                 need = std::max(need, v2_smem_inv(meta[j].M, std::max(meta[j].L, 0)));
-                need_dir = std::max(need_dir, v2_smem_dir(meta[j].M, meta[j].n));
+                need_dir = std::max(need_dir, v2_smem_dir(meta[j].M, meta[j].n, std::max(meta[j].L, 0)));
             }
             else need = std::max(need, block_smem_bytes(meta[j].M, mode == 1 ? 1 : meta[j].F));
         }

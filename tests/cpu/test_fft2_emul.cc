@@ -91,7 +91,7 @@ static int run_case(const Case& c) {
     for (int t = 0; t < kM2; ++t) W1[t] = make_double2(std::cos(-2 * M_PI * t / M), std::sin(-2 * M_PI * t / M));
     for (int q = 0; q < 16; ++q)
         for (int l = 0; l < 16; ++l) T[q * 16 + l] = make_double2(std::cos(-2 * M_PI * q * l / 256), std::sin(-2 * M_PI * q * l / 256));
-    const size_t smem = (size_t)M + 256 + 2 * (L + 1) + n + 16;  // double2 units: X, then the larger of the two staging areas
+    const size_t smem = (size_t)M + 256 + 4 * (L + 1) + n + (L + 1) + 16;  // double2 units: X, then the larger of the two staging areas
     std::vector<double2> X(smem);
     emu::run_block(NT, [&](int tid) { filter_table_body<M1, NT>(pm, tid, X.data(), W1.data(), T.data(), filt.data()); });
 

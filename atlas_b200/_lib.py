@@ -58,6 +58,19 @@ def _load():
         "sptrans_invtrans_adj_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_dirtrans_wind2vordiv": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "sptrans_invtrans_grad": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_invtrans_adj": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp]),
+        "sptrans_invtrans_vordiv2wind_adj": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "sptrans_invtrans_grad_adj": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_dirtrans_adj_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_invtrans_field": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_dirtrans_field": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_invtrans_adj_field": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_invtrans_vordiv2wind_field": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "sptrans_dirtrans_wind2vordiv_field": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "sptrans_invtrans_grad_field": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_dirtrans_adj_field": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_invtrans_vordiv2wind_adj_field": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "sptrans_invtrans_grad_adj_field": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_vordiv_to_uv": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]),
         "sptrans_fourier_elems_per_field": (C.c_size_t, [vp]),
         "sptrans_invtrans_legendre": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),

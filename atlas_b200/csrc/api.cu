@@ -8,18 +8,9 @@
 
 #include "plan.hpp"
 
-struct sptrans_plan {
-    sptrans::Plan p;
-};
-
-namespace sptrans {
-int launch_merge_uv_scalar(cudaStream_t s, int T, int nvd, int nsc, const double* d_vor, const double* d_div,
-                           const double* d_sc, double* d_all, uint64_t* launches);
-}
-
 using namespace sptrans;
 
-namespace {
+namespace sptrans {
 
 bool is_device_pointer(const void* ptr) {
     if (!ptr) return false;
@@ -41,6 +32,10 @@ int ensure(double*& buf, size_t& cap, size_t need_doubles) {
     cap = need_doubles;
     return SPTRANS_OK;
 }
+
+}  // namespace sptrans
+
+namespace {
 
 template <class T>
 int upload(T*& dptr, const std::vector<T>& h, cudaStream_t s) {
@@ -242,6 +237,9 @@ int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, con
         if (!g.weights.empty()) {
             std::vector<double> w(g.weights.begin(), g.weights.begin() + g.nleg);
             if ((rc = upload(p.d_weights, w, p.stream))) return fail(rc);
+            std::vector<double> wn(g.nleg);
+            for (int j = 0; j < g.nleg; ++j) wn[j] = w[j] / g.nx[j];
+            if ((rc = upload(p.d_dirscale, wn, p.stream))) return fail(rc);
         }
     }
     if (cudaMalloc(&p.d_tile_counter, sizeof(int)) != cudaSuccess) {
@@ -275,9 +273,9 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     tc_free(p);
     peer_release(p);
     void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_owner, p.d_pair_done, p.d_weights,
-                    p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
+                    p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_dirscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
                     p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
-                    p.d_gp};
+                    p.d_gp, p.d_rows};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p.h_pinned) cudaFreeHost(p.h_pinned);
@@ -301,7 +299,7 @@ int sptrans_get_nlat0(const sptrans_plan* plan, int* nlat0) {
 size_t sptrans_device_bytes(const sptrans_plan* plan) {
     if (!plan) return 0;
     const Plan& p = plan->p;
-    return p.bytes_tables + (p.packed_cap + p.fourier_cap + p.spec_cap + p.spec2_cap + p.gp_cap) * sizeof(double);
+    return p.bytes_tables + (p.packed_cap + p.fourier_cap + p.spec_cap + p.spec2_cap + p.gp_cap + p.rows_cap) * sizeof(double);
 }
 
 size_t sptrans_legendre_cache_size(const sptrans_plan* plan) {

@@ -827,17 +827,18 @@ static Fft2Args make_v2_args(Plan& p, const FftGroups& grp, int nf) {
     return a;
 }
 
-int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv) {
+int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv, const double* d_scale) {
     int rc = ensure_block_lists(p, nf);
     if (rc) return rc;
     const FftGroups& grp = g_groups[&p];
+    const double* lat_scale = d_scale ? d_scale : p.d_coslatinv;  // per latitude pair, applied to fields < nb_uv
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         if (grp.nblocks[gi] == 0) continue;
         if (grp.mode[gi] == 2) {
             Fft2Args a = make_v2_args(p, grp, nf);
             a.mlimit = mlimit;
             a.nb_uv = nb_uv;
-            a.scale_lat = p.d_coslatinv;
+            a.scale_lat = lat_scale;
             a.fb = const_cast<double2*>(reinterpret_cast<const double2*>(d_fourier));
             a.gp = d_gp;
             switch (grp.m1[gi]) {
@@ -858,7 +859,7 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
             fourier_inv_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
                 reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
                 reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp,
-                p.d_filt, p.d_coslatinv, d_gp, p.g.npts);
+                p.d_filt, lat_scale, d_gp, p.g.npts);
             p.launches++;
             SPT_CUDA(cudaGetLastError());
             continue;
@@ -866,7 +867,7 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
         fourier_inv_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
             reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp,
-            p.d_filt, p.d_coslatinv, d_gp, p.g.npts);
+            p.d_filt, lat_scale, d_gp, p.g.npts);
         p.launches++;
         SPT_CUDA(cudaGetLastError());
     }
@@ -882,12 +883,15 @@ static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* 
     int rc = ensure_block_lists(p, nf);
     if (rc) return rc;
     const FftGroups& grp = g_groups[&p];
+    // wind fields enter the vor/div transform as u,v / (a cos(lat)); the adjoint of the inverse wind transform
+    // applies the inverse's own 1 / cos(lat)
+    const double* uv_scale = adjoint ? p.d_coslatinv : p.d_uvscale;
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         if (grp.nblocks[gi] == 0) continue;
         if (grp.mode[gi] == 2) {
             Fft2Args a = make_v2_args(p, grp, nf);
             a.nb_uv = nb_uv;
-            a.scale_lat = p.d_uvscale;
+            a.scale_lat = uv_scale;
             a.weights = p.d_weights;
             a.fb = reinterpret_cast<double2*>(d_fourier);
             a.gp = const_cast<double*>(d_gp);
@@ -911,7 +915,7 @@ static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* 
         if (grp.mode[gi]) {
             fourier_dir_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
                 reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
-                p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
+                p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, uv_scale,
                 reinterpret_cast<double2*>(d_fourier), adjoint);
             p.launches++;
             SPT_CUDA(cudaGetLastError());
@@ -919,7 +923,7 @@ static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* 
         }
         fourier_dir_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], p.stream>>>(
             reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
-            p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, p.d_uvscale,
+            p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, uv_scale,
             reinterpret_cast<double2*>(d_fourier), adjoint, d_owner, dst, p.g.rank, p.d_pair_done);
         p.launches++;
         SPT_CUDA(cudaGetLastError());

@@ -141,6 +141,7 @@ struct Plan {
     double* d_coslatinv = nullptr;     // [nleg] 1/cos(lat), latitude clamped to +-89.9999999 (TransLocal.cc:1447-1458)
     double* d_coslat = nullptr;        // [nleg]
     double* d_uvscale = nullptr;       // [nleg] 1/(a cos(lat)): wind -> scaled wind of the direct vor/div transform
+    double* d_dirscale = nullptr;      // [nleg] quadrature weight / nx: latitude factor of the adjoint of the direct transform
     long long* d_sp_rowoff = nullptr;  // [2(T+1)+1]
     int* d_my_m = nullptr;             // [my_m.size()]
     int* d_owner = nullptr;            // [T+1] rank that owns zonal wavenumber m
@@ -199,6 +200,10 @@ const char* last_error_cstr();
 
 void build_exchange(const HostGeom& g, ExchangeLayout& ex);
 
+// ---- api.cu ----
+bool is_device_pointer(const void* ptr);                          // cudaPointerGetAttributes: device or managed
+int ensure(double*& buf, size_t& cap, size_t need_doubles);       // grow-only device workspace
+
 // ---- host_setup.cc ----
 int fourier_truncation(int truncation, int nx, int nxmax, int ndgl, double lat, bool fullgrid);
 void gaussian_quadrature(int N, double* lat_deg_2N, double* weights_2N);
@@ -215,7 +220,7 @@ size_t legendre_cache_doubles(const HostGeom& g);
 
 // ---- legendre_f64.cu ----
 int build_tiles(Plan& p, int nf, int trunc, int dir_trunc);
-int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed);
+int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed, int dir_adj = 0);
 int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec, int drop_mT = 0);
 int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier);
 // same, every output row stored into the exchange buffer of the rank that owns its latitude band
@@ -232,7 +237,9 @@ void tc_free(Plan& p);
 // ---- fourier.cu ----
 int build_fft_tables(Plan& p);
 void free_fft_tables(Plan& p);
-int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv);
+// fields < nb_uv are multiplied by d_scale[latitude pair] in the store (default: 1 / cos(lat), the wind scaling)
+int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv,
+                       const double* d_scale = nullptr);
 int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint = 0);
 // sharded direct transform: every output row is stored into the exchange buffer of the rank that owns its zonal
 // wavenumber (NVLink stores).  *fused = false if the plan has row-mode groups, which write the local buffer only
@@ -253,7 +260,19 @@ int launch_gp_repack(Plan& p, int nlev, int ncomp, const double* d_in, double* d
 int launch_grad_spectra(cudaStream_t s, int T, int nf, const double* d_sp, double* d_all, uint64_t* launches);
 int launch_uv_to_vordiv(cudaStream_t s, int T, int nf, const long long* d_sp_rowoff, const double* d_packed,
                         double* d_vor, double* d_div, uint64_t* launches);
+int launch_merge_uv_scalar(cudaStream_t s, int T, int nvd, int nsc, const double* d_vor, const double* d_div,
+                           const double* d_sc, double* d_all, uint64_t* launches);
+// adjoints of the two spectral operators above, reading the packed output of the direct Legendre kernel at T+1
+int launch_merge_uv_scalar_adj(cudaStream_t s, int T, int nvd, int nsc, const long long* d_sp_rowoff, const double* d_packed,
+                               double* d_vor, double* d_div, double* d_sc, uint64_t* launches);
+int launch_grad_spectra_adj(cudaStream_t s, int T, int nf, const long long* d_sp_rowoff, const double* d_packed, double* d_sp,
+                            uint64_t* launches);
 int launch_vd2uv(cudaStream_t s, int T, int nf, const double* d_vor, const double* d_div, double* d_U, double* d_V,
                  uint64_t* launches);
 
 }  // namespace sptrans
+
+// the opaque handle of the C ABI
+struct sptrans_plan {
+    sptrans::Plan p;
+};

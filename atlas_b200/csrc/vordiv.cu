@@ -215,7 +215,116 @@ __global__ void uv_to_vordiv_kernel(int T, int nf, const long long* __restrict__
     }
 }
 
+
+// Adjoint (transpose over the reals) of merge_uv_scalar_kernel: from the adjoint variables of the merged fields
+// [U_1..U_k | V_1..V_k | s_1..s_j] at truncation T+1 -- read straight from the packed output of the direct Legendre
+// kernel, layout [m][parity][k][2 fld + re/im] -- to the adjoint variables of vor, div and the scalars at truncation T.
+// With c(n) = m lap(n), pm(n) = (n-1) eps(n,m) lap(n-1), pp(n) = (n+2) eps(n+1,m) lap(n+1) (the forward stencil above):
+//   zeta^_r(n) = [ pm(n+1) U^_r(n+1) - pp(n-1) U^_r(n-1) + c(n) V^_i(n) ] / a
+//   zeta^_i(n) = [ pm(n+1) U^_i(n+1) - pp(n-1) U^_i(n-1) - c(n) V^_r(n) ] / a
+//   D^_r(n)    = [-pm(n+1) V^_r(n+1) + pp(n-1) V^_r(n-1) + c(n) U^_i(n) ] / a
+//   D^_i(n)    = [-pm(n+1) V^_i(n+1) + pp(n-1) V^_i(n-1) - c(n) U^_r(n) ] / a
+// and the imaginary parts at m = 0, which the forward operator ignores, get zero.
+__global__ void merge_uv_scalar_adj_kernel(int T, int nvd, int nsc, const long long* __restrict__ sp_rowoff,
+                                           const double* __restrict__ packed, double* __restrict__ vor,
+                                           double* __restrict__ div, double* __restrict__ sc) {
+    const long long ncoef = static_cast<long long>(T + 1) * (T + 2) / 2;
+    const int nout = nvd + nsc;
+    const long long total = ncoef * nout;
+    const int ld = 2 * (2 * nvd + nsc);
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(e % nout);
+        const long long c = e / nout;
+        int m = static_cast<int>(((2.0 * T + 3.0) - sqrt((2.0 * T + 3.0) * (2.0 * T + 3.0) - 8.0 * static_cast<double>(c))) * 0.5);
+        while (static_cast<long long>(2 * T + 3 - m) * m / 2 > c) --m;
+        while (static_cast<long long>(2 * T + 3 - (m + 1)) * (m + 1) / 2 <= c) ++m;
+        const int n = m + static_cast<int>(c - static_cast<long long>(2 * T + 3 - m) * m / 2);
+        auto ext = [&](int nn, int imag, int fld) -> double {
+            if (nn < m || nn > T + 1) return 0.;
+            const int p = (nn - m) & 1, k = (nn - m) >> 1;
+            return packed[(sp_rowoff[2 * m + p] + k) * ld + 2 * fld + imag];
+        };
+        if (f >= nvd) {
+            const int fs = f - nvd, fm = 2 * nvd + fs;
+            sc[(2 * c) * nsc + fs] = ext(n, 0, fm);
+            sc[(2 * c + 1) * nsc + fs] = m == 0 ? 0. : ext(n, 1, fm);
+            continue;
+        }
+        const int fu = f, fv = nvd + f;
+        const double za_r = 1. / kEarthRadius;
+        const double cn = m * lapin(n);
+        const double pmn = n * epsnm(n + 1, m) * lapin(n);        // pm(n+1)
+        const double ppn = (n + 1) * epsnm(n, m) * lapin(n);      // pp(n-1)
+        double zr = (pmn * ext(n + 1, 0, fu) - ppn * ext(n - 1, 0, fu) + cn * ext(n, 1, fv)) * za_r;
+        double zi = (pmn * ext(n + 1, 1, fu) - ppn * ext(n - 1, 1, fu) - cn * ext(n, 0, fv)) * za_r;
+        double dr = (-pmn * ext(n + 1, 0, fv) + ppn * ext(n - 1, 0, fv) + cn * ext(n, 1, fu)) * za_r;
+        double di = (-pmn * ext(n + 1, 1, fv) + ppn * ext(n - 1, 1, fv) - cn * ext(n, 0, fu)) * za_r;
+        if (m == 0) zi = di = 0.;
+        vor[(2 * c) * nvd + f] = zr;
+        vor[(2 * c + 1) * nvd + f] = zi;
+        div[(2 * c) * nvd + f] = dr;
+        div[(2 * c + 1) * nvd + f] = di;
+    }
+}
+
+// Adjoint of grad_spectra_kernel: packed adjoint variables of [E-W_1..E-W_k | N-S_1..N-S_k] at T+1 -> scalar adjoint at T.
+// With cp(n) = (n+2) eps(n+1,m), cm(n) = (n-1) eps(n,m):
+//   X^_r(n) = [ +m EW^_i(n) + cp(n-1) NS^_r(n-1) - cm(n+1) NS^_r(n+1) ] / a
+//   X^_i(n) = [ -m EW^_r(n) + cp(n-1) NS^_i(n-1) - cm(n+1) NS^_i(n+1) ] / a      (zero at m = 0)
+__global__ void grad_spectra_adj_kernel(int T, int nf, const long long* __restrict__ sp_rowoff,
+                                        const double* __restrict__ packed, double* __restrict__ sp) {
+    const long long ncoef = static_cast<long long>(T + 1) * (T + 2) / 2;
+    const long long total = ncoef * nf;
+    const int ld = 4 * nf;
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(e % nf);
+        const long long c = e / nf;
+        int m = static_cast<int>(((2.0 * T + 3.0) - sqrt((2.0 * T + 3.0) * (2.0 * T + 3.0) - 8.0 * static_cast<double>(c))) * 0.5);
+        while (static_cast<long long>(2 * T + 3 - m) * m / 2 > c) --m;
+        while (static_cast<long long>(2 * T + 3 - (m + 1)) * (m + 1) / 2 <= c) ++m;
+        const int n = m + static_cast<int>(c - static_cast<long long>(2 * T + 3 - m) * m / 2);
+        auto ext = [&](int nn, int imag, int fld) -> double {
+            if (nn < m || nn > T + 1) return 0.;
+            const int p = (nn - m) & 1, k = (nn - m) >> 1;
+            return packed[(sp_rowoff[2 * m + p] + k) * ld + 2 * fld + imag];
+        };
+        const int few = f, fns = nf + f;
+        const double inv_a = 1. / kEarthRadius;
+        const double cpm = (n + 1) * epsnm(n, m);      // cp(n-1)
+        const double cmp = n * epsnm(n + 1, m);        // cm(n+1)
+        double xr = (+m * ext(n, 1, few) + cpm * ext(n - 1, 0, fns) - cmp * ext(n + 1, 0, fns)) * inv_a;
+        double xi = (-m * ext(n, 0, few) + cpm * ext(n - 1, 1, fns) - cmp * ext(n + 1, 1, fns)) * inv_a;
+        if (m == 0) xi = 0.;
+        sp[(2 * c) * nf + f] = xr;
+        sp[(2 * c + 1) * nf + f] = xi;
+    }
+}
+
 }  // namespace
+
+int launch_merge_uv_scalar_adj(cudaStream_t s, int T, int nvd, int nsc, const long long* d_sp_rowoff, const double* d_packed,
+                               double* d_vor, double* d_div, double* d_sc, uint64_t* launches) {
+    const long long total = static_cast<long long>(T + 1) * (T + 2) / 2 * (nvd + nsc);
+    if (total == 0) return SPTRANS_OK;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    merge_uv_scalar_adj_kernel<<<blocks, 256, 0, s>>>(T, nvd, nsc, d_sp_rowoff, d_packed, d_vor, d_div, d_sc);
+    if (launches) ++*launches;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int launch_grad_spectra_adj(cudaStream_t s, int T, int nf, const long long* d_sp_rowoff, const double* d_packed, double* d_sp,
+                            uint64_t* launches) {
+    const long long total = static_cast<long long>(T + 1) * (T + 2) / 2 * nf;
+    if (total == 0) return SPTRANS_OK;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    grad_spectra_adj_kernel<<<blocks, 256, 0, s>>>(T, nf, d_sp_rowoff, d_packed, d_sp);
+    if (launches) ++*launches;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
 
 int launch_grad_spectra(cudaStream_t s, int T, int nf, const double* d_sp, double* d_all, uint64_t* launches) {
     const long long total = static_cast<long long>(T + 2) * (T + 3) / 2 * (2 * nf);

@@ -114,7 +114,7 @@ class Trans:
         out = (C.c_float * 8)()
         _lib.check(_lib.lib.sptrans_last_timings(self._h, out))
         t = list(out)
-        return {"pack": t[0], "legendre": t[1], "fourier": t[2], "h2d": t[3], "d2h": t[4], "exchange_wait": t[5]}
+        return {"pack": t[0], "legendre": t[1], "fourier": t[2], "h2d": t[3], "d2h": t[4], "exchange_wait": t[5], "repack": t[6]}
 
     def set_precision(self, name):
         """'fp64' (default, DMMA) or 'tc' (tcgen05 split-TF32 Legendre stage, fp32-level accuracy)."""
@@ -166,10 +166,88 @@ class Trans:
         else:
             raise TypeError("dirtrans: wrong number of arguments")
 
-    def invtrans_adj(self, nb_fields, gp_fields, scalar_spectra):
-        """adjoint of invtrans(nb_fields, spectra, gp): <invtrans x, y> == <x, invtrans_adj y>  (TransImpl.h:155-157)"""
-        self._sync(gp_fields, scalar_spectra)
-        _lib.check(_lib.lib.sptrans_invtrans_adj_scalar(self._h, int(nb_fields), _ptr(gp_fields), _ptr(scalar_spectra)))
+    def invtrans_adj(self, *args):
+        """Adjoints of the three invtrans overloads, <invtrans x, y> == <x, invtrans_adj y>  (TransImpl.h:147-166):
+        invtrans_adj(nb_scalar, gp, scalar_spectra)
+        invtrans_adj(nb_vordiv, wind, vor, div)
+        invtrans_adj(nb_scalar, gp, nb_vordiv, vor, div, scalar_spectra)"""
+        self._sync(*args)
+        if len(args) == 3:
+            n, gp, sp = args
+            _lib.check(_lib.lib.sptrans_invtrans_adj_scalar(self._h, int(n), _ptr(gp), _ptr(sp)))
+        elif len(args) == 4:
+            n, wind, vor, div = args
+            _lib.check(_lib.lib.sptrans_invtrans_vordiv2wind_adj(self._h, int(n), _ptr(wind), _ptr(vor), _ptr(div)))
+        elif len(args) == 6:
+            ns, gp, nv, vor, div, sp = args
+            _lib.check(_lib.lib.sptrans_invtrans_adj(self._h, int(ns), _ptr(gp), int(nv), _ptr(vor), _ptr(div), _ptr(sp)))
+        else:
+            raise TypeError("invtrans_adj: wrong number of arguments")
+
+    def invtrans_grad_adj(self, nb_fields, grad_fields, scalar_spectra):
+        """adjoint of invtrans_grad (TransImpl.h:93-97)"""
+        self._sync(grad_fields, scalar_spectra)
+        _lib.check(_lib.lib.sptrans_invtrans_grad_adj(self._h, int(nb_fields), _ptr(grad_fields), _ptr(scalar_spectra)))
+
+    def dirtrans_adj(self, nb_fields, scalar_spectra, gp_fields):
+        """adjoint of dirtrans(nb_fields, gp, spectra) (TransImpl.h:63-67): spectra in, grid fields out"""
+        self._sync(scalar_spectra, gp_fields)
+        _lib.check(_lib.lib.sptrans_dirtrans_adj_scalar(self._h, int(nb_fields), _ptr(scalar_spectra), _ptr(gp_fields)))
+
+    # --- atlas Field layouts (TransImpl.h:54-100): spectral (nspec2, nlev); grid (npts, nlev) or (npts, nlev, 2) ---
+    def _nlev(self, sp, gp, ncomp):
+        """Number of levels from the array shapes, checked like the reference's Field overloads check ranks/sizes."""
+        nspec2, npts = self.nb_spectral_coefficients(), self.nb_gridpoints()
+        sshape, gshape = tuple(sp.shape), tuple(gp.shape)
+        if len(sshape) != 2 or sshape[0] != nspec2:
+            raise ValueError(f"spectral field must have shape ({nspec2}, nlev), got {sshape}")
+        nlev = int(sshape[1])
+        want = (npts, nlev) if ncomp == 1 else (npts, nlev, ncomp)
+        if gshape != want:
+            raise ValueError(f"grid-point field must have shape {want}, got {gshape}")
+        return nlev
+
+    def invtrans_field(self, spfield, gpfield):
+        self._sync(spfield, gpfield)
+        _lib.check(_lib.lib.sptrans_invtrans_field(self._h, self._nlev(spfield, gpfield, 1), _ptr(spfield), _ptr(gpfield)))
+
+    def dirtrans_field(self, gpfield, spfield):
+        self._sync(spfield, gpfield)
+        _lib.check(_lib.lib.sptrans_dirtrans_field(self._h, self._nlev(spfield, gpfield, 1), _ptr(gpfield), _ptr(spfield)))
+
+    def invtrans_adj_field(self, gpfield, spfield):
+        self._sync(spfield, gpfield)
+        _lib.check(_lib.lib.sptrans_invtrans_adj_field(self._h, self._nlev(spfield, gpfield, 1), _ptr(gpfield), _ptr(spfield)))
+
+    def invtrans_vordiv2wind_field(self, spvor, spdiv, gpwind):
+        self._sync(spvor, spdiv, gpwind)
+        nlev = self._nlev(spvor, gpwind, 2)
+        self._nlev(spdiv, gpwind, 2)
+        _lib.check(_lib.lib.sptrans_invtrans_vordiv2wind_field(self._h, nlev, _ptr(spvor), _ptr(spdiv), _ptr(gpwind)))
+
+    def dirtrans_wind2vordiv_field(self, gpwind, spvor, spdiv):
+        self._sync(spvor, spdiv, gpwind)
+        nlev = self._nlev(spvor, gpwind, 2)
+        self._nlev(spdiv, gpwind, 2)
+        _lib.check(_lib.lib.sptrans_dirtrans_wind2vordiv_field(self._h, nlev, _ptr(gpwind), _ptr(spvor), _ptr(spdiv)))
+
+    def dirtrans_adj_field(self, spfield, gpfield):
+        self._sync(spfield, gpfield)
+        _lib.check(_lib.lib.sptrans_dirtrans_adj_field(self._h, self._nlev(spfield, gpfield, 1), _ptr(spfield), _ptr(gpfield)))
+
+    def invtrans_vordiv2wind_adj_field(self, gpwind, spvor, spdiv):
+        self._sync(spvor, spdiv, gpwind)
+        nlev = self._nlev(spvor, gpwind, 2)
+        self._nlev(spdiv, gpwind, 2)
+        _lib.check(_lib.lib.sptrans_invtrans_vordiv2wind_adj_field(self._h, nlev, _ptr(gpwind), _ptr(spvor), _ptr(spdiv)))
+
+    def invtrans_grad_adj_field(self, gradfield, spfield):
+        self._sync(spfield, gradfield)
+        _lib.check(_lib.lib.sptrans_invtrans_grad_adj_field(self._h, self._nlev(spfield, gradfield, 2), _ptr(gradfield), _ptr(spfield)))
+
+    def invtrans_grad_field(self, spfield, gradfield):
+        self._sync(spfield, gradfield)
+        _lib.check(_lib.lib.sptrans_invtrans_grad_field(self._h, self._nlev(spfield, gradfield, 2), _ptr(spfield), _ptr(gradfield)))
 
     def invtrans_grad(self, nb_fields, scalar_spectra, grad_fields):
         """grad_fields = [E-W_1..E-W_k | N-S_1..N-S_k][npts]  (TransIFS::__invtrans_grad, ifs/TransIFS.cc:2075-2142)"""

@@ -100,28 +100,37 @@ public:
                   double divergence_spectra[], const eckit::Configuration& = util::NoConfig()) const override {
         check(sptrans_dirtrans_wind2vordiv(plan_, nb_fields, wind_fields, vorticity_spectra, divergence_spectra));
     }
-    void invtrans_adj(const int, const double[], const int, double[], double[], double[],
+    void invtrans_adj(const int nb_scalar_fields, const double gp_fields[], const int nb_vordiv_fields,
+                      double vorticity_spectra[], double divergence_spectra[], double scalar_spectra[],
                       const eckit::Configuration& = util::NoConfig()) const override {
-        ATLAS_NOTIMPLEMENTED;
+        check(sptrans_invtrans_adj(plan_, nb_scalar_fields, gp_fields, nb_vordiv_fields, vorticity_spectra,
+                                   divergence_spectra, scalar_spectra));
     }
     void invtrans_adj(const int nb_scalar_fields, const double gp_fields[], double scalar_spectra[],
                       const eckit::Configuration& = util::NoConfig()) const override {
         check(sptrans_invtrans_adj_scalar(plan_, nb_scalar_fields, gp_fields, scalar_spectra));
     }
-    void invtrans_adj(const int, const double[], double[], double[],
-                      const eckit::Configuration& = util::NoConfig()) const override {
-        ATLAS_NOTIMPLEMENTED;
+    void invtrans_adj(const int nb_vordiv_fields, const double wind_fields[], double vorticity_spectra[],
+                      double divergence_spectra[], const eckit::Configuration& = util::NoConfig()) const override {
+        check(sptrans_invtrans_vordiv2wind_adj(plan_, nb_vordiv_fields, wind_fields, vorticity_spectra, divergence_spectra));
     }
 
-    // ---- Field interface.  Like TransLocal (TransLocal.cc:818-844) rank-1 fields are one scalar field; in
-    // addition a rank-2 spectral field (nspec2, levels) / grid field (npts, levels) whose device copy is
-    // valid is transformed in place on the device (array/Array.h:177-183 device_data). ----
-    void invtrans(const Field& spfield, Field& gpfield, const eckit::Configuration& config = util::NoConfig()) const override {
-        ATLAS_ASSERT(spfield.rank() == 1, "Only rank-1 fields supported at the moment");
-        ATLAS_ASSERT(gpfield.rank() == 1, "Only rank-1 fields supported at the moment");
-        const auto sp = array::make_view<double, 1>(spfield);
-        auto gp       = array::make_view<double, 1>(gpfield);
-        invtrans(1, sp.data(), gp.data(), config);
+    // ---- Field interface.  TransLocal accepts rank-1 fields only (one scalar field, TransLocal.cc:818-844) and the
+    // (2, npts) / (npts, 2) wind field (:871-897).  This backend accepts those and, in addition, multi-level Fields in
+    // atlas's own layouts -- spectral (nspec2, levels), grid-point (nodes, levels), wind / gradient (nodes, levels, 2),
+    // last index fastest, owned nodes first (functionspace/detail/StructuredColumns.h:104-137) -- exactly what TransIFS
+    // packs on the host (ifs/TransIFS.cc:610-709, :1392-1437, :2113-2137).  If a Field's device copy is allocated and
+    // current (field/Field.h:191-202) the transform runs on it in place: array().device_data() (array/Array.h:177-183)
+    // goes straight to the engine, the level-fastest <-> row repack is a device transpose, nothing touches the host. ----
+    void invtrans(const Field& spfield, Field& gpfield, const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spfield, nb_spectral_coefficients(), "spectral field");
+        ATLAS_ASSERT(levels(gpfield, grid_.size(), "grid-point field") == nlev);
+        if (spfield.rank() == 1 && gpfield.rank() == 1) {
+            check(sptrans_invtrans_scalar(plan_, 1, in(spfield), out(gpfield)));
+        }
+        else {
+            check(sptrans_invtrans_field(plan_, nlev, in(spfield), out(gpfield)));
+        }
     }
     void invtrans(const FieldSet& spfields, FieldSet& gpfields, const eckit::Configuration& config = util::NoConfig()) const override {
         ATLAS_ASSERT(spfields.size() == gpfields.size());
@@ -129,12 +138,15 @@ public:
             invtrans(spfields[f], gpfields[f], config);
         }
     }
-    void dirtrans(const Field& gpfield, Field& spfield, const eckit::Configuration& config = util::NoConfig()) const override {
-        ATLAS_ASSERT(spfield.rank() == 1, "Only rank-1 fields supported at the moment");
-        ATLAS_ASSERT(gpfield.rank() == 1, "Only rank-1 fields supported at the moment");
-        const auto gp = array::make_view<double, 1>(gpfield);
-        auto sp       = array::make_view<double, 1>(spfield);
-        dirtrans(1, gp.data(), sp.data(), config);
+    void dirtrans(const Field& gpfield, Field& spfield, const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spfield, nb_spectral_coefficients(), "spectral field");
+        ATLAS_ASSERT(levels(gpfield, grid_.size(), "grid-point field") == nlev);
+        if (spfield.rank() == 1 && gpfield.rank() == 1) {
+            check(sptrans_dirtrans_scalar(plan_, 1, in(gpfield), out(spfield)));
+        }
+        else {
+            check(sptrans_dirtrans_field(plan_, nlev, in(gpfield), out(spfield)));
+        }
     }
     void dirtrans(const FieldSet& gpfields, FieldSet& spfields, const eckit::Configuration& config = util::NoConfig()) const override {
         ATLAS_ASSERT(spfields.size() == gpfields.size());
@@ -143,40 +155,136 @@ public:
         }
     }
     void invtrans_vordiv2wind(const Field& spvor, const Field& spdiv, Field& gpwind,
-                              const eckit::Configuration& config = util::NoConfig()) const override {
-        ATLAS_ASSERT(spvor.rank() == 1 && spdiv.rank() == 1, "Only rank-1 fields supported at the moment");
-        const auto vor = array::make_view<double, 1>(spvor);
-        const auto div = array::make_view<double, 1>(spdiv);
-        auto gp        = array::make_view<double, 2>(gpwind);
-        if (gp.shape(0) == 2) {  // (2, npts): the layout the engine writes (TransLocal.cc:885-887)
-            invtrans(1, vor.data(), div.data(), gp.data(), config);
+                              const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spvor, nb_spectral_coefficients(), "vorticity field");
+        ATLAS_ASSERT(levels(spdiv, nb_spectral_coefficients(), "divergence field") == nlev);
+        if (rows_layout(gpwind, nlev)) {  // (2, npts): the layout the engine works in (TransLocal.cc:885-887)
+            check(sptrans_invtrans_vordiv2wind(plan_, 1, in(spvor), in(spdiv), out(gpwind)));
+        }
+        else {  // (npts, 2) (TransLocal.cc:888-893) or (npts, levels, 2)
+            check_components(gpwind, nlev, "wind field");
+            check(sptrans_invtrans_vordiv2wind_field(plan_, nlev, in(spvor), in(spdiv), out(gpwind)));
+        }
+    }
+    void dirtrans_wind2vordiv(const Field& gpwind, Field& spvor, Field& spdiv,
+                              const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spvor, nb_spectral_coefficients(), "vorticity field");
+        ATLAS_ASSERT(levels(spdiv, nb_spectral_coefficients(), "divergence field") == nlev);
+        if (rows_layout(gpwind, nlev)) {
+            check(sptrans_dirtrans_wind2vordiv(plan_, 1, in(gpwind), out(spvor), out(spdiv)));
         }
         else {
-            ATLAS_NOTIMPLEMENTED;  // (npts, 2) needs a transpose pass -- see INTEGRATION.md
+            check_components(gpwind, nlev, "wind field");
+            check(sptrans_dirtrans_wind2vordiv_field(plan_, nlev, in(gpwind), out(spvor), out(spdiv)));
         }
     }
-    void dirtrans_wind2vordiv(const Field&, Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void dirtrans_adj(const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void dirtrans_adj(const FieldSet&, FieldSet&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void dirtrans_wind2vordiv_adj(const Field&, const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
     void invtrans_grad(const Field& spfield, Field& gradfield, const eckit::Configuration& = util::NoConfig()) const override {
-        // gradfield (2, npts): row 0 = E-W, row 1 = N-S (component order of ifs/TransIFS.cc:2113-2137)
-        ATLAS_ASSERT(spfield.rank() == 1 && gradfield.rank() == 2, "rank-1 spectral field, (2, npts) gradient field");
-        const auto sp = array::make_view<double, 1>(spfield);
-        auto g        = array::make_view<double, 2>(gradfield);
-        if (g.shape(0) != 2) {
-            ATLAS_NOTIMPLEMENTED;
+        // component 0 = E-W, 1 = N-S (ifs/TransIFS.cc:2113-2137)
+        const int nlev = levels(spfield, nb_spectral_coefficients(), "spectral field");
+        if (rows_layout(gradfield, nlev)) {
+            check(sptrans_invtrans_grad(plan_, 1, in(spfield), out(gradfield)));
         }
-        check(sptrans_invtrans_grad(plan_, 1, sp.data(), g.data()));
+        else {
+            check_components(gradfield, nlev, "gradient field");
+            check(sptrans_invtrans_grad_field(plan_, nlev, in(spfield), out(gradfield)));
+        }
     }
-    void invtrans_grad(const FieldSet&, FieldSet&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void invtrans_adj(const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void invtrans_adj(const FieldSet&, FieldSet&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void invtrans_grad_adj(const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void invtrans_grad_adj(const FieldSet&, FieldSet&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
-    void invtrans_vordiv2wind_adj(const Field&, Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
+    void invtrans_grad(const FieldSet& spfields, FieldSet& gradfields, const eckit::Configuration& config = util::NoConfig()) const override {
+        ATLAS_ASSERT(spfields.size() == gradfields.size());
+        for (idx_t f = 0; f < spfields.size(); ++f) {
+            invtrans_grad(spfields[f], gradfields[f], config);
+        }
+    }
+    // adjoints (ATLAS_NOTIMPLEMENTED in TransLocal, TransLocal.cc:899-929, :1647-1667)
+    void invtrans_adj(const Field& gpfield, Field& spfield, const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spfield, nb_spectral_coefficients(), "spectral field");
+        ATLAS_ASSERT(levels(gpfield, grid_.size(), "grid-point field") == nlev);
+        check(sptrans_invtrans_adj_field(plan_, nlev, in(gpfield), out(spfield)));
+    }
+    void invtrans_adj(const FieldSet& gpfields, FieldSet& spfields, const eckit::Configuration& config = util::NoConfig()) const override {
+        ATLAS_ASSERT(spfields.size() == gpfields.size());
+        for (idx_t f = 0; f < spfields.size(); ++f) {
+            invtrans_adj(gpfields[f], spfields[f], config);
+        }
+    }
+    void invtrans_grad_adj(const Field& gradfield, Field& spfield, const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spfield, nb_spectral_coefficients(), "spectral field");
+        if (rows_layout(gradfield, nlev)) {
+            check(sptrans_invtrans_grad_adj(plan_, 1, in(gradfield), out(spfield)));
+        }
+        else {
+            check_components(gradfield, nlev, "gradient field");
+            check(sptrans_invtrans_grad_adj_field(plan_, nlev, in(gradfield), out(spfield)));
+        }
+    }
+    void invtrans_grad_adj(const FieldSet& gradfields, FieldSet& spfields, const eckit::Configuration& config = util::NoConfig()) const override {
+        ATLAS_ASSERT(spfields.size() == gradfields.size());
+        for (idx_t f = 0; f < spfields.size(); ++f) {
+            invtrans_grad_adj(gradfields[f], spfields[f], config);
+        }
+    }
+    void invtrans_vordiv2wind_adj(const Field& gpwind, Field& spvor, Field& spdiv,
+                                  const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spvor, nb_spectral_coefficients(), "vorticity field");
+        ATLAS_ASSERT(levels(spdiv, nb_spectral_coefficients(), "divergence field") == nlev);
+        if (rows_layout(gpwind, nlev)) {
+            check(sptrans_invtrans_vordiv2wind_adj(plan_, 1, in(gpwind), out(spvor), out(spdiv)));
+        }
+        else {
+            check_components(gpwind, nlev, "wind field");
+            check(sptrans_invtrans_vordiv2wind_adj_field(plan_, nlev, in(gpwind), out(spvor), out(spdiv)));
+        }
+    }
+    void dirtrans_adj(const Field& spfield, Field& gpfield, const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spfield, nb_spectral_coefficients(), "spectral field");
+        ATLAS_ASSERT(levels(gpfield, grid_.size(), "grid-point field") == nlev);
+        check(sptrans_dirtrans_adj_field(plan_, nlev, in(spfield), out(gpfield)));
+    }
+    void dirtrans_adj(const FieldSet& spfields, FieldSet& gpfields, const eckit::Configuration& config = util::NoConfig()) const override {
+        ATLAS_ASSERT(spfields.size() == gpfields.size());
+        for (idx_t f = 0; f < spfields.size(); ++f) {
+            dirtrans_adj(spfields[f], gpfields[f], config);
+        }
+    }
+    // adjoint of wind -> vor/div: not provided by this engine either (TransLocal.cc:1661-1667)
+    void dirtrans_wind2vordiv_adj(const Field&, const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
 
 private:
+    // Pointer the engine reads: the device copy of the Field if it is allocated and current, else the host copy.
+    static const double* in(const Field& f) {
+        if (f.deviceAllocated() && !f.deviceNeedsUpdate()) {
+            return f.array().template device_data<double>();
+        }
+        return f.array().template host_data<double>();
+    }
+    // Pointer the engine writes; the other copy of the Field is marked stale.
+    static double* out(Field& f) {
+        if (f.deviceAllocated() && !f.deviceNeedsUpdate()) {
+            f.setHostNeedsUpdate(true);
+            return f.array().template device_data<double>();
+        }
+        f.setDeviceNeedsUpdate(true);
+        return f.array().template host_data<double>();
+    }
+    // levels of a spectral (nspec2[, levels]) or scalar grid-point (nodes[, levels]) Field; like TransLocal a grid-point
+    // Field may carry halo nodes after the owned ones (TransLocal.cc:825-830)
+    static int levels(const Field& f, size_t min_leading, const char* what) {
+        ATLAS_ASSERT(f.rank() == 1 || f.rank() == 2, what);
+        ATLAS_ASSERT(static_cast<size_t>(f.shape()[0]) >= min_leading, what);
+        return f.rank() == 1 ? 1 : static_cast<int>(f.shape()[1]);
+    }
+    // (2, npts): one level in the engine's own row layout
+    bool rows_layout(const Field& f, int nlev) const {
+        return nlev == 1 && f.rank() == 2 && f.shape()[0] == 2 && f.shape()[1] == grid_.size();
+    }
+    // (npts, 2) for one level, (npts, levels, 2) otherwise
+    void check_components(const Field& f, int nlev, const char* what) const {
+        const bool ok = (f.rank() == 2 && nlev == 1 && f.shape()[0] >= grid_.size() && f.shape()[1] == 2) ||
+                        (f.rank() == 3 && f.shape()[0] >= grid_.size() && f.shape()[1] == nlev && f.shape()[2] == 2);
+        if (!ok) {
+            throw_NotImplemented(std::string("TransB200: unsupported shape of the ") + what, Here());
+        }
+    }
     static void check(int rc) {
         if (rc == SPTRANS_OK) {
             return;

@@ -158,6 +158,47 @@ int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nb_fields, const double
  * (ifs/TransIFS.cc:2075-2142).  NotImplemented in TransLocal (TransLocal.cc:848-857).                          */
 int sptrans_invtrans_grad(sptrans_plan* plan, int nb_fields, const double* scalar_spectra, double* grad_fields);
 
+/* ---- adjoints.  ATLAS_NOTIMPLEMENTED in TransLocal (TransLocal.cc:899-929, :1599-1667); semantics of the reference's
+ * adjoint tests (src/tests/trans/test_transgeneral.cc:1591-1818): the transpose over the reals of the forward operator,
+ * <A x, y> = <x, A^T y> with Euclidean sums over every stored double. ---------------------------------------------- */
+
+/* TransImpl::invtrans_adj(nb_scalar_fields, gp_fields, nb_vordiv_fields, vor, div, scalar_spectra)  TransImpl.h:147-149
+ * adjoint of sptrans_invtrans: gp layout [u_1..u_k | v_1..v_k | s_1..s_j][npts] in, spectra at truncation T out. */
+int sptrans_invtrans_adj(sptrans_plan* plan, int nb_scalar_fields, const double* gp_fields, int nb_vordiv_fields,
+                         double* vorticity_spectra, double* divergence_spectra, double* scalar_spectra);
+/* TransImpl::invtrans_adj(nb_vordiv_fields, wind_fields, vor, div)                                  TransImpl.h:165-166
+ * = atlas__Trans__invtrans_vordiv2wind_adj (trans/detail/TransInterface.h:66-67) */
+int sptrans_invtrans_vordiv2wind_adj(sptrans_plan* plan, int nb_vordiv_fields, const double* wind_fields,
+                                     double* vorticity_spectra, double* divergence_spectra);
+/* TransImpl::invtrans_grad_adj(gradfield, spfield) in IFS-style pointers (TransImpl.h:93-97): adjoint of
+ * sptrans_invtrans_grad, grad layout [E-W_1..E-W_k | N-S_1..N-S_k][npts] in. */
+int sptrans_invtrans_grad_adj(sptrans_plan* plan, int nb_fields, const double* grad_fields, double* scalar_spectra);
+/* TransImpl::dirtrans_adj(spfield, gpfield) in IFS-style pointers (TransImpl.h:63-67): adjoint of
+ * sptrans_dirtrans_scalar -- spectra in, grid fields out (needs quadrature weights). */
+int sptrans_dirtrans_adj_scalar(sptrans_plan* plan, int nb_fields, const double* scalar_spectra, double* gp_fields);
+
+/* ---- atlas Field layouts (multi-level Fields).  Entry points behind TransImpl's Field overloads
+ * (trans/detail/TransImpl.h:54-100; C bindings atlas__Trans__*_field, trans/detail/TransInterface.h:72-96).
+ * A spectral Field (nspec2, nlev) IS the raw [coeff][field] layout.  A grid-point Field is (node, level) for scalars and
+ * (node, level, 2) for wind / gradient, LAST index fastest (owned nodes 0..npts-1 in grid order,
+ * functionspace/detail/StructuredColumns.h:104-137): the transpose of the [field][node] rows above, with
+ * field = component * nlev + level exactly as TransIFS packs them on the host (trans/ifs/TransIFS.cc:610-667,
+ * :1392-1437, :2113-2137).  Here the repack is one tiled transpose on the device; pointers may be host or device
+ * (an atlas Field whose device copy is valid passes array().device_data(), array/Array.h:177-183). ----------------- */
+int sptrans_invtrans_field(sptrans_plan* plan, int nlev, const double* spfield, double* gpfield);
+int sptrans_dirtrans_field(sptrans_plan* plan, int nlev, const double* gpfield, double* spfield);
+int sptrans_invtrans_adj_field(sptrans_plan* plan, int nlev, const double* gpfield, double* spfield);
+int sptrans_invtrans_vordiv2wind_field(sptrans_plan* plan, int nlev, const double* spvor, const double* spdiv,
+                                       double* gpwind /* (npts, nlev, 2): component 0 = u, 1 = v */);
+int sptrans_dirtrans_wind2vordiv_field(sptrans_plan* plan, int nlev, const double* gpwind, double* spvor,
+                                       double* spdiv);
+int sptrans_invtrans_grad_field(sptrans_plan* plan, int nlev, const double* spfield,
+                                double* gradfield /* (npts, nlev, 2): component 0 = E-W, 1 = N-S */);
+int sptrans_dirtrans_adj_field(sptrans_plan* plan, int nlev, const double* spfield, double* gpfield);
+int sptrans_invtrans_vordiv2wind_adj_field(sptrans_plan* plan, int nlev, const double* gpwind, double* spvor,
+                                           double* spdiv);
+int sptrans_invtrans_grad_adj_field(sptrans_plan* plan, int nlev, const double* gradfield, double* spfield);
+
 /* VorDivToUV::execute(nb_coeff, nb_fields, vor, div, U, V)   trans/VorDivToUV.h:121-122,
  * = vd2uv, trans/local/VorDivToUVLocal.cc:62-184.  Plan-free: spectral space only.                            */
 int sptrans_vordiv_to_uv(int truncation, int nb_fields, const double* vorticity, const double* divergence,
@@ -224,7 +265,8 @@ int sptrans_peer_advance(sptrans_plan* plan);
 
 /* kernel time of the last call's stages in milliseconds (CUDA events on the plan's stream):
  * out[0]=pack/unpack+vd2uv, out[1]=Legendre GEMM, out[2]=Fourier, out[3]=H2D, out[4]=D2H,
- * out[5]=wait at the exchange barrier (sharded calls; these read their events lazily here) */
+ * out[5]=wait at the exchange barrier (sharded calls; these read their events lazily here),
+ * out[6]=Field-layout repack (the *_field entry points) */
 int sptrans_last_timings(const sptrans_plan* plan, float out_ms[8]);
 /* number of kernels this library launched on behalf of the plan since creation */
 uint64_t sptrans_kernel_launches(const sptrans_plan* plan);

@@ -1,4 +1,5 @@
-// Mock of atlas::Field / FieldSet (field/Field.h:64-206): rank, shape and contiguous double storage.
+// Mock of atlas::Field / FieldSet (field/Field.h:64-206): rank, shape, contiguous double storage, and the host/device
+// state interface of field/Field.h:191-202 + array/Array.h:168-183 (this mock has no device copy).
 #pragma once
 #include <memory>
 #include <string>
@@ -17,6 +18,18 @@ public:
     const std::vector<idx_t>& shape() const { return shape_; }
     double* data() { return store_->data(); }
     const double* data() const { return store_->data(); }
+    // array().host_data<T>() / device_data<T>()  (array/Array.h:168-183)
+    struct ArrayRef {
+        double* p;
+        template <typename T> T* host_data() const { return p; }
+        template <typename T> T* device_data() const { return nullptr; }
+    };
+    ArrayRef array() const { return ArrayRef{store_->data()}; }
+    bool deviceAllocated() const { return false; }
+    bool hostNeedsUpdate() const { return false; }
+    bool deviceNeedsUpdate() const { return true; }
+    void setHostNeedsUpdate(bool) const {}
+    void setDeviceNeedsUpdate(bool) const {}
 private:
     std::string name_;
     std::vector<idx_t> shape_;

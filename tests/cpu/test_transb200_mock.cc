@@ -52,14 +52,32 @@ int main() {
     t->dirtrans(gp, back);
     double err2 = std::fabs(back.data()[0] - 4.);
     for (size_t i = 1; i < t->nb_spectral_coefficients(); ++i) err2 = std::fmax(err2, std::fabs(back.data()[i]));
+    // multi-level Fields in atlas's layouts: spectral (nspec2, nlev), grid-point (npts, nlev) level-fastest
+    const idx_t nlev = 3;
+    const idx_t nspec2 = idx_t(t->nb_spectral_coefficients());
+    Field spl("spl", {nspec2, nlev}), gpl("gpl", {grid.size(), nlev}), backl("backl", {nspec2, nlev});
+    for (idx_t l = 0; l < nlev; ++l) spl.data()[0 * nlev + l] = 1. + l;  // (m=0,n=0) of level l
+    t->invtrans(spl, gpl);
+    double err3 = 0;
+    for (idx_t i = 0; i < grid.size(); ++i)
+        for (idx_t l = 0; l < nlev; ++l) err3 = std::fmax(err3, std::fabs(gpl.data()[i * nlev + l] - (1. + l)));
+    t->dirtrans(gpl, backl);
+    for (idx_t l = 0; l < nlev; ++l) err3 = std::fmax(err3, std::fabs(backl.data()[l] - (1. + l)));
+    // wind Field (npts, nlev, 2) from zero vorticity / divergence is zero; the adjoint Field overloads run
+    Field vor("vor", {nspec2, nlev}), dv("div", {nspec2, nlev}), wind("wind", {grid.size(), nlev, 2});
+    wind.data()[5] = 7.;
+    t->invtrans_vordiv2wind(vor, dv, wind);
+    for (idx_t i = 0; i < grid.size() * nlev * 2; ++i) err3 = std::fmax(err3, std::fabs(wind.data()[i]));
+    t->invtrans_adj(gpl, backl);
+    t->dirtrans_adj(spl, gpl);
     bool threw = false;
     try {
-        FieldSet a, b;
-        t->invtrans_grad(a, b);
+        t->dirtrans_wind2vordiv_adj(vor, dv, wind);
     }
     catch (const eckit::NotImplemented&) {
         threw = true;
     }
-    std::printf("TransB200 via factory: invtrans err %.3e, dirtrans err %.3e, NotImplemented thrown: %d\n", err, err2, threw);
-    return (err < 1e-13 && err2 < 1e-13 && threw) ? 0 : 1;
+    std::printf("TransB200 via factory: invtrans err %.3e, dirtrans err %.3e, multi-level Field err %.3e, NotImplemented thrown: %d\n",
+                err, err2, err3, threw);
+    return (err < 1e-13 && err2 < 1e-13 && err3 < 1e-13 && threw) ? 0 : 1;
 }

@@ -1,0 +1,170 @@
+"""GPU tests of the atlas Field-layout entry points and of the adjoint transforms.
+
+Field layouts: a multi-level grid-point Field is (node, level[, component]) with the last index fastest, the transpose
+of the IFS-style [field][node] rows; TransIFS packs field = component * nlev + level (trans/ifs/TransIFS.cc:610-667,
+:1392-1437, :2113-2137).  The *_field entry points must give exactly (bit for bit) the transposed result of the
+raw-pointer entry points, which the parity tests pin against the oracle.
+
+Adjoints: the reference's own adjoint tests (src/tests/trans/test_transgeneral.cc:1591-1818) check the dot-product
+identity <A x, y> == <x, A^T y>; TransLocal itself implements no adjoint (parity unpinned), so the identity -- against
+the forward operators the other tests pin -- is the definition.  Tolerance: 1e-12 relative to |Ax||y|.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def make(gridname, T):
+    import atlas_b200
+
+    grid = atlas_b200.Grid(gridname)
+    return grid, atlas_b200.Trans(grid, T, atlas_b200.option.type("b200"))
+
+
+def rows_to_field(rows, npts, nlev, ncomp):
+    """[ncomp * nlev][npts] -> (npts, nlev, ncomp) / (npts, nlev)"""
+    a = rows.reshape(ncomp, nlev, npts).transpose(2, 1, 0)
+    return np.ascontiguousarray(a if ncomp > 1 else a[:, :, 0])
+
+
+def field_to_rows(field, npts, nlev, ncomp):
+    a = field.reshape(npts, nlev, ncomp).transpose(2, 1, 0)
+    return np.ascontiguousarray(a).reshape(-1)
+
+
+@pytest.mark.parametrize("gridname,T,nlev", [("O48", 47, 5), ("F24", 23, 1), ("O80", 79, 37)])
+def test_field_layout_scalar(gridname, T, nlev):
+    grid, trans = make(gridname, T)
+    npts, nspec2 = grid.size(), trans.nb_spectral_coefficients()
+    sp = H.synthetic_spectra(T, nlev).reshape(nspec2, nlev)
+    rows = np.full(nlev * npts, np.nan)
+    trans.invtrans(nlev, sp.reshape(-1), rows)
+    gpf = np.full((npts, nlev), np.nan)
+    trans.invtrans_field(sp, gpf)
+    assert np.array_equal(gpf, rows_to_field(rows, npts, nlev, 1))
+    # direct transform and adjoint of the inverse from the Field layout
+    back_rows = np.full(nspec2 * nlev, np.nan)
+    trans.dirtrans(nlev, rows, back_rows)
+    back = np.full((nspec2, nlev), np.nan)
+    trans.dirtrans_field(gpf, back)
+    assert np.array_equal(back.reshape(-1), back_rows)
+    adj_rows = np.full(nspec2 * nlev, np.nan)
+    trans.invtrans_adj(nlev, rows, adj_rows)
+    adj = np.full((nspec2, nlev), np.nan)
+    trans.invtrans_adj_field(gpf, adj)
+    assert np.array_equal(adj.reshape(-1), adj_rows)
+    assert trans.last_timings()["repack"] > 0.0
+
+
+@pytest.mark.parametrize("gridname,T,nlev", [("O48", 47, 3), ("F24", 23, 2)])
+def test_field_layout_wind_and_gradient(gridname, T, nlev):
+    grid, trans = make(gridname, T)
+    npts, nspec2 = grid.size(), trans.nb_spectral_coefficients()
+    vor = H.synthetic_spectra(T, nlev, seed=3).reshape(nspec2, nlev)
+    div = H.synthetic_spectra(T, nlev, seed=4).reshape(nspec2, nlev)
+    rows = np.full(2 * nlev * npts, np.nan)
+    trans.invtrans(nlev, vor.reshape(-1), div.reshape(-1), rows)
+    wind = np.full((npts, nlev, 2), np.nan)
+    trans.invtrans_vordiv2wind_field(vor, div, wind)
+    assert np.array_equal(wind, rows_to_field(rows, npts, nlev, 2))
+    v_rows, d_rows = np.full(nspec2 * nlev, np.nan), np.full(nspec2 * nlev, np.nan)
+    trans.dirtrans(nlev, rows, v_rows, d_rows)
+    v_f, d_f = np.full((nspec2, nlev), np.nan), np.full((nspec2, nlev), np.nan)
+    trans.dirtrans_wind2vordiv_field(wind, v_f, d_f)
+    assert np.array_equal(v_f.reshape(-1), v_rows) and np.array_equal(d_f.reshape(-1), d_rows)
+    g_rows = np.full(2 * nlev * npts, np.nan)
+    trans.invtrans_grad(nlev, vor.reshape(-1), g_rows)
+    grad = np.full((npts, nlev, 2), np.nan)
+    trans.invtrans_grad_field(vor, grad)
+    assert np.array_equal(grad, rows_to_field(g_rows, npts, nlev, 2))
+
+
+def test_field_layout_device_pointers_and_errors():
+    import torch
+
+    from atlas_b200 import _lib
+
+    grid, trans = make("O48", 47)
+    T, nlev = 47, 4
+    npts, nspec2 = grid.size(), trans.nb_spectral_coefficients()
+    sp = H.synthetic_spectra(T, nlev).reshape(nspec2, nlev)
+    want = np.full((npts, nlev), np.nan)
+    trans.invtrans_field(sp, want)
+    d_sp = torch.from_numpy(sp).cuda()
+    d_gp = torch.full((npts, nlev), float("nan"), dtype=torch.float64, device="cuda")
+    trans.invtrans_field(d_sp, d_gp)
+    assert np.array_equal(d_gp.cpu().numpy(), want)
+    d_back = torch.full((nspec2, nlev), float("nan"), dtype=torch.float64, device="cuda")
+    trans.dirtrans_field(d_gp, d_back)
+    back = np.full((nspec2, nlev), np.nan)
+    trans.dirtrans_field(want, back)
+    assert np.array_equal(d_back.cpu().numpy(), back)
+    with pytest.raises(ValueError):
+        trans.invtrans_field(sp, np.zeros((npts, nlev + 1)))
+    with pytest.raises(_lib.SptransError):
+        _lib.check(_lib.lib.sptrans_invtrans_field(trans._h, 2, None, None))
+    _lib.check(_lib.lib.sptrans_invtrans_field(trans._h, 0, None, None))  # zero levels: nothing to do
+
+
+def _close(lhs, rhs, scale):
+    return abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), scale * 1e-3)
+
+
+@pytest.mark.parametrize("gridname,T,nvd,nsc", [("F24", 23, 2, 0), ("O48", 47, 3, 2), ("L9", 17, 1, 1), ("O400", 399, 2, 1)])
+def test_invtrans_wind_adjoint_identity(gridname, T, nvd, nsc):
+    """<invtrans(scalars, vor, div), y> == <(scalars, vor, div), invtrans_adj y>  (TransImpl.h:147-149, :165-166)."""
+    grid, trans = make(gridname, T)
+    npts = grid.size()
+    nspec2 = trans.nb_spectral_coefficients()
+    rng = np.random.default_rng(11)
+    vor = rng.standard_normal(nspec2 * nvd)
+    div = rng.standard_normal(nspec2 * nvd)
+    sc = rng.standard_normal(nspec2 * max(nsc, 1))
+    y = rng.standard_normal((2 * nvd + nsc) * npts)
+    ax = np.full((2 * nvd + nsc) * npts, np.nan)
+    if nsc:
+        trans.invtrans(nsc, sc, nvd, vor, div, ax)
+    else:
+        trans.invtrans(nvd, vor, div, ax)
+    av, ad, asc = np.full_like(vor, np.nan), np.full_like(div, np.nan), np.full_like(sc, np.nan)
+    if nsc:
+        trans.invtrans_adj(nsc, y, nvd, av, ad, asc)
+    else:
+        trans.invtrans_adj(nvd, y, av, ad)
+    lhs = float(ax @ y)
+    rhs = float(vor @ av + div @ ad) + (float(sc @ asc) if nsc else 0.0)
+    assert _close(lhs, rhs, np.linalg.norm(ax) * np.linalg.norm(y)), (lhs, rhs)
+
+
+@pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("O400", 399, 2)])
+def test_invtrans_grad_adjoint_identity(gridname, T, nf):
+    grid, trans = make(gridname, T)
+    npts, nspec2 = grid.size(), trans.nb_spectral_coefficients()
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal(nspec2 * nf)
+    y = rng.standard_normal(2 * nf * npts)
+    ax = np.full(2 * nf * npts, np.nan)
+    trans.invtrans_grad(nf, x, ax)
+    ay = np.full_like(x, np.nan)
+    trans.invtrans_grad_adj(nf, y, ay)
+    lhs, rhs = float(ax @ y), float(x @ ay)
+    assert _close(lhs, rhs, np.linalg.norm(ax) * np.linalg.norm(y)), (lhs, rhs)
+
+
+@pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("O160", 159, 5), ("O400", 399, 2)])
+def test_dirtrans_adjoint_identity(gridname, T, nf):
+    """<dirtrans g, s> == <g, dirtrans_adj s>  (TransImpl::dirtrans_adj, TransImpl.h:63-67)."""
+    grid, trans = make(gridname, T)
+    npts, nspec2 = grid.size(), trans.nb_spectral_coefficients()
+    rng = np.random.default_rng(13)
+    g = rng.standard_normal(nf * npts)
+    s = rng.standard_normal(nspec2 * nf)
+    dg = np.full(nspec2 * nf, np.nan)
+    trans.dirtrans(nf, g, dg)
+    ds = np.full(nf * npts, np.nan)
+    trans.dirtrans_adj(nf, s, ds)
+    lhs, rhs = float(dg @ s), float(g @ ds)
+    assert _close(lhs, rhs, np.linalg.norm(dg) * np.linalg.norm(s)), (lhs, rhs)

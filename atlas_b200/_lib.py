@@ -49,6 +49,7 @@ def _load():
         "sptrans_device_bytes": (C.c_size_t, [vp]),
         "sptrans_legendre_cache_size": (C.c_size_t, [vp]),
         "sptrans_export_legendre_cache": (C.c_int, [vp, vp]),
+        "sptrans_import_legendre_cache": (C.c_int, [vp, vp, C.c_size_t]),
         "sptrans_set_stream": (C.c_int, [vp, vp]),
         "sptrans_set_precision": (C.c_int, [vp, C.c_int]),
         "sptrans_invtrans_scalar": (C.c_int, [vp, C.c_int, vp, vp]),

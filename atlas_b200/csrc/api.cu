@@ -250,6 +250,7 @@ int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, con
     if ((rc = upload(p.d_ex_m, p.ex.m_side, p.stream))) return fail(rc);
     if ((rc = upload(p.d_ex_band, p.ex.band_side, p.stream))) return fail(rc);
     if ((rc = generate_legendre_table(p))) return fail(rc);
+    if ((rc = build_transposed_table(p))) return fail(rc);
     if ((rc = build_fft_tables(p))) return fail(rc);
     if (cudaStreamSynchronize(p.stream) != cudaSuccess) {
         set_error(std::string("plan setup failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -272,7 +273,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     free_fft_tables(p);
     tc_free(p);
     peer_release(p);
-    void* ptrs[] = {p.d_tab, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_owner, p.d_pair_done, p.d_weights,
+    void* ptrs[] = {p.d_tab, p.d_tabT, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_owner, p.d_pair_done, p.d_weights,
                     p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_dirscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
                     p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
                     p.d_gp, p.d_rows};
@@ -312,6 +313,16 @@ int sptrans_export_legendre_cache(const sptrans_plan* plan, void* out) {
     }
     SPT_CUDA(cudaSetDevice(plan->p.device));
     return export_legendre_cache(plan->p, static_cast<double*>(out));
+}
+
+int sptrans_import_legendre_cache(sptrans_plan* plan, const void* blob, size_t bytes) {
+    if (!plan || !blob) {
+        set_error("sptrans_import_legendre_cache: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    return import_legendre_cache(plan->p, static_cast<const double*>(blob), bytes);
 }
 
 int sptrans_set_precision(sptrans_plan* plan, int precision) {

@@ -1,0 +1,231 @@
+// fp64 Legendre GEMM kernel, TMA-fed and warp-decoupled variant (the default; legendre_f64.cu keeps the per-thread
+// cp.async kernel behind -DSPT_BULK=0 as the baseline it was measured against).
+//
+// Same tiling as the baseline -- one CTA per SM, 8 warps as 4 x 2, warp tile 32 x 72 = 4 x 9 DMMA m8n8k4 tiles, a ring of
+// kStages shared-memory stages of kBK contraction steps -- but
+//   * operands are fetched by the TMA engine: per stage 16 + 16 one-dimensional bulk copies (cp.async.bulk.shared.global,
+//     SASS UBLKCP), one per operand row (A: 128 doubles of the table, B: <= 144 doubles of spectra / Fourier rows),
+//     completing on the stage's `full` mbarrier (expect-tx byte counts).  Every warp issues the copies of its own two A
+//     rows and two B rows -- ~20 instructions per warp and stage instead of ~220 per thread with cp.async, and no single
+//     producer warp that the others wait for (UBLKCP takes uniform operands: a warp issuing all 32 copies runs a 32-trip
+//     serial loop and was measured to hold the block barrier up by ~900 cycles per stage);
+//   * stages are still handed back through one __syncthreads() per stage: replacing it by per-stage `empty` mbarriers
+//     (warps drifting up to a stage apart) was measured SLOWER (19.8 ms vs 17.6 ms inverse at TCo1279 L137) -- the two
+//     warps of a sub-partition share the DMMA pipe best when they alternate 9-DMMA groups in lock step;
+//   * both directions read K-major A tiles: the direct transform uses a transposed copy of the table (P^T, [lat][k] per
+//     (m, parity) block, same block offsets), so its A rows are 1 KB copies as well (128-byte copies of the untransposed
+//     table made the TMA issue rate the bottleneck: 35 ms instead of 18 ms).
+//
+// Rows / columns of a stage that lie outside the operand are never copied: the stale shared-memory values there only
+// reach rows / columns of C that are not stored.  The one exception are latitude rows of B past the end of a direct
+// tile's block, whose table entries are zero: they are cleared, because 0 x (stale NaN) would poison the sum.
+// (included by legendre_f64.cu inside namespace sptrans::<anonymous>, after the tile constants and dmma884)
+#pragma once
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking probe
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // bounded spin: a protocol bug ends in a trap (reported as a CUDA error), never in a hung device
+    for (long long it = 0; it < (1ll << 31); ++it)
+        if (mbar_try(bar, parity)) return;
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kBulkAStage = kBK * (kBM + 4);  // As[kBK][kBM + 4] for both directions
+constexpr int kBulkAPitch = kBM + 4;
+constexpr size_t kBulkSmemBytes = static_cast<size_t>(kStages) * (kBulkAStage + kBStage) * sizeof(double) + 16;
+static_assert(kBK == 16, "one operand row per lane of the producer warp");
+
+// kDirect == false : A = table P   (tile [kBK n-rows][kBM latitudes]),  B = packed spectra,  C = Fourier buffer
+// kDirect == true  : A = table P^T (tile [kBK latitudes][kBM n-rows]),  B = Fourier buffer,  C = packed spectra
+template <bool kDirect, bool kPeers>
+__global__ void __launch_bounds__(kLegThreads, 1)
+legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
+                     const double* __restrict__ tab, const double* __restrict__ B, double* __restrict__ C, int ldb,
+                     const __grid_constant__ PeerDst dst) {
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + kStages * kBulkAStage;
+    __shared__ LegTile s_tl[2];   // current / next tile descriptor (fetched one tile ahead by thread 0)
+    __shared__ int s_ti[2];
+    __shared__ __align__(8) uint64_t s_full[kStages];   // the bulk copies of stage s have landed
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    // warp -> (row block, column block): consecutive warps (= the four SM sub-partitions) cover the first two row
+    // blocks, so that a partial tile with <= 64 valid rows still keeps every sub-partition's FP64 pipe busy
+    const int wm = warp / kWarpsN, wn = warp % kWarpsN;
+    uint32_t full_phase = 0;                        // bit s: parity of the completion of s_full[s] to wait for next
+
+    // Every warp fetches its own share of a stage: rows [rpw * warp, rpw * (warp + 1)) of A and of B, one bulk copy per
+    // lane (lanes 0..rpw-1: A rows, lanes rpw..2 rpw-1: B rows), after ONE arrive.expect_tx for the warp's bytes
+    // (`full` counts the eight warps).  The stage must have been released by all warps (block barrier).
+    constexpr int rpw = kBK / (kLegThreads / 32);
+    auto load_stage = [&](const LegTile& tl, int kb, int st) {
+        const double* Ag = tab + tl.a_off;
+        const double* Bg = B + tl.b_off;
+        double* as = As + st * kBulkAStage;
+        double* bs = Bs + st * kBStage;
+        uint64_t* bar = &s_full[st];
+        const uint32_t a_bytes = static_cast<uint32_t>(min(kBM, tl.a_rows)) * 8u;  // readable part of an A row
+        const uint32_t b_bytes = static_cast<uint32_t>(tl.n_valid) * 8u;
+        const int row0 = rpw * warp;                                              // first row of this warp's share
+        const int b_tot = kDirect ? max(0, min(kBK, tl.b_rows - kb * kBK)) : kBK;  // B rows inside the block
+        const int b_n = max(0, min(rpw, b_tot - row0));                            // ... of this warp's share
+        if (kDirect && lane >= rpw + b_n && lane < 2 * rpw)  // latitude past the block: table entries are zero, B must be finite
+            for (int c = 0; c < kBN; c += 2)
+                *reinterpret_cast<double2*>(bs + (row0 + lane - rpw) * kBPitch + c) = make_double2(0., 0.);
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(bar, rpw * a_bytes + static_cast<uint32_t>(b_n) * b_bytes);
+        __syncwarp();
+        if (lane < rpw)
+            bulk_g2s(as + (row0 + lane) * kBulkAPitch, Ag + static_cast<long long>(kb * kBK + row0 + lane) * tl.a_pitch, a_bytes, bar);
+        else if (lane < rpw + b_n)
+            bulk_g2s(bs + (row0 + lane - rpw) * kBPitch, Bg + static_cast<long long>(kb * kBK + row0 + lane - rpw) * ldb, b_bytes, bar);
+    };
+    // first kStages-1 stages of a tile; every stage of the ring is free at this point (tile boundary)
+    auto prologue = [&](const LegTile& tl) {
+#pragma unroll
+        for (int s = 0; s < kStages - 1; ++s)
+            if (s < tl.k_steps) load_stage(tl, s, s);
+    };
+
+    if (tid == 0) {
+        for (int st = 0; st < kStages; ++st) {
+            mbar_init(&s_full[st], kLegThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int ti = atomicAdd(counter, 1);
+        s_ti[0] = ti;
+        if (ti < ntiles) s_tl[0] = tiles[ti];
+    }
+    __syncthreads();
+    if (s_ti[0] >= ntiles) return;
+    prologue(s_tl[0]);
+
+    for (int buf = 0;; buf ^= 1) {
+        const LegTile tl = s_tl[buf];
+        // claim the next tile and fetch its descriptor while this one computes
+        if (tid == 0) {
+            const int ti = atomicAdd(counter, 1);
+            s_ti[buf ^ 1] = ti;
+            if (ti < ntiles) s_tl[buf ^ 1] = tiles[ti];
+        }
+
+        double acc[kMI][kNJ][2];
+#pragma unroll
+        for (int i = 0; i < kMI; ++i)
+#pragma unroll
+            for (int j = 0; j < kNJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
+
+        const int ksteps = tl.k_steps;
+        const int row_w = wm * (kMI * 8);   // warp's first row in the tile
+        const int col_w = wn * (kNJ * 8);   // warp's first column
+        const bool warp_active = (row_w < tl.m_valid) && (col_w < tl.n_valid);
+
+        for (int kb = 0; kb < ksteps; ++kb) {
+            const int st = kb % kStages;
+            mbar_wait(&s_full[st], (full_phase >> st) & 1u);
+            full_phase ^= 1u << st;
+            __syncthreads();  // everybody is done with stage kb-1: its buffer is refilled with block kb + kStages - 1
+            {
+                const int nk = kb + kStages - 1;
+                if (nk < ksteps) load_stage(tl, nk, nk % kStages);
+            }
+            if (warp_active) {
+                const double* as = As + st * kBulkAStage;
+                const double* bs = Bs + st * kBStage;
+                // fragments are double buffered: the shared-memory loads of k-step ks+1 are issued before the DMMAs of step ks
+                double a[2][kMI], b[2][kNJ];
+                auto load_frag = [&](int ks, int fb) {
+#pragma unroll
+                    for (int i = 0; i < kMI; ++i) a[fb][i] = as[(ks * 4 + t) * kBulkAPitch + row_w + 8 * i + g];
+#pragma unroll
+                    for (int j = 0; j < kNJ; ++j) b[fb][j] = bs[(ks * 4 + t) * kBPitch + col_w + 8 * j + g];
+                };
+                load_frag(0, 0);
+#pragma unroll
+                for (int ks = 0; ks < kBK / 4; ++ks) {
+                    if (ks + 1 < kBK / 4) load_frag(ks + 1, (ks + 1) & 1);
+#pragma unroll
+                    for (int i = 0; i < kMI; ++i) {
+                        if (row_w + 8 * i < tl.m_valid) {
+#pragma unroll
+                            for (int j = 0; j < kNJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[ks & 1][i], b[ks & 1][j]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // every warp is through the tile: the ring is free; the next descriptor written by thread 0 is visible
+        const int next_ti = s_ti[buf ^ 1];
+        // start streaming the next tile's operands before this tile's results are written out
+        if (next_ti < ntiles) prologue(s_tl[buf ^ 1]);
+        // epilogue: thread holds C[row_w+8i+g][col_w+8j+2t .. +1] = (re, im) of one field
+        if (warp_active) {
+#pragma unroll
+            for (int i = 0; i < kMI; ++i) {
+                const int row = row_w + 8 * i + g;
+                if (row < tl.m_valid) {
+                    double* Cg;
+                    if (!kPeers) Cg = C + tl.c_off;
+                    else {
+                        // fused exchange: the row goes straight into the Fourier-side buffer of the rank whose
+                        // latitude band contains it (NVLink store; same layout on every rank)
+                        const int lat = tl.lat0 + row;
+                        int d = 0;
+                        while (d + 1 < dst.nranks && lat >= dst.band[d + 1]) ++d;
+                        Cg = dst.base[d] + tl.c_off;
+                    }
+#pragma unroll
+                    for (int j = 0; j < kNJ; ++j) {
+                        const int col = col_w + 8 * j + 2 * t;
+                        if (col < tl.n_valid) {
+                            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                            *reinterpret_cast<double2*>(Cg + static_cast<long long>(row) * ldb + col) = v;
+                        }
+                    }
+                }
+            }
+        }
+        if (next_ti >= ntiles) break;
+    }
+    if (kPeers) __threadfence_system();  // remote rows are visible to the peers before this kernel completes
+}

@@ -33,12 +33,16 @@ constexpr int kMI = 4;   // 8-row DMMA tiles per warp  (32 rows)
 constexpr int kNJ = 9;   // 8-col DMMA tiles per warp  (72 cols)
 static_assert(kWarpsM * kMI * 8 == kBM && kWarpsN * kNJ * 8 == kBN, "tile shape");
 
+constexpr int kBPitch = kBN + 4;     // Bs[kBK][kBN+4]
+constexpr int kBStage = kBK * kBPitch;
+#ifndef SPT_BULK
+#define SPT_BULK 1   // 1: TMA-fed, warp-decoupled kernel (legendre_bulk.cuh); 0: per-thread cp.async baseline below
+#endif
+#if !SPT_BULK
 constexpr int kAInvPitch = kBM + 4;  // inverse: As[kBK][kBM+4]
 constexpr int kADirPitch = kBK + 4;  // direct : As[kBM][kBK+4]
-constexpr int kBPitch = kBN + 4;     // Bs[kBK][kBN+4]
 constexpr int kAInvStage = kBK * kAInvPitch;
 constexpr int kADirStage = kBM * kADirPitch;
-constexpr int kBStage = kBK * kBPitch;
 constexpr int kAStage = (kAInvStage > kADirStage ? kAInvStage : kADirStage);
 constexpr size_t kLegSmemBytes = static_cast<size_t>(kStages) * (kAStage + kBStage) * sizeof(double) + 16;
 
@@ -52,12 +56,14 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
+#endif
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
 
+#if !SPT_BULK
 // kDirect == false : A tile is [kBK][kBM] (k rows, latitude contiguous)   -> C rows are latitudes
 // kDirect == true  : A tile is [kBM][kBK] (table rows, latitude contiguous) -> C rows are table rows (n)
 template <bool kDirect, bool kPeers>
@@ -222,6 +228,10 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
     if (kPeers) __threadfence_system();  // remote rows are visible to the peers before this kernel completes
 }
 
+#else
+#include "legendre_bulk.cuh"
+#endif  // !SPT_BULK
+
 // spectra [m][n][re/im][fld]  ->  packed [m][p][k][2 fld + re/im], rows k >= K_eff (and whole blocks with
 // m >= trunc) are zero: this is the split + zero padding of TransLocal.cc:970-1003, including the
 // `jn <= truncation && jm < truncation` rule (:982) that drops the m == truncation column.
@@ -327,9 +337,16 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
                 for (int r0 = 0; r0 < Kdir; r0 += kBM) {
                     for (int n0 = 0; n0 < ld; n0 += kBN) {
                         LegTile t{};
+#if SPT_BULK
+                        // A = transposed table block [pitch latitudes][rows_tab n-rows]: K-major like the inverse's
+                        t.a_off = g.tab_off[2 * m + par] + r0;
+                        t.a_pitch = rows_tab;
+                        t.a_rows = rows_tab - r0;
+#else
                         t.a_off = g.tab_off[2 * m + par] + static_cast<long long>(r0) * pitch;
                         t.a_pitch = pitch;
                         t.a_rows = rows_tab - r0;
+#endif
                         t.b_off = fb_row0 * ld + n0;
                         t.b_rows = ncol;
                         t.c_off = (g.sp_rowoff[2 * m + par] + r0) * ld + n0;
@@ -388,16 +405,23 @@ template <bool kDirect, bool kPeers>
 static int launch_gemm(Plan& p, int nf, const LegTile* tiles, int ntiles, const double* B, double* C,
                        const PeerDst& dst) {
     if (ntiles == 0) return SPTRANS_OK;
+#if SPT_BULK
+    constexpr size_t smem_bytes = kBulkSmemBytes;
+    const double* table = kDirect ? p.d_tabT : p.d_tab;  // the direct transform contracts over latitudes: P^T is K-major
+#else
+    constexpr size_t smem_bytes = kLegSmemBytes;
+    const double* table = p.d_tab;
+#endif
     static bool attr_set[4] = {false, false, false, false};
     if (!attr_set[2 * kDirect + kPeers]) {
         SPT_CUDA(cudaFuncSetAttribute(legendre_dmma_kernel<kDirect, kPeers>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(kLegSmemBytes)));
+                                      static_cast<int>(smem_bytes)));
         attr_set[2 * kDirect + kPeers] = true;
     }
     SPT_CUDA(cudaMemsetAsync(p.d_tile_counter, 0, sizeof(int), p.stream));
     const int grid = std::min(ntiles, p.num_sms);
-    legendre_dmma_kernel<kDirect, kPeers><<<grid, kLegThreads, kLegSmemBytes, p.stream>>>(
-        tiles, ntiles, p.d_tile_counter, p.d_tab, B, C, 2 * nf, dst);
+    legendre_dmma_kernel<kDirect, kPeers><<<grid, kLegThreads, smem_bytes, p.stream>>>(
+        tiles, ntiles, p.d_tile_counter, table, B, C, 2 * nf, dst);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;
@@ -411,6 +435,58 @@ int launch_legendre_inv_peers(Plan& p, int nf, const double* d_packed, const Pee
 }
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed) {
     return launch_gemm<true, false>(p, nf, p.d_tiles_dir, p.n_tiles_dir, d_fourier, d_packed, PeerDst{});
+}
+
+namespace {
+// one (m, parity) block: in [rows][pitch] -> out [pitch][rows]  (rows = n-rows padded to kBK, pitch = latitudes padded to 16)
+__global__ void transpose_table_kernel(const long long* __restrict__ tab_off, const int* __restrict__ tab_K,
+                                       const int* __restrict__ tab_pitch, const double* __restrict__ in,
+                                       double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int b = blockIdx.z;
+    const long long off = tab_off[b];
+    if (off < 0) return;  // block of another rank
+    const int rows = (max(tab_K[b], 1) + kBK - 1) / kBK * kBK, pitch = tab_pitch[b >> 1];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    if (r0 >= rows || c0 >= pitch) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 32; r += 8)
+        if (r0 + r < rows && c0 + tx < pitch) tile[r][tx] = in[off + static_cast<long long>(r0 + r) * pitch + c0 + tx];
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8)
+        if (c0 + c < pitch && r0 + tx < rows) out[off + static_cast<long long>(c0 + c) * rows + r0 + tx] = tile[tx][c];
+}
+}  // namespace
+
+// P^T for the direct transform (same block offsets and sizes as the table itself); a no-op for the cp.async baseline
+int build_transposed_table(Plan& p) {
+#if SPT_BULK
+    const HostGeom& g = p.g;
+    const size_t tab_bytes = static_cast<size_t>(g.tab_size) * sizeof(double);
+    if (!p.d_tabT) {
+        SPT_CUDA(cudaMalloc(&p.d_tabT, std::max<size_t>(tab_bytes, 16)));
+        p.bytes_tables += tab_bytes;
+    }
+    SPT_CUDA(cudaMemsetAsync(p.d_tabT, 0, tab_bytes, p.stream));
+    long long* d_off = nullptr;
+    int *d_K = nullptr, *d_pitch = nullptr;
+    SPT_CUDA(cudaMalloc(&d_off, g.tab_off.size() * sizeof(long long)));
+    SPT_CUDA(cudaMalloc(&d_K, g.tab_K.size() * sizeof(int)));
+    SPT_CUDA(cudaMalloc(&d_pitch, g.tab_pitch.size() * sizeof(int)));
+    SPT_CUDA(cudaMemcpyAsync(d_off, g.tab_off.data(), g.tab_off.size() * sizeof(long long), cudaMemcpyHostToDevice, p.stream));
+    SPT_CUDA(cudaMemcpyAsync(d_K, g.tab_K.data(), g.tab_K.size() * sizeof(int), cudaMemcpyHostToDevice, p.stream));
+    SPT_CUDA(cudaMemcpyAsync(d_pitch, g.tab_pitch.data(), g.tab_pitch.size() * sizeof(int), cudaMemcpyHostToDevice, p.stream));
+    const int max_rows = round_up(g.T / 2 + 2, kBK), max_pitch = round_up(std::max(g.nleg, 1), 16);
+    dim3 grid((max_pitch + 31) / 32, (max_rows + 31) / 32, 2 * (g.T + 1));
+    transpose_table_kernel<<<grid, dim3(32, 8), 0, p.stream>>>(d_off, d_K, d_pitch, p.d_tab, p.d_tabT);
+    p.launches++;
+    SPT_CUDA(cudaGetLastError());
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    cudaFree(d_off);
+    cudaFree(d_K);
+    cudaFree(d_pitch);
+#endif
+    return SPTRANS_OK;
 }
 
 }  // namespace sptrans

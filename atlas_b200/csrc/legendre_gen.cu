@@ -245,6 +245,89 @@ int export_legendre_cache(const Plan& p, double* h_out) {
     return SPTRANS_OK;
 }
 
+namespace {
+// reference cache block (m, parity): index k_ref + K * lat, k_ref = 0 <-> highest n   ->   table block [k][lat - nlat0[m]], n ascending
+__global__ void import_cache_kernel(int nleg, const int* __restrict__ nlat0, const long long* __restrict__ ref_begin,
+                                    const int* __restrict__ ref_K, const long long* __restrict__ tab_off,
+                                    const int* __restrict__ tab_pitch, const double* __restrict__ blob,
+                                    double* __restrict__ tab) {
+    const int b = blockIdx.y;  // 2 m + parity
+    const int m = b >> 1;
+    const int K = ref_K[b];
+    const int l0 = nlat0[m];
+    const int ncol = nleg - l0;
+    if (K <= 0 || ncol <= 0) return;
+    const long long total = static_cast<long long>(K) * ncol;
+    const double* src = blob + ref_begin[b];
+    double* dst = tab + tab_off[b];
+    const int pitch = tab_pitch[m];
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int lat = static_cast<int>(e / K), kr = static_cast<int>(e - static_cast<long long>(lat) * K);  // read order
+        dst[static_cast<long long>(K - 1 - kr) * pitch + lat] = src[static_cast<long long>(K) * (l0 + lat) + kr];
+    }
+}
+}  // namespace
+
+// Replace the contents of the device Legendre table by the values of a reference-layout cache blob (what
+// sptrans_export_legendre_cache writes, and what the reference's LegendreCacheCreatorLocal / TransLocal write:
+// TransLocal.cc:592-647).  Entries the table does not hold (latitudes below nlat0[m], the m = T+1 blocks) are skipped.
+int import_legendre_cache(Plan& p, const double* h_blob, size_t bytes) {
+    const HostGeom& g = p.g;
+    const int T = g.T, trc = T + 1;
+    if (bytes != legendre_cache_doubles(g) * sizeof(double)) {
+        set_error("sptrans_import_legendre_cache: blob size " + std::to_string(bytes) + " does not match this grid / truncation (" +
+                  std::to_string(legendre_cache_doubles(g) * sizeof(double)) + " bytes expected)");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (g.nranks != 1) {
+        set_error("sptrans_import_legendre_cache: not available for sharded plans");
+        return SPTRANS_ERR_NOT_IMPLEMENTED;
+    }
+    std::vector<long long> begin(2 * (T + 1), 0);
+    std::vector<int> Ks(2 * (T + 1), 0);
+    long long size_sym = 0, size_asym = 0;
+    auto pad8 = [](long long n) { return (n + 7) / 8 * 8; };
+    for (int m = 0; m <= T + 1; ++m) {
+        const int ks = num_n(trc, m, 0), ka = num_n(trc, m, 1);
+        if (m <= T) {
+            Ks[2 * m] = ks;
+            Ks[2 * m + 1] = ka;
+            begin[2 * m] = size_sym;
+            begin[2 * m + 1] = size_asym;
+        }
+        size_sym += pad8(static_cast<long long>(ks) * g.nleg);
+        size_asym += pad8(static_cast<long long>(ka) * g.nleg);
+    }
+    for (int m = 0; m <= T; ++m) begin[2 * m + 1] += size_sym;
+    double* d_blob = nullptr;
+    long long *d_begin = nullptr, *d_off = nullptr;
+    int *d_K = nullptr, *d_pitch = nullptr;
+    SPT_CUDA(cudaMalloc(&d_blob, std::max<size_t>(bytes, 8)));
+    SPT_CUDA(cudaMalloc(&d_begin, begin.size() * sizeof(long long)));
+    SPT_CUDA(cudaMalloc(&d_off, g.tab_off.size() * sizeof(long long)));
+    SPT_CUDA(cudaMalloc(&d_K, Ks.size() * sizeof(int)));
+    SPT_CUDA(cudaMalloc(&d_pitch, g.tab_pitch.size() * sizeof(int)));
+    SPT_CUDA(cudaMemcpy(d_blob, h_blob, bytes, cudaMemcpyHostToDevice));
+    SPT_CUDA(cudaMemcpy(d_begin, begin.data(), begin.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    SPT_CUDA(cudaMemcpy(d_off, g.tab_off.data(), g.tab_off.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    SPT_CUDA(cudaMemcpy(d_K, Ks.data(), Ks.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SPT_CUDA(cudaMemcpy(d_pitch, g.tab_pitch.data(), g.tab_pitch.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    dim3 grid(64, 2 * (T + 1));
+    import_cache_kernel<<<grid, 256, 0, p.stream>>>(g.nleg, p.d_nlat0, d_begin, d_K, d_off, d_pitch, d_blob, p.d_tab);
+    p.launches++;
+    SPT_CUDA(cudaGetLastError());
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    cudaFree(d_blob);
+    cudaFree(d_begin);
+    cudaFree(d_off);
+    cudaFree(d_K);
+    cudaFree(d_pitch);
+    tc_free(p);  // tensor-core operand images are derived from this table: rebuilt on next use
+    return build_transposed_table(p);
+}
+
 size_t legendre_cache_doubles(const HostGeom& g) {
     auto pad8 = [](long long n) { return (n + 7) / 8 * 8; };
     long long tot = 0;

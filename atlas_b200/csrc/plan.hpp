@@ -133,6 +133,7 @@ struct Plan {
     int num_sms = 148;
     // device tables
     double* d_tab = nullptr;       // Legendre table
+    double* d_tabT = nullptr;      // its transpose per (m, parity) block: K-major operand of the direct transform
     int* d_nlat0 = nullptr;        // [T+2]
     long long* d_fb_rowoff = nullptr;  // [T+2]
     long long* d_rowoff = nullptr;     // [nlat+1]
@@ -216,6 +217,7 @@ void legendre_seeds(int trc, int nlats, const double* lats_rad, std::vector<doub
 // ---- legendre_gen.cu ----
 int generate_legendre_table(Plan& p);
 int export_legendre_cache(const Plan& p, double* h_out);
+int import_legendre_cache(Plan& p, const double* h_blob, size_t bytes);
 size_t legendre_cache_doubles(const HostGeom& g);
 
 // ---- legendre_f64.cu ----
@@ -226,6 +228,7 @@ int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fouri
 // same, every output row stored into the exchange buffer of the rank that owns its latitude band
 int launch_legendre_inv_peers(Plan& p, int nf, const double* d_packed, const PeerDst& dst);
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed);
+int build_transposed_table(Plan& p);   // after the table has been generated or imported
 
 // ---- legendre_tc.cu (tcgen05 split-TF32 path) ----
 int tc_prepare_tables(Plan& p);

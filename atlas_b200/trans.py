@@ -131,6 +131,11 @@ class Trans:
         _lib.check(_lib.lib.sptrans_export_legendre_cache(self._h, C.c_void_p(out.ctypes.data)))
         return out
 
+    def import_legendre_cache(self, blob):
+        """Replace the Legendre tables by a reference-layout cache blob (`Cache::legendre()`, trans/Cache.h:98-136)."""
+        blob = np.ascontiguousarray(blob, dtype=np.float64)
+        _lib.check(_lib.lib.sptrans_import_legendre_cache(self._h, C.c_void_p(blob.ctypes.data), blob.nbytes))
+
     def _sync(self, *arrays):
         if not getattr(self, "_external_stream", False):
             _wait_for_producers(*arrays)

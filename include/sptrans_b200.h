@@ -108,6 +108,13 @@ size_t sptrans_device_bytes(const sptrans_plan* plan);
  * `out` is a HOST buffer of sptrans_legendre_cache_size() bytes. */
 size_t sptrans_legendre_cache_size(const sptrans_plan* plan);
 int sptrans_export_legendre_cache(const sptrans_plan* plan, void* out);
+/* Load the Legendre tables from a blob in that same layout -- a cache file written by the reference
+ * (LegendreCacheCreatorLocal::create, trans/local/LegendreCacheCreatorLocal.cc:137-146; TransLocal reads it at
+ * TransLocal.cc:608-647 when Cache::legendre() is set) or by sptrans_export_legendre_cache.  `blob` is a HOST buffer of
+ * exactly sptrans_legendre_cache_size() bytes (anything else is SPTRANS_ERR_INVALID, like the reference's size
+ * assertion TransLocal.cc:612).  A plan always generates its own tables at creation (30 ms at T1279 on the device,
+ * faster than reading the 8.4 GB file); importing replaces them, e.g. to reproduce a run of the reference bit for bit. */
+int sptrans_import_legendre_cache(sptrans_plan* plan, const void* blob, size_t bytes);
 
 /* Select the arithmetic of the Legendre stage: SPTRANS_PREC_FP64 (default; DMMA, results match the fp64 oracle to
  * 1e-13) or SPTRANS_PREC_TC_SPLIT (tcgen05 kind::tf32 with split operands and fp32 accumulation in tensor memory:

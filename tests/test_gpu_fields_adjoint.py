@@ -109,8 +109,8 @@ def test_field_layout_device_pointers_and_errors():
     _lib.check(_lib.lib.sptrans_invtrans_field(trans._h, 0, None, None))  # zero levels: nothing to do
 
 
-def _close(lhs, rhs, scale):
-    return abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), scale * 1e-3)
+def _close(lhs, rhs, scale, tol=1e-12):
+    return abs(lhs - rhs) <= tol * max(abs(lhs), abs(rhs), scale * 1e-3)
 
 
 @pytest.mark.parametrize("gridname,T,nvd,nsc", [("F24", 23, 2, 0), ("O48", 47, 3, 2), ("L9", 17, 1, 1), ("O400", 399, 2, 1)])
@@ -136,7 +136,10 @@ def test_invtrans_wind_adjoint_identity(gridname, T, nvd, nsc):
         trans.invtrans_adj(nvd, y, av, ad)
     lhs = float(ax @ y)
     rhs = float(vor @ av + div @ ad) + (float(sc @ asc) if nsc else 0.0)
-    assert _close(lhs, rhs, np.linalg.norm(ax) * np.linalg.norm(y)), (lhs, rhs)
+    # L9 has rows at the poles, where u, v = U, V / cos(89.9999999 deg) (TransLocal.cc:1447-1458): the operator norm
+    # carries the factor 5.7e8 and so does the rounding error of both sides (the reference's own wind tolerance is 2e-6)
+    tol = 1e-7 if gridname == "L9" else 1e-12
+    assert _close(lhs, rhs, np.linalg.norm(ax) * np.linalg.norm(y), tol), (lhs, rhs)
 
 
 @pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("O400", 399, 2)])
@@ -168,3 +171,34 @@ def test_dirtrans_adjoint_identity(gridname, T, nf):
     trans.dirtrans_adj(nf, s, ds)
     lhs, rhs = float(dg @ s), float(g @ ds)
     assert _close(lhs, rhs, np.linalg.norm(dg) * np.linalg.norm(s)), (lhs, rhs)
+
+
+@pytest.mark.parametrize("gridname,T", [("O32", 31), ("F24", 23), ("O80", 79)])
+def test_legendre_cache_import(gridname, T):
+    """Reference-layout Legendre cache (TransLocal.cc:592-647): export -> import round trip leaves the transform bit
+    identical; a modified blob is what the transform then uses; a blob of the wrong size is refused like the reference's
+    size assertion (TransLocal.cc:612)."""
+    from atlas_b200 import _lib
+
+    grid, trans = make(gridname, T)
+    nf = 3
+    sp = H.synthetic_spectra(T, nf)
+    want = np.full(nf * grid.size(), np.nan)
+    trans.invtrans(nf, sp, want)
+    blob = trans.export_legendre_cache()
+    _, other = make(gridname, T)
+    other.import_legendre_cache(blob)
+    assert np.array_equal(other.export_legendre_cache(), blob)  # export regenerates: independent of the import
+    got = np.full_like(want, np.nan)
+    other.invtrans(nf, sp, got)
+    assert np.array_equal(got, want)
+    other.import_legendre_cache(2.0 * blob)
+    other.invtrans(nf, sp, got)
+    assert np.array_equal(got, 2.0 * want)
+    back = np.full_like(sp, np.nan)
+    other.dirtrans(nf, want, back)   # the direct transform reads the same table
+    ref = np.full_like(sp, np.nan)
+    trans.dirtrans(nf, want, ref)
+    assert np.array_equal(back, 2.0 * ref)
+    with pytest.raises(_lib.SptransError):
+        other.import_legendre_cache(blob[:-8])

@@ -189,7 +189,7 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
     long long off = 0;
     for (int m = 0; m <= T; ++m) {
         const int ncol = g.nleg - g.nlat0[m];
-        g.tab_pitch[m] = round_up(std::max(ncol, 0), 16);
+        g.tab_pitch[m] = round_up(std::max(ncol, 0), kBK > 16 ? kBK : 16);  // whole contraction steps of the direct GEMM
         for (int p = 0; p < 2; ++p) {
             const int K = num_n(T + 1, m, p);
             g.tab_K[2 * m + p] = K;

@@ -21,6 +21,9 @@
 // tile's block, whose table entries are zero: they are cleared, because 0 x (stale NaN) would poison the sum.
 // (included by legendre_f64.cu inside namespace sptrans::<anonymous>, after the tile constants and dmma884)
 #pragma once
+#ifndef SPT_SPLIT
+#define SPT_SPLIT 0
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -70,7 +73,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 constexpr int kBulkAStage = kBK * (kBM + 4);  // As[kBK][kBM + 4] for both directions
 constexpr int kBulkAPitch = kBM + 4;
 constexpr size_t kBulkSmemBytes = static_cast<size_t>(kStages) * (kBulkAStage + kBStage) * sizeof(double) + 16;
-static_assert(kBK == 16, "one operand row per lane of the producer warp");
+static_assert(kBK % (kLegThreads / 32) == 0 && 2 * kBK / (kLegThreads / 32) <= 32, "rows of a stage are split evenly over the warps");
 
 // kDirect == false : A = table P   (tile [kBK n-rows][kBM latitudes]),  B = packed spectra,  C = Fourier buffer
 // kDirect == true  : A = table P^T (tile [kBK latitudes][kBM n-rows]),  B = Fourier buffer,  C = packed spectra
@@ -85,6 +88,10 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
     __shared__ LegTile s_tl[2];   // current / next tile descriptor (fetched one tile ahead by thread 0)
     __shared__ int s_ti[2];
     __shared__ __align__(8) uint64_t s_full[kStages];   // the bulk copies of stage s have landed
+#if SPT_SPLIT
+    __shared__ __align__(8) uint64_t s_empty[kStages];  // all eight warps are done reading stage s
+    uint32_t empty_phase = (1u << kStages) - 1u;        // the first wait on a fresh `empty` barrier passes (parity 1)
+#endif
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -124,12 +131,34 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
     auto prologue = [&](const LegTile& tl) {
 #pragma unroll
         for (int s = 0; s < kStages - 1; ++s)
-            if (s < tl.k_steps) load_stage(tl, s, s);
+            if (s < tl.k_steps) {
+#if SPT_SPLIT
+                mbar_wait(&s_empty[s], (empty_phase >> s) & 1u);
+                empty_phase ^= 1u << s;
+#endif
+                load_stage(tl, s, s);
+            }
+    };
+
+    // thread 0: publish the claimed tile index and start copying its descriptor (4 x 16 bytes) into s_tl[slot]
+    auto fetch_next = [&](int ti, int slot) {
+        s_ti[slot] = ti;
+        if (ti < ntiles) {
+            const char* src = reinterpret_cast<const char*>(tiles + ti);
+            const uint32_t dstaddr = smem_u32(&s_tl[slot]);
+            static_assert(sizeof(LegTile) % 16 == 0, "descriptor is copied in 16-byte pieces");
+#pragma unroll
+            for (int c = 0; c < static_cast<int>(sizeof(LegTile)); c += 16)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dstaddr + c), "l"(src + c) : "memory");
+        }
     };
 
     if (tid == 0) {
         for (int st = 0; st < kStages; ++st) {
             mbar_init(&s_full[st], kLegThreads / 32);
+#if SPT_SPLIT
+            mbar_init(&s_empty[st], kLegThreads / 32);
+#endif
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const int ti = atomicAdd(counter, 1);
@@ -142,12 +171,12 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
 
     for (int buf = 0;; buf ^= 1) {
         const LegTile tl = s_tl[buf];
-        // claim the next tile and fetch its descriptor while this one computes
-        if (tid == 0) {
-            const int ti = atomicAdd(counter, 1);
-            s_ti[buf ^ 1] = ti;
-            if (ti < ntiles) s_tl[buf ^ 1] = tiles[ti];
-        }
+        // Claim the next tile now, but do not wait for the atomic: its result is first touched after the first stage of
+        // this tile, when thread 0 starts an asynchronous copy of the descriptor into shared memory (awaited at the end of
+        // the tile).  Done synchronously, warp 0 sat out ~2 us of global-memory latency at the start of every tile and
+        // the other seven warps waited for it at the first stage barrier.
+        int claimed = 0;
+        if (tid == 0) claimed = atomicAdd(counter, 1);
 
         double acc[kMI][kNJ][2];
 #pragma unroll
@@ -164,11 +193,14 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
             const int st = kb % kStages;
             mbar_wait(&s_full[st], (full_phase >> st) & 1u);
             full_phase ^= 1u << st;
+#if !SPT_SPLIT
             __syncthreads();  // everybody is done with stage kb-1: its buffer is refilled with block kb + kStages - 1
             {
                 const int nk = kb + kStages - 1;
                 if (nk < ksteps) load_stage(tl, nk, nk % kStages);
             }
+#endif
+            if (tid == 0 && kb == 1) fetch_next(claimed, buf ^ 1);
             if (warp_active) {
                 const double* as = As + st * kBulkAStage;
                 const double* bs = Bs + st * kBStage;
@@ -193,6 +225,21 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
                     }
                 }
             }
+#if SPT_SPLIT
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
+            const int nk = kb + kStages - 1;
+            if (nk < ksteps) {   // stage released by this warp one step ago; refilled once everybody has released it
+                const int ns = nk % kStages;
+                mbar_wait(&s_empty[ns], (empty_phase >> ns) & 1u);
+                empty_phase ^= 1u << ns;
+                load_stage(tl, nk, ns);
+            }
+#endif
+        }
+        if (tid == 0) {
+            if (ksteps < 2) fetch_next(claimed, buf ^ 1);
+            asm volatile("cp.async.wait_all;\n" ::: "memory");
         }
         __syncthreads();  // every warp is through the tile: the ring is free; the next descriptor written by thread 0 is visible
         const int next_ti = s_ti[buf ^ 1];

@@ -9,9 +9,11 @@
 //     rows and two B rows -- ~20 instructions per warp and stage instead of ~220 per thread with cp.async, and no single
 //     producer warp that the others wait for (UBLKCP takes uniform operands: a warp issuing all 32 copies runs a 32-trip
 //     serial loop and was measured to hold the block barrier up by ~900 cycles per stage);
-//   * stages are still handed back through one __syncthreads() per stage: replacing it by per-stage `empty` mbarriers
-//     (warps drifting up to a stage apart) was measured SLOWER (19.8 ms vs 17.6 ms inverse at TCo1279 L137) -- the two
-//     warps of a sub-partition share the DMMA pipe best when they alternate 9-DMMA groups in lock step;
+//   * stages are handed back split-phase (SPT_SPLIT, default): a warp releases a stage with one arrival on its `empty`
+//     mbarrier (count 8) and waits for everybody's release only one stage LATER, just before it refills its share, so
+//     nobody waits unless a whole stage ahead.  Measured at TCo1279 L137 with 32-step stages: 15.98 / 15.83 ms against
+//     17.0 / 16.86 ms with a __syncthreads() per stage (-DSPT_SPLIT=0).  (A single producer warp refilling for everybody
+//     was slower than either: 19.8 ms.)
 //   * both directions read K-major A tiles: the direct transform uses a transposed copy of the table (P^T, [lat][k] per
 //     (m, parity) block, same block offsets), so its A rows are 1 KB copies as well (128-byte copies of the untransposed
 //     table made the TMA issue rate the bottleneck: 35 ms instead of 18 ms).
@@ -22,7 +24,7 @@
 // (included by legendre_f64.cu inside namespace sptrans::<anonymous>, after the tile constants and dmma884)
 #pragma once
 #ifndef SPT_SPLIT
-#define SPT_SPLIT 0
+#define SPT_SPLIT 1
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -212,9 +214,12 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
 #pragma unroll
                     for (int j = 0; j < kNJ; ++j) b[fb][j] = bs[(ks * 4 + t) * kBPitch + col_w + 8 * j + g];
                 };
+                // the last stage of a tile holds operand rows in its first ks_last k-steps only
+                const int ks_n = (kb == ksteps - 1) ? tl.ks_last : kBK / 4;
                 load_frag(0, 0);
 #pragma unroll
                 for (int ks = 0; ks < kBK / 4; ++ks) {
+                    if (ks >= ks_n) break;
                     if (ks + 1 < kBK / 4) load_frag(ks + 1, (ks + 1) & 1);
 #pragma unroll
                     for (int i = 0; i < kMI; ++i) {

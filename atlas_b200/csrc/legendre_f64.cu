@@ -325,6 +325,7 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
                         t.m_valid = std::min(kBM, ncol - l0);
                         t.n_valid = std::min(kBN, ld - n0);
                         t.k_steps = ksteps;
+                        t.ks_last = (Kinv - (ksteps - 1) * kBK + 3) / 4;
                         inv.push_back({static_cast<double>(ksteps) * round_up(t.m_valid, 8), t});
                     }
                 }
@@ -353,6 +354,7 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
                         t.m_valid = std::min(kBM, Kdir - r0);
                         t.n_valid = std::min(kBN, ld - n0);
                         t.k_steps = ksteps;
+                        t.ks_last = (ncol - (ksteps - 1) * kBK + 3) / 4;
                         dir.push_back({static_cast<double>(ksteps) * round_up(t.m_valid, 8), t});
                     }
                 }

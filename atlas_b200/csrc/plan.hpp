@@ -38,7 +38,7 @@ struct alignas(16) LegTile {
     int a_rows;       // inverse: #lat columns readable from a_off (pitch - lat0); direct: #table rows readable
     int b_rows;       // rows of B that may be read (rest zero-filled)
     int lat0;         // inverse: latitude-pair index of tile row 0 (selects the destination rank of a sharded plan)
-    int pad1;
+    int ks_last;      // 4-wide DMMA k-steps of the LAST stage that hold operand rows (the rest of the stage is padding)
 };
 
 struct HostGeom {

@@ -28,9 +28,24 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
-METRIC = "TCo1279 L137 transforms/sec (inv+dir)"
+METRIC = "TCo1279 L137 transforms/sec (inv+dir)"  # BASELINE.json's metric; other --workload values rename it (metric_name)
 UNIT = "transforms/s"
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (profiles/microbench_f64_r01.txt); no fp64 entry in MEASURED_PEAKS.json
+
+
+def metric_name(workload_name):
+    _, _, nf = workload(workload_name)
+    return f"{workload_name} L{nf} transforms/sec (inv+dir)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic_r01.json:
+    dram__bytes_read.sum + dram__bytes_write.sum, mean of the inverse and the direct launch), or None."""
+    try:
+        t = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic_r01.json")))[kernel]
+        return 0.5 * (float(t["inverse"]) + float(t["direct"]))
+    except Exception:
+        return None
 
 
 def workload(name):
@@ -170,7 +185,7 @@ def run_reference(args, rank, world):
     per_step = float(np.mean(times)) * nf / nfs  # work is exactly linear in the number of fields
     value = 1.0 / per_step
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload} L{nf} invtrans+dirtrans fp64 (grid {gridname}, T{T})"},
@@ -235,7 +250,7 @@ def main():
 
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        out = spdist.bench_sharded(args, rank, world, local_rank, METRIC, UNIT, FP64_DMMA_PEAK_TFLOPS)
+        out = spdist.bench_sharded(args, rank, world, local_rank, metric_name(args.workload), UNIT, FP64_DMMA_PEAK_TFLOPS)
         if out is not None:
             emit_json(out)
         return
@@ -312,8 +327,9 @@ def main():
                     "ms_per_launch": {"inverse": leg_inv, "direct": leg_dir}, "share_of_step": (leg_inv + leg_dir) / ms_per_step}
     else:
       roofline = {
-        "kernel": "legendre_dmma_kernel<inverse|direct> (fp64 mma.sync m8n8k4)", "bound": "tensor", "achieved": achieved,
-        "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+        "kernel": "legendre_dmma_kernel<inverse|direct> (fp64 mma.sync m8n8k4, operands staged by TMA bulk copies)", "bound": "tensor", "achieved": achieved,
+        "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
+        "traffic": ncu_traffic("legendre_dmma_kernel") if args.workload == "TCo1279" else None,
         "peak_source": "fp64 DMMA/DFMA microbenchmark on this pool's B200 (profiles/microbench_f64_r01.txt); "
                        "MEASURED_PEAKS.json holds only bf16 and HBM peaks, tcgen05 has no f64 kind",
         "flops_per_launch": {"inverse": fl_inv, "direct": fl_dir},
@@ -331,7 +347,7 @@ def main():
     four_bytes = fb_bytes + 8.0 * npts * nf
     f_inv = float(np.mean([a for a, _ in four_ms]))
     f_dir = float(np.mean([b for _, b in four_ms]))
-    roofline_fourier = {"kernel": "fourier_inv_kernel / fourier_dir_kernel (chirp-z in shared memory)", "bound": "hbm",
+    roofline_fourier = {"kernel": "fourier2_inv_kernel / fourier2_dir_kernel (+ v1 kernels on short rows): chirp-z in shared memory", "bound": "hbm",
                         "achieved": 2 * four_bytes / ((f_inv + f_dir) * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                         "frac": 2 * four_bytes / ((f_inv + f_dir) * 1e-3) / 1e9 / hbm, "traffic": None, "peak_note": hbm_src,
                         "ms_per_launch_group": {"inverse": f_inv, "direct": f_dir}, "share_of_step": (f_inv + f_dir) / ms_per_step}
@@ -383,7 +399,7 @@ def main():
                                   f"(inv {t_inv:.2f}s, dir {t_dir:.2f}s; plan setup {osetup:.1f}s untimed)"}
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if args.precision == "fp64" else "tf32x3 (fp32-level Legendre stage, fp64 Fourier stage)",
         "data": "synthetic",

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <new>
 
 #include "plan.hpp"
@@ -90,13 +91,20 @@ int check_plan(sptrans_plan* plan) {
 // inverse transform of `nf` fields whose spectra sit on the device at truncation `trunc` (T or T+1)
 int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, int nb_uv, StageTimer& tm,
                 int& marks, int* slots) {
-    int rc = build_tiles(p, nf, trunc, p.g.T);
+    // Point sets sum EVERY zonal wavenumber up to the truncation of the data (TransLocal.cc:1331,:1347-1362), grids drop
+    // the m == truncation column of a scalar transform (:982): the tiles then run to T+1 over zero rows
+    const bool keep_mT = p.g.points && trunc == p.g.T;
+    int rc = build_tiles(p, nf, keep_mT ? trunc + 1 : trunc, p.g.T);
     if (rc) return rc;
     rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf));
     if (rc) return rc;
     rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nf));
     if (rc) return rc;
     if (p.precision == SPTRANS_PREC_TC_SPLIT) {
+        if (p.g.points) {
+            set_error("point-set plans run the fp64 Legendre kernel only");
+            return SPTRANS_ERR_NOT_IMPLEMENTED;
+        }
         if ((rc = tc_prepare_tables(p))) return rc;
         if ((rc = tc_build_tiles(p, nf, trunc, p.g.T))) return rc;
         tm.mark(marks);
@@ -108,7 +116,7 @@ int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, 
     }
     else {
         tm.mark(marks);
-        rc = launch_pack_spectra(p, nf, trunc, d_spec, p.d_packed);
+        rc = launch_pack_spectra(p, nf, trunc, d_spec, p.d_packed, keep_mT ? kPackKeepMT : 0);
         if (rc) return rc;
         slots[marks++] = 0;
         tm.mark(marks);
@@ -117,7 +125,8 @@ int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, 
         slots[marks++] = 1;
     }
     tm.mark(marks);
-    rc = launch_fourier_inv(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, d_gp, nb_uv);
+    if (p.g.points) rc = launch_points_inv(p, nf, std::min(p.g.T, trunc), p.d_fourier, d_gp, nb_uv);
+    else rc = launch_fourier_inv(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, d_gp, nb_uv);
     if (rc) return rc;
     slots[marks++] = 2;
     tm.mark(marks);
@@ -161,9 +170,15 @@ int sptrans_fourier_truncation(int truncation, int nx, int nxmax, int ndgl, doub
     return fourier_truncation(truncation, nx, nxmax, ndgl, lat_rad, fullgrid != 0);
 }
 
-int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, const double* lat_deg,
-                                const double* weights, int truncation, unsigned flags, int device, int rank,
-                                int nranks) {
+namespace {
+struct PointSet {   // sptrans_plan_create_points: per point, its row among the distinct |latitudes| etc. (see HostGeom)
+    std::vector<int> row;
+    std::vector<double> sign, lon, coslatinv;
+};
+}  // namespace
+
+static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double* lat_deg, const double* weights,
+                       int truncation, unsigned flags, int device, int rank, int nranks, const PointSet* pts) {
     if (!out) {
         set_error("sptrans_plan_create: null output pointer");
         return SPTRANS_ERR_INVALID;
@@ -209,6 +224,18 @@ int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, con
     p.own_stream = true;
     for (auto& e : p.ev) cudaEventCreate(&e);
     HostGeom& g = p.g;
+    if (pts) {
+        g.points = true;
+        g.pt_row = pts->row;
+        g.pt_sign = pts->sign;
+        g.pt_lon = pts->lon;
+        g.pt_coslatinv = pts->coslatinv;
+        g.npts = static_cast<long long>(pts->row.size());  // grid-point arrays of this plan are [field][point]
+        if ((rc = upload(p.d_pt_row, g.pt_row, p.stream))) return fail(rc);
+        if ((rc = upload(p.d_pt_sign, g.pt_sign, p.stream))) return fail(rc);
+        if ((rc = upload(p.d_pt_lon, g.pt_lon, p.stream))) return fail(rc);
+        if ((rc = upload(p.d_pt_coslatinv, g.pt_coslatinv, p.stream))) return fail(rc);
+    }
     if ((rc = upload(p.d_nlat0, g.nlat0, p.stream))) return fail(rc);
     if ((rc = upload(p.d_fb_rowoff, g.fb_rowoff, p.stream))) return fail(rc);
     if ((rc = upload(p.d_sp_rowoff, g.sp_rowoff, p.stream))) return fail(rc);
@@ -260,9 +287,55 @@ int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, con
     return SPTRANS_OK;
 }
 
+int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, const double* lat_deg,
+                                const double* weights, int truncation, unsigned flags, int device, int rank,
+                                int nranks) {
+    return create_plan(out, nlat, nx, lat_deg, weights, truncation, flags, device, rank, nranks, nullptr);
+}
+
 int sptrans_plan_create(sptrans_plan** plan, int nlat, const int* nx, const double* lat_deg, const double* weights,
                         int truncation, unsigned flags, int device) {
-    return sptrans_plan_create_sharded(plan, nlat, nx, lat_deg, weights, truncation, flags, device, 0, 1);
+    return create_plan(plan, nlat, nx, lat_deg, weights, truncation, flags, device, 0, 1, nullptr);
+}
+
+int sptrans_plan_create_points(sptrans_plan** plan, size_t npoints, const double* lon_deg, const double* lat_deg,
+                               int truncation, int device) {
+    if (!plan || npoints == 0 || !lon_deg || !lat_deg || truncation < 0) {
+        set_error("sptrans_plan_create_points: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    // rows = distinct |latitude| values, north to south, mirrored about the equator (an equator row stays single)
+    std::vector<double> a(npoints);
+    for (size_t i = 0; i < npoints; ++i) {
+        a[i] = std::fabs(lat_deg[i]);
+        if (!(a[i] <= 90.)) {
+            set_error("sptrans_plan_create_points: latitude outside [-90, 90]");
+            return SPTRANS_ERR_INVALID;
+        }
+    }
+    std::vector<double> north(a);
+    std::sort(north.begin(), north.end(), std::greater<double>());
+    north.erase(std::unique(north.begin(), north.end()), north.end());
+    const bool equator = north.back() == 0.;
+    if (equator && north.size() == 1) north.insert(north.begin(), 45.);  // the geometry needs one off-equator row pair
+    const int nn = static_cast<int>(north.size());
+    std::vector<double> lat(north);
+    for (int j = nn - 1 - (equator ? 1 : 0); j >= 0; --j) lat.push_back(-north[j]);
+    const int nlat = static_cast<int>(lat.size());
+    // no zonal truncation at any latitude (TransLocal.cc:1331-1362 sums every m): rows long enough for the linear rule
+    std::vector<int> nx(nlat, 2 * truncation + 2);
+    PointSet ps;
+    ps.row.resize(npoints);
+    ps.sign.resize(npoints);
+    ps.lon.resize(npoints);
+    ps.coslatinv.resize(npoints);
+    for (size_t i = 0; i < npoints; ++i) {
+        ps.row[i] = static_cast<int>(std::lower_bound(north.begin(), north.end(), a[i], std::greater<double>()) - north.begin());
+        ps.sign[i] = lat_deg[i] < 0. ? -1. : 1.;
+        ps.lon[i] = lon_deg[i] * (M_PI / 180.);                    // util::Constants::degreesToRadians()
+        ps.coslatinv[i] = 1. / std::cos(lat_deg[i] * (M_PI / 180.));  // no pole clamp in this path (:1380-1384)
+    }
+    return create_plan(plan, nlat, nx.data(), lat.data(), nullptr, truncation, SPTRANS_GRID_REGULAR, device, 0, 1, &ps);
 }
 
 int sptrans_plan_destroy(sptrans_plan* sp) {
@@ -276,7 +349,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     void* ptrs[] = {p.d_tab, p.d_tabT, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_owner, p.d_pair_done, p.d_weights,
                     p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_dirscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
                     p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
-                    p.d_gp, p.d_rows};
+                    p.d_gp, p.d_rows, p.d_pt_row, p.d_pt_sign, p.d_pt_lon, p.d_pt_coslatinv};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p.h_pinned) cudaFreeHost(p.h_pinned);
@@ -465,6 +538,10 @@ static int dirtrans_scalar_impl(sptrans_plan* plan, int nf, const double* gp, do
         return SPTRANS_ERR_INVALID;
     }
     if (nf == 0) return SPTRANS_OK;
+    if (p.g.points) {  // TransLocal: ATLAS_NOTIMPLEMENTED (TransLocal.cc:1599-1604, :1671-1676)
+        set_error("direct and adjoint transforms are not available for point-set plans");
+        return SPTRANS_ERR_NOT_IMPLEMENTED;
+    }
     if (p.g.nranks != 1) {
         set_error("whole-transform entry points need an unsharded plan; use the stage-level API");
         return SPTRANS_ERR_INVALID;
@@ -536,6 +613,10 @@ int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nf, const double* wind,
         return SPTRANS_ERR_INVALID;
     }
     if (nf == 0) return SPTRANS_OK;
+    if (p.g.points) {
+        set_error("direct and adjoint transforms are not available for point-set plans");
+        return SPTRANS_ERR_NOT_IMPLEMENTED;
+    }
     if (p.g.nranks != 1) {
         set_error("whole-transform entry points need an unsharded plan; use the stage-level API");
         return SPTRANS_ERR_INVALID;

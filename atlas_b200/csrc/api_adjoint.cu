@@ -20,6 +20,10 @@ int adj_args_ok(sptrans_plan* plan, const char* who) {
         return SPTRANS_ERR_INVALID;
     }
     SPT_CUDA(cudaSetDevice(plan->p.device));
+    if (plan->p.g.points) {
+        set_error(std::string(who) + ": direct and adjoint transforms are not available for point-set plans");
+        return SPTRANS_ERR_NOT_IMPLEMENTED;
+    }
     if (plan->p.g.nranks != 1) {
         set_error(std::string(who) + ": whole-transform entry points need an unsharded plan; use the stage-level API");
         return SPTRANS_ERR_INVALID;
@@ -173,7 +177,7 @@ int sptrans_dirtrans_adj_scalar(sptrans_plan* plan, int nf, const double* spectr
     if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
     if ((rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nf)))) return rc;
     cudaEventRecord(p.ev[1], p.stream);
-    if ((rc = launch_pack_spectra(p, nf, T, d_spec, p.d_packed, /*dir_adj=*/1))) return rc;
+    if ((rc = launch_pack_spectra(p, nf, T, d_spec, p.d_packed, kPackKeepMT | kPackDirAdj))) return rc;
     cudaEventRecord(p.ev[2], p.stream);
     if ((rc = launch_legendre_inv(p, nf, p.d_packed, p.d_fourier))) return rc;
     cudaEventRecord(p.ev[3], p.stream);

@@ -880,6 +880,10 @@ static void fan_free(Plan& p) {
 }
 
 int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv, const double* d_scale) {
+    if (p.g.points) {
+        set_error("this entry point is not available for point-set plans");
+        return SPTRANS_ERR_NOT_IMPLEMENTED;
+    }
     int rc = ensure_block_lists(p, nf);
     if (rc) return rc;
     const FftGroups& grp = g_groups[&p];
@@ -932,6 +936,10 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
 
 static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint,
                                    const int* d_owner, const PeerDst& dst) {
+    if (p.g.points) {  // like TransLocal: no direct / adjoint transform from scattered points
+        set_error("direct and adjoint transforms are not available for point-set plans");
+        return SPTRANS_ERR_NOT_IMPLEMENTED;
+    }
     if (!p.d_weights && !adjoint) {
         set_error("dirtrans: plan was created without quadrature weights");
         return SPTRANS_ERR_INVALID;

@@ -161,7 +161,7 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
         std::sort(g.my_m.begin(), g.my_m.end());
         // contiguous bands of latitude pairs with ~equal Fourier-stage cost: a row pair of length n with zonal
         // wavenumbers up to L is one chirp-z transform of length ~ n + 2L (fourier.cu), i.e. ~ M log M work, plus a
-        // per-row constant (block set-up; calibrated on the 8-GPU stage timings, profiles/scaling_r01.md)
+        // per-row constant (block set-up)
         auto fcost = [&](int j) {
             const double M = nx[j] + 2.0 * std::max(0, g.mmax[j]);
             return M * std::log2(M + 2.0) + 2500.;

@@ -237,11 +237,12 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
 // `jn <= truncation && jm < truncation` rule (:982) that drops the m == truncation column.
 constexpr int kPackRows = 16;  // rows of one (m, parity) block per CTA: keeps the m = 0 blocks from being the long pole
 
-// dir_adj: operand of the adjoint of the DIRECT transform instead -- every coefficient the direct transform writes
-// (all m <= trunc, n <= trunc) enters, halved for m > 0 (the inverse Fourier kernel doubles them), Im(m = 0) dropped.
+// flags & kPackKeepMT: the m == trunc column is kept (unstructured point sets, TransLocal.cc:1331; adjoint of the direct
+// transform); flags & kPackDirAdj: operand of the adjoint of the DIRECT transform -- coefficients halved for m > 0 (the
+// inverse Fourier kernel doubles them), Im(m = 0) dropped.
 __global__ void pack_spectra_kernel(int /*T*/, int nf, int trunc, const long long* __restrict__ sp_rowoff,
                                     const int* __restrict__ my_m, const double* __restrict__ spec,
-                                    double* __restrict__ packed, int dir_adj) {
+                                    double* __restrict__ packed, int flags) {
     const int m = my_m[blockIdx.x];
     const int p = blockIdx.y;
     const long long row0 = sp_rowoff[2 * m + p];
@@ -258,8 +259,8 @@ __global__ void pack_spectra_kernel(int /*T*/, int nf, int trunc, const long lon
         const int imag = r / nf, f = r % nf;
         const int n = m + p + 2 * k;
         double v = 0.;
-        if (n <= trunc && (m < trunc || dir_adj)) v = spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f];
-        if (dir_adj) v = m > 0 ? 0.5 * v : (imag ? 0. : v);
+        if (n <= trunc && (m < trunc || (flags & kPackKeepMT))) v = spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f];
+        if (flags & kPackDirAdj) v = m > 0 ? 0.5 * v : (imag ? 0. : v);
         packed[(row0 + k) * ld + 2 * f + imag] = v;
     }
 }
@@ -383,11 +384,11 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
     return SPTRANS_OK;
 }
 
-int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed, int dir_adj) {
+int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed, int flags) {
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
     dim3 grid(nm, 2, (round_up(p.g.T / 2 + 2, kBK) + kPackRows - 1) / kPackRows);
-    pack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, trunc, p.d_sp_rowoff, p.d_my_m, d_spec, d_packed, dir_adj);
+    pack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, trunc, p.d_sp_rowoff, p.d_my_m, d_spec, d_packed, flags);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;

@@ -112,7 +112,7 @@ int generate_legendre_table(Plan& p) {
     std::vector<double> lats(g.nleg), xcos, col0, col1, diag;
     for (int j = 0; j < g.nleg; ++j) {
         double lat = g.lat_deg[j];
-        const double pole = 89.9999999;  // latPole, trans/local/TransLocal.cc:49,:533-546
+        const double pole = g.points ? 90. : 89.9999999;  // latPole, trans/local/TransLocal.cc:49,:533-546 (grids only)
         if (lat > pole) lat = pole;
         if (lat < -pole) lat = -pole;
         lats[j] = lat * (M_PI / 180.);
@@ -195,7 +195,7 @@ int export_legendre_cache(const Plan& p, double* h_out) {
     std::vector<double> lats(g.nleg), xcos, col0, col1, diag;
     for (int j = 0; j < g.nleg; ++j) {
         double lat = g.lat_deg[j];
-        const double pole = 89.9999999;
+        const double pole = g.points ? 90. : 89.9999999;
         if (lat > pole) lat = pole;
         if (lat < -pole) lat = -pole;
         lats[j] = lat * (M_PI / 180.);

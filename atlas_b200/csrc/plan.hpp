@@ -70,6 +70,13 @@ struct HostGeom {
     std::vector<int> owner;      // [T+1] rank that owns zonal wavenumber m
     std::vector<int> band;       // [nranks+1] latitude-pair band boundaries
     int pair_begin = 0, pair_end = 0;  // latitude pairs [begin,end) of this rank's Fourier band
+    // point-set plans (sptrans_plan_create_points): the rows are the distinct |latitudes| of the points, mirrored;
+    // the Fourier stage is a direct sum per point
+    bool points = false;
+    std::vector<int> pt_row;        // [npts] northern row index of the point's |latitude|
+    std::vector<double> pt_sign;    // [npts] +1 north / equator, -1 south (antisymmetric part flips)
+    std::vector<double> pt_lon;     // [npts] longitude in radians (degrees * pi/180, as the reference forms it)
+    std::vector<double> pt_coslatinv;  // [npts] 1 / cos(lat), not clamped (TransLocal.cc:1380-1384)
 };
 
 inline int num_n(int truncation, int m, int parity) {  // #n in [m, truncation] with (n-m)%2 == parity
@@ -149,6 +156,10 @@ struct Plan {
     int* d_my_m = nullptr;             // [my_m.size()]
     int* d_owner = nullptr;            // [T+1] rank that owns zonal wavenumber m
     int* d_pair_done = nullptr;        // [nleg] field-group blocks finished per latitude pair (sharded direct Fourier)
+    int* d_pt_row = nullptr;           // point-set plans: see HostGeom
+    double* d_pt_sign = nullptr;
+    double* d_pt_lon = nullptr;
+    double* d_pt_coslatinv = nullptr;
     // FFT tables
     std::vector<FftLen> fft_len;       // distinct lengths
     std::vector<int> pair_len_idx;     // [nleg] -> index into fft_len
@@ -224,7 +235,10 @@ size_t legendre_cache_doubles(const HostGeom& g);
 
 // ---- legendre_f64.cu ----
 int build_tiles(Plan& p, int nf, int trunc, int dir_trunc);
-int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed, int dir_adj = 0);
+// flags: kPackKeepMT keeps the m == trunc column (dropped by the scalar inverse, TransLocal.cc:982);
+//        kPackDirAdj halves m > 0 and drops Im(m = 0) (operand of the adjoint of the direct transform)
+constexpr int kPackKeepMT = 1, kPackDirAdj = 2;
+int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed, int flags = 0);
 int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec, int drop_mT = 0);
 int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fourier);
 // same, every output row stored into the exchange buffer of the rank that owns its latitude band
@@ -256,6 +270,10 @@ int launch_exchange_copy(Plan& p, int nf, const ExSeg* d_segs, int nseg, double*
 PeerDst make_peer_dst(const Plan& p);      // exchange buffers of the current parity on every rank
 int launch_exchange_push(Plan& p, int nf);  // band-side rows of the local buffer -> owners of their zonal wavenumber
 int launch_peer_barrier(Plan& p);
+
+// ---- points.cu ----
+// Fourier stage of a point-set plan: gp[f][ip] = sum_m c_m Re((S_m +- A_m)(lat of ip) e^{i m lon_ip}), m <= mlimit
+int launch_points_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv);
 
 // ---- fields.cu ----
 // atlas Field layout (node, level, component) <-> transform rows [component * nlev + level][node]

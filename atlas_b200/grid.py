@@ -54,6 +54,28 @@ class StructuredGrid:
         return lon, lat
 
 
+class UnstructuredGrid:
+    """`atlas::UnstructuredGrid(points)` (grid/detail/grid/Unstructured.h): a list of (lon, lat) points in degrees."""
+
+    regular = False
+
+    def __init__(self, lon_deg, lat_deg, name="unstructured"):
+        self.name = name
+        self._lon = np.ascontiguousarray(lon_deg, dtype=np.float64).reshape(-1)
+        self._lat = np.ascontiguousarray(lat_deg, dtype=np.float64).reshape(-1)
+        if self._lon.size != self._lat.size:
+            raise ValueError("lon and lat must have the same length")
+
+    def size(self):
+        return int(self._lon.size)
+
+    def lonlat(self):
+        return self._lon, self._lat
+
+    def weights(self):
+        return None
+
+
 def gaussian_latitudes(N):
     lat = np.empty(2 * N)
     w = np.empty(2 * N)

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .grid import Grid, StructuredGrid
+from .grid import Grid, StructuredGrid, UnstructuredGrid
 
 
 class option:
@@ -57,8 +57,8 @@ class Trans:
     def __init__(self, grid, truncation, config=None, device=0, rank=0, nranks=1):
         if isinstance(grid, str):
             grid = Grid(grid)
-        if not isinstance(grid, StructuredGrid):
-            raise TypeError("Trans needs a StructuredGrid")
+        if not isinstance(grid, (StructuredGrid, UnstructuredGrid)):
+            raise TypeError("Trans needs a StructuredGrid or an UnstructuredGrid")
         cfg = dict(config or {})
         backend = cfg.get("type", "b200")
         if backend != "b200":
@@ -66,6 +66,13 @@ class Trans:
         self._grid = grid
         self._T = int(truncation)
         self._h = C.c_void_p()
+        if isinstance(grid, UnstructuredGrid):  # TransLocal's unstructured path (TransLocal.cc:740-770, :1289-1392)
+            if nranks != 1:
+                raise ValueError("point-set plans are not sharded")
+            lon, lat = grid.lonlat()
+            _lib.check(_lib.lib.sptrans_plan_create_points(C.byref(self._h), lon.size, lon.ctypes.data_as(_lib.c_double_p),
+                                                           lat.ctypes.data_as(_lib.c_double_p), self._T, int(device)))
+            return
         nx = grid.nx()
         lat = grid.y()
         w = grid.weights()

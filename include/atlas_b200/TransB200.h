@@ -38,9 +38,27 @@ public:
     TransB200(const Cache& /*cache*/, const Grid& grid, const Domain& /*domain*/, const long truncation,
               const eckit::Configuration& config = util::NoConfig()):
         grid_(grid), truncation_(static_cast<int>(truncation)) {
+        int device = 0;
+        config.get("device", device);
         StructuredGrid g(grid_);
-        if (!g || grid_.projection()) {
-            throw_NotImplemented("TransB200 supports global structured grids without projection", Here());
+        if (!g || !grid_.domain().global()) {
+            // Unstructured grid: the transform is evaluated point by point (TransLocal.cc:740-770, :1289-1392).
+            // Regional structured grids take the same route: for non-nested regular grids that is what TransLocal does
+            // too (no FFT, no zonal truncation: `no_nest`, :397-407, :462-467); a cropped reduced grid is evaluated
+            // WITHOUT the global grid's zonal truncation towards the poles (:468-488), i.e. it keeps terms the reference
+            // drops (below 1e-13 at operational resolutions).  One table row per distinct latitude either way.
+            std::vector<double> lon, lat;
+            lon.reserve(grid_.size());
+            lat.reserve(grid_.size());
+            for (const PointLonLat p : grid_.lonlat()) {
+                lon.push_back(p.lon());
+                lat.push_back(p.lat());
+            }
+            check(sptrans_plan_create_points(&plan_, lon.size(), lon.data(), lat.data(), truncation_, device));
+            return;
+        }
+        if (grid_.projection()) {
+            throw_NotImplemented("TransB200 supports structured grids without projection", Here());
         }
         const int nlat = static_cast<int>(g.ny());
         std::vector<int> nx(nlat);
@@ -54,8 +72,6 @@ public:
             w.resize(nlat);
             check(sptrans_gaussian_latitudes(nlat / 2, l2.data(), w.data()));
         }
-        int device = 0;
-        config.get("device", device);
         const unsigned flags = RegularGrid(grid_) ? SPTRANS_GRID_REGULAR : 0u;
         check(sptrans_plan_create(&plan_, nlat, nx.data(), lat.data(), w.empty() ? nullptr : w.data(), truncation_,
                                   flags, device));

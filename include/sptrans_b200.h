@@ -92,6 +92,16 @@ int sptrans_plan_create_sharded(sptrans_plan** plan, int nlat, const int* nx, co
                                 const double* weights, int truncation, unsigned flags, int device, int rank,
                                 int nranks);
 
+/* Trans(UnstructuredGrid, truncation): a plan for `npoints` arbitrary points (lon, lat in degrees), the counterpart of
+ * TransLocal's unstructured path (TransLocal.cc:740-770 set-up, :1289-1392 invtrans_unstructured).  Grid-point arrays of
+ * such a plan are [field][point]; every zonal wavenumber m <= T enters at every point (no reduced-grid truncation, and
+ * unlike the structured path the m == T column of a scalar call is kept, :1331); u, v = U, V / cos(lat) without pole
+ * clamp (:1380-1384).  Inverse transforms only (scalar, vor/div -> wind, general, gradient): like TransLocal there is no
+ * direct transform from scattered points (SPTRANS_ERR_NOT_IMPLEMENTED).  The Legendre stage runs once per DISTINCT
+ * |latitude| on the tensor pipe, so regional lon-lat boxes (TransLocal.cc:397-407: "no_nest" regular grids, which the
+ * reference also evaluates without FFT) cost one table row per latitude, not per point. */
+int sptrans_plan_create_points(sptrans_plan** plan, size_t npoints, const double* lon_deg, const double* lat_deg,
+                               int truncation, int device);
 int sptrans_plan_destroy(sptrans_plan* plan); /* atlas__Trans__delete, trans/detail/TransInterface.cc:86-89 */
 
 /* inspectors: TransImpl::truncation / grid().size() / nb_spectral_coefficients (TransLocal.h:84-91) */

@@ -7,17 +7,32 @@ namespace atlas {
 using idx_t = int;
 class Domain {
 public:
-    bool global() const { return true; }
+    explicit Domain(bool global = true): global_(global) {}
+    bool global() const { return global_; }
+private:
+    bool global_;
 };
 class Projection {
 public:
     explicit operator bool() const { return false; }
+};
+class PointLonLat {  // util/Point.h
+public:
+    PointLonLat(double lon, double lat): lon_(lon), lat_(lat) {}
+    double lon() const { return lon_; }
+    double lat() const { return lat_; }
+private:
+    double lon_, lat_;
 };
 struct GridData {
     std::string name;
     std::vector<int> nx;
     std::vector<double> lat;
     bool gaussian = false, regular = false;
+    bool structured = true;
+    bool global = true;               // domain().global()
+    std::vector<PointLonLat> lonlat;  // filled for regional structured grids (Grid::lonlat())
+    std::vector<PointLonLat> points;  // UnstructuredGrid
 };
 class Grid {
 public:
@@ -25,12 +40,14 @@ public:
     explicit Grid(std::shared_ptr<GridData> d): d_(std::move(d)) {}
     explicit operator bool() const { return bool(d_); }
     Projection projection() const { return Projection(); }
-    Domain domain() const { return Domain(); }
+    Domain domain() const { return Domain(d_->global); }
     idx_t size() const {
+        if (!d_->structured) return static_cast<idx_t>(d_->points.size());
         idx_t s = 0;
         for (int n : d_->nx) s += n;
         return s;
     }
+    const std::vector<PointLonLat>& lonlat() const { return d_->structured ? d_->lonlat : d_->points; }  // grid/Grid.h
     std::string name() const { return d_->name; }
     std::shared_ptr<GridData> d_;
 };
@@ -38,6 +55,7 @@ class StructuredGrid : public Grid {
 public:
     StructuredGrid() = default;
     StructuredGrid(const Grid& g): Grid(g) {}
+    explicit operator bool() const { return d_ && d_->structured; }
     idx_t ny() const { return static_cast<idx_t>(d_->nx.size()); }
     idx_t nx(idx_t j) const { return d_->nx[j]; }
     double y(idx_t j) const { return d_->lat[j]; }

@@ -70,6 +70,25 @@ int main() {
     for (idx_t i = 0; i < grid.size() * nlev * 2; ++i) err3 = std::fmax(err3, std::fabs(wind.data()[i]));
     t->invtrans_adj(gpl, backl);
     t->dirtrans_adj(spl, gpl);
+    // unstructured grid through the same factory: coefficient (0,0) = 4 => every point = 4; no direct transform
+    auto du = std::make_shared<GridData>();
+    du->name = "unstructured";
+    du->structured = false;
+    du->points = {PointLonLat(0., 10.), PointLonLat(33., -10.), PointLonLat(271.5, 0.), PointLonLat(5., 90.)};
+    Grid ugrid(du);
+    std::unique_ptr<const trans::TransImpl> tu(trans::TransFactory::build("b200", ugrid, T, util::NoConfig()));
+    Field spu("spu", {nspec2}), gpu("gpu", {ugrid.size()});
+    spu.data()[0] = 4.;
+    tu->invtrans(spu, gpu);
+    for (idx_t i = 0; i < ugrid.size(); ++i) err3 = std::fmax(err3, std::fabs(gpu.data()[i] - 4.));
+    bool threw_u = false;
+    try {
+        tu->dirtrans(gpu, spu);
+    }
+    catch (const eckit::NotImplemented&) {
+        threw_u = true;
+    }
+    if (!threw_u) err3 = 1.;
     bool threw = false;
     try {
         t->dirtrans_wind2vordiv_adj(vor, dv, wind);

@@ -202,3 +202,109 @@ def test_legendre_cache_import(gridname, T):
     assert np.array_equal(back, 2.0 * ref)
     with pytest.raises(_lib.SptransError):
         other.import_legendre_cache(blob[:-8])
+
+
+# ---- point sets: TransLocal's unstructured path (TransLocal.cc:1289-1392) -------------------------------------------
+def _points_oracle(T, trunc, nf, spec, lon_deg, lat_deg, nb_uv=0):
+    """Literal restatement of invtrans_unstructured (:1289-1392) with the oracle's pinned Legendre functions:
+    per point Pnm(lat) -> sum over n for every m <= trunc -> dot product with (1, 0, 2cos, -2sin, ...) -> 1/cos for wind.
+    `spec` is [m][n][re/im][fld] at truncation `trunc`."""
+    from oracle import pyoracle as po
+
+    sp = spec.reshape(-1, 2, nf)
+    out = np.zeros((nf, lon_deg.size))
+    for ip, (lo, la) in enumerate(zip(lon_deg, lat_deg)):
+        lon, lat = np.deg2rad(lo), np.deg2rad(la)
+        leg = po.legendre_lat(trunc, lat)
+        acc = np.zeros(nf)
+        for m in range(trunc + 1):
+            off = (2 * trunc + 3 - m) * m // 2
+            ns = trunc - m + 1
+            c = leg[off:off + ns] @ sp[off:off + ns, 0, :] + 1j * (leg[off:off + ns] @ sp[off:off + ns, 1, :])
+            if m == 0:
+                acc += c.real
+            else:
+                acc += 2.0 * np.cos(m * lon) * c.real - 2.0 * np.sin(m * lon) * c.imag
+        acc[:nb_uv] /= np.cos(lat)
+        out[:, ip] = acc
+    return out.reshape(-1)
+
+
+def _some_points(rng, n):
+    lon = rng.uniform(-180.0, 360.0, n)
+    lat = rng.uniform(-89.0, 89.0, n)
+    # shared latitudes, mirrored latitudes, the equator, a pole
+    lat[1] = lat[0]
+    lat[2] = -lat[0]
+    lat[3] = 0.0
+    lat[4] = 90.0
+    lon[4] = 12.5
+    return lon, lat
+
+
+@pytest.mark.parametrize("T,nf,npt", [(21, 3, 40), (63, 5, 33), (159, 2, 17)])
+def test_unstructured_points_scalar(T, nf, npt):
+    import atlas_b200
+
+    rng = np.random.default_rng(3)
+    lon, lat = _some_points(rng, npt)
+    trans = atlas_b200.Trans(atlas_b200.UnstructuredGrid(lon, lat), T)
+    assert trans.nb_gridpoints() == npt
+    sp = H.synthetic_spectra(T, nf)
+    gp = np.full(nf * npt, np.nan)
+    trans.invtrans(nf, sp, gp)
+    want = _points_oracle(T, T, nf, sp, lon, lat)
+    assert H.rel_max(gp, want) < 1e-12 and H.compute_rms(gp, want) < 1e-13
+    # the same values as the structured transform on the points of a regular grid (no zonal truncation towards the
+    # poles there), except that the point path keeps m == T
+    grid = atlas_b200.Grid("F16")
+    glon, glat = grid.lonlat()
+    tp = atlas_b200.Trans(atlas_b200.UnstructuredGrid(glon, glat), 15)
+    tg = atlas_b200.Trans(grid, 15)
+    s15 = H.synthetic_spectra(15, 2)
+    s15.reshape(-1, 2, 2)[-1] = 0.0   # zero the m == T coefficient: both paths then agree
+    a, b = np.full(2 * grid.size(), np.nan), np.full(2 * grid.size(), np.nan)
+    tp.invtrans(2, s15, a)
+    tg.invtrans(2, s15, b)
+    assert H.rel_max(a, b) < 1e-12
+
+
+def test_unstructured_points_wind_and_errors():
+    import atlas_b200
+    from atlas_b200 import _lib
+    from oracle import pyoracle as po
+
+    T, nvd, nsc, npt = 31, 2, 1, 25
+    rng = np.random.default_rng(4)
+    lon = rng.uniform(0.0, 360.0, npt)
+    lat = rng.uniform(-80.0, 80.0, npt)
+    lat[1] = -lat[0]
+    trans = atlas_b200.Trans(atlas_b200.UnstructuredGrid(lon, lat), T)
+    vor, div, sc = H.synthetic_spectra(T, nvd, seed=5), H.synthetic_spectra(T, nvd, seed=6), H.synthetic_spectra(T, nsc, seed=7)
+    gp = np.full((2 * nvd + nsc) * npt, np.nan)
+    trans.invtrans(nsc, sc, nvd, vor, div, gp)
+    # reference :1523-1597: extend to T+1, vd2uv at T+1, fields [U.. | V.. | scalars] -> unstructured transform at T+1
+    Te = T + 1
+    ext = lambda a, n: np.ascontiguousarray(_extend(a, T, n))
+    U, V = po.vd2uv(Te, nvd, ext(vor, nvd), ext(div, nvd))
+    allsp = np.concatenate([U.reshape(-1, 2, nvd), V.reshape(-1, 2, nvd), ext(sc, nsc).reshape(-1, 2, nsc)], axis=2)
+    want = _points_oracle(T, Te, 2 * nvd + nsc, np.ascontiguousarray(allsp).reshape(-1), lon, lat, nb_uv=2 * nvd)
+    assert H.compute_rms(gp, want) < 1e-12
+    with pytest.raises(_lib.NotImplementedInBackend):
+        trans.dirtrans(1, np.zeros(npt), np.zeros(trans.nb_spectral_coefficients()))
+    with pytest.raises(_lib.NotImplementedInBackend):
+        trans.invtrans_adj(1, np.zeros(npt), np.zeros(trans.nb_spectral_coefficients()))
+
+
+def _extend(sp, T, nf):
+    """extend_truncation (TransLocal.cc:1496-1519): [m][n] at T -> T+1 with zeros at n == T+1 and m == T+1."""
+    a = sp.reshape(-1, 2, nf)
+    Te = T + 1
+    out = np.zeros(((Te + 1) * (Te + 2) // 2, 2, nf))
+    k = ke = 0
+    for m in range(T + 1):
+        cnt = T - m + 1
+        out[ke:ke + cnt] = a[k:k + cnt]
+        k += cnt
+        ke += cnt + 1
+    return out.reshape(-1)

@@ -276,8 +276,7 @@ static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double
     build_exchange(g, p.ex);
     if ((rc = upload(p.d_ex_m, p.ex.m_side, p.stream))) return fail(rc);
     if ((rc = upload(p.d_ex_band, p.ex.band_side, p.stream))) return fail(rc);
-    if ((rc = generate_legendre_table(p))) return fail(rc);
-    if ((rc = build_transposed_table(p))) return fail(rc);
+    if ((rc = generate_legendre_table(p))) return fail(rc);  // (its transpose is built by the first direct transform)
     if ((rc = build_fft_tables(p))) return fail(rc);
     if (cudaStreamSynchronize(p.stream) != cudaSuccess) {
         set_error(std::string("plan setup failed: ") + cudaGetErrorString(cudaGetLastError()));

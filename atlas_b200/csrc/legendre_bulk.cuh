@@ -13,7 +13,8 @@
 //     mbarrier (count 8) and waits for everybody's release only one stage LATER, just before it refills its share, so
 //     nobody waits unless a whole stage ahead.  Measured at TCo1279 L137 with 32-step stages: 15.98 / 15.83 ms against
 //     17.0 / 16.86 ms with a __syncthreads() per stage (-DSPT_SPLIT=0).  (A single producer warp refilling for everybody
-//     was slower than either: 19.8 ms.)
+//     was slower than either: 19.8 ms.  So was dropping the one __syncthreads() per TILE as well -- operand ring and tile
+//     descriptors running on across tile boundaries, epilogues not aligned: 15.72 / 16.34 ms against 15.37 / 15.45 ms.)
 //   * both directions read K-major A tiles: the direct transform uses a transposed copy of the table (P^T, [lat][k] per
 //     (m, parity) block, same block offsets), so its A rows are 1 KB copies as well (128-byte copies of the untransposed
 //     table made the TMA issue rate the bottleneck: 35 ms instead of 18 ms).
@@ -60,10 +61,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // 
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // bounded spin: a protocol bug ends in a trap (reported as a CUDA error), never in a hung device
-    for (long long it = 0; it < (1ll << 31); ++it)
-        if (mbar_try(bar, parity)) return;
-    asm volatile("trap;");
+    if (mbar_try(bar, parity)) return;
+    // bounded spin (~4 s of SM clock): a protocol bug ends in a trap (reported as a CUDA error), never in a hung device
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+        if (clock64() - t0 > 8000000000ll) asm volatile("trap;");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

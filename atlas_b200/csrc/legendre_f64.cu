@@ -410,21 +410,24 @@ static int launch_gemm(Plan& p, int nf, const LegTile* tiles, int ntiles, const 
     if (ntiles == 0) return SPTRANS_OK;
 #if SPT_BULK
     constexpr size_t smem_bytes = kBulkSmemBytes;
+    if (kDirect && !p.d_tabT) {  // first direct transform of this plan: inverse-only users never pay for the second table
+        int rc = build_transposed_table(p);
+        if (rc) return rc;
+    }
     const double* table = kDirect ? p.d_tabT : p.d_tab;  // the direct transform contracts over latitudes: P^T is K-major
 #else
     constexpr size_t smem_bytes = kLegSmemBytes;
     const double* table = p.d_tab;
 #endif
+    auto kernel = legendre_dmma_kernel<kDirect, kPeers>;
     static bool attr_set[4] = {false, false, false, false};
     if (!attr_set[2 * kDirect + kPeers]) {
-        SPT_CUDA(cudaFuncSetAttribute(legendre_dmma_kernel<kDirect, kPeers>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem_bytes)));
+        SPT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
         attr_set[2 * kDirect + kPeers] = true;
     }
     SPT_CUDA(cudaMemsetAsync(p.d_tile_counter, 0, sizeof(int), p.stream));
     const int grid = std::min(ntiles, p.num_sms);
-    legendre_dmma_kernel<kDirect, kPeers><<<grid, kLegThreads, smem_bytes, p.stream>>>(
-        tiles, ntiles, p.d_tile_counter, table, B, C, 2 * nf, dst);
+    kernel<<<grid, kLegThreads, smem_bytes, p.stream>>>(tiles, ntiles, p.d_tile_counter, table, B, C, 2 * nf, dst);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;

@@ -325,7 +325,7 @@ int import_legendre_cache(Plan& p, const double* h_blob, size_t bytes) {
     cudaFree(d_K);
     cudaFree(d_pitch);
     tc_free(p);  // tensor-core operand images are derived from this table: rebuilt on next use
-    return build_transposed_table(p);
+    return p.d_tabT ? build_transposed_table(p) : SPTRANS_OK;  // keep an existing transpose in step
 }
 
 size_t legendre_cache_doubles(const HostGeom& g) {

@@ -244,7 +244,7 @@ int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fouri
 // same, every output row stored into the exchange buffer of the rank that owns its latitude band
 int launch_legendre_inv_peers(Plan& p, int nf, const double* d_packed, const PeerDst& dst);
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed);
-int build_transposed_table(Plan& p);   // after the table has been generated or imported
+int build_transposed_table(Plan& p);   // lazily, by the first direct transform; rebuilt after a cache import
 
 // ---- legendre_tc.cu (tcgen05 split-TF32 path) ----
 int tc_prepare_tables(Plan& p);

@@ -48,6 +48,16 @@ def ncu_traffic(kernel):
         return None
 
 
+def host_threads():
+    """Threads for the CPU arm: every core this process may run on.  (Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would silently turn the reference arm into a single-thread run; the oracle's
+    parallel regions take an explicit num_threads.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def workload(name):
     table = {
         "TCo1279": ("O1280", 1279, 137),
@@ -168,7 +178,7 @@ def run_reference(args, rank, world):
     N = int(gridname[1:])
     lat, w = po.gaussian_quadrature(N)
     nx = np.array([20 + 4 * j for j in range(N)] + [20 + 4 * j for j in range(N - 1, -1, -1)], dtype=np.int32)
-    threads = po.max_threads()
+    threads = host_threads()
     t0 = time.time()
     plan = po.OraclePlan(nx, lat, T, weights=w, nthreads=threads)
     setup_s = time.time() - t0
@@ -381,7 +391,7 @@ def main():
         from oracle import pyoracle as po
 
         N = int(gridname[1:])
-        threads = po.max_threads()
+        threads = host_threads()
         t0 = time.time()
         plan = po.OraclePlan(grid.nx(), grid.y(), T, weights=grid.weights(), nthreads=threads)
         osetup = time.time() - t0

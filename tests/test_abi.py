@@ -85,6 +85,27 @@ def test_no_cpu_fallback():
         atlas_b200.VorDivToUV(1).execute(6, 1, z, z, z.copy(), z.copy())
 
 
+def test_point_set_plan_refuses_loudly_and_validates_arguments():
+    """sptrans_plan_create_points: bad arguments are SPTRANS_ERR_INVALID; without a device it refuses like every plan."""
+    import atlas_b200
+    from atlas_b200 import _lib
+
+    h = C.c_void_p()
+    lon = np.array([0.0, 10.0])
+    lat = np.array([45.0, 95.0])  # latitude outside [-90, 90]
+    dp = _lib.c_double_p
+    rc = _lib.lib.sptrans_plan_create_points(C.byref(h), 2, lon.ctypes.data_as(dp), lat.ctypes.data_as(dp), 15, 0)
+    assert rc == 1 and b"latitude" in _lib.lib.sptrans_last_error()
+    rc = _lib.lib.sptrans_plan_create_points(C.byref(h), 0, lon.ctypes.data_as(dp), lat.ctypes.data_as(dp), 15, 0)
+    assert rc == 1
+    if _lib.lib.sptrans_device_count() == 0:
+        with pytest.raises(_lib.SptransError) as e:
+            atlas_b200.Trans(atlas_b200.UnstructuredGrid([0.0, 90.0], [10.0, -10.0]), 15)
+        assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(ValueError):
+        atlas_b200.UnstructuredGrid([0.0, 1.0], [0.0])
+
+
 def test_product_never_imports_the_oracle():
     for root, _, files in os.walk(os.path.join(REPO, "atlas_b200")):
         for f in files:

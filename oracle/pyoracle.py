@@ -48,6 +48,7 @@ def load_oracle():
     lib.orc_legendre_lat.argtypes = [C.c_int, C.c_double, _dp, _dp]
     lib.orc_fourier_truncation.restype = C.c_int
     lib.orc_fourier_truncation.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+    lib.orc_invtrans_unstructured.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_int]
     lib.orc_c2r.argtypes = [C.c_int, _dp, _dp, C.c_int]
     lib.orc_r2c.argtypes = [C.c_int, _dp, _dp]
     lib.orc_max_threads.restype = C.c_int
@@ -166,6 +167,17 @@ class OraclePlan:
         grad = np.zeros(2 * nf * self.npts)
         lib().orc_invtrans_grad(self.h, nf, _p(np.ascontiguousarray(spectra)), _p(grad))
         return grad
+
+
+def invtrans_unstructured(truncation, nb_fields, nb_vordiv_fields, spectra, lon_deg, lat_deg, nthreads=0):
+    """TransLocal::invtrans_unstructured (TransLocal.cc:1289-1392) at the given points; gp is [field][point]."""
+    lon = np.ascontiguousarray(lon_deg, dtype=np.float64)
+    lat = np.ascontiguousarray(lat_deg, dtype=np.float64)
+    gp = np.zeros(nb_fields * lon.size)
+    lib().orc_invtrans_unstructured(int(truncation), int(nb_fields), int(nb_vordiv_fields),
+                                    _p(np.ascontiguousarray(spectra, dtype=np.float64)), lon.size, _p(lon), _p(lat), _p(gp),
+                                    nthreads if nthreads > 0 else max_threads())
+    return gp
 
 
 def vd2uv(T, nf, vor, div):

@@ -1080,6 +1080,54 @@ void invtrans_grad(const Plan& p, int nb_fields, const double* spectra, double* 
 // =====================================================================================
 // C ABI for ctypes (tests/, bench.py cpu_baseline) -- test infrastructure only.
 // =====================================================================================
+// TransLocal::invtrans_unstructured (TransLocal.cc:1289-1392), the default path of an UnstructuredGrid: for every point
+// the Legendre functions at the point's latitude (compute_legendre_polynomials_lat, :1322), one (2 nf x ns)(ns x 1)
+// product per zonal wavenumber jm <= truncation (:1327-1336: `jm <= truncation`, i.e. the m == truncation column IS
+// used here, unlike the structured path's `jm < truncation`, :982), the Fourier sum as a dot product with
+// (1, 0, 2 cos(jm lon), -2 sin(jm lon), ...) (:1352-1362), and u, v = U, V / cos(lat) for the first 2 nb_vordiv
+// fields without any pole clamp (:1375-1384).  `spectra` is [m][n][re/im][fld] at `truncation`; gp is [fld][point].
+static void invtrans_unstructured(int truncation, int nb_fields, int nb_vordiv_fields, const double* spectra, int npts,
+                                  const double* lon_deg, const double* lat_deg, double* gp, int nthreads) {
+    std::vector<double> zfn(static_cast<size_t>(truncation + 1) * (truncation + 1));
+    legendre_zfn(truncation, zfn.data());
+    const double deg2rad = M_PI / 180.;
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+    {
+        std::vector<double> legendre(static_cast<size_t>(truncation + 2) * (truncation + 1) / 2), vs, vc;
+        std::vector<double> scl(static_cast<size_t>(2) * nb_fields * (truncation + 1));
+#pragma omp for schedule(dynamic, 1)
+        for (int ip = 0; ip < npts; ++ip) {
+            const double lon = lon_deg[ip] * deg2rad, lat = lat_deg[ip] * deg2rad;
+            legendre_lat(truncation, lat, legendre.data(), zfn.data(), vs, vc);
+            // Legendre transform: scl[jm][imag][fld] = sum_n spectra[m][n][imag][fld] * P_n^m      (:1327-1336)
+            std::fill(scl.begin(), scl.end(), 0.);
+            for (int jm = 0; jm <= truncation; ++jm) {
+                const size_t noff = static_cast<size_t>(2 * truncation + 3 - jm) * jm / 2;
+                const int ns = truncation - jm + 1;
+                double* c = scl.data() + static_cast<size_t>(jm) * 2 * nb_fields;
+                for (int k = 0; k < ns; ++k) {
+                    const double pk = legendre[noff + k];
+                    const double* a = spectra + (noff + k) * 2 * nb_fields;
+                    for (int r = 0; r < 2 * nb_fields; ++r) c[r] += a[r] * pk;
+                }
+            }
+            // Fourier transformation                                                                 (:1352-1372)
+            for (int f = 0; f < nb_fields; ++f) {
+                double acc = 1. * scl[f] + 0. * scl[nb_fields + f];
+                for (int jm = 1; jm <= truncation; ++jm) {
+                    const double* c = scl.data() + static_cast<size_t>(jm) * 2 * nb_fields;
+                    acc += (+2. * std::cos(jm * lon)) * c[f] + (-2. * std::sin(jm * lon)) * c[nb_fields + f];
+                }
+                gp[static_cast<size_t>(f) * npts + ip] = acc;
+            }
+            if (nb_vordiv_fields > 0) {                                                            // (:1375-1384)
+                const double coslat = std::cos(lat);
+                for (int j = 0; j < 2 * nb_vordiv_fields && j < nb_fields; ++j) gp[static_cast<size_t>(j) * npts + ip] /= coslat;
+            }
+        }
+    }
+}
+
 extern "C" {
 
 int orc_max_threads() {
@@ -1168,6 +1216,13 @@ void orc_invtrans_grad(void* plan, int nb_fields, const double* spectra, double*
 }
 
 // FFT self-checks
+// TransLocal on an UnstructuredGrid; `truncation` is that of the data (T for scalar calls, T+1 after extend_truncation +
+// vd2uv for the wind path, TransLocal.cc:1556-1589)
+void orc_invtrans_unstructured(int truncation, int nb_fields, int nb_vordiv_fields, const double* spectra, int npts,
+                               const double* lon_deg, const double* lat_deg, double* gp, int nthreads) {
+    invtrans_unstructured(truncation, nb_fields, nb_vordiv_fields, spectra, npts, lon_deg, lat_deg, gp, nthreads);
+}
+
 void orc_c2r(int n, const double* in_complex, double* out, int naive) {
     const cplx* in = reinterpret_cast<const cplx*>(in_complex);
     if (naive) {

@@ -226,3 +226,67 @@ def test_wind_direct_transform_round_trip_and_gradient_closed_form():
     a = H.EARTH_RADIUS
     assert H.compute_rms(g1[0], -np.sqrt(7.5) * s * 2 * np.sin(lon) / a) < 1e-13
     assert H.compute_rms(g1[1], np.sqrt(7.5) * (c * c - s * s) * 2 * np.cos(lon) / a) < 1e-13
+
+
+def test_unstructured_path_agrees_with_structured_path_and_closed_forms():
+    """orc_invtrans_unstructured (restatement of TransLocal.cc:1289-1392): (a) on the points of a regular Gaussian grid
+    -- where the structured path applies no zonal truncation -- it reproduces the structured oracle, provided the
+    m == T coefficient is zero (the structured scalar path drops that column, :982, the unstructured one keeps it, :1331);
+    (b) the reference's closed-form harmonics at scattered points (test_transgeneral.cc:80-374, used by its own
+    unstructured test :1144-1336 with tolerance 1e-13); (c) wind: the merged T+1 spectra of :1556-1589 give the
+    structured wind fields."""
+    N, T, nf = 16, 15, 3
+    lat, w = po.gaussian_quadrature(N)
+    nx = np.full(2 * N, 4 * N, dtype=np.int32)
+    plan = po.OraclePlan(nx, lat, T, regular=True, weights=w)
+    lon_g, lat_g = H.grid_lonlat(nx, lat)
+    sp = H.synthetic_spectra(T, nf)
+    sp.reshape(-1, 2, nf)[-1] = 0.0
+    want = plan.invtrans(nf, sp, mode=0)
+    got = po.invtrans_unstructured(T, nf, 0, sp, np.rad2deg(lon_g), np.rad2deg(lat_g))
+    assert H.rel_max(got, want) < 1e-13
+    # (b) closed forms at scattered points, including the m == T sectoral harmonic the structured path cannot see
+    rng = np.random.default_rng(9)
+    lon = rng.uniform(-180.0, 360.0, 50)
+    latp = rng.uniform(-90.0, 90.0, 50)
+    for (n, m, imag) in [(0, 0, 0), (1, 0, 0), (2, 1, 1), (3, 2, 0), (3, 3, 1), (T, T, 0)]:
+        s1 = np.zeros((T + 1) * (T + 2))
+        s1[H.spec_index(T, m, n, imag)] = 1.0
+        g = po.invtrans_unstructured(T, 1, 0, s1, lon, latp)
+        ref = H.analytic_harmonic(n, m, imag, np.deg2rad(lon), np.deg2rad(latp))
+        assert H.compute_rms(g, ref) < 1e-13, (n, m, imag)
+    # (c) wind
+    nvd = 2
+    vor, div = H.synthetic_spectra(T, nvd, seed=5), H.synthetic_spectra(T, nvd, seed=6)
+    wantw = plan.invtrans(0, None, nvd, vor, div, mode=0)
+    Te = T + 1
+    import ctypes
+
+    dp = ctypes.POINTER(ctypes.c_double)
+    ve, de = np.zeros((Te + 1) * (Te + 2) * nvd), np.zeros((Te + 1) * (Te + 2) * nvd)
+    po.lib().orc_extend_truncation(T, nvd, vor.ctypes.data_as(dp), ve.ctypes.data_as(dp))
+    po.lib().orc_extend_truncation(T, nvd, div.ctypes.data_as(dp), de.ctypes.data_as(dp))
+    U, V = po.vd2uv(Te, nvd, ve, de)
+    allsp = np.ascontiguousarray(np.concatenate([U.reshape(-1, 2, nvd), V.reshape(-1, 2, nvd)], axis=2)).reshape(-1)
+    gotw = po.invtrans_unstructured(Te, 2 * nvd, nvd, allsp, np.rad2deg(lon_g), np.rad2deg(lat_g))
+    assert H.compute_rms(gotw, wantw) < 1e-13
+
+
+def test_gpu_test_point_checker_is_pinned_to_the_oracle():
+    """tests/test_gpu_fields_adjoint.py checks the CUDA point-set path against a literal NumPy transcription of
+    TransLocal.cc:1289-1392; that transcription is held to the C oracle here (no GPU needed)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gpu_fields", os.path.join(os.path.dirname(__file__), "test_gpu_fields_adjoint.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(2)
+    lon, lat = mod._some_points(rng, 12)
+    T, nf = 21, 3
+    sp = H.synthetic_spectra(T, nf)
+    a = mod._points_oracle(T, T, nf, sp, lon, lat)
+    b = po.invtrans_unstructured(T, nf, 0, sp, lon, lat)
+    assert H.rel_max(a, b) < 1e-14
+    a = mod._points_oracle(T, T, nf, sp, lon[5:], lat[5:], nb_uv=2)   # (without the pole point: 1 / cos(90 deg))
+    b = po.invtrans_unstructured(T, nf, 1, sp, lon[5:], lat[5:])
+    assert H.rel_max(a, b) < 1e-14

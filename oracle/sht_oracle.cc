@@ -11,7 +11,9 @@
 //     closed-form harmonic tests (src/tests/trans/test_transgeneral.cc:80-374, tolerances
 //     1e-13 scalar / 2e-6 wind) -- the reference cannot be built here (needs eckit/ecbuild).
 //   * Gaussian latitudes                      : PINNED against the reference's 12-decimal
-//     tables (tests/golden/gaussian_latitudes_N*.txt).
+//     tables (tests/golden/gaussian_latitudes_N*.npy).
+//   * unstructured path (orc_invtrans_unstructured): PINNED against the structured path on a
+//     regular grid's points and the same closed-form harmonics at scattered points (1e-13).
 //   * dirtrans / invtrans_grad / uv->vordiv   : "parity unpinned" -- NotImplemented in
 //     TransLocal (TransLocal.cc:848-857,1599-1685); defined here as the exact quadrature
 //     adjoint of the inverse and validated by round trip / adjoint identity only.

@@ -172,7 +172,9 @@ def bench_sharded(args, rank, world, local_rank, metric, unit, fp64_peak):
     torch.cuda.synchronize()
     dist.barrier()
     launches0 = st.trans.kernel_launches()
-    sampler = B.ClockSampler(local_rank)
+    # (polled less often than in the single-GPU bench: NVML queries from rank 0's process contend with its kernel launches,
+    # and every rank waits for rank 0 at the exchange barriers)
+    sampler = B.ClockSampler(local_rank, period_s=0.05)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -89,8 +89,9 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_s=0.01):
         self.index = index
+        self.period_s = period_s
         self.sm, self.mx, self.bits = [], [], 0
         self.proc = None
         self.nvml = None
@@ -129,7 +130,7 @@ class ClockSampler:
             self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
 
     def _poll(self):
-        while not self._stop.wait(0.01):
+        while not self._stop.wait(self.period_s):
             try:
                 self._poll_once()
             except Exception:

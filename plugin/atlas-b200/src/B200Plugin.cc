@@ -11,6 +11,7 @@
 
 #include "atlas/library/Plugin.h"
 #include "atlas_b200/TransB200.h"
+#include "atlas_b200/VorDivToUVB200.h"
 
 namespace atlas_b200_plugin {
 
@@ -30,6 +31,8 @@ REGISTER_LIBRARY(B200Plugin);
 namespace {
 // backend name "b200", registered for Trans(grid, truncation, config) like "local" and "ectrans" are
 atlas::trans::TransBuilderGrid<atlas::trans::TransB200> register_trans_b200("b200", "b200");
+// VorDivToUV(truncation, option::type("b200")): same idiom as trans/local/VorDivToUVLocal.cc:25
+atlas::trans::VorDivToUVBuilder<atlas::trans::VorDivToUVB200> register_vordiv_to_uv_b200("b200");
 }  // namespace
 
 }  // namespace atlas_b200_plugin

@@ -14,6 +14,7 @@
  */
 #pragma once
 
+#include <cstdio>
 #include <memory>
 #include <sstream>
 #include <string>
@@ -35,9 +36,48 @@ namespace trans {
 class TransB200 : public TransImpl {
 public:
     // constructor signature required by TransBuilderGrid<T> (trans/detail/TransFactory.h:116-119)
-    TransB200(const Cache& /*cache*/, const Grid& grid, const Domain& /*domain*/, const long truncation,
+    TransB200(const Cache& cache, const Grid& grid, const Domain& /*domain*/, const long truncation,
               const eckit::Configuration& config = util::NoConfig()):
         grid_(grid), truncation_(static_cast<int>(truncation)) {
+        create_plan(config);
+        if (!plan_is_points_) {
+            // Legendre cache, as TransLocal handles it (TransLocal.cc:608-647): a cache handed in replaces the
+            // tables (same blob layout, sizes checked), option "write_legendre" writes them out
+            try {
+                if (cache.legendre()) {
+                    check(sptrans_import_legendre_cache(plan_, cache.legendre().data(), cache.legendre().size()));
+                }
+                std::string path;
+                if (config.get("write_legendre", path) && !path.empty()) {
+                    write_legendre(path);
+                }
+            }
+            catch (...) {
+                sptrans_plan_destroy(plan_);
+                plan_ = nullptr;
+                throw;
+            }
+        }
+    }
+    TransB200(const Grid& grid, const long truncation, const eckit::Configuration& config = util::NoConfig()):
+        TransB200(Cache(), grid, grid.domain(), truncation, config) {}
+
+    ~TransB200() override { sptrans_plan_destroy(plan_); }
+
+private:
+    void write_legendre(const std::string& path) const {
+        std::vector<char> blob(sptrans_legendre_cache_size(plan_));
+        check(sptrans_export_legendre_cache(plan_, blob.data()));
+        std::FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f || std::fwrite(blob.data(), 1, blob.size(), f) != blob.size()) {
+            if (f) {
+                std::fclose(f);
+            }
+            throw_Exception("TransB200: cannot write Legendre cache file " + path, Here());
+        }
+        std::fclose(f);
+    }
+    void create_plan(const eckit::Configuration& config) {
         int device = 0;
         config.get("device", device);
         StructuredGrid g(grid_);
@@ -55,6 +95,7 @@ public:
                 lat.push_back(p.lat());
             }
             check(sptrans_plan_create_points(&plan_, lon.size(), lon.data(), lat.data(), truncation_, device));
+            plan_is_points_ = true;
             return;
         }
         if (grid_.projection()) {
@@ -76,11 +117,8 @@ public:
         check(sptrans_plan_create(&plan_, nlat, nx.data(), lat.data(), w.empty() ? nullptr : w.data(), truncation_,
                                   flags, device));
     }
-    TransB200(const Grid& grid, const long truncation, const eckit::Configuration& config = util::NoConfig()):
-        TransB200(Cache(), grid, grid.domain(), truncation, config) {}
 
-    ~TransB200() override { sptrans_plan_destroy(plan_); }
-
+public:
     std::string type() const override { return "b200"; }
     int truncation() const override { return truncation_; }
     size_t nb_spectral_coefficients() const override { return sptrans_nb_spectral_coefficients(plan_); }
@@ -316,6 +354,7 @@ private:
     Grid grid_;
     int truncation_;
     sptrans_plan* plan_{nullptr};
+    bool plan_is_points_{false};
     mutable functionspace::Spectral spectral_;
 };
 

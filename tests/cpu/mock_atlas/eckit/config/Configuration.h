@@ -12,11 +12,22 @@ public:
         v = it->second;
         return true;
     }
+    bool get(const std::string& key, std::string& v) const {
+        auto it = strings_.find(key);
+        if (it == strings_.end()) return false;
+        v = it->second;
+        return true;
+    }
     Configuration& set(const std::string& key, int v) {
         ints_[key] = v;
         return *this;
     }
+    Configuration& set(const std::string& key, const std::string& v) {
+        strings_[key] = v;
+        return *this;
+    }
 private:
     std::map<std::string, int> ints_;
+    std::map<std::string, std::string> strings_;
 };
 }  // namespace eckit

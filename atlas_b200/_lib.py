@@ -64,6 +64,12 @@ def _load():
         "sptrans_invtrans_vordiv2wind_adj": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "sptrans_invtrans_grad_adj": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_dirtrans_adj_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_dirtrans_wind2vordiv_adj": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "sptrans_dirtrans_wind2vordiv_adj_field": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "sptrans_set_async": (C.c_int, [vp, C.c_int]),
+        "sptrans_synchronize": (C.c_int, [vp]),
+        "sptrans_plan_clone": (C.c_int, [vp, C.POINTER(vp)]),
+        "sptrans_local_sizes": (C.c_int, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
         "sptrans_invtrans_field": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_dirtrans_field": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_invtrans_adj_field": (C.c_int, [vp, C.c_int, vp, vp]),

@@ -3,6 +3,7 @@
 // There is no CPU path: without a CUDA device every entry point returns SPTRANS_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <new>
@@ -59,6 +60,11 @@ struct StageTimer {
     }
     void mark(int i) { cudaEventRecord(p.ev[i], p.stream); }
     void finish(int n_marks, const int* slot) {
+        if (p.async) {  // sptrans_set_async: return after enqueueing; sptrans_last_timings reads the events lazily
+            p.pending_marks = n_marks;
+            for (int i = 0; i + 1 < n_marks; ++i) p.pending_slots[i] = slot[i];
+            return;
+        }
         cudaStreamSynchronize(p.stream);
         for (int i = 0; i + 1 < n_marks; ++i) {
             float ms = 0.f;
@@ -67,6 +73,70 @@ struct StageTimer {
         }
     }
 };
+
+// ---- host-pointer pipelines ------------------------------------------------------------------------------------
+// Fields are independent through the Fourier stage, and the grid-point arrays are [field][point]: the device<->host
+// copy of one chunk of fields runs on a copy stream while the Fourier kernels work on the next chunk (the reference's
+// contract -- results visible on return, TransLocal.cc:1523-1597 -- holds: the call synchronises at its end unless
+// sptrans_set_async is on).  With an inverse and a direct transform in flight on two plans (sptrans_plan_clone) both
+// directions of the PCIe link are busy at the same time.
+constexpr int kMaxHostChunks = 16;
+int host_chunks(int nf) {
+    static int v = [] {
+        const char* e = std::getenv("SPTRANS_HOST_CHUNKS");
+        const int x = e ? std::atoi(e) : 6;
+        return std::max(1, std::min(kMaxHostChunks, x));
+    }();
+    return std::max(1, std::min(v, nf));
+}
+int copy_streams(Plan& p) {
+    if (p.s_h2d) return SPTRANS_OK;
+    SPT_CUDA(cudaStreamCreateWithFlags(&p.s_h2d, cudaStreamNonBlocking));
+    SPT_CUDA(cudaStreamCreateWithFlags(&p.s_d2h, cudaStreamNonBlocking));
+    for (auto& e : p.ev_chunk) SPT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return SPTRANS_OK;
+}
+// Fourier-inverse stage of `nf` fields, chunk by chunk, every finished chunk copied to the host array on the D2H stream
+int fourier_inv_to_host(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv, double* h_gp) {
+    int rc = copy_streams(p);
+    if (rc) return rc;
+    std::vector<int> fb;
+    if ((rc = fourier_set_chunks(p, nf, host_chunks(nf), &fb))) return rc;
+    const int nc = static_cast<int>(fb.size()) - 1;
+    const size_t stride = static_cast<size_t>(p.g.points ? p.g.npts : p.g.gp_stride);
+    for (int c = 0; c < nc; ++c) {
+        if ((rc = launch_fourier_inv(p, nf, mlimit, d_fourier, d_gp, nb_uv, nullptr, c))) return rc;
+        SPT_CUDA(cudaEventRecord(p.ev_chunk[c], p.stream));
+        SPT_CUDA(cudaStreamWaitEvent(p.s_d2h, p.ev_chunk[c], 0));
+        SPT_CUDA(cudaMemcpyAsync(h_gp + fb[c] * stride, d_gp + fb[c] * stride, (fb[c + 1] - fb[c]) * stride * sizeof(double),
+                                 cudaMemcpyDeviceToHost, p.s_d2h));
+    }
+    SPT_CUDA(cudaEventRecord(p.ev_chunk[nc], p.s_d2h));
+    SPT_CUDA(cudaStreamWaitEvent(p.stream, p.ev_chunk[nc], 0));  // the plan's stream completes when the last copy has landed
+    return SPTRANS_OK;
+}
+// Fourier-direct stage of `nf` fields read from a host array: chunk c + 1 crosses the bus while chunk c is transformed
+int fourier_dir_from_host(Plan& p, int nf, const double* h_gp, double* d_gp, double* d_fourier, int nb_uv, int adjoint) {
+    int rc = copy_streams(p);
+    if (rc) return rc;
+    std::vector<int> fb;
+    if ((rc = fourier_set_chunks(p, nf, host_chunks(nf), &fb))) return rc;
+    const int nc = static_cast<int>(fb.size()) - 1;
+    const size_t stride = static_cast<size_t>(p.g.gp_stride);
+    // the staging buffer may still be read by the previous call on this plan
+    SPT_CUDA(cudaEventRecord(p.ev_chunk[nc + 1], p.stream));
+    SPT_CUDA(cudaStreamWaitEvent(p.s_h2d, p.ev_chunk[nc + 1], 0));
+    for (int c = 0; c < nc; ++c) {
+        SPT_CUDA(cudaMemcpyAsync(d_gp + fb[c] * stride, h_gp + fb[c] * stride, (fb[c + 1] - fb[c]) * stride * sizeof(double),
+                                 cudaMemcpyHostToDevice, p.s_h2d));
+        SPT_CUDA(cudaEventRecord(p.ev_chunk[c], p.s_h2d));
+    }
+    for (int c = 0; c < nc; ++c) {
+        SPT_CUDA(cudaStreamWaitEvent(p.stream, p.ev_chunk[c], 0));
+        if ((rc = launch_fourier_dir(p, nf, d_gp, d_fourier, nb_uv, adjoint, c))) return rc;
+    }
+    return SPTRANS_OK;
+}
 
 void peer_release(Plan& p) {
     PeerState& ps = p.peer;
@@ -90,7 +160,7 @@ int check_plan(sptrans_plan* plan) {
 
 // inverse transform of `nf` fields whose spectra sit on the device at truncation `trunc` (T or T+1)
 int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, int nb_uv, StageTimer& tm,
-                int& marks, int* slots) {
+                int& marks, int* slots, double* h_gp = nullptr) {
     // Point sets sum EVERY zonal wavenumber up to the truncation of the data (TransLocal.cc:1331,:1347-1362), grids drop
     // the m == truncation column of a scalar transform (:982): the tiles then run to T+1 over zero rows
     const bool keep_mT = p.g.points && trunc == p.g.T;
@@ -126,6 +196,7 @@ int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, 
     }
     tm.mark(marks);
     if (p.g.points) rc = launch_points_inv(p, nf, std::min(p.g.T, trunc), p.d_fourier, d_gp, nb_uv);
+    else if (h_gp) rc = fourier_inv_to_host(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, d_gp, nb_uv, h_gp);
     else rc = launch_fourier_inv(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, d_gp, nb_uv);
     if (rc) return rc;
     slots[marks++] = 2;
@@ -207,6 +278,7 @@ static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double
         delete sp;
         return rc;
     }
+    set_io_layout(p.g, (flags & SPTRANS_SHARD_LOCAL_IO) != 0);
     auto fail = [&](int code) {
         sptrans_plan_destroy(sp);
         return code;
@@ -243,6 +315,7 @@ static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double
     if ((rc = upload(p.d_nx, g.nx, p.stream))) return fail(rc);
     if ((rc = upload(p.d_my_m, g.my_m, p.stream))) return fail(rc);
     if ((rc = upload(p.d_owner, g.owner, p.stream))) return fail(rc);
+    if (g.local_io && (rc = upload(p.d_spec_off, g.spec_off, p.stream))) return fail(rc);
     if ((rc = upload(p.d_pair_done, std::vector<int>(std::max(g.nleg, 1), 0), p.stream))) return fail(rc);
     {
         std::vector<double> ci(g.nleg), c(g.nleg);
@@ -267,6 +340,8 @@ static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double
             std::vector<double> wn(g.nleg);
             for (int j = 0; j < g.nleg; ++j) wn[j] = w[j] / g.nx[j];
             if ((rc = upload(p.d_dirscale, wn, p.stream))) return fail(rc);
+            for (int j = 0; j < g.nleg; ++j) wn[j] = w[j] / (g.nx[j] * 6371229. * c[j]);
+            if ((rc = upload(p.d_dirscale_uv, wn, p.stream))) return fail(rc);
         }
     }
     if (cudaMalloc(&p.d_tile_counter, sizeof(int)) != cudaSuccess) {
@@ -340,20 +415,32 @@ int sptrans_plan_create_points(sptrans_plan** plan, size_t npoints, const double
 int sptrans_plan_destroy(sptrans_plan* sp) {
     if (!sp) return SPTRANS_OK;
     Plan& p = sp->p;
+    if (p.clones > 0) {
+        set_error("sptrans_plan_destroy: the plan still has clones that borrow its tables; destroy them first");
+        return SPTRANS_ERR_INVALID;
+    }
     cudaSetDevice(p.device);
     if (p.stream) cudaStreamSynchronize(p.stream);
     free_fft_tables(p);
     tc_free(p);
     peer_release(p);
-    void* ptrs[] = {p.d_tab, p.d_tabT, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_owner, p.d_pair_done, p.d_weights,
-                    p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_dirscale, p.d_pair_meta, p.d_twiddle, p.d_chirp, p.d_filt, p.d_fft_order,
-                    p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_ex_m, p.d_ex_band, p.d_packed, p.d_fourier, p.d_spec, p.d_spec2,
-                    p.d_gp, p.d_rows, p.d_pt_row, p.d_pt_sign, p.d_pt_lon, p.d_pt_coslatinv};
+    std::vector<void*> ptrs = {p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_pair_done, p.d_packed, p.d_fourier, p.d_spec,
+                               p.d_spec2, p.d_gp, p.d_rows};
+    if (p.parent) p.parent->clones--;   // a clone borrows every table from its parent
+    else
+        ptrs.insert(ptrs.end(), {p.d_tab, p.d_tabT, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_owner,
+                                 p.d_weights, p.d_coslatinv, p.d_coslat, p.d_uvscale, p.d_dirscale, p.d_dirscale_uv, p.d_pair_meta, p.d_twiddle,
+                                 p.d_chirp, p.d_filt, p.d_fft_order, p.d_ex_m, p.d_ex_band, p.d_pt_row, p.d_pt_sign, p.d_pt_lon,
+                                 p.d_pt_coslatinv, p.d_spec_off});
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p.h_pinned) cudaFreeHost(p.h_pinned);
     for (auto& e : p.ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : p.ev_chunk)
+        if (e) cudaEventDestroy(e);
+    if (p.s_h2d) cudaStreamDestroy(p.s_h2d);
+    if (p.s_d2h) cudaStreamDestroy(p.s_d2h);
     if (p.own_stream && p.stream) cudaStreamDestroy(p.stream);
     delete sp;
     return SPTRANS_OK;
@@ -373,6 +460,13 @@ size_t sptrans_device_bytes(const sptrans_plan* plan) {
     if (!plan) return 0;
     const Plan& p = plan->p;
     return p.bytes_tables + (p.packed_cap + p.fourier_cap + p.spec_cap + p.spec2_cap + p.gp_cap + p.rows_cap) * sizeof(double);
+}
+
+int sptrans_local_sizes(const sptrans_plan* plan, size_t* spec_doubles_per_field, size_t* gridpoints_per_field) {
+    if (!plan) return SPTRANS_ERR_INVALID;
+    if (spec_doubles_per_field) *spec_doubles_per_field = 2 * static_cast<size_t>(plan->p.g.spec_ncoef);
+    if (gridpoints_per_field) *gridpoints_per_field = static_cast<size_t>(plan->p.g.points ? plan->p.g.npts : plan->p.g.gp_stride);
+    return SPTRANS_OK;
 }
 
 size_t sptrans_legendre_cache_size(const sptrans_plan* plan) {
@@ -421,6 +515,74 @@ int sptrans_set_stream(sptrans_plan* plan, void* cuda_stream) {
     return SPTRANS_OK;
 }
 
+int sptrans_set_async(sptrans_plan* plan, int on) {
+    if (!plan) return SPTRANS_ERR_INVALID;
+    plan->p.async = on != 0;
+    return SPTRANS_OK;
+}
+
+int sptrans_synchronize(sptrans_plan* plan) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    SPT_CUDA(cudaStreamSynchronize(plan->p.stream));
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int sptrans_plan_clone(sptrans_plan* src, sptrans_plan** out) {
+    if (!src || !out) {
+        set_error("sptrans_plan_clone: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    *out = nullptr;
+    int rc = check_plan(src);
+    if (rc) return rc;
+    Plan& s = src->p;
+    if (s.parent || s.g.nranks != 1 || s.g.points) {
+        set_error("sptrans_plan_clone: only unsharded grid plans that are not clones themselves can be cloned");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (!s.d_tabT && s.d_weights && (rc = build_transposed_table(s))) return rc;  // shared by the clones' direct transforms
+    sptrans_plan* sp = new (std::nothrow) sptrans_plan();
+    if (!sp) {
+        set_error("out of host memory");
+        return SPTRANS_ERR_INVALID;
+    }
+    Plan& p = sp->p;
+    p.g = s.g;
+    p.device = s.device;
+    p.flags = s.flags;
+    p.num_sms = s.num_sms;
+    p.parent = &s;
+    // borrowed (never freed by the clone): geometry arrays, Legendre tables, Fourier tables
+    p.d_tab = s.d_tab; p.d_tabT = s.d_tabT; p.d_nlat0 = s.d_nlat0; p.d_fb_rowoff = s.d_fb_rowoff; p.d_rowoff = s.d_rowoff;
+    p.d_nx = s.d_nx; p.d_weights = s.d_weights; p.d_coslatinv = s.d_coslatinv; p.d_coslat = s.d_coslat;
+    p.d_uvscale = s.d_uvscale; p.d_dirscale = s.d_dirscale; p.d_dirscale_uv = s.d_dirscale_uv; p.d_sp_rowoff = s.d_sp_rowoff; p.d_my_m = s.d_my_m;
+    p.d_owner = s.d_owner; p.d_spec_off = s.d_spec_off; p.d_pair_meta = s.d_pair_meta; p.d_twiddle = s.d_twiddle;
+    p.d_chirp = s.d_chirp; p.d_filt = s.d_filt; p.d_fft_order = s.d_fft_order; p.d_ex_m = s.d_ex_m; p.d_ex_band = s.d_ex_band;
+    p.ex = s.ex;
+    clone_fft_state(s, p);
+    auto fail = [&](int code) {
+        sptrans_plan_destroy(sp);
+        return code;
+    };
+    s.clones++;
+    if (cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        return fail(SPTRANS_ERR_CUDA);
+    }
+    p.own_stream = true;
+    for (auto& e : p.ev) cudaEventCreate(&e);
+    if (cudaMalloc(&p.d_tile_counter, sizeof(int)) != cudaSuccess) {
+        set_error("cudaMalloc failed");
+        return fail(SPTRANS_ERR_CUDA);
+    }
+    if ((rc = upload(p.d_pair_done, std::vector<int>(std::max(p.g.nleg, 1), 0), p.stream))) return fail(rc);
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    *out = sp;
+    return SPTRANS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 int sptrans_invtrans_scalar(sptrans_plan* plan, int nf, const double* spectra, double* gp) {
     int rc = check_plan(plan);
@@ -453,8 +615,9 @@ int sptrans_invtrans_scalar(sptrans_plan* plan, int nf, const double* spectra, d
         if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
         d_gp = p.d_gp;
     }
-    if ((rc = run_inverse(p, nf, T, d_spec, d_gp, 0, tm, marks, slots))) return rc;
-    if (gp_host) {
+    const bool pipelined = gp_host && !p.g.points;   // D2H of finished field chunks behind the Fourier kernels
+    if ((rc = run_inverse(p, nf, T, d_spec, d_gp, 0, tm, marks, slots, pipelined ? gp : nullptr))) return rc;
+    if (gp_host && !pipelined) {
         SPT_CUDA(cudaMemcpyAsync(gp, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
         slots[marks++] = 4;
         tm.mark(marks);
@@ -513,8 +676,9 @@ int sptrans_invtrans(sptrans_plan* plan, int nsc, const double* scalar_spectra, 
         if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
         d_gp = p.d_gp;
     }
-    if ((rc = run_inverse(p, nall, T + 1, p.d_spec, d_gp, 2 * nvd, tm, marks, slots))) return rc;
-    if (gp_host) {
+    const bool pipelined = gp_host && !p.g.points;
+    if ((rc = run_inverse(p, nall, T + 1, p.d_spec, d_gp, 2 * nvd, tm, marks, slots, pipelined ? gp : nullptr))) return rc;
+    if (gp_host && !pipelined) {
         SPT_CUDA(cudaMemcpyAsync(gp, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
         slots[marks++] = 4;
         tm.mark(marks);
@@ -558,9 +722,6 @@ static int dirtrans_scalar_impl(sptrans_plan* plan, int nf, const double* gp, do
     double* d_spec = spectra;
     if (gp_host) {
         if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
-        tm.mark(marks);
-        SPT_CUDA(cudaMemcpyAsync(p.d_gp, gp, ngp * sizeof(double), cudaMemcpyHostToDevice, p.stream));
-        slots[marks++] = 3;
         d_gp = p.d_gp;
     }
     if (spec_host) {
@@ -571,7 +732,9 @@ static int dirtrans_scalar_impl(sptrans_plan* plan, int nf, const double* gp, do
     if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
     if ((rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nf)))) return rc;
     tm.mark(marks);
-    if ((rc = launch_fourier_dir(p, nf, d_gp, p.d_fourier, 0, adjoint))) return rc;
+    if (gp_host) rc = fourier_dir_from_host(p, nf, gp, p.d_gp, p.d_fourier, 0, adjoint);  // H2D of chunk c+1 || transforms of chunk c
+    else rc = launch_fourier_dir(p, nf, d_gp, p.d_fourier, 0, adjoint);
+    if (rc) return rc;
     slots[marks++] = 2;
     tm.mark(marks);
     if (p.precision == SPTRANS_PREC_TC_SPLIT) {
@@ -634,9 +797,6 @@ int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nf, const double* wind,
     double *d_vor = vor, *d_div = div;
     if (gp_host) {
         if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
-        tm.mark(marks);
-        SPT_CUDA(cudaMemcpyAsync(p.d_gp, wind, ngp * sizeof(double), cudaMemcpyHostToDevice, p.stream));
-        slots[marks++] = 3;
         d_gp = p.d_gp;
     }
     if (sp_host) {
@@ -648,7 +808,9 @@ int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nf, const double* wind,
     if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nall)))) return rc;
     if ((rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nall)))) return rc;
     tm.mark(marks);
-    if ((rc = launch_fourier_dir(p, nall, d_gp, p.d_fourier, nall))) return rc;
+    if (gp_host) rc = fourier_dir_from_host(p, nall, wind, p.d_gp, p.d_fourier, nall, 0);
+    else rc = launch_fourier_dir(p, nall, d_gp, p.d_fourier, nall);
+    if (rc) return rc;
     slots[marks++] = 2;
     tm.mark(marks);
     if ((rc = launch_legendre_dir(p, nall, p.d_fourier, p.d_packed))) return rc;
@@ -704,8 +866,9 @@ int sptrans_invtrans_grad(sptrans_plan* plan, int nf, const double* spectra, dou
         if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
         d_gp = p.d_gp;
     }
-    if ((rc = run_inverse(p, nall, T + 1, p.d_spec, d_gp, nall, tm, marks, slots))) return rc;
-    if (gp_host) {
+    const bool pipelined = gp_host && !p.g.points;
+    if ((rc = run_inverse(p, nall, T + 1, p.d_spec, d_gp, nall, tm, marks, slots, pipelined ? grad : nullptr))) return rc;
+    if (gp_host && !pipelined) {
         SPT_CUDA(cudaMemcpyAsync(grad, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
         slots[marks++] = 4;
         tm.mark(marks);

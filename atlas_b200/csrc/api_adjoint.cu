@@ -1,11 +1,16 @@
-// C ABI, adjoint transforms (TransImpl::invtrans_adj / invtrans_grad_adj / dirtrans_adj, trans/detail/TransImpl.h:63-100,
-// :147-166).  All of them are ATLAS_NOTIMPLEMENTED in TransLocal (trans/local/TransLocal.cc:899-929, :1599-1667); the
-// semantics are those of the reference's adjoint tests (src/tests/trans/test_transgeneral.cc:1591-1818): the transpose
-// over the reals of the corresponding forward operator, <A x, y> = <x, A^T y> with plain Euclidean sums over every stored
-// double.  The same kernels run backwards:
-//   (inverse)^T = unpack o Legendre-direct GEMM o Fourier-direct kernel without quadrature weight and 1/nx, m > 0 doubled,
-//                 the wind rows scaled by the inverse's own 1 / cos(lat), then the transposed spectral stencils (vordiv.cu);
-//   (direct)^T  = Fourier-inverse kernel o Legendre-inverse GEMM o pack, rows scaled by weight / nx, m > 0 halved.
+// C ABI, adjoint transforms (TransImpl::invtrans_adj / invtrans_grad_adj / dirtrans_adj / dirtrans_wind2vordiv_adj,
+// trans/detail/TransImpl.h:63-100, :147-166).  All of them are ATLAS_NOTIMPLEMENTED in TransLocal
+// (trans/local/TransLocal.cc:899-929, :1599-1667); the semantics are those of the reference's adjoint tests, which TransIFS /
+// ectrans pass at 1e-12 (src/tests/trans/test_transgeneral.cc:1591-1818): <A x, y>_grid = <x, A* y>_spec, where the grid
+// inner product is the Euclidean sum over grid points and the SPECTRAL inner product counts every stored coefficient with
+// m > 0 twice (`adj_value += (m1 > 0 ? 2 * temp : temp)`, :1683-1686, :1790-1793).  With C = diag(1 for m = 0, 2 for m > 0):
+//   invtrans_adj = C^-1 (inverse)^T,   dirtrans_adj = (direct)^T C,   dirtrans_wind2vordiv_adj = (wind2vordiv)^T C.
+// The same kernels run backwards:
+//   C^-1 (inverse)^T = unpack o Legendre-direct GEMM o Fourier-direct kernel without quadrature weight and 1/nx (the factor
+//                 2 of the m > 0 harmonics cancels against C^-1), the wind rows scaled by the inverse's own 1 / cos(lat),
+//                 then the transposed spectral stencils (vordiv.cu; they act within one m, so they commute with C);
+//   (direct)^T C = Fourier-inverse kernel o Legendre-inverse GEMM o pack, rows scaled by weight / nx (the inverse Fourier
+//                 kernel's factor 2 for m > 0 is exactly C).
 #include <algorithm>
 
 #include "plan.hpp"
@@ -184,6 +189,65 @@ int sptrans_dirtrans_adj_scalar(sptrans_plan* plan, int nf, const double* spectr
     if ((rc = launch_fourier_inv(p, nf, T, p.d_fourier, d_gp, nf, p.d_dirscale))) return rc;
     cudaEventRecord(p.ev[4], p.stream);
     if (gp_host) SPT_CUDA(cudaMemcpyAsync(gp, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+    cudaEventRecord(p.ev[5], p.stream);
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    for (float& t : p.t_ms) t = 0.f;
+    const int slot[5] = {3, 0, 1, 2, 4};
+    for (int i = 0; i < 5; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
+        p.t_ms[slot[i]] += ms;
+    }
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int sptrans_dirtrans_wind2vordiv_adj(sptrans_plan* plan, int nf, const double* vor, const double* div, double* wind) {
+    int rc = adj_args_ok(plan, "sptrans_dirtrans_wind2vordiv_adj");
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if (nf < 0 || (nf > 0 && (!vor || !div || !wind))) {
+        set_error("sptrans_dirtrans_wind2vordiv_adj: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    if (nf == 0) return SPTRANS_OK;
+    if (!p.d_dirscale_uv) {
+        set_error("sptrans_dirtrans_wind2vordiv_adj: plan was created without quadrature weights");
+        return SPTRANS_ERR_INVALID;
+    }
+    // wind2vordiv = S o B(T+1) o diag(1 / (a cos)), S the spectral stencil (uv_to_vordiv_kernel).  Its adjoint w.r.t. the
+    // spectral inner product that counts m > 0 twice: diag(1 / (a cos)) B(T+1)^T C S^T -- S acts within one m, so C passes
+    // through it -- i.e. the transposed stencil followed by the machinery of dirtrans_adj at truncation T+1.
+    const int T = p.g.T, nall = 2 * nf;
+    const size_t nspec = spec_doubles(nf, T), ngp = static_cast<size_t>(p.g.npts) * nall;
+    const double *d_vor = vor, *d_div = div;
+    double* d_gp = wind;
+    cudaEventRecord(p.ev[0], p.stream);
+    if (!is_device_pointer(vor)) {
+        if ((rc = ensure(p.d_spec2, p.spec2_cap, 2 * nspec))) return rc;
+        SPT_CUDA(cudaMemcpyAsync(p.d_spec2, vor, nspec * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+        SPT_CUDA(cudaMemcpyAsync(p.d_spec2 + nspec, div, nspec * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+        d_vor = p.d_spec2;
+        d_div = p.d_spec2 + nspec;
+    }
+    const bool gp_host = !is_device_pointer(wind);
+    if (gp_host) {
+        if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
+        d_gp = p.d_gp;
+    }
+    if ((rc = ensure(p.d_spec, p.spec_cap, spec_doubles(nall, T + 1)))) return rc;
+    if ((rc = build_tiles(p, nall, T + 1, T))) return rc;
+    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nall)))) return rc;
+    if ((rc = ensure(p.d_fourier, p.fourier_cap, fourier_doubles(p, nall)))) return rc;
+    cudaEventRecord(p.ev[1], p.stream);
+    if ((rc = launch_uv_to_vordiv_adj(p.stream, T, nf, d_vor, d_div, p.d_spec, &p.launches))) return rc;
+    if ((rc = launch_pack_spectra(p, nall, T + 1, p.d_spec, p.d_packed, kPackDirAdj))) return rc;
+    cudaEventRecord(p.ev[2], p.stream);
+    if ((rc = launch_legendre_inv(p, nall, p.d_packed, p.d_fourier))) return rc;
+    cudaEventRecord(p.ev[3], p.stream);
+    if ((rc = launch_fourier_inv(p, nall, T, p.d_fourier, d_gp, nall, p.d_dirscale_uv))) return rc;
+    cudaEventRecord(p.ev[4], p.stream);
+    if (gp_host) SPT_CUDA(cudaMemcpyAsync(wind, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
     cudaEventRecord(p.ev[5], p.stream);
     SPT_CUDA(cudaStreamSynchronize(p.stream));
     for (float& t : p.t_ms) t = 0.f;

@@ -176,4 +176,18 @@ int sptrans_invtrans_grad_adj_field(sptrans_plan* plan, int nlev, const double* 
     return SPTRANS_OK;
 }
 
+int sptrans_dirtrans_wind2vordiv_adj_field(sptrans_plan* plan, int nlev, const double* spvor, const double* spdiv,
+                                           double* gpwind) {
+    int rc = field_args_ok(plan, nlev, spvor, gpwind, "sptrans_dirtrans_wind2vordiv_adj_field");
+    if (rc || nlev == 0) return rc;
+    if (!spdiv) {
+        set_error("sptrans_dirtrans_wind2vordiv_adj_field: invalid arguments");
+        return SPTRANS_ERR_INVALID;
+    }
+    Plan& p = plan->p;
+    if ((rc = ensure(p.d_rows, p.rows_cap, static_cast<size_t>(p.g.npts) * nlev * 2))) return rc;
+    if ((rc = sptrans_dirtrans_wind2vordiv_adj(plan, nlev, spvor, spdiv, p.d_rows))) return rc;
+    return rows_to_field(p, nlev, 2, gpwind);
+}
+
 }  // extern "C"

@@ -355,10 +355,9 @@ SPT2_DEV void stage_inv_inputs_first(const Fft2Args& a, int pair, int f, int Lc,
 }
 
 template <int M1, int NT>
-SPT2_DEV void fourier2_inv_body(const Fft2Args& a, int pair, int f0, int tid, double2* X) {
+SPT2_DEV void fourier2_inv_body(const Fft2Args& a, int pair, int f0, int nfb, int tid, double2* X) {
     using CN = V2Counts<M1>;
     const PairMeta pm = a.meta[pair];
-    const int nfb = min(a.F, a.nf - f0);
     const int n = pm.n, L = pm.L;
     const int Lc = min(L, a.mlimit);
     double2* Tsm = X + M1 * kM2;
@@ -459,10 +458,9 @@ SPT2_DEV void stage_dir_inputs(const Fft2Args& a, const PairMeta& pm, int f, int
 }
 
 template <int M1, int NT>
-SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, double2* X) {
+SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int nfb, int tid, double2* X) {
     using CN = V2Counts<M1>;
     const PairMeta pm = a.meta[pair];
-    const int nfb = min(a.F, a.nf - f0);
     const int n = pm.n, L = pm.L;
     double2* Tsm = X + M1 * kM2;
     double* S = reinterpret_cast<double*>(Tsm + 256);
@@ -471,8 +469,8 @@ SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, do
     const double2* __restrict__ C = A + (2 * L + 1);
     const double2* __restrict__ W1 = a.twid + pm.tw_off;
     const double2* __restrict__ F2 = a.filt + pm.filt_off;
-    // direct transform: quadrature weight, 1/n normalisation.  Adjoint of the inverse (invtrans_adj): no weight,
-    // no normalisation, and the factor 2 of the m > 0 harmonics (f = sum_n X_n^0 P + 2 Re sum_{m>0} ...)
+    // direct transform: quadrature weight, 1/n normalisation.  Adjoint of the inverse (invtrans_adj): no weight and no
+    // normalisation; w.r.t. the ectrans / TransIFS spectral inner product (m > 0 counted twice) every m gets the same factor
     const double wq0 = a.adjoint ? 1.0 : a.weights[pair];
     const double inv_n = a.adjoint ? 1.0 : 1.0 / n;
     stage_dir_inputs<NT>(a, pm, f0, tid, S);
@@ -531,7 +529,7 @@ SPT2_DEV void fourier2_dir_body(const Fft2Args& a, int pair, int f0, int tid, do
             for (int u = 0; u < 4; ++u) {
                 const int m = m0 + u * NT;
                 if (m <= L) {
-                    const double wq = (a.adjoint && m > 0) ? 2.0 * wq0 : wq0;
+                    const double wq = wq0;
                     double2 Gp = cmulc(X[L + m], ap[u]);
                     double2 Gm = cmulc(X[L - m], am_[u]);
                     Gp.x *= inv_n; Gp.y *= inv_n; Gm.x *= inv_n; Gm.y *= inv_n;

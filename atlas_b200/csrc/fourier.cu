@@ -113,9 +113,9 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
                    const double* __restrict__ coslatinv, double* __restrict__ gp, long long npts) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
-    const int pair = bd.x, f0 = bd.y;
+    const int pair = bd.x, f0 = bd.y & 0xffff;
     const PairMeta pm = meta[pair];
-    const int nfb = min(pm.F, nf - f0);
+    const int nfb = bd.y >> 16;  // fields of this block (block descriptor: f0 | count << 16)
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n = pm.n, L = pm.L;
     const int M = pm.M, PL = M;
@@ -214,9 +214,9 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
                    int* __restrict__ pair_done) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
-    const int pair = bd.x, f0 = bd.y;
+    const int pair = bd.x, f0 = bd.y & 0xffff;
     const PairMeta pm = meta[pair];
-    const int nfb = min(pm.F, nf - f0);
+    const int nfb = bd.y >> 16;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n = pm.n, L = pm.L;
     if (L < 0) return;
@@ -243,13 +243,15 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     __syncthreads();
     fft_dif_g(X, nfb, M, sc, sW, sW + (M / 64 + 1), tid, nthr);
     fft_dit_g<true>(X, nfb, M, sc, sW, sW + (M / 64 + 1), filt + pm.filt_off, tid, nthr);
-    // direct transform: quadrature weight, 1/n normalisation.  Adjoint of the inverse (invtrans_adj): no weight,
-    // no normalisation, and the factor 2 of the m > 0 harmonics (f = sum_n X_n^0 P + 2 Re sum_{m>0} ...)
+    // direct transform: quadrature weight, 1/n normalisation.  Adjoint of the inverse (invtrans_adj): no weight and no
+    // normalisation.  The adjoint is taken w.r.t. the spectral inner product of ectrans / TransIFS, which counts the
+    // m > 0 coefficients twice (test_transgeneral.cc:1683-1686), so the factor 2 of the m > 0 harmonics in
+    // f = sum_n X_n^0 P + 2 Re sum_{m>0} ... cancels and every m gets the same factor.
     const double wq0 = adjoint ? 1.0 : weights[pair];
     const double inv_n = adjoint ? 1.0 : 1.0 / n;
     for (int w = tid; w < nfb * (L + 1); w += nthr) {
         const int m = w / nfb, fi = w - m * nfb;
-        const double wq = (adjoint && m > 0) ? 2.0 * wq0 : wq0;
+        const double wq = wq0;
         double2 Gp = cmulc(X[fi * PL + swz(L + m)], A[L + m]);
         double2 Gm = cmulc(X[fi * PL + swz(L - m)], A[L - m]);
         Gp.x *= inv_n; Gp.y *= inv_n; Gm.x *= inv_n; Gm.y *= inv_n;
@@ -306,7 +308,7 @@ fourier_inv_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
                         const double* __restrict__ coslatinv, double* __restrict__ gp, long long npts) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
-    const int pair = bd.x, f = bd.y;
+    const int pair = bd.x, f = bd.y & 0xffff;
     const PairMeta pm = meta[pair];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int L = pm.L, M = pm.M, nh = pm.n / 2;
@@ -358,7 +360,7 @@ fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
                         double2* __restrict__ fb, int adjoint) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
-    const int pair = bd.x, f = bd.y;
+    const int pair = bd.x, f = bd.y & 0xffff;
     const PairMeta pm = meta[pair];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int L = pm.L, M = pm.M, nh = pm.n / 2;
@@ -393,7 +395,7 @@ fourier_dir_rows_kernel(const PairMeta* __restrict__ meta, const int2* __restric
             const double2 Ev = make_double2(0.5 * (Hp.x + Hm.x), 0.5 * (Hp.y - Hm.y));
             const double2 Ov = make_double2(0.5 * (Hp.y + Hm.y), -0.5 * (Hp.x - Hm.x));
             const double2 t = cmulc(Ov, Wr[m]);
-            const double wq = (adjoint && m > 0) ? 2.0 * wq0 : wq0;
+            const double wq = wq0;  // adjoint: every m alike (spectral inner product counts m > 0 twice, see fourier_dir_kernel)
             const double2 Fm = make_double2(0.5 * (Ev.x + t.x) * wq, 0.5 * (Ev.y + t.y) * wq);
             const int n0 = nlat0[m];
             const long long is = (fb_rowoff[m] + (pair - n0)) * nf + f;
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(v2_threads(M1), v2_min_blocks(M1))
 fourier2_inv_kernel(const __grid_constant__ Fft2Args a, const int2* __restrict__ blocks) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
-    fft2::fourier2_inv_body<M1, v2_threads(M1)>(a, bd.x, bd.y, threadIdx.x, X);
+    fft2::fourier2_inv_body<M1, v2_threads(M1)>(a, bd.x, bd.y & 0xffff, bd.y >> 16, threadIdx.x, X);
 }
 
 template <int M1>
@@ -482,7 +484,7 @@ fourier2_dir_kernel(const __grid_constant__ Fft2Args a, const int2* __restrict__
                     const __grid_constant__ PeerDst dst, int me, int* __restrict__ pair_done) {
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
-    fft2::fourier2_dir_body<M1, v2_threads(M1)>(a, bd.x, bd.y, threadIdx.x, X);
+    fft2::fourier2_dir_body<M1, v2_threads(M1)>(a, bd.x, bd.y & 0xffff, bd.y >> 16, threadIdx.x, X);
     if (owner) {  // sharded plan: the block that completes a latitude pair ships its rows to their owners (see v1)
         __shared__ int s_last;
         __threadfence();
@@ -568,13 +570,34 @@ struct FftGroups {
     std::vector<int> mode;                 // 0: packed north/south kernels, 1: row kernels, 2: v2 kernels
     std::vector<int> m1;                   // v2: block-level radix of the group
     int nf = -1;                           // block lists below are built for this number of fields
+    int nchunks = 0;                       // ... split into this many field chunks (host-pointer pipelines; 1 otherwise)
     int F2 = 1;                            // v2: fields per block for this nf
-    std::vector<int2*> d_blocks;
+    std::vector<int2*> d_blocks;           // per group: [chunk][pair][field run] descriptors (pair, f0 | count << 16)
     std::vector<int> nblocks;
+    std::vector<std::vector<int>> chunk_begin;  // per group: first block of every chunk (+ end)
+    std::vector<int> chunk_field;          // [nchunks + 1] field boundaries of the chunks
 };
-static std::map<Plan*, FftGroups> g_groups;
-static std::map<Plan*, std::vector<PairMeta>> g_meta;
-static std::map<Plan*, double2*> g_t256;
+// Launch groups of one Fourier stage are independent (disjoint latitude pairs); with SPTRANS_FFT_STREAMS = N > 1 (default 2:
+// measured 12.2 -> 11.6 ms inverse, 12.7 -> 12.2 ms direct at TCo1279 L137; more streams add nothing) they are
+// spread round-robin over N streams (fork / join with events around the stage), so that the blocks of the next group
+// fill the SMs the tail of the previous group leaves idle (every group is a 20-30 wave launch at one block per SM).
+struct StreamFan {
+    std::vector<cudaStream_t> aux;
+    std::vector<cudaEvent_t> done;
+    cudaEvent_t fork = nullptr;
+};
+// Per-plan state of the Fourier stage, owned by the plan (Plan::fft): no process-global tables, so threads working on
+// different plans never touch shared host state (the contract stays "one in-flight call per plan", like TransLocal).
+struct FftState {
+    FftGroups grp;
+    std::vector<PairMeta> meta;
+    double2* t256 = nullptr;
+    StreamFan fan;
+};
+static FftState& fft_state(Plan& p) {
+    if (!p.fft) p.fft = new FftState();
+    return *static_cast<FftState*>(p.fft);
+}
 
 namespace {
 int env_int(const char* name, int dflt) {
@@ -618,8 +641,8 @@ int build_fft_tables(Plan& p) {
         PairMeta pm{};
         pm.n = g.nx[j];
         pm.L = g.mmax[j];
-        pm.rowN = g.rowoff[j];
-        pm.rowS = g.rowoff[g.nlat - 1 - j];
+        pm.rowN = g.gp_rowoff[j];  // (global offsets, or offsets into this rank's band with SPTRANS_SHARD_LOCAL_IO)
+        pm.rowS = g.gp_rowoff[g.nlat - 1 - j];
         pm.has_s = (g.nlat - 1 - j != j) ? 1 : 0;
         if (pm.L >= 0 && 2 * pm.L >= pm.n) {
             set_error("sptrans_plan_create: zonal truncation at a latitude row reaches nx/2 (aliasing); unsupported");
@@ -675,7 +698,7 @@ int build_fft_tables(Plan& p) {
     SPT_CUDA(cudaMalloc(&p.d_filt, std::max<long long>(filt_total, 1) * sizeof(double2)));
     SPT_CUDA(cudaMalloc(&p.d_twiddle, std::max<long long>(tw_total, 1) * sizeof(double2)));
     p.bytes_tables += (chirp_total + filt_total + tw_total) * sizeof(double2);
-    g_t256[&p] = p.d_twiddle;
+    fft_state(p).t256 = p.d_twiddle;
     {
         std::vector<ScheduleG> sch(classes.size());
         for (size_t c = 0; c < classes.size(); ++c)
@@ -768,48 +791,88 @@ int build_fft_tables(Plan& p) {
     SPT_CUDA(cudaStreamSynchronize(p.stream));
     cudaFree(d_cls1);
     cudaFree(d_cls2);
-    g_groups[&p] = grp;
-    g_meta[&p] = meta;
+    fft_state(p).grp = grp;
+    fft_state(p).meta = meta;
     return SPTRANS_OK;
+}
+
+void clone_fft_state(Plan& src, Plan& dst) {
+    FftState& d = fft_state(dst);
+    const FftState& s = fft_state(src);
+    d.meta = s.meta;
+    d.t256 = s.t256;
+    d.grp = s.grp;
+    d.grp.d_blocks.clear();   // block lists are per plan (built for the field count of its calls)
+    d.grp.nblocks.clear();
+    d.grp.chunk_begin.clear();
+    d.grp.nf = -1;
+    d.grp.nchunks = 0;
 }
 
 static void fan_free(Plan& p);
 void free_fft_tables(Plan& p) {
-    auto it = g_groups.find(&p);
-    if (it != g_groups.end()) {
-        for (int2* d : it->second.d_blocks) cudaFree(d);
-        g_groups.erase(it);
-    }
-    g_meta.erase(&p);
-    g_t256.erase(&p);
+    if (!p.fft) return;
+    for (int2* d : fft_state(p).grp.d_blocks) cudaFree(d);
     fan_free(p);
+    delete static_cast<FftState*>(p.fft);
+    p.fft = nullptr;
 }
 
-static int ensure_block_lists(Plan& p, int nf) {
-    FftGroups& grp = g_groups[&p];
-    if (grp.nf == nf) return SPTRANS_OK;
+// Block lists for `nf` fields split into `nchunks` contiguous field chunks.  Within a group the blocks are ordered
+// [chunk][pair][field run], so that one chunk is a contiguous range of descriptors (launched on its own when the host
+// pipelines overlap copies of one chunk with transforms of the next) and the whole group is still one launch otherwise.
+static int ensure_block_lists(Plan& p, int nf, int nchunks = 1) {
+    FftGroups& grp = fft_state(p).grp;
+    if (nf > 0xffff) {
+        set_error("fourier stage: more than 65535 fields in one call");
+        return SPTRANS_ERR_INVALID;
+    }
+    nchunks = std::max(1, std::min(nchunks, nf));
+    if (grp.nf == nf && grp.nchunks == nchunks) return SPTRANS_OK;
     for (int2* d : grp.d_blocks) cudaFree(d);
     grp.d_blocks.clear();
     grp.nblocks.clear();
-    const std::vector<PairMeta>& meta = g_meta[&p];
+    grp.chunk_begin.clear();
+    const std::vector<PairMeta>& meta = fft_state(p).meta;
     // v2: fields per block, chosen so that the blocks of a pair carry (almost) equal numbers of fields
     const int ft = std::max(1, env_int("SPTRANS_FFT2_F", 6));
     const int nblk = (nf + ft - 1) / ft;
     grp.F2 = (nf + nblk - 1) / std::max(nblk, 1);
+    grp.chunk_field.assign(nchunks + 1, nf);
+    for (int c = 0; c < nchunks; ++c) grp.chunk_field[c] = static_cast<int>(static_cast<long long>(nf) * c / nchunks);
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
         std::vector<int2> blocks;
-        for (int j : grp.pairs[gi]) {
-            const int step = grp.mode[gi] == 2 ? grp.F2 : meta[j].F;
-            for (int f0 = 0; f0 < nf; f0 += step) blocks.push_back(make_int2(j, f0));
+        std::vector<int> cb(nchunks + 1, 0);
+        for (int c = 0; c < nchunks; ++c) {
+            cb[c] = static_cast<int>(blocks.size());
+            const int fb = grp.chunk_field[c], fe = grp.chunk_field[c + 1];
+            for (int j : grp.pairs[gi]) {
+                int step = grp.mode[gi] == 2 ? grp.F2 : meta[j].F;
+                if (grp.mode[gi] == 2 && nchunks > 1) {  // equal runs within the chunk
+                    const int nb = (fe - fb + ft - 1) / ft;
+                    step = (fe - fb + nb - 1) / std::max(nb, 1);
+                }
+                for (int f0 = fb; f0 < fe; f0 += step) blocks.push_back(make_int2(j, f0 | (std::min(step, fe - f0) << 16)));
+            }
         }
+        cb[nchunks] = static_cast<int>(blocks.size());
         int2* d = nullptr;
         SPT_CUDA(cudaMalloc(&d, std::max<size_t>(blocks.size(), 1) * sizeof(int2)));
         SPT_CUDA(cudaMemcpyAsync(d, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, p.stream));
         SPT_CUDA(cudaStreamSynchronize(p.stream));
         grp.d_blocks.push_back(d);
         grp.nblocks.push_back(static_cast<int>(blocks.size()));
+        grp.chunk_begin.push_back(cb);
     }
     grp.nf = nf;
+    grp.nchunks = nchunks;
+    return SPTRANS_OK;
+}
+
+int fourier_set_chunks(Plan& p, int nf, int nchunks, std::vector<int>* field_bounds) {
+    int rc = ensure_block_lists(p, nf, nchunks);
+    if (rc) return rc;
+    if (field_bounds) *field_bounds = fft_state(p).grp.chunk_field;
     return SPTRANS_OK;
 }
 
@@ -822,29 +885,20 @@ static Fft2Args make_v2_args(Plan& p, const FftGroups& grp, int nf) {
     a.nlat0 = p.d_nlat0;
     a.nleg = p.g.nleg;
     a.twid = p.d_twiddle;
-    a.t256 = g_t256[&p];
+    a.t256 = fft_state(p).t256;
     a.chirp = p.d_chirp;
     a.filt = p.d_filt;
-    a.npts = p.g.npts;
+    a.npts = p.g.gp_stride;
     return a;
 }
 
-// Launch groups of one Fourier stage are independent (disjoint latitude pairs); with SPTRANS_FFT_STREAMS = N > 1 (default 2:
-// measured 12.2 -> 11.6 ms inverse, 12.7 -> 12.2 ms direct at TCo1279 L137; more streams add nothing) they are
-// spread round-robin over N streams (fork / join with events around the stage), so that the blocks of the next group
-// fill the SMs the tail of the previous group leaves idle (every group is a 20-30 wave launch at one block per SM).
-struct StreamFan {
-    std::vector<cudaStream_t> aux;
-    std::vector<cudaEvent_t> done;
-    cudaEvent_t fork = nullptr;
-};
-static std::map<Plan*, StreamFan> g_fan;
+
 
 static StreamFan* fan_begin(Plan& p) {
     const int ns = std::max(1, std::min(8, env_int("SPTRANS_FFT_STREAMS", 2)));
-    if (ns > 1 && g_fan.count(&p) && static_cast<int>(g_fan[&p].aux.size()) != ns - 1) fan_free(p);
+    StreamFan& f = fft_state(p).fan;
+    if (ns > 1 && f.fork && static_cast<int>(f.aux.size()) != ns - 1) fan_free(p);
     if (ns <= 1) return nullptr;
-    StreamFan& f = g_fan[&p];
     if (!f.fork) {
         cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming);
         f.aux.resize(ns - 1);
@@ -871,71 +925,102 @@ static void fan_end(Plan& p, StreamFan* f) {
     }
 }
 static void fan_free(Plan& p) {
-    auto it = g_fan.find(&p);
-    if (it == g_fan.end()) return;
-    for (cudaStream_t a : it->second.aux) cudaStreamDestroy(a);
-    for (cudaEvent_t e : it->second.done) cudaEventDestroy(e);
-    if (it->second.fork) cudaEventDestroy(it->second.fork);
-    g_fan.erase(it);
+    if (!p.fft) return;
+    StreamFan& f = fft_state(p).fan;
+    for (cudaStream_t a : f.aux) cudaStreamDestroy(a);
+    for (cudaEvent_t e : f.done) cudaEventDestroy(e);
+    if (f.fork) cudaEventDestroy(f.fork);
+    f = StreamFan{};
 }
 
-int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv, const double* d_scale) {
+// Block range of launch group gi for `chunk` (-1: every chunk of the current lists, i.e. all fields)
+static void chunk_range(const FftGroups& grp, size_t gi, int chunk, int* first, int* count) {
+    if (chunk < 0) {
+        *first = 0;
+        *count = grp.nblocks[gi];
+    }
+    else {
+        *first = grp.chunk_begin[gi][chunk];
+        *count = grp.chunk_begin[gi][chunk + 1] - *first;
+    }
+}
+static int lists_for(Plan& p, int nf, int chunk) {
+    const FftGroups& grp = fft_state(p).grp;
+    if (chunk >= 0) {
+        if (grp.nf != nf || chunk >= grp.nchunks) {
+            set_error("fourier stage: field chunk requested without matching block lists (fourier_set_chunks)");
+            return SPTRANS_ERR_INVALID;
+        }
+        return SPTRANS_OK;
+    }
+    return ensure_block_lists(p, nf, grp.nf == nf ? grp.nchunks : 1);
+}
+
+int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv, const double* d_scale,
+                       int chunk) {
     if (p.g.points) {
         set_error("this entry point is not available for point-set plans");
         return SPTRANS_ERR_NOT_IMPLEMENTED;
     }
-    int rc = ensure_block_lists(p, nf);
+    int rc = lists_for(p, nf, chunk);
     if (rc) return rc;
-    const FftGroups& grp = g_groups[&p];
+    const FftGroups& grp = fft_state(p).grp;
     const double* lat_scale = d_scale ? d_scale : p.d_coslatinv;  // per latitude pair, applied to fields < nb_uv
     StreamFan* fan = fan_begin(p);
     int launched = 0;
-    for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
-        if (grp.nblocks[gi] == 0) continue;
-        const cudaStream_t st = fan_stream(p, fan, launched++);
-        if (grp.mode[gi] == 2) {
-            Fft2Args a = make_v2_args(p, grp, nf);
-            a.mlimit = mlimit;
-            a.nb_uv = nb_uv;
-            a.scale_lat = lat_scale;
-            a.fb = const_cast<double2*>(reinterpret_cast<const double2*>(d_fourier));
-            a.gp = d_gp;
-            switch (grp.m1[gi]) {
-#define SPT_LAUNCH(R)                                                                                                 \
-    case R:                                                                                                           \
-        fourier2_inv_kernel<R><<<grp.nblocks[gi], v2_threads(R), grp.smem[gi], st>>>(a, grp.d_blocks[gi]);      \
+    auto launch_groups = [&]() -> int {
+        for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
+            int first = 0, nblk = 0;
+            chunk_range(grp, gi, chunk, &first, &nblk);
+            if (nblk == 0) continue;
+            const int2* blk = grp.d_blocks[gi] + first;
+            const cudaStream_t st = fan_stream(p, fan, launched++);
+            if (grp.mode[gi] == 2) {
+                Fft2Args a = make_v2_args(p, grp, nf);
+                a.mlimit = mlimit;
+                a.nb_uv = nb_uv;
+                a.scale_lat = lat_scale;
+                a.fb = const_cast<double2*>(reinterpret_cast<const double2*>(d_fourier));
+                a.gp = d_gp;
+                switch (grp.m1[gi]) {
+#define SPT_LAUNCH(R)                                                                          \
+    case R:                                                                                    \
+        fourier2_inv_kernel<R><<<nblk, v2_threads(R), grp.smem[gi], st>>>(a, blk);             \
         break;
-                SPT_V2_RADICES(SPT_LAUNCH)
+                    SPT_V2_RADICES(SPT_LAUNCH)
 #undef SPT_LAUNCH
-                default: set_error("fourier: unsupported v2 radix"); return SPTRANS_ERR_INVALID;
+                    default: set_error("fourier: unsupported v2 radix"); return SPTRANS_ERR_INVALID;
+                }
+                p.launches++;
+                SPT_CUDA(cudaGetLastError());
+                continue;
             }
+            const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;  // one block per SM: 16 warps
+            if (grp.mode[gi]) {
+                fourier_inv_rows_kernel<<<nblk, threads, grp.smem[gi], st>>>(
+                    reinterpret_cast<const PairMeta*>(p.d_pair_meta), blk, nf, mlimit, nb_uv,
+                    reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg,
+                    reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, lat_scale, d_gp, p.g.gp_stride);
+                p.launches++;
+                SPT_CUDA(cudaGetLastError());
+                continue;
+            }
+            fourier_inv_kernel<<<nblk, threads, grp.smem[gi], st>>>(
+                reinterpret_cast<const PairMeta*>(p.d_pair_meta), blk, nf, mlimit, nb_uv,
+                reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg,
+                reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, lat_scale, d_gp, p.g.gp_stride);
             p.launches++;
             SPT_CUDA(cudaGetLastError());
-            continue;
         }
-        const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;  // one block per SM: 16 warps
-        if (grp.mode[gi]) {
-            fourier_inv_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], st>>>(
-                reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
-                reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp,
-                p.d_filt, lat_scale, d_gp, p.g.npts);
-            p.launches++;
-            SPT_CUDA(cudaGetLastError());
-            continue;
-        }
-        fourier_inv_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], st>>>(
-            reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, mlimit, nb_uv,
-            reinterpret_cast<const double2*>(d_fourier), p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp,
-            p.d_filt, lat_scale, d_gp, p.g.npts);
-        p.launches++;
-        SPT_CUDA(cudaGetLastError());
-    }
-    fan_end(p, fan);
-    return SPTRANS_OK;
+        return SPTRANS_OK;
+    };
+    rc = launch_groups();
+    fan_end(p, fan);  // the auxiliary streams are joined on every exit path
+    return rc;
 }
 
 static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint,
-                                   const int* d_owner, const PeerDst& dst) {
+                                   const int* d_owner, const PeerDst& dst, int chunk) {
     if (p.g.points) {  // like TransLocal: no direct / adjoint transform from scattered points
         set_error("direct and adjoint transforms are not available for point-set plans");
         return SPTRANS_ERR_NOT_IMPLEMENTED;
@@ -944,73 +1029,82 @@ static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* 
         set_error("dirtrans: plan was created without quadrature weights");
         return SPTRANS_ERR_INVALID;
     }
-    int rc = ensure_block_lists(p, nf);
+    // (the fused push of a sharded plan counts the blocks of a latitude pair: unchunked lists only)
+    int rc = d_owner ? ensure_block_lists(p, nf, 1) : lists_for(p, nf, chunk);
     if (rc) return rc;
-    const FftGroups& grp = g_groups[&p];
+    const FftGroups& grp = fft_state(p).grp;
     // wind fields enter the vor/div transform as u,v / (a cos(lat)); the adjoint of the inverse wind transform
     // applies the inverse's own 1 / cos(lat)
     const double* uv_scale = adjoint ? p.d_coslatinv : p.d_uvscale;
     StreamFan* fan = fan_begin(p);
     int launched = 0;
-    for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
-        if (grp.nblocks[gi] == 0) continue;
-        const cudaStream_t st = fan_stream(p, fan, launched++);
-        if (grp.mode[gi] == 2) {
-            Fft2Args a = make_v2_args(p, grp, nf);
-            a.nb_uv = nb_uv;
-            a.scale_lat = uv_scale;
-            a.weights = p.d_weights;
-            a.fb = reinterpret_cast<double2*>(d_fourier);
-            a.gp = const_cast<double*>(d_gp);
-            a.adjoint = adjoint;
-            a.gp_aligned16 = (reinterpret_cast<uintptr_t>(d_gp) % 16 == 0) ? 1 : 0;
-            switch (grp.m1[gi]) {
-#define SPT_LAUNCH(R)                                                                                                 \
-    case R:                                                                                                           \
-        fourier2_dir_kernel<R><<<grp.nblocks[gi], v2_threads(R), grp.smem_dir[gi], st>>>(                       \
-            a, grp.d_blocks[gi], d_owner, dst, p.g.rank, p.d_pair_done);                                              \
+    auto launch_groups = [&]() -> int {
+        for (size_t gi = 0; gi < grp.pairs.size(); ++gi) {
+            int first = 0, nblk = 0;
+            chunk_range(grp, gi, d_owner ? -1 : chunk, &first, &nblk);
+            if (nblk == 0) continue;
+            const int2* blk = grp.d_blocks[gi] + first;
+            const cudaStream_t st = fan_stream(p, fan, launched++);
+            if (grp.mode[gi] == 2) {
+                Fft2Args a = make_v2_args(p, grp, nf);
+                a.nb_uv = nb_uv;
+                a.scale_lat = uv_scale;
+                a.weights = p.d_weights;
+                a.fb = reinterpret_cast<double2*>(d_fourier);
+                a.gp = const_cast<double*>(d_gp);
+                a.adjoint = adjoint;
+                a.gp_aligned16 = (reinterpret_cast<uintptr_t>(d_gp) % 16 == 0 && p.g.gp_stride % 2 == 0) ? 1 : 0;
+                switch (grp.m1[gi]) {
+#define SPT_LAUNCH(R)                                                                                             \
+    case R:                                                                                                       \
+        fourier2_dir_kernel<R><<<nblk, v2_threads(R), grp.smem_dir[gi], st>>>(a, blk, d_owner, dst, p.g.rank,     \
+                                                                             p.d_pair_done);                      \
         break;
-                SPT_V2_RADICES(SPT_LAUNCH)
+                    SPT_V2_RADICES(SPT_LAUNCH)
 #undef SPT_LAUNCH
-                default: set_error("fourier: unsupported v2 radix"); return SPTRANS_ERR_INVALID;
+                    default: set_error("fourier: unsupported v2 radix"); return SPTRANS_ERR_INVALID;
+                }
+                p.launches++;
+                SPT_CUDA(cudaGetLastError());
+                continue;
             }
+            const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;
+            if (grp.mode[gi]) {
+                fourier_dir_rows_kernel<<<nblk, threads, grp.smem[gi], st>>>(
+                    reinterpret_cast<const PairMeta*>(p.d_pair_meta), blk, nf, nb_uv, d_gp, p.g.gp_stride, p.d_fb_rowoff, p.d_nlat0,
+                    p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights,
+                    uv_scale, reinterpret_cast<double2*>(d_fourier), adjoint);
+                p.launches++;
+                SPT_CUDA(cudaGetLastError());
+                continue;
+            }
+            fourier_dir_kernel<<<nblk, threads, grp.smem[gi], st>>>(
+                reinterpret_cast<const PairMeta*>(p.d_pair_meta), blk, nf, nb_uv, d_gp, p.g.gp_stride, p.d_fb_rowoff, p.d_nlat0,
+                p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, uv_scale,
+                reinterpret_cast<double2*>(d_fourier), adjoint, d_owner, dst, p.g.rank, p.d_pair_done);
             p.launches++;
             SPT_CUDA(cudaGetLastError());
-            continue;
         }
-        const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;
-        if (grp.mode[gi]) {
-            fourier_dir_rows_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], st>>>(
-                reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
-                p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, uv_scale,
-                reinterpret_cast<double2*>(d_fourier), adjoint);
-            p.launches++;
-            SPT_CUDA(cudaGetLastError());
-            continue;
-        }
-        fourier_dir_kernel<<<grp.nblocks[gi], threads, grp.smem[gi], st>>>(
-            reinterpret_cast<const PairMeta*>(p.d_pair_meta), grp.d_blocks[gi], nf, nb_uv, d_gp, p.g.npts,
-            p.d_fb_rowoff, p.d_nlat0, p.g.nleg, reinterpret_cast<const ScheduleG*>(p.d_fft_order), p.d_twiddle, p.d_chirp, p.d_filt, p.d_weights, uv_scale,
-            reinterpret_cast<double2*>(d_fourier), adjoint, d_owner, dst, p.g.rank, p.d_pair_done);
-        p.launches++;
-        SPT_CUDA(cudaGetLastError());
-    }
+        return SPTRANS_OK;
+    };
+    rc = launch_groups();
     fan_end(p, fan);
-    return SPTRANS_OK;
+    return rc;
 }
 
-int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint) {
-    return launch_fourier_dir_impl(p, nf, d_gp, d_fourier, nb_uv, adjoint, nullptr, PeerDst{});
+int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint, int chunk) {
+    return launch_fourier_dir_impl(p, nf, d_gp, d_fourier, nb_uv, adjoint, nullptr, PeerDst{}, chunk);
 }
 
 int launch_fourier_dir_peers(Plan& p, int nf, const double* d_gp, const PeerDst& dst, bool* fused) {
-    int rc = ensure_block_lists(p, nf);
+    int rc = ensure_block_lists(p, nf, 1);
     if (rc) return rc;
-    const FftGroups& grp = g_groups[&p];
+    const FftGroups& grp = fft_state(p).grp;
     bool rows = false;
     for (size_t gi = 0; gi < grp.pairs.size(); ++gi) rows = rows || (grp.mode[gi] == 1 && grp.nblocks[gi] > 0);
     *fused = !rows;
-    return launch_fourier_dir_impl(p, nf, d_gp, dst.base[p.g.rank], 0, 0, rows ? nullptr : p.d_owner, dst);
+    if (rows) return launch_fourier_dir_impl(p, nf, d_gp, dst.base[p.g.rank], 0, 0, nullptr, dst, -1);
+    return launch_fourier_dir_impl(p, nf, d_gp, dst.base[p.g.rank], 0, 0, p.d_owner, dst, -1);
 }
 
 }  // namespace sptrans

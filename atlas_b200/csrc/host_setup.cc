@@ -206,6 +206,40 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
     return SPTRANS_OK;
 }
 
+void set_io_layout(HostGeom& g, bool local_io) {
+    g.local_io = local_io && g.nranks > 1;
+    const int T = g.T, nlat = g.nlat;
+    g.gp_rowoff.assign(nlat, -1);
+    g.spec_off.assign(T + 1, -1);
+    if (!g.local_io) {
+        for (int j = 0; j < nlat; ++j) g.gp_rowoff[j] = g.rowoff[j];
+        g.gp_stride = g.npts;
+        for (int m = 0; m <= T; ++m) g.spec_off[m] = static_cast<long long>(2 * T + 3 - m) * m / 2;  // reference :970
+        g.spec_ncoef = static_cast<long long>(T + 1) * (T + 2) / 2;
+        return;
+    }
+    // grid: northern rows [pair_begin, pair_end) in order, then their southern mirrors north -> south (the equator row
+    // of a grid with an odd number of rows is a northern row and has no mirror)
+    long long off = 0;
+    for (int j = g.pair_begin; j < g.pair_end; ++j) {
+        g.gp_rowoff[j] = off;
+        off += g.nx[j];
+    }
+    for (int j = g.pair_end - 1; j >= g.pair_begin; --j) {
+        const int js = nlat - 1 - j;
+        if (js == j) continue;
+        g.gp_rowoff[js] = off;
+        off += g.nx[js];
+    }
+    g.gp_stride = off + (off & 1);  // even: 16-byte row starts of every field for the staged loads of the direct kernel
+    long long c = 0;
+    for (int m : g.my_m) {   // ascending
+        g.spec_off[m] = c;
+        c += T - m + 1;
+    }
+    g.spec_ncoef = c;
+}
+
 // Segment lists of the transposition between the two shardings.  Both sides enumerate (m ascending, parity,
 // latitude ascending) so that the packed buffers of sender and receiver line up without any metadata exchange.
 void build_exchange(const HostGeom& g, ExchangeLayout& ex) {

@@ -238,11 +238,12 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
 constexpr int kPackRows = 16;  // rows of one (m, parity) block per CTA: keeps the m = 0 blocks from being the long pole
 
 // flags & kPackKeepMT: the m == trunc column is kept (unstructured point sets, TransLocal.cc:1331; adjoint of the direct
-// transform); flags & kPackDirAdj: operand of the adjoint of the DIRECT transform -- coefficients halved for m > 0 (the
-// inverse Fourier kernel doubles them), Im(m = 0) dropped.
+// transform); flags & kPackDirAdj: operand of the adjoint of the DIRECT transform -- Im(m = 0) dropped.  (The transpose
+// over the reals would halve m > 0 because the inverse Fourier kernel doubles them; the adjoint w.r.t. the ectrans /
+// TransIFS spectral inner product, which counts m > 0 twice, multiplies them by 2 again: test_transgeneral.cc:1683-1703.)
 __global__ void pack_spectra_kernel(int /*T*/, int nf, int trunc, const long long* __restrict__ sp_rowoff,
                                     const int* __restrict__ my_m, const double* __restrict__ spec,
-                                    double* __restrict__ packed, int flags) {
+                                    double* __restrict__ packed, int flags, const long long* __restrict__ spec_off) {
     const int m = my_m[blockIdx.x];
     const int p = blockIdx.y;
     const long long row0 = sp_rowoff[2 * m + p];
@@ -251,7 +252,8 @@ __global__ void pack_spectra_kernel(int /*T*/, int nf, int trunc, const long lon
     if (k0 >= rows) return;
     const int kn = min(kPackRows, rows - k0);
     const int ld = 2 * nf;
-    const long long ioff = static_cast<long long>(2 * trunc + 3 - m) * m / 2 * nf * 2;  // reference :970
+    // reference :970; spec_off: the spectral array holds only this rank's zonal wavenumbers (SPTRANS_SHARD_LOCAL_IO)
+    const long long ioff = (spec_off ? spec_off[m] : static_cast<long long>(2 * trunc + 3 - m) * m / 2) * nf * 2;
     for (int e = threadIdx.x; e < kn * ld; e += blockDim.x) {
         const int k = k0 + e / ld;
         const int r = e % ld;
@@ -260,7 +262,7 @@ __global__ void pack_spectra_kernel(int /*T*/, int nf, int trunc, const long lon
         const int n = m + p + 2 * k;
         double v = 0.;
         if (n <= trunc && (m < trunc || (flags & kPackKeepMT))) v = spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f];
-        if (flags & kPackDirAdj) v = m > 0 ? 0.5 * v : (imag ? 0. : v);
+        if ((flags & kPackDirAdj) && m == 0 && imag) v = 0.;
         packed[(row0 + k) * ld + 2 * f + imag] = v;
     }
 }
@@ -268,7 +270,7 @@ __global__ void pack_spectra_kernel(int /*T*/, int nf, int trunc, const long lon
 // packed [m][p][k][2 fld + re/im] -> spectra [m][n][re/im][fld] for all n <= T
 __global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict__ sp_rowoff,
                                       const int* __restrict__ my_m, const double* __restrict__ packed,
-                                      double* __restrict__ spec, int drop_mT) {
+                                      double* __restrict__ spec, int drop_mT, const long long* __restrict__ spec_off) {
     const int m = my_m[blockIdx.x];
     const int p = blockIdx.y;
     const long long row0 = sp_rowoff[2 * m + p];
@@ -277,7 +279,7 @@ __global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict
     if (k0 >= K) return;
     const int kn = min(kPackRows, K - k0);
     const int ld = 2 * nf;
-    const long long ioff = static_cast<long long>(2 * T + 3 - m) * m / 2 * nf * 2;
+    const long long ioff = (spec_off ? spec_off[m] : static_cast<long long>(2 * T + 3 - m) * m / 2) * nf * 2;
     for (int e = threadIdx.x; e < kn * ld; e += blockDim.x) {
         const int k = k0 + e / ld;
         const int r = e % ld;
@@ -388,7 +390,12 @@ int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
     dim3 grid(nm, 2, (round_up(p.g.T / 2 + 2, kBK) + kPackRows - 1) / kPackRows);
-    pack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, trunc, p.d_sp_rowoff, p.d_my_m, d_spec, d_packed, flags);
+    if (p.d_spec_off && trunc != p.g.T) {
+        set_error("SPTRANS_SHARD_LOCAL_IO: spectral arrays hold this rank's zonal wavenumbers at truncation T only");
+        return SPTRANS_ERR_INVALID;
+    }
+    pack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, trunc, p.d_sp_rowoff, p.d_my_m, d_spec, d_packed, flags,
+                                                    p.d_spec_off);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;
@@ -398,7 +405,8 @@ int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spe
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
     dim3 grid(nm, 2, (p.g.T / 2 + 1 + kPackRows - 1) / kPackRows);
-    unpack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, p.d_sp_rowoff, p.d_my_m, d_packed, d_spec, drop_mT);
+    unpack_spectra_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, p.d_sp_rowoff, p.d_my_m, d_packed, d_spec, drop_mT,
+                                                      p.d_spec_off);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;
@@ -420,10 +428,11 @@ static int launch_gemm(Plan& p, int nf, const LegTile* tiles, int ntiles, const 
     const double* table = p.d_tab;
 #endif
     auto kernel = legendre_dmma_kernel<kDirect, kPeers>;
-    static bool attr_set[4] = {false, false, false, false};
-    if (!attr_set[2 * kDirect + kPeers]) {
+    // the opt-in is per device (context), and one process may hold plans on several devices: remembered per ordinal
+    static bool attr_set[4][64] = {};
+    if (p.device >= 64 || !attr_set[2 * kDirect + kPeers][p.device]) {
         SPT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-        attr_set[2 * kDirect + kPeers] = true;
+        if (p.device < 64) attr_set[2 * kDirect + kPeers][p.device] = true;
     }
     SPT_CUDA(cudaMemsetAsync(p.d_tile_counter, 0, sizeof(int), p.stream));
     const int grid = std::min(ntiles, p.num_sms);

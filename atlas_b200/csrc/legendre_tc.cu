@@ -580,10 +580,11 @@ static int launch_tc_gemm(Plan& p, int nf, const TcTile* tiles, int ntiles, cons
         set_error("tensor-core Legendre path: stage buffers exceed shared memory for this field count");
         return SPTRANS_ERR_INVALID;
     }
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    // the opt-in is per device (context), and one process may hold plans on several devices: remembered per ordinal
+    static size_t attr_smem[64] = {};
+    if (p.device >= 64 || smem > attr_smem[p.device]) {
         SPT_CUDA(cudaFuncSetAttribute(legendre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_smem = smem;
+        if (p.device < 64) attr_smem[p.device] = smem;
     }
     const int grid = std::min(ntiles, p.num_sms);
     legendre_tc_kernel<<<grid, kTcThreads, smem, p.stream>>>(prm);

@@ -55,6 +55,15 @@ struct HostGeom {
     std::vector<int> mmax;          // [nleg] highest m with nlat0[m] <= j  (-1 if none)
     int nxmax = 0;
     long long npts = 0;
+    // layout of the grid-point and spectral arrays the entry points read / write.  Default: the global arrays of the
+    // reference ([field][all points], [all coefficients][field]).  With SPTRANS_SHARD_LOCAL_IO a sharded plan addresses
+    // only its own share: grid arrays [field][rows of my latitude band: northern rows, then their southern mirrors],
+    // spectral arrays [my zonal wavenumbers ascending][n][re/im][field].
+    bool local_io = false;
+    std::vector<long long> gp_rowoff;    // [nlat] offset of row j within one field of the grid array (-1: not held)
+    long long gp_stride = 0;             // points per field in the grid array
+    std::vector<long long> spec_off;     // [T+1] first complex coefficient of zonal wavenumber m at truncation T (-1: not held)
+    long long spec_ncoef = 0;            // complex coefficients per field in the spectral array
     // Legendre table layout (n ascending, k = (n-m-p)/2), built for truncation T+1
     std::vector<long long> tab_off;  // [2*(T+1)] index 2*m+p : offset in doubles
     std::vector<int> tab_K;          // [2*(T+1)] rows with n <= T+1
@@ -152,8 +161,10 @@ struct Plan {
     double* d_coslat = nullptr;        // [nleg]
     double* d_uvscale = nullptr;       // [nleg] 1/(a cos(lat)): wind -> scaled wind of the direct vor/div transform
     double* d_dirscale = nullptr;      // [nleg] quadrature weight / nx: latitude factor of the adjoint of the direct transform
+    double* d_dirscale_uv = nullptr;   // [nleg] weight / (nx a cos(lat)): the same for the adjoint of wind -> vor/div
     long long* d_sp_rowoff = nullptr;  // [2(T+1)+1]
     int* d_my_m = nullptr;             // [my_m.size()]
+    long long* d_spec_off = nullptr;   // [T+1] HostGeom::spec_off (only with SPTRANS_SHARD_LOCAL_IO, else null)
     int* d_owner = nullptr;            // [T+1] rank that owns zonal wavenumber m
     int* d_pair_done = nullptr;        // [nleg] field-group blocks finished per latitude pair (sharded direct Fourier)
     int* d_pt_row = nullptr;           // point-set plans: see HostGeom
@@ -186,6 +197,13 @@ struct Plan {
     void* h_pinned = nullptr;     size_t pinned_cap = 0;
     int precision = 0;           // SPTRANS_PREC_FP64 | SPTRANS_PREC_TC_SPLIT
     void* tc = nullptr;          // TcState (legendre_tc.cu)
+    void* fft = nullptr;         // FftState (fourier.cu): launch groups, per-pair metadata, auxiliary streams
+    // host-pointer pipelines: copies run on their own streams, field chunk by field chunk, next to the transforms
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_chunk[34] = {};   // hand-over events of the chunks (+ start / end of a call)
+    bool async = false;              // sptrans_set_async: whole-transform calls return after enqueueing
+    Plan* parent = nullptr;          // sptrans_plan_clone: tables are borrowed from this plan
+    int clones = 0;
     ExchangeLayout ex;
     ExSeg* d_ex_m = nullptr;
     ExSeg* d_ex_band = nullptr;
@@ -223,6 +241,7 @@ int fourier_truncation(int truncation, int nx, int nxmax, int ndgl, double lat, 
 void gaussian_quadrature(int N, double* lat_deg_2N, double* weights_2N);
 int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, const double* weights, int T,
                    bool regular, int rank, int nranks);
+void set_io_layout(HostGeom& g, bool local_io);   // fills gp_rowoff / gp_stride / spec_off / spec_ncoef
 // per-latitude seeds for the device Legendre recurrence: x=cos(theta), s=sin(theta), columns m=0,1 and the diagonal
 void legendre_seeds(int trc, int nlats, const double* lats_rad, std::vector<double>& x, std::vector<double>& col0,
                     std::vector<double>& col1, std::vector<double>& diag);
@@ -236,7 +255,7 @@ size_t legendre_cache_doubles(const HostGeom& g);
 // ---- legendre_f64.cu ----
 int build_tiles(Plan& p, int nf, int trunc, int dir_trunc);
 // flags: kPackKeepMT keeps the m == trunc column (dropped by the scalar inverse, TransLocal.cc:982);
-//        kPackDirAdj halves m > 0 and drops Im(m = 0) (operand of the adjoint of the direct transform)
+//        kPackDirAdj drops Im(m = 0) (operand of the adjoint of the direct transform)
 constexpr int kPackKeepMT = 1, kPackDirAdj = 2;
 int launch_pack_spectra(Plan& p, int nf, int trunc, const double* d_spec, double* d_packed, int flags = 0);
 int launch_unpack_spectra(Plan& p, int nf, const double* d_packed, double* d_spec, int drop_mT = 0);
@@ -256,10 +275,14 @@ void tc_free(Plan& p);
 // ---- fourier.cu ----
 int build_fft_tables(Plan& p);
 void free_fft_tables(Plan& p);
+void clone_fft_state(Plan& src, Plan& dst);   // launch groups / per-pair metadata of a plan that borrows src's tables
 // fields < nb_uv are multiplied by d_scale[latitude pair] in the store (default: 1 / cos(lat), the wind scaling)
+// chunk >= 0: only the fields of that chunk of the split set up by fourier_set_chunks (host-pointer pipelines)
 int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, double* d_gp, int nb_uv,
-                       const double* d_scale = nullptr);
-int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint = 0);
+                       const double* d_scale = nullptr, int chunk = -1);
+int launch_fourier_dir(Plan& p, int nf, const double* d_gp, double* d_fourier, int nb_uv, int adjoint = 0, int chunk = -1);
+// split the fields of the next Fourier-stage launches into `nchunks` contiguous chunks; returns the nchunks + 1 field bounds
+int fourier_set_chunks(Plan& p, int nf, int nchunks, std::vector<int>* field_bounds);
 // sharded direct transform: every output row is stored into the exchange buffer of the rank that owns its zonal
 // wavenumber (NVLink stores).  *fused = false if the plan has row-mode groups, which write the local buffer only
 // (the caller then pushes the rows with launch_exchange_push)
@@ -289,6 +312,9 @@ int launch_merge_uv_scalar(cudaStream_t s, int T, int nvd, int nsc, const double
 int launch_merge_uv_scalar_adj(cudaStream_t s, int T, int nvd, int nsc, const long long* d_sp_rowoff, const double* d_packed,
                                double* d_vor, double* d_div, double* d_sc, uint64_t* launches);
 int launch_grad_spectra_adj(cudaStream_t s, int T, int nf, const long long* d_sp_rowoff, const double* d_packed, double* d_sp,
+                            uint64_t* launches);
+// transpose of launch_uv_to_vordiv: (vor, div) adjoint variables at T -> [Ut | Vt] adjoint variables at T+1, [m][n][re/im][field]
+int launch_uv_to_vordiv_adj(cudaStream_t s, int T, int nf, const double* d_vor, const double* d_div, double* d_all,
                             uint64_t* launches);
 int launch_vd2uv(cudaStream_t s, int T, int nf, const double* d_vor, const double* d_div, double* d_U, double* d_V,
                  uint64_t* launches);

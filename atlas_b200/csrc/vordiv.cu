@@ -302,7 +302,58 @@ __global__ void grad_spectra_adj_kernel(int T, int nf, const long long* __restri
     }
 }
 
+// Transpose of uv_to_vordiv_kernel (spectral part of dirtrans_wind2vordiv_adj, TransImpl.h:69-70): adjoint variables of
+// (vor, div) at truncation T -> adjoint variables of the scaled wind transforms [Ut_1..Ut_k | Vt_1..Vt_k] at truncation
+// T+1 in the [m][n][re/im][field] layout the pack kernel reads.  With em(n) = (n+1) eps(n,m), ep(n) = n eps(n+1,m):
+//   Ut^_r(n) = em(n+1) z^_r(n+1) - ep(n-1) z^_r(n-1) + m d^_i(n)      Ut^_i(n) = em(n+1) z^_i(n+1) - ep(n-1) z^_i(n-1) - m d^_r(n)
+//   Vt^_r(n) = -em(n+1) d^_r(n+1) + ep(n-1) d^_r(n-1) + m z^_i(n)     Vt^_i(n) = -em(n+1) d^_i(n+1) + ep(n-1) d^_i(n-1) - m z^_r(n)
+// (z^, d^ vanish outside m <= n <= T; the imaginary parts at m = 0 do not enter, the forward operator sets them to zero).
+__global__ void uv_to_vordiv_adj_kernel(int T, int nf, const double* __restrict__ vor, const double* __restrict__ div,
+                                        double* __restrict__ all) {
+    const int Te = T + 1;
+    const int nall = 2 * nf;
+    const long long ncoef_e = static_cast<long long>(Te + 1) * (Te + 2) / 2;
+    const long long total = ncoef_e * nall;
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(e % nall);
+        const long long c = e / nall;
+        int m = static_cast<int>(((2.0 * Te + 3.0) - sqrt((2.0 * Te + 3.0) * (2.0 * Te + 3.0) - 8.0 * static_cast<double>(c))) * 0.5);
+        while (static_cast<long long>(2 * Te + 3 - m) * m / 2 > c) --m;
+        while (static_cast<long long>(2 * Te + 3 - (m + 1)) * (m + 1) / 2 <= c) ++m;
+        const int n = m + static_cast<int>(c - static_cast<long long>(2 * Te + 3 - m) * m / 2);
+        const bool isU = f < nf;
+        const int fs = isU ? f : f - nf;
+        auto at = [&](const double* a, int nn, int imag) -> double {
+            if (m > T || nn > T || nn < m || (m == 0 && imag)) return 0.;
+            const long long ct = static_cast<long long>(2 * T + 3 - m) * m / 2 + (nn - m);
+            return a[(2 * ct + imag) * nf + fs];
+        };
+        const double emp = (n + 2) * epsnm(n + 1, m);  // em(n+1)
+        const double epm = (n - 1) * epsnm(n, m);      // ep(n-1)
+        const double* S = isU ? vor : div;             // stencil operand
+        const double* X = isU ? div : vor;             // i m operand
+        const double sg = isU ? 1. : -1.;
+        double out_r = sg * (emp * at(S, n + 1, 0) - epm * at(S, n - 1, 0)) + m * at(X, n, 1);
+        double out_i = sg * (emp * at(S, n + 1, 1) - epm * at(S, n - 1, 1)) - m * at(X, n, 0);
+        if (m == 0) out_i = 0.;
+        all[(2 * c) * nall + f] = out_r;
+        all[(2 * c + 1) * nall + f] = out_i;
+    }
+}
+
 }  // namespace
+
+int launch_uv_to_vordiv_adj(cudaStream_t s, int T, int nf, const double* d_vor, const double* d_div, double* d_all,
+                            uint64_t* launches) {
+    const long long total = static_cast<long long>(T + 2) * (T + 3) / 2 * (2 * nf);
+    if (total == 0) return SPTRANS_OK;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    uv_to_vordiv_adj_kernel<<<blocks, 256, 0, s>>>(T, nf, d_vor, d_div, d_all);
+    if (launches) ++*launches;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
 
 int launch_merge_uv_scalar_adj(cudaStream_t s, int T, int nvd, int nsc, const long long* d_sp_rowoff, const double* d_packed,
                                double* d_vor, double* d_div, double* d_sc, uint64_t* launches) {

@@ -20,9 +20,6 @@ The reference has no counterpart: TransLocal throws for mpi::size() > 1 (trans/l
 All arithmetic happens in the CUDA library; this module only sequences stages and the collective.
 """
 import ctypes as C
-import json
-import os
-import time
 
 import numpy as np
 
@@ -62,7 +59,7 @@ def shard_segments(grid, truncation, rank, nranks, side):
 class ShardedTrans:
     """m-sharded / latitude-band-sharded transform over an initialised torch.distributed process group."""
 
-    def __init__(self, grid, truncation, device, group=None, exchange="peer"):
+    def __init__(self, grid, truncation, device, group=None, exchange="peer", local_io=False):
         import torch
         import torch.distributed as dist
 
@@ -71,7 +68,11 @@ class ShardedTrans:
         if isinstance(grid, str):
             grid = Grid(grid)
         self.grid, self.T = grid, int(truncation)
-        self.trans = Trans(grid, truncation, device=device, rank=self.rank, nranks=self.world)
+        # local_io (SPTRANS_SHARD_LOCAL_IO): the arrays handed to invtrans / dirtrans hold only this rank's share --
+        # spectra of its zonal wavenumbers, grid rows of its latitude band -- instead of full-size arrays of which only
+        # that share is touched (36 GB per rank at TCo2559 L137)
+        self.local_io = bool(local_io)
+        self.trans = Trans(grid, truncation, device=device, rank=self.rank, nranks=self.world, local_io=self.local_io)
         ms = np.zeros(self.world, dtype=np.int64)
         bs = np.zeros(self.world, dtype=np.int64)
         LL = C.POINTER(C.c_longlong)
@@ -79,6 +80,8 @@ class ShardedTrans:
         self.m_rows, self.band_rows = ms, bs
         self.device = torch.device("cuda", device)
         self._nf = None
+        self._owner, self._band, _, _ = shard_layout(grid, self.T, self.rank, self.world)
+        self._rowoff = np.concatenate([[0], np.cumsum(grid.nx(), dtype=np.int64)])
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.exchange = exchange
@@ -110,9 +113,50 @@ class ShardedTrans:
         self.buf_b = t.empty(max(int(self.band_rows.sum()), 1) * 2 * nf, dtype=t.float64, device=self.device)
         self._nf = nf
 
+    # ---- host-side views of this rank's share (NumPy; tests, benchmark set-up) ----
+    def my_m(self):
+        return [m for m in range(self.T + 1) if self._owner[m] == self.rank]
+
+    def local_spectra(self, sp_global, nf):
+        """[my zonal wavenumbers ascending][n][re/im][field] slab of a global [m][n][re/im][field] array."""
+        T = self.T
+        parts = [sp_global[(2 * T + 3 - m) * m // 2 * 2 * nf:((2 * T + 3 - m) * m // 2 + T - m + 1) * 2 * nf] for m in self.my_m()]
+        return np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0)
+
+    def scatter_local_spectra(self, sp_local, sp_global, nf):
+        """inverse of local_spectra: writes this rank's zonal wavenumbers into a global array"""
+        T, o = self.T, 0
+        for m in self.my_m():
+            n = (T - m + 1) * 2 * nf
+            g0 = (2 * T + 3 - m) * m // 2 * 2 * nf
+            sp_global[g0:g0 + n] = sp_local[o:o + n]
+            o += n
+
+    def local_grid_rows(self, gp_global, nf):
+        """[field][rows of my band: northern rows, then their southern mirrors] from a global [field][point] array,
+        padded to the plan's per-field stride (sptrans_local_sizes)."""
+        _, stride = self.trans.local_sizes()
+        g2 = np.asarray(gp_global).reshape(nf, self.grid.size())
+        out = np.zeros((nf, stride))
+        o = 0
+        for a, b in self._band_spans(self.rank):
+            out[:, o:o + b - a] = g2[:, a:b]
+            o += b - a
+        return out.reshape(-1)
+
+    def scatter_local_grid_rows(self, gp_local, gp_global, nf):
+        _, stride = self.trans.local_sizes()
+        g2 = np.asarray(gp_global).reshape(nf, self.grid.size())
+        l2 = np.asarray(gp_local).reshape(nf, stride)
+        o = 0
+        for a, b in self._band_spans(self.rank):
+            g2[:, a:b] = l2[:, o:o + b - a]
+            o += b - a
+
     def invtrans(self, nf, d_spec, d_gp):
         """d_spec: full-size spectral array (only this rank's zonal wavenumbers are read);
-        d_gp: full-size grid array (only this rank's latitude rows are written)."""
+        d_gp: full-size grid array (only this rank's latitude rows are written).  With local_io both hold only this
+        rank's share (see local_spectra / local_grid_rows)."""
         self._buffers(nf)
         tr, h = self.trans, self.trans._h
         if self.exchange == "peer":
@@ -143,159 +187,52 @@ class ShardedTrans:
 
     def band_rows_slice(self):
         """Grid rows owned by this rank: (north rows [j0,j1), south rows [nlat-j1, nlat-j0))."""
-        owner, band, _, _ = shard_layout(self.grid, self.T, self.rank, self.world)
-        return int(band[self.rank]), int(band[self.rank + 1])
+        return int(self._band[self.rank]), int(self._band[self.rank + 1])
 
-    def gather_grid(self, nf, d_gp):
-        """Replicate the latitude-band-distributed grid fields on every rank (one all-reduce of disjoint rows)."""
-        self.dist.all_reduce(d_gp, group=self.group)
-
-
-def bench_sharded(args, rank, world, local_rank, metric, unit, fp64_peak):
-    """bench.py for N > 1 (strong scaling: the TCo1279 L137 job is fixed, split over N GPUs)."""
-    import torch
-    import torch.distributed as dist
-
-    import bench as B
-    import helpers as H
-
-    gridname, T, nf = B.workload(args.workload)
-    grid = Grid(gridname)
-    st = ShardedTrans(grid, T, local_rank, exchange=args.exchange)
-    npts = grid.size()
-    d_sp = torch.from_numpy(H.synthetic_spectra(T, nf)).to(st.device)
-    d_gp = torch.zeros(nf * npts, dtype=torch.float64, device=st.device)
-    d_sp2 = torch.zeros_like(d_sp)
-    for _ in range(args.warmup):
-        st.invtrans(nf, d_sp, d_gp)
-        st.dirtrans(nf, d_gp, d_sp2)
-    torch.cuda.synchronize()
-    dist.barrier()
-    launches0 = st.trans.kernel_launches()
-    # (polled less often than in the single-GPU bench: NVML queries from rank 0's process contend with its kernel launches,
-    # and every rank waits for rank 0 at the exchange barriers)
-    sampler = B.ClockSampler(local_rank, period_s=0.05)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        st.invtrans(nf, d_sp, d_gp)
-        st.dirtrans(nf, d_gp, d_sp2)
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=st.device, dtype=torch.float64)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = torch.tensor([st.trans.kernel_launches() - launches0], device=st.device, dtype=torch.float64)
-    dist.all_reduce(launches)
-    # stage times of the last inverse + direct pair on every rank (outside the timed region)
-    stage = torch.zeros(6, device=st.device, dtype=torch.float64)
-    if args.exchange == "peer":
-        st.invtrans(nf, d_sp, d_gp)
-        ti = st.trans.last_timings()
-        st.dirtrans(nf, d_gp, d_sp2)
-        td = st.trans.last_timings()
-        stage = torch.tensor([ti["legendre"], ti["exchange_wait"], ti["fourier"], td["fourier"], td["exchange_wait"], td["legendre"]],
-                             device=st.device, dtype=torch.float64)
-    stage_all = [torch.zeros_like(stage) for _ in range(world)]
-    dist.all_gather(stage_all, stage)
-    # steady-state duration of the two calls on every rank (back to back, no host synchronisation), again untimed
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    dist.barrier()
-    for e in evs:
-        e[0].record()
-        st.invtrans(nf, d_sp, d_gp)
-        e[1].record()
-        st.dirtrans(nf, d_gp, d_sp2)
-        e[2].record()
-    torch.cuda.synchronize()
-    calls = torch.tensor([float(np.median([e[0].elapsed_time(e[1]) for e in evs])), float(np.median([e[1].elapsed_time(e[2]) for e in evs]))],
-                         device=st.device, dtype=torch.float64)
-    calls_all = [torch.zeros_like(calls) for _ in range(world)]
-    dist.all_gather(calls_all, calls)
-    owner, band, _, _ = shard_layout(grid, T, rank, world)
-    # ---- end to end with pinned HOST buffers: every rank moves its own share (the spectra of its zonal wavenumbers,
-    # the grid rows of its latitude band) over its own PCIe link, inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        rowoff = np.concatenate([[0], np.cumsum(grid.nx(), dtype=np.int64)])
-        nlat = grid.ny()
-        j0, j1 = int(band[rank]), int(band[rank + 1])
-        spans = [(int(rowoff[j0]), int(rowoff[j1])), (int(rowoff[nlat - j1]), int(rowoff[nlat - j0]))]
-        if spans[0][1] > spans[1][0]:   # band contains the equator row of an odd grid: one span
+    def _band_spans(self, r):
+        """Point ranges [a, b) of the grid rows owned by rank r: its northern rows and their southern mirrors."""
+        nlat, ro = self.grid.ny(), self._rowoff
+        j0, j1 = int(self._band[r]), int(self._band[r + 1])
+        spans = [(int(ro[j0]), int(ro[j1])), (int(ro[nlat - j1]), int(ro[nlat - j0]))]
+        if spans[0][1] > spans[1][0]:   # the band holds the equator row of a grid with an odd number of rows
             spans = [(spans[0][0], spans[1][1])]
-        my_m = [m for m in range(T + 1) if owner[m] == rank]
-        chunks = [((2 * T + 3 - m) * m // 2 * nf * 2, (T - m + 1) * 2 * nf) for m in my_m]
-        h_sp = torch.from_numpy(H.synthetic_spectra(T, nf)).pin_memory()
-        h_sp2 = torch.zeros_like(h_sp).pin_memory()
-        h_gp = [torch.zeros(nf, b - a, dtype=torch.float64).pin_memory() for a, b in spans]
-        gp2d = d_gp.view(nf, npts)
+        return [(a, b) for a, b in spans if b > a]
 
-        def e2e_step():
-            for off, n in chunks:
-                d_sp[off:off + n].copy_(h_sp[off:off + n], non_blocking=True)
-            st.invtrans(nf, d_sp, d_gp)
-            for (a, b), h in zip(spans, h_gp):
-                h.copy_(gp2d[:, a:b], non_blocking=True)
-            for (a, b), h in zip(spans, h_gp):
-                gp2d[:, a:b].copy_(h, non_blocking=True)
-            st.dirtrans(nf, d_gp, d_sp2)
-            for off, n in chunks:
-                h_sp2[off:off + n].copy_(d_sp2[off:off + n], non_blocking=True)
-
-        for _ in range(2):
-            e2e_step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        g1.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        ems = torch.tensor([g0.elapsed_time(g1)], device=st.device, dtype=torch.float64)
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        nbytes = torch.tensor([8.0 * (sum(n for _, n in chunks) + nf * sum(b - a for a, b in spans))], device=st.device, dtype=torch.float64)
-        dist.all_reduce(nbytes)
-        e2e_ms = float(ems.item()) / args.steps
-        e2e = {"value": 1e3 / e2e_ms, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(nbytes.item()),
-               "d2h_bytes_per_step": int(nbytes.item()),
-               "note": "bytes summed over ranks; every rank copies its own shard from/to pinned host memory"}
-    if rank == 0:
-        clocks = sampler.stop()
-        ms_per_step = float(ms.item()) / args.steps
-        roofline = None
-        if args.exchange == "peer":
-            nlat0 = st.trans.nlat0()
-            nleg = (grid.ny() + 1) // 2
-            fl = [B.legendre_flops(nlat0, T, nleg, nf, T, [m for m in range(T + 1) if owner[m] == 0]),
-                  sum(2.0 * nf * (1 if m == 0 else 2) * (T - m + 1) * max(0, nleg - int(nlat0[m])) for m in range(T + 1) if owner[m] == 0)]
-            leg = [float(stage_all[0][0]), float(stage_all[0][5])]
-            ach = (fl[0] + fl[1]) / ((leg[0] + leg[1]) * 1e-3) / 1e12
-            roofline = {"kernel": "legendre_dmma_kernel<inverse + peer stores | direct> on rank 0 (its share of the zonal wavenumbers; "
-                                  "launch time includes the spectra pack / unpack kernel)",
-                        "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                        "traffic": None, "flops_per_launch": {"inverse": fl[0], "direct": fl[1]},
-                        "ms_per_launch": {"inverse": leg[0], "direct": leg[1]}, "share_of_step": (leg[0] + leg[1]) / ms_per_step,
-                        "peak_source": "fp64 DMMA/DFMA microbenchmark on this pool's B200 (profiles/microbench_f64_r01.txt)"}
-        out = {
-            "metric": metric, "value": 1e3 / ms_per_step, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload} L{nf} invtrans+dirtrans fp64 (grid {gridname}, T{T})",
-                       "parallelism": f"zonal-wavenumber sharded Legendre x latitude-band sharded Fourier over {world} GPUs; "
-                                      + ("exchange fused into the kernels over NVLink peer memory (Legendre epilogue stores / "
-                                         "push kernel, device-side barrier)" if args.exchange == "peer"
-                                         else "one NCCL all-to-all per direction") + "; grid fields stay band-distributed",
-                       "l2": "inputs larger than L2"},
-            "clocks": clocks, "gpu_launches": int(launches.item()),
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": None,
-            "stage_ms_per_rank": {k: [round(float(x[i]), 3) for x in stage_all] for i, k in enumerate(
-                ["inv_legendre", "inv_exchange_wait", "inv_fourier", "dir_fourier_push", "dir_exchange_wait", "dir_legendre"])},
-            "call_ms_per_rank": {"invtrans": [round(float(x[0]), 3) for x in calls_all], "dirtrans": [round(float(x[1]), 3) for x in calls_all]},
-        }
-    dist.destroy_process_group()
-    return out if rank == 0 else None
+    def gather_grid(self, nf, d_gp, d_global=None):
+        """Replicate the latitude-band-distributed grid fields on every rank: ONE all-gather (the "single NCCL allgather
+        that reassembles the grid-point Field" of the north star).  Every rank contributes exactly the rows it
+        owns, padded to the longest contribution, and every other row of the global array is overwritten with its owner's
+        values -- no precondition on what the rows of the other bands held before the call.
+        Full-size arrays: gathered in place in `d_gp`.  local_io: `d_gp` is this rank's band, `d_global` [field][point]
+        receives all bands."""
+        t = self.torch
+        npts = self.grid.size()
+        spans = [self._band_spans(r) for r in range(self.world)]
+        lens = [sum(b - a for a, b in sp) for sp in spans]
+        lmax = max(max(lens), 1)
+        if self.local_io:
+            _, stride = self.trans.local_sizes()
+            if d_global is None:
+                raise ValueError("gather_grid: local_io plans need the global output array")
+            gp2d = d_global.view(nf, npts)
+            mine = d_gp.view(nf, stride)[:, :lens[self.rank]]
+        else:
+            gp2d = d_gp.view(nf, npts)
+            mine = None
+        send = t.empty(nf, lmax, dtype=t.float64, device=self.device)
+        if mine is not None:
+            send[:, :lens[self.rank]].copy_(mine)
+        else:
+            o = 0
+            for a, b in spans[self.rank]:
+                send[:, o:o + b - a].copy_(gp2d[:, a:b])
+                o += b - a
+        recv = t.empty(self.world, nf, lmax, dtype=t.float64, device=self.device)
+        self.dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+        for r in range(self.world):
+            if r == self.rank and not self.local_io:
+                continue
+            o = 0
+            for a, b in spans[r]:
+                gp2d[:, a:b].copy_(recv[r, :, o:o + b - a])
+                o += b - a

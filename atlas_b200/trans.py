@@ -54,7 +54,7 @@ def _wait_for_producers(*arrays):
 class Trans:
     """`trans::Trans(grid, truncation, option::type("b200"))`."""
 
-    def __init__(self, grid, truncation, config=None, device=0, rank=0, nranks=1):
+    def __init__(self, grid, truncation, config=None, device=0, rank=0, nranks=1, local_io=False):
         if isinstance(grid, str):
             grid = Grid(grid)
         if not isinstance(grid, (StructuredGrid, UnstructuredGrid)):
@@ -76,13 +76,35 @@ class Trans:
         nx = grid.nx()
         lat = grid.y()
         w = grid.weights()
-        flags = 1 if grid.regular else 0
+        flags = (1 if grid.regular else 0) | (4 if local_io else 0)  # SPTRANS_GRID_REGULAR | SPTRANS_SHARD_LOCAL_IO
         _lib.check(
             _lib.lib.sptrans_plan_create_sharded(
                 C.byref(self._h), grid.ny(), nx.ctypes.data_as(_lib.c_int_p), lat.ctypes.data_as(_lib.c_double_p),
                 None if w is None else w.ctypes.data_as(_lib.c_double_p), self._T, flags, int(device), int(rank), int(nranks),
             )
         )
+
+    def clone(self):
+        """A second plan on the same device that borrows this plan's tables (sptrans_plan_clone): one transform can be in
+        flight on each.  The clone keeps this object alive."""
+        other = object.__new__(Trans)
+        other._grid, other._T, other._parent = self._grid, self._T, self
+        other._h = C.c_void_p()
+        _lib.check(_lib.lib.sptrans_plan_clone(self._h, C.byref(other._h)))
+        return other
+
+    def set_async(self, on=True):
+        """Whole-transform calls return after enqueueing; call synchronize() before touching the buffers."""
+        _lib.check(_lib.lib.sptrans_set_async(self._h, 1 if on else 0))
+
+    def synchronize(self):
+        _lib.check(_lib.lib.sptrans_synchronize(self._h))
+
+    def local_sizes(self):
+        """(spectral doubles per field, grid points per field) of the arrays the sharded entry points address."""
+        a, b = C.c_size_t(), C.c_size_t()
+        _lib.check(_lib.lib.sptrans_local_sizes(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -205,6 +227,18 @@ class Trans:
         """adjoint of dirtrans(nb_fields, gp, spectra) (TransImpl.h:63-67): spectra in, grid fields out"""
         self._sync(scalar_spectra, gp_fields)
         _lib.check(_lib.lib.sptrans_dirtrans_adj_scalar(self._h, int(nb_fields), _ptr(scalar_spectra), _ptr(gp_fields)))
+
+    def dirtrans_wind2vordiv_adj(self, nb_fields, vorticity_spectra, divergence_spectra, wind_fields):
+        """adjoint of dirtrans(nb_fields, wind, vor, div) (TransImpl.h:69-70): vor/div spectra in, wind fields out"""
+        self._sync(vorticity_spectra, divergence_spectra, wind_fields)
+        _lib.check(_lib.lib.sptrans_dirtrans_wind2vordiv_adj(self._h, int(nb_fields), _ptr(vorticity_spectra),
+                                                             _ptr(divergence_spectra), _ptr(wind_fields)))
+
+    def dirtrans_wind2vordiv_adj_field(self, spvor, spdiv, gpwind):
+        self._sync(spvor, spdiv, gpwind)
+        nlev = self._nlev(spvor, gpwind, 2)
+        self._nlev(spdiv, gpwind, 2)
+        _lib.check(_lib.lib.sptrans_dirtrans_wind2vordiv_adj_field(self._h, nlev, _ptr(spvor), _ptr(spdiv), _ptr(gpwind)))
 
     # --- atlas Field layouts (TransImpl.h:54-100): spectral (nspec2, nlev); grid (npts, nlev) or (npts, nlev, 2) ---
     def _nlev(self, sp, gp, ncomp):

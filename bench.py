@@ -6,7 +6,10 @@ truncation 1279 (fp64), synthetic spectra (PCG64 seed 20260925, N(0,1
 
   value : steps/s with inputs and outputs resident in HBM (device pointers handed to the C ABI)
   e2e   : steps/s through the same C-ABI calls with pinned HOST buffers; the H2D copy of every input and
-          the D2H copy of every output happen inside the timed region
+          the D2H copy of every output happen inside the timed region.  Headline e2e = asynchronous calls
+          (sptrans_set_async) on a plan and its clone: the inverse of step i and the direct transform of the grid
+          fields of step i-1 are in flight together, so both directions of the PCIe link are busy;
+          e2e.blocking = the same two calls issued blocking, one after the other, on the same data
   roofline : the dominant kernel (fp64 DMMA Legendre GEMM): algorithmic flops / CUDA-event time of that kernel
   cpu_baseline : the CPU oracle (restatement of TransLocal; the reference itself cannot be built here) on the
           host cores, on a bounded sample, reported next to the GPU number
@@ -60,6 +63,7 @@ def host_threads():
 
 def workload(name):
     table = {
+        "TCo2559": ("O2560", 2559, 137),
         "TCo1279": ("O1280", 1279, 137),
         "TCo399": ("O400", 399, 137),
         "TCo159": ("O160", 159, 137),
@@ -231,8 +235,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="TCo1279", choices=["TCo1279", "TCo399", "TCo159", "O32"])
-    ap.add_argument("--cpu-fields", type=int, default=16, help="fields in the bounded CPU sample")
+    ap.add_argument("--workload", default="TCo1279", choices=["TCo2559", "TCo1279", "TCo399", "TCo159", "O32"])
+    ap.add_argument("--cpu-fields", type=int, default=0, help="fields in the CPU sample (0 = all fields of the workload: nothing extrapolated)")
+    ap.add_argument("--direction", default="both", choices=["both", "inv"],
+                    help="N > 1: 'inv' times the inverse transform only (BASELINE config 5: TCo2559 L137 invtrans)")
+    ap.add_argument("--gather", action="store_true", help="N > 1: also time the all-gather that replicates the grid fields")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "tc"],
                     help="Legendre arithmetic: fp64 DMMA (headline) or tcgen05 split-TF32 (BASELINE config 4; fp32-level accuracy)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

@@ -14,7 +14,7 @@
  *             lambda_i = 2 pi i / nx(row) from 0 (trans/local/TransLocal.cc:1160-1187)
  *   wind    : all u fields, then all v fields (then scalars)   (TransLocal.cc:1561-1589)
  * All data pointers may be device pointers (used in place) or host pointers (staged through
- * the plan's device workspace with pinned-memory copies); the engine detects which with
+ * the plan's device workspace, the grid-point side in field chunks on copy streams next to the Fourier kernels); the engine detects which with
  * cudaPointerGetAttributes, as atlas itself does in parallel/detail/DevicePacker.hic:20-28.
  * There is NO CPU fallback: every call fails with SPTRANS_ERR_CUDA if no device is present.
  *
@@ -43,7 +43,12 @@ enum {
 /* flags for sptrans_plan_create */
 enum {
     SPTRANS_GRID_REGULAR = 1u,  /* RegularGrid(grid): linear zonal truncation (TransLocal.cc:281-284) */
-    SPTRANS_NO_FP64_TABLE = 2u  /* keep only the split-integer Legendre table (saves HBM; fp64 kernels unavailable) */
+    SPTRANS_NO_FP64_TABLE = 2u, /* keep only the split-integer Legendre table (saves HBM; fp64 kernels unavailable) */
+    /* sharded plans: the spectral / grid-point arrays of the sharded entry points hold ONLY this rank's share --
+     * spectra [my zonal wavenumbers, ascending][n = m..T][re/im][field], grid fields [field][rows of my latitude
+     * band: northern rows north->south, then their southern mirrors north->south] (stride: sptrans_local_sizes).
+     * Without it every rank passes full-size arrays and touches only its share (36 GB per rank at TCo2559 L137). */
+    SPTRANS_SHARD_LOCAL_IO = 4u
 };
 
 /* precision selector for sptrans_set_precision */
@@ -110,6 +115,9 @@ size_t sptrans_nb_gridpoints(const sptrans_plan* plan);
 size_t sptrans_nb_spectral_coefficients(const sptrans_plan* plan); /* (T+1)(T+2) */
 /* first northern latitude index at which wavenumber m is resolved (TransLocal.cc:462-488); out[T+1] */
 int sptrans_get_nlat0(const sptrans_plan* plan, int* nlat0);
+/* per-field sizes of the arrays the (sharded) entry points address: doubles of the spectral array, points of the grid
+ * array.  (T+1)(T+2) and nb_gridpoints unless the plan was created with SPTRANS_SHARD_LOCAL_IO. */
+int sptrans_local_sizes(const sptrans_plan* plan, size_t* spec_doubles_per_field, size_t* gridpoints_per_field);
 /* bytes of device memory held by the plan (tables + workspaces) */
 size_t sptrans_device_bytes(const sptrans_plan* plan);
 
@@ -133,6 +141,18 @@ int sptrans_set_precision(sptrans_plan* plan, int precision);
 
 /* run all subsequent calls on this cudaStream_t (default: the plan's own stream) */
 int sptrans_set_stream(sptrans_plan* plan, void* cuda_stream);
+
+/* Asynchronous calls (the optional explicit-stream variant of SURVEY 8b "Threading"; the reference is blocking only).
+ * With sptrans_set_async(plan, 1) the whole-transform entry points (invtrans*, dirtrans*, invtrans_grad) return as soon
+ * as their work is enqueued on the plan's streams; host buffers must be page-locked for the copies to be asynchronous and
+ * must not be touched until sptrans_synchronize(plan) returns.  Calls on one plan still execute in issue order.
+ * sptrans_plan_clone gives a second plan on the same device that BORROWS the tables of `src` (Legendre tables, Fourier
+ * tables, geometry) and owns only its streams and workspaces: one transform can be in flight on each, e.g. an inverse
+ * and a direct transform whose host<->device copies then use both directions of the PCIe link at once.  Clones must be
+ * destroyed before `src`. */
+int sptrans_set_async(sptrans_plan* plan, int on);
+int sptrans_synchronize(sptrans_plan* plan);
+int sptrans_plan_clone(sptrans_plan* src, sptrans_plan** clone);
 
 /* ---- transforms ------------------------------------------------------------------------------------ */
 
@@ -160,7 +180,8 @@ int sptrans_dirtrans_scalar(sptrans_plan* plan, int nb_fields, const double* gp_
  * (ifs/TransIFS.cc:2075-2142).  NotImplemented in TransLocal (TransLocal.cc:848-857).                          */
 
 /* TransImpl::invtrans_adj(nb_scalar_fields, gp_fields, scalar_spectra)            trans/detail/TransImpl.h:155-157
- * adjoint of sptrans_invtrans_scalar w.r.t. the Euclidean inner products: <invtrans x, y> = <x, invtrans_adj y>.
+ * adjoint of sptrans_invtrans_scalar in the ectrans / TransIFS convention: <invtrans x, y>_grid = <x, invtrans_adj y>_spec
+ * with the spectral inner product that counts m > 0 coefficients twice (test_transgeneral.cc:1683-1686).
  * NotImplemented in TransLocal (TransLocal.cc:1599-1604); semantics of the adjoint tests test_transgeneral.cc:1591-1818. */
 int sptrans_invtrans_adj_scalar(sptrans_plan* plan, int nb_fields, const double* gp_fields, double* scalar_spectra);
 
@@ -176,8 +197,9 @@ int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nb_fields, const double
 int sptrans_invtrans_grad(sptrans_plan* plan, int nb_fields, const double* scalar_spectra, double* grad_fields);
 
 /* ---- adjoints.  ATLAS_NOTIMPLEMENTED in TransLocal (TransLocal.cc:899-929, :1599-1667); semantics of the reference's
- * adjoint tests (src/tests/trans/test_transgeneral.cc:1591-1818): the transpose over the reals of the forward operator,
- * <A x, y> = <x, A^T y> with Euclidean sums over every stored double. ---------------------------------------------- */
+ * adjoint tests (src/tests/trans/test_transgeneral.cc:1591-1818), which TransIFS / ectrans pass: <A x, y>_grid =
+ * <x, A* y>_spec with the Euclidean sum over grid points and a spectral inner product that counts every stored m > 0
+ * coefficient twice (:1683-1686, :1790-1793).  I.e. invtrans_adj = C^-1 A^T, dirtrans_adj = B^T C, C = diag(1 | 2). --- */
 
 /* TransImpl::invtrans_adj(nb_scalar_fields, gp_fields, nb_vordiv_fields, vor, div, scalar_spectra)  TransImpl.h:147-149
  * adjoint of sptrans_invtrans: gp layout [u_1..u_k | v_1..v_k | s_1..s_j][npts] in, spectra at truncation T out. */
@@ -193,6 +215,11 @@ int sptrans_invtrans_grad_adj(sptrans_plan* plan, int nb_fields, const double* g
 /* TransImpl::dirtrans_adj(spfield, gpfield) in IFS-style pointers (TransImpl.h:63-67): adjoint of
  * sptrans_dirtrans_scalar -- spectra in, grid fields out (needs quadrature weights). */
 int sptrans_dirtrans_adj_scalar(sptrans_plan* plan, int nb_fields, const double* scalar_spectra, double* gp_fields);
+/* TransImpl::dirtrans_wind2vordiv_adj(spvor, spdiv, gpwind) in IFS-style pointers (TransImpl.h:69-70; the reference's
+ * test_2level_adjoint_test_with_vortdiv, test_transgeneral.cc:1725-1818): adjoint of sptrans_dirtrans_wind2vordiv --
+ * vor/div spectra at truncation T in, wind fields [u_1..u_k | v_1..v_k][npts] out (needs quadrature weights). */
+int sptrans_dirtrans_wind2vordiv_adj(sptrans_plan* plan, int nb_fields, const double* vorticity_spectra,
+                                     const double* divergence_spectra, double* wind_fields);
 
 /* ---- atlas Field layouts (multi-level Fields).  Entry points behind TransImpl's Field overloads
  * (trans/detail/TransImpl.h:54-100; C bindings atlas__Trans__*_field, trans/detail/TransInterface.h:72-96).
@@ -215,6 +242,8 @@ int sptrans_dirtrans_adj_field(sptrans_plan* plan, int nlev, const double* spfie
 int sptrans_invtrans_vordiv2wind_adj_field(sptrans_plan* plan, int nlev, const double* gpwind, double* spvor,
                                            double* spdiv);
 int sptrans_invtrans_grad_adj_field(sptrans_plan* plan, int nlev, const double* gradfield, double* spfield);
+int sptrans_dirtrans_wind2vordiv_adj_field(sptrans_plan* plan, int nlev, const double* spvor, const double* spdiv,
+                                           double* gpwind);
 
 /* VorDivToUV::execute(nb_coeff, nb_fields, vor, div, U, V)   trans/VorDivToUV.h:121-122,
  * = vd2uv, trans/local/VorDivToUVLocal.cc:62-184.  Plan-free: spectral space only.                            */

@@ -109,7 +109,7 @@ static int run_case(const Case& c) {
     // ---- inverse ----
     for (auto& v : fb) v = make_double2(urand(), urand());
     for (int f0 = 0; f0 < nf; f0 += c.F)
-        emu::run_block(NT, [&](int tid) { fourier2_inv_body<M1, NT>(a, 0, f0, tid, X.data()); });
+        emu::run_block(NT, [&](int tid) { fourier2_inv_body<M1, NT>(a, 0, f0, std::min(c.F, nf - f0), tid, X.data()); });
     const int Lc = std::min(L, c.mlimit);
     double err_inv = 0, nrm_inv = 0;
     for (int f = 0; f < nf; ++f) {
@@ -137,7 +137,7 @@ static int run_case(const Case& c) {
     for (auto& v : gp) v = urand();
     for (auto& v : fb) v = make_double2(1e30, 1e30);
     for (int f0 = 0; f0 < nf; f0 += c.F)
-        emu::run_block(NT, [&](int tid) { fourier2_dir_body<M1, NT>(a, 0, f0, tid, X.data()); });
+        emu::run_block(NT, [&](int tid) { fourier2_dir_body<M1, NT>(a, 0, f0, std::min(c.F, nf - f0), tid, X.data()); });
     double err_dir = 0, nrm_dir = 0;
     for (int f = 0; f < nf; ++f) {
         const double sc = f < c.nb_uv ? scale[0] : 1.0;
@@ -149,7 +149,8 @@ static int run_case(const Case& c) {
                 fn.x += xn * cs_[r]; fn.y -= xn * sn_[r];
                 fs.x += xs * cs_[r]; fs.y -= xs * sn_[r];
             }
-            double w = c.adjoint ? (m > 0 ? 2.0 : 1.0) : weights[0] / n;
+            // adjoint of the inverse w.r.t. the spectral inner product that counts m > 0 twice: every m alike
+            double w = c.adjoint ? 1.0 : weights[0] / n;
             double2 s, as;
             if (c.has_s) { s = make_double2((fn.x + fs.x) * w, (fn.y + fs.y) * w); as = make_double2((fn.x - fs.x) * w, (fn.y - fs.y) * w); }
             else { s = make_double2(fn.x * w, fn.y * w); as = s; }

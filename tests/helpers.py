@@ -101,6 +101,24 @@ def synthetic_spectra(T, nf, seed=20260925):
     return np.ascontiguousarray(sp.reshape(-1))
 
 
+def spectral_weights(T, nf=1):
+    """Weights of the spectral inner product of ectrans / TransIFS in the [coeff][fld] layout: a coefficient with
+    m > 0 stands for the pair (m, -m) and counts twice (`adj_value += (m1 > 0 ? 2 * temp : temp)`,
+    src/tests/trans/test_transgeneral.cc:1683-1686, :1790-1793)."""
+    w = np.empty(((T + 1) * (T + 2) // 2, 2, nf))
+    k = 0
+    for m in range(T + 1):
+        cnt = T - m + 1
+        w[k:k + cnt] = 1.0 if m == 0 else 2.0
+        k += cnt
+    return w.reshape(-1)
+
+
+def spectral_dot(T, nf, a, b):
+    """<a, b> over spectral coefficients as the reference's adjoint tests form it (m > 0 counted twice)."""
+    return float(np.dot(np.asarray(a).reshape(-1) * spectral_weights(T, nf), np.asarray(b).reshape(-1)))
+
+
 def grid_lonlat(nx, lat_deg):
     lon = np.concatenate([2.0 * np.pi * np.arange(n) / n for n in nx])
     lat = np.repeat(np.deg2rad(lat_deg), nx)

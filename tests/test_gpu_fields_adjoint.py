@@ -6,8 +6,10 @@ of the IFS-style [field][node] rows; TransIFS packs field = component * nlev + l
 raw-pointer entry points, which the parity tests pin against the oracle.
 
 Adjoints: the reference's own adjoint tests (src/tests/trans/test_transgeneral.cc:1591-1818) check the dot-product
-identity <A x, y> == <x, A^T y>; TransLocal itself implements no adjoint (parity unpinned), so the identity -- against
-the forward operators the other tests pin -- is the definition.  Tolerance: 1e-12 relative to |Ax||y|.
+identity <A x, y>_grid == <x, A* y>_spec where the grid inner product is the Euclidean sum over points and the SPECTRAL
+inner product counts every m > 0 coefficient twice (`adj_value += (m1 > 0 ? 2 * temp : temp)`, :1683-1686, :1790-1793;
+TransIFS passes it at 1e-12).  TransLocal itself implements no adjoint (parity unpinned), so this identity -- against the
+forward operators the other tests pin -- is the definition (helpers.spectral_dot).  Tolerance: 1e-12 relative to |Ax||y|.
 """
 import numpy as np
 import pytest
@@ -135,7 +137,7 @@ def test_invtrans_wind_adjoint_identity(gridname, T, nvd, nsc):
     else:
         trans.invtrans_adj(nvd, y, av, ad)
     lhs = float(ax @ y)
-    rhs = float(vor @ av + div @ ad) + (float(sc @ asc) if nsc else 0.0)
+    rhs = H.spectral_dot(T, nvd, vor, av) + H.spectral_dot(T, nvd, div, ad) + (H.spectral_dot(T, nsc, sc, asc) if nsc else 0.0)
     # L9 has rows at the poles, where u, v = U, V / cos(89.9999999 deg) (TransLocal.cc:1447-1458): the operator norm
     # carries the factor 5.7e8 and so does the rounding error of both sides (the reference's own wind tolerance is 2e-6)
     tol = 1e-7 if gridname == "L9" else 1e-12
@@ -153,13 +155,14 @@ def test_invtrans_grad_adjoint_identity(gridname, T, nf):
     trans.invtrans_grad(nf, x, ax)
     ay = np.full_like(x, np.nan)
     trans.invtrans_grad_adj(nf, y, ay)
-    lhs, rhs = float(ax @ y), float(x @ ay)
+    lhs, rhs = float(ax @ y), H.spectral_dot(T, nf, x, ay)
     assert _close(lhs, rhs, np.linalg.norm(ax) * np.linalg.norm(y)), (lhs, rhs)
 
 
 @pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("O160", 159, 5), ("O400", 399, 2)])
 def test_dirtrans_adjoint_identity(gridname, T, nf):
-    """<dirtrans g, s> == <g, dirtrans_adj s>  (TransImpl::dirtrans_adj, TransImpl.h:63-67)."""
+    """<dirtrans g, s>_spec == <g, dirtrans_adj s>_grid  (TransImpl::dirtrans_adj, TransImpl.h:63-67; the "direct" leg of
+    test_transgeneral.cc:1650-1722)."""
     grid, trans = make(gridname, T)
     npts, nspec2 = grid.size(), trans.nb_spectral_coefficients()
     rng = np.random.default_rng(13)
@@ -169,8 +172,33 @@ def test_dirtrans_adjoint_identity(gridname, T, nf):
     trans.dirtrans(nf, g, dg)
     ds = np.full(nf * npts, np.nan)
     trans.dirtrans_adj(nf, s, ds)
-    lhs, rhs = float(dg @ s), float(g @ ds)
+    lhs, rhs = H.spectral_dot(T, nf, dg, s), float(g @ ds)
     assert _close(lhs, rhs, np.linalg.norm(dg) * np.linalg.norm(s)), (lhs, rhs)
+
+
+@pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("O160", 159, 2)])
+def test_dirtrans_wind2vordiv_adjoint_identity(gridname, T, nf):
+    """<wind2vordiv(u, v), (z, d)>_spec == <(u, v), wind2vordiv_adj(z, d)>_grid  (TransImpl::dirtrans_wind2vordiv_adj,
+    TransImpl.h:69-70; the reference's test_2level_adjoint_test_with_vortdiv, test_transgeneral.cc:1725-1818, with the
+    spectral inner product that counts m > 0 twice), raw-pointer and Field layouts."""
+    grid, trans = make(gridname, T)
+    npts, nspec2 = grid.size(), trans.nb_spectral_coefficients()
+    rng = np.random.default_rng(17)
+    wind = rng.standard_normal(2 * nf * npts)
+    z = rng.standard_normal(nspec2 * nf)
+    d = rng.standard_normal(nspec2 * nf)
+    vor, div = np.full(nspec2 * nf, np.nan), np.full(nspec2 * nf, np.nan)
+    trans.dirtrans(nf, wind, vor, div)
+    back = np.full(2 * nf * npts, np.nan)
+    trans.dirtrans_wind2vordiv_adj(nf, z, d, back)
+    lhs = H.spectral_dot(T, nf, vor, z) + H.spectral_dot(T, nf, div, d)
+    rhs = float(wind @ back)
+    scale = np.sqrt(np.linalg.norm(vor) ** 2 + np.linalg.norm(div) ** 2) * np.sqrt(np.linalg.norm(z) ** 2 + np.linalg.norm(d) ** 2)
+    assert _close(lhs, rhs, scale), (lhs, rhs)
+    # Field layout: (nspec2, nlev) spectra, (npts, nlev, 2) wind -- bit-identical to the raw-pointer result
+    gpw = np.full((npts, nf, 2), np.nan)
+    trans.dirtrans_wind2vordiv_adj_field(z.reshape(nspec2, nf), d.reshape(nspec2, nf), gpw)
+    assert np.array_equal(field_to_rows(gpw, npts, nf, 2), back)
 
 
 @pytest.mark.parametrize("gridname,T", [("O32", 31), ("F24", 23), ("O80", 79)])

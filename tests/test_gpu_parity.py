@@ -604,8 +604,9 @@ def test_config5_tco2559_inverse_sample():
 
 @pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("L9", 17, 1)])
 def test_invtrans_adjoint_identity(gridname, T, nf):
-    """<invtrans x, y> == <x, invtrans_adj y>  (the reference's adjoint test, test_transgeneral.cc:1591-1818, runs this
-    identity through TransIFS; TransLocal has no adjoint)."""
+    """<invtrans x, y>_grid == <x, invtrans_adj y>_spec with the spectral inner product that counts m > 0 twice (the
+    reference's adjoint test, test_transgeneral.cc:1591-1722, runs this identity through TransIFS; TransLocal has no
+    adjoint)."""
     grid, trans, plan = make(gridname, T)
     rng = np.random.default_rng(5)
     x = H.synthetic_spectra(T, nf, seed=41)
@@ -614,7 +615,7 @@ def test_invtrans_adjoint_identity(gridname, T, nf):
     trans.invtrans(nf, x, ix)
     ay = np.full_like(x, np.nan)
     trans.invtrans_adj(nf, y, ay)
-    lhs, rhs = float(ix @ y), float(x @ ay)
+    lhs, rhs = float(ix @ y), H.spectral_dot(T, nf, x, ay)
     assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), np.linalg.norm(ix) * np.linalg.norm(y) * 1e-3)
     # the adjoint annihilates what the inverse ignores: Im(m = 0) and the m == T column
     ay3 = ay.reshape(-1, 2, nf)
@@ -658,3 +659,42 @@ def test_fourier_v2_kernels_match_v1_kernels(torch_cuda, monkeypatch, gridname, 
     scale = fb1.abs().max().item()
     err = (fb1 - fb2).abs().max().item()
     assert scale > 0 and err <= 1e-12 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("gridname,T,nf", [("O48", 47, 5), ("O160", 159, 23), ("O400", 399, 137)])
+def test_async_cloned_plans_pipelined_host_buffers(torch_cuda, gridname, T, nf):
+    """sptrans_set_async + sptrans_plan_clone + the field-chunked host pipelines: an inverse on one plan and a direct
+    transform on its clone (which borrows the tables) in flight at the same time, both on pinned host buffers, give
+    bit-identical results to the blocking calls on device buffers (which the other tests pin against the oracle)."""
+    torch = torch_cuda
+    grid, trans, plan = make(gridname, T)
+    npts = grid.size()
+    sp = H.synthetic_spectra(T, nf)
+    d_sp = torch.from_numpy(sp).cuda()
+    d_gp = torch.empty(nf * npts, dtype=torch.float64, device="cuda")
+    d_back = torch.empty_like(d_sp)
+    trans.invtrans(nf, d_sp, d_gp)
+    trans.dirtrans(nf, d_gp, d_back)
+    want_gp, want_back = d_gp.cpu().numpy(), d_back.cpu().numpy()
+    # blocking calls on host buffers go through the chunked pipelines too
+    gp_blk = np.full(nf * npts, np.nan)
+    back_blk = np.full_like(sp, np.nan)
+    trans.invtrans(nf, sp, gp_blk)
+    trans.dirtrans(nf, gp_blk, back_blk)
+    assert np.array_equal(gp_blk, want_gp) and np.array_equal(back_blk, want_back)
+    other = trans.clone()
+    h_sp = torch.from_numpy(sp).pin_memory()
+    h_gp_in = torch.from_numpy(want_gp).pin_memory()
+    h_gp = torch.full((nf * npts,), float("nan"), dtype=torch.float64).pin_memory()
+    h_back = torch.full((sp.size,), float("nan"), dtype=torch.float64).pin_memory()
+    trans.set_async(True)
+    other.set_async(True)
+    for _ in range(3):   # back-to-back asynchronous calls reuse the plans' staging buffers in stream order
+        trans.invtrans(nf, h_sp.numpy(), h_gp.numpy())
+        other.dirtrans(nf, h_gp_in.numpy(), h_back.numpy())
+    trans.synchronize()
+    other.synchronize()
+    assert np.array_equal(h_gp.numpy(), want_gp)
+    assert np.array_equal(h_back.numpy(), want_back)
+    trans.set_async(False)
+    del other

@@ -51,6 +51,9 @@ def _load():
         "sptrans_legendre_cache_size": (C.c_size_t, [vp]),
         "sptrans_export_legendre_cache": (C.c_int, [vp, vp]),
         "sptrans_import_legendre_cache": (C.c_int, [vp, vp, C.c_size_t]),
+        "sptrans_legendre_cache_uid": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                C.c_int, c_double_p, C.c_int]),
+        "sptrans_legendre_cache_estimate": (C.c_size_t, [C.c_int]),
         "sptrans_set_stream": (C.c_int, [vp, vp]),
         "sptrans_set_precision": (C.c_int, [vp, C.c_int]),
         "sptrans_invtrans_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -68,6 +71,9 @@ def _load():
         "sptrans_dirtrans_wind2vordiv_adj_field": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "sptrans_set_async": (C.c_int, [vp, C.c_int]),
         "sptrans_synchronize": (C.c_int, [vp]),
+        "sptrans_mark": (C.c_int, [vp, C.POINTER(vp)]),
+        "sptrans_wait_mark": (C.c_int, [vp, vp]),
+        "sptrans_release_mark": (C.c_int, [vp]),
         "sptrans_plan_clone": (C.c_int, [vp, C.POINTER(vp)]),
         "sptrans_local_sizes": (C.c_int, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
         "sptrans_invtrans_field": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -104,6 +110,12 @@ def _load():
         "sptrans_dirtrans_fourier_peers": (C.c_int, [vp, C.c_int, vp]),
         "sptrans_peer_barrier": (C.c_int, [vp]),
         "sptrans_peer_advance": (C.c_int, [vp]),
+        "sptrans_multi_create": (C.c_int, [C.POINTER(vp), C.c_int, c_int_p, c_double_p, c_double_p, C.c_int, C.c_uint, C.c_int, c_int_p]),
+        "sptrans_multi_destroy": (C.c_int, [vp]),
+        "sptrans_multi_size": (C.c_int, [vp]),
+        "sptrans_multi_plan": (vp, [vp, C.c_int]),
+        "sptrans_multi_invtrans_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
+        "sptrans_multi_dirtrans_scalar": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_last_timings": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "sptrans_kernel_launches": (C.c_uint64, [vp]),
     }

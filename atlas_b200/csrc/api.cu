@@ -66,6 +66,8 @@ struct StageTimer {
             return;
         }
         cudaStreamSynchronize(p.stream);
+        if (p.s_d2h) cudaStreamSynchronize(p.s_d2h);   // chunked copies of the grid fields back to the host
+        p.d2h_pending = false;
         for (int i = 0; i + 1 < n_marks; ++i) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
@@ -81,6 +83,7 @@ struct StageTimer {
 // sptrans_set_async is on).  With an inverse and a direct transform in flight on two plans (sptrans_plan_clone) both
 // directions of the PCIe link are busy at the same time.
 constexpr int kMaxHostChunks = 16;
+constexpr int kEvD2HDone = 32, kEvGpConsumed = 33;   // slots of Plan::ev_chunk beyond the per-chunk hand-over events
 int host_chunks(int nf) {
     static int v = [] {
         const char* e = std::getenv("SPTRANS_HOST_CHUNKS");
@@ -104,6 +107,9 @@ int fourier_inv_to_host(Plan& p, int nf, int mlimit, const double* d_fourier, do
     if ((rc = fourier_set_chunks(p, nf, host_chunks(nf), &fb))) return rc;
     const int nc = static_cast<int>(fb.size()) - 1;
     const size_t stride = static_cast<size_t>(p.g.points ? p.g.npts : p.g.gp_stride);
+    // the staging buffer may still be being copied out by the previous call on this plan (asynchronous mode): only the
+    // Fourier kernels wait for that, the spectra upload and the Legendre stage of this call have already overlapped it
+    if (p.d2h_pending) SPT_CUDA(cudaStreamWaitEvent(p.stream, p.ev_chunk[kEvD2HDone], 0));
     for (int c = 0; c < nc; ++c) {
         if ((rc = launch_fourier_inv(p, nf, mlimit, d_fourier, d_gp, nb_uv, nullptr, c))) return rc;
         SPT_CUDA(cudaEventRecord(p.ev_chunk[c], p.stream));
@@ -111,8 +117,8 @@ int fourier_inv_to_host(Plan& p, int nf, int mlimit, const double* d_fourier, do
         SPT_CUDA(cudaMemcpyAsync(h_gp + fb[c] * stride, d_gp + fb[c] * stride, (fb[c + 1] - fb[c]) * stride * sizeof(double),
                                  cudaMemcpyDeviceToHost, p.s_d2h));
     }
-    SPT_CUDA(cudaEventRecord(p.ev_chunk[nc], p.s_d2h));
-    SPT_CUDA(cudaStreamWaitEvent(p.stream, p.ev_chunk[nc], 0));  // the plan's stream completes when the last copy has landed
+    SPT_CUDA(cudaEventRecord(p.ev_chunk[kEvD2HDone], p.s_d2h));
+    p.d2h_pending = true;   // the call is complete when this event is (StageTimer::finish / sptrans_synchronize wait for it)
     return SPTRANS_OK;
 }
 // Fourier-direct stage of `nf` fields read from a host array: chunk c + 1 crosses the bus while chunk c is transformed
@@ -123,9 +129,8 @@ int fourier_dir_from_host(Plan& p, int nf, const double* h_gp, double* d_gp, dou
     if ((rc = fourier_set_chunks(p, nf, host_chunks(nf), &fb))) return rc;
     const int nc = static_cast<int>(fb.size()) - 1;
     const size_t stride = static_cast<size_t>(p.g.gp_stride);
-    // the staging buffer may still be read by the previous call on this plan
-    SPT_CUDA(cudaEventRecord(p.ev_chunk[nc + 1], p.stream));
-    SPT_CUDA(cudaStreamWaitEvent(p.s_h2d, p.ev_chunk[nc + 1], 0));
+    // the staging buffer may still be read by the Fourier kernels of the previous call on this plan (asynchronous mode)
+    if (p.gp_in_use) SPT_CUDA(cudaStreamWaitEvent(p.s_h2d, p.ev_chunk[kEvGpConsumed], 0));
     for (int c = 0; c < nc; ++c) {
         SPT_CUDA(cudaMemcpyAsync(d_gp + fb[c] * stride, h_gp + fb[c] * stride, (fb[c + 1] - fb[c]) * stride * sizeof(double),
                                  cudaMemcpyHostToDevice, p.s_h2d));
@@ -135,6 +140,8 @@ int fourier_dir_from_host(Plan& p, int nf, const double* h_gp, double* d_gp, dou
         SPT_CUDA(cudaStreamWaitEvent(p.stream, p.ev_chunk[c], 0));
         if ((rc = launch_fourier_dir(p, nf, d_gp, d_fourier, nb_uv, adjoint, c))) return rc;
     }
+    SPT_CUDA(cudaEventRecord(p.ev_chunk[kEvGpConsumed], p.stream));
+    p.gp_in_use = true;
     return SPTRANS_OK;
 }
 
@@ -439,6 +446,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
         if (e) cudaEventDestroy(e);
     for (auto& e : p.ev_chunk)
         if (e) cudaEventDestroy(e);
+    if (p.s_mark) cudaStreamDestroy(p.s_mark);
     if (p.s_h2d) cudaStreamDestroy(p.s_h2d);
     if (p.s_d2h) cudaStreamDestroy(p.s_d2h);
     if (p.own_stream && p.stream) cudaStreamDestroy(p.stream);
@@ -491,6 +499,25 @@ int sptrans_import_legendre_cache(sptrans_plan* plan, const void* blob, size_t b
     return import_legendre_cache(plan->p, static_cast<const double*>(blob), bytes);
 }
 
+int sptrans_legendre_cache_uid(char* out, size_t out_len, const char* prefix, int truncation, int kind, int n_or_ny, double south,
+                               double north, int nlat, const double* lat_deg, int flt) {
+    if (!out || !prefix || out_len == 0 || (kind == SPTRANS_UID_OTHER && (nlat <= 0 || !lat_deg))) {
+        set_error("sptrans_legendre_cache_uid: invalid arguments");
+        return -1;
+    }
+    const std::string uid = legendre_cache_uid(prefix, truncation, kind, n_or_ny, south, north, nlat, lat_deg, flt != 0);
+    if (uid.size() + 1 > out_len) {
+        set_error("sptrans_legendre_cache_uid: output buffer too small");
+        return -1;
+    }
+    std::memcpy(out, uid.c_str(), uid.size() + 1);
+    return static_cast<int>(uid.size());
+}
+
+size_t sptrans_legendre_cache_estimate(int truncation) {
+    return static_cast<size_t>(truncation) * truncation * truncation / 2 * sizeof(double);
+}
+
 int sptrans_set_precision(sptrans_plan* plan, int precision) {
     if (!plan || (precision != SPTRANS_PREC_FP64 && precision != SPTRANS_PREC_TC_SPLIT)) {
         set_error("sptrans_set_precision: invalid arguments");
@@ -524,8 +551,59 @@ int sptrans_set_async(sptrans_plan* plan, int on) {
 int sptrans_synchronize(sptrans_plan* plan) {
     int rc = check_plan(plan);
     if (rc) return rc;
-    SPT_CUDA(cudaStreamSynchronize(plan->p.stream));
+    Plan& p = plan->p;
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    if (p.s_d2h) SPT_CUDA(cudaStreamSynchronize(p.s_d2h));
+    if (p.s_h2d) SPT_CUDA(cudaStreamSynchronize(p.s_h2d));
+    p.d2h_pending = false;
     SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+int sptrans_mark(sptrans_plan* plan, void** mark) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    if (!mark) {
+        set_error("sptrans_mark: null output pointer");
+        return SPTRANS_ERR_INVALID;
+    }
+    Plan& p = plan->p;
+    cudaEvent_t ev = nullptr;
+    SPT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (p.s_d2h && p.d2h_pending) {
+        // the work enqueued so far ends on two streams (transforms, copies back to the host): join them on a side stream
+        // so that neither has to wait for the other
+        if (!p.s_mark) SPT_CUDA(cudaStreamCreateWithFlags(&p.s_mark, cudaStreamNonBlocking));
+        cudaEvent_t tail = nullptr;
+        SPT_CUDA(cudaEventCreateWithFlags(&tail, cudaEventDisableTiming));
+        SPT_CUDA(cudaEventRecord(tail, p.stream));
+        SPT_CUDA(cudaStreamWaitEvent(p.s_mark, tail, 0));
+        SPT_CUDA(cudaStreamWaitEvent(p.s_mark, p.ev_chunk[kEvD2HDone], 0));
+        SPT_CUDA(cudaEventRecord(ev, p.s_mark));
+        cudaEventDestroy(tail);   // (released once the recorded work has completed)
+    }
+    else SPT_CUDA(cudaEventRecord(ev, p.stream));
+    *mark = ev;
+    return SPTRANS_OK;
+}
+
+int sptrans_wait_mark(sptrans_plan* plan, void* mark) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    if (!mark) {
+        set_error("sptrans_wait_mark: null mark");
+        return SPTRANS_ERR_INVALID;
+    }
+    Plan& p = plan->p;
+    cudaEvent_t ev = static_cast<cudaEvent_t>(mark);
+    SPT_CUDA(cudaStreamWaitEvent(p.stream, ev, 0));
+    if ((rc = copy_streams(p))) return rc;
+    SPT_CUDA(cudaStreamWaitEvent(p.s_h2d, ev, 0));   // a direct transform starts with uploads on the copy stream
+    return SPTRANS_OK;
+}
+
+int sptrans_release_mark(void* mark) {
+    if (mark) cudaEventDestroy(static_cast<cudaEvent_t>(mark));
     return SPTRANS_OK;
 }
 

@@ -8,7 +8,9 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <cstdio>
 #include <numeric>
+#include <sstream>
 #include <thread>
 
 #include "plan.hpp"
@@ -360,4 +362,91 @@ void legendre_seeds(int trc, int nlats, const double* lats_rad, std::vector<doub
     for (auto& th : pool) th.join();
 }
 
+}  // namespace sptrans
+
+// ---- Legendre-cache unique identifier (LegendreCacheCreatorLocal::uid, trans/local/LegendreCacheCreatorLocal.cc:34-119) ----
+// The reference hashes with eckit::MD5 (third party, not vendored): RFC 1321, restated here.  eckit's Hash::add(const
+// char*) feeds strlen bytes, add(bool) one byte, add(long) the eight bytes of the value.
+namespace sptrans {
+namespace {
+struct Md5 {
+    uint32_t h[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+    unsigned char buf[64];
+    uint64_t len = 0;
+    static uint32_t rol(uint32_t x, int c) { return (x << c) | (x >> (32 - c)); }
+    void block(const unsigned char* p) {
+        static const int s[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9,  14, 20, 5, 9,
+                                  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
+                                  4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+        uint32_t w[16];
+        for (int i = 0; i < 16; ++i)
+            w[i] = static_cast<uint32_t>(p[4 * i]) | (static_cast<uint32_t>(p[4 * i + 1]) << 8) |
+                   (static_cast<uint32_t>(p[4 * i + 2]) << 16) | (static_cast<uint32_t>(p[4 * i + 3]) << 24);
+        uint32_t a = h[0], b = h[1], c = h[2], d = h[3];
+        for (int i = 0; i < 64; ++i) {
+            uint32_t f;
+            int g;
+            if (i < 16) { f = (b & c) | (~b & d); g = i; }
+            else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+            else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+            else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+            const uint32_t k = static_cast<uint32_t>(std::floor(std::fabs(std::sin(static_cast<double>(i + 1))) * 4294967296.0));
+            const uint32_t t = d;
+            d = c;
+            c = b;
+            b = b + rol(a + f + k + w[g], s[i]);
+            a = t;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d;
+    }
+    void update(const void* data, size_t n) {
+        const unsigned char* p = static_cast<const unsigned char*>(data);
+        for (size_t i = 0; i < n; ++i) {
+            buf[len++ & 63] = p[i];
+            if ((len & 63) == 0) block(buf);
+        }
+    }
+    std::string hexdigest() {
+        const uint64_t bits = len * 8;
+        const unsigned char one = 0x80, zero = 0;
+        update(&one, 1);
+        while ((len & 63) != 56) update(&zero, 1);
+        unsigned char lb[8];
+        for (int i = 0; i < 8; ++i) lb[i] = static_cast<unsigned char>(bits >> (8 * i));
+        update(lb, 8);
+        char out[33];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) std::snprintf(out + 8 * i + 2 * j, 3, "%02x", (h[i] >> (8 * j)) & 0xffu);
+        return std::string(out, 32);
+    }
+};
+}  // namespace
+
+std::string legendre_cache_uid(const char* prefix, int truncation, int kind, int n_or_ny, double south, double north,
+                               int nlat, const double* lat_deg, bool flt) {
+    std::ostringstream stream;
+    stream << prefix << "-T" << truncation << "-";
+    switch (kind) {
+        case SPTRANS_UID_GAUSSIAN: stream << "GaussianN" << n_or_ny; break;                     // :82-85
+        case SPTRANS_UID_LONLAT: stream << "L" << "-ny" << n_or_ny; break;                      // :97-100
+        case SPTRANS_UID_SHIFTED_LONLAT: stream << "S" << "-ny" << n_or_ny; break;              // :101-104
+        case SPTRANS_UID_REGIONAL:                                                              // :109-116
+            stream << "Regional" << "-south" << south << "-north" << north << "-ny" << n_or_ny;
+            break;
+        default: {                                                                              // give_up, :70-73, :46-58
+            Md5 h;
+            for (int j = 0; j < nlat; ++j) {
+                const long v = std::lround(lat_deg[j] * 1.e8);
+                h.update(&v, sizeof(v));
+            }
+            stream << "grid-" << h.hexdigest().substr(0, 10);
+        }
+    }
+    Md5 o;                                                                                      // hash(config), :60-67
+    o.update("flt", 3);
+    const bool b = flt;
+    o.update(&b, sizeof(b));
+    stream << "-OPT" << o.hexdigest().substr(0, 10);
+    return stream.str();
+}
 }  // namespace sptrans

@@ -199,8 +199,10 @@ struct Plan {
     void* tc = nullptr;          // TcState (legendre_tc.cu)
     void* fft = nullptr;         // FftState (fourier.cu): launch groups, per-pair metadata, auxiliary streams
     // host-pointer pipelines: copies run on their own streams, field chunk by field chunk, next to the transforms
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_chunk[34] = {};   // hand-over events of the chunks (+ start / end of a call)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_mark = nullptr;
+    cudaEvent_t ev_chunk[34] = {};   // hand-over events of the chunks; [32] last D2H copy done, [33] staged grid fields consumed
+    bool d2h_pending = false;        // a chunked copy back to the host may still be running on s_d2h
+    bool gp_in_use = false;          // ev_chunk[33] has been recorded
     bool async = false;              // sptrans_set_async: whole-transform calls return after enqueueing
     Plan* parent = nullptr;          // sptrans_plan_clone: tables are borrowed from this plan
     int clones = 0;
@@ -241,7 +243,9 @@ int fourier_truncation(int truncation, int nx, int nxmax, int ndgl, double lat, 
 void gaussian_quadrature(int N, double* lat_deg_2N, double* weights_2N);
 int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, const double* weights, int T,
                    bool regular, int rank, int nranks);
-void set_io_layout(HostGeom& g, bool local_io);   // fills gp_rowoff / gp_stride / spec_off / spec_ncoef
+void set_io_layout(HostGeom& g, bool local_io);
+std::string legendre_cache_uid(const char* prefix, int truncation, int kind, int n_or_ny, double south, double north, int nlat,
+                               const double* lat_deg, bool flt);   // fills gp_rowoff / gp_stride / spec_off / spec_ncoef
 // per-latitude seeds for the device Legendre recurrence: x=cos(theta), s=sin(theta), columns m=0,1 and the diagonal
 void legendre_seeds(int trc, int nlats, const double* lats_rad, std::vector<double>& x, std::vector<double>& col0,
                     std::vector<double>& col1, std::vector<double>& diag);

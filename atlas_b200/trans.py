@@ -100,6 +100,19 @@ class Trans:
     def synchronize(self):
         _lib.check(_lib.lib.sptrans_synchronize(self._h))
 
+    def mark(self):
+        """End of everything enqueued on this plan so far (sptrans_mark); hand it to another plan's wait_mark."""
+        m = C.c_void_p()
+        _lib.check(_lib.lib.sptrans_mark(self._h, C.byref(m)))
+        return m
+
+    def wait_mark(self, mark):
+        _lib.check(_lib.lib.sptrans_wait_mark(self._h, mark))
+
+    @staticmethod
+    def release_mark(mark):
+        _lib.lib.sptrans_release_mark(mark)
+
     def local_sizes(self):
         """(spectral doubles per field, grid points per field) of the arrays the sharded entry points address."""
         a, b = C.c_size_t(), C.c_size_t()
@@ -319,6 +332,44 @@ class Trans:
     def dirtrans_legendre(self, nf, d_fourier, d_spec):
         self._sync(d_fourier, d_spec)
         _lib.check(_lib.lib.sptrans_dirtrans_legendre(self._h, int(nf), _ptr(d_fourier), _ptr(d_spec)))
+
+
+class MultiTrans:
+    """Single-process multi-GPU transform (sptrans_multi_*): what `Trans(grid, T, option::type("b200") | ("gpus", N))`
+    selects in the C++ adaptor.  Global arrays in the reference's layouts, NumPy (host) or torch CUDA tensors; scalar
+    inverse and direct transforms."""
+
+    def __init__(self, grid, truncation, devices):
+        if isinstance(grid, str):
+            grid = Grid(grid)
+        self._grid, self._T = grid, int(truncation)
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        nx, lat, w = grid.nx(), grid.y(), grid.weights()
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib.sptrans_multi_create(C.byref(self._h), grid.ny(), nx.ctypes.data_as(_lib.c_int_p),
+                                                 lat.ctypes.data_as(_lib.c_double_p),
+                                                 None if w is None else w.ctypes.data_as(_lib.c_double_p), self._T,
+                                                 1 if grid.regular else 0, devs.size, devs.ctypes.data_as(_lib.c_int_p)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _lib is not None and getattr(_lib, "lib", None) is not None:
+            _lib.lib.sptrans_multi_destroy(h)
+            self._h = C.c_void_p()
+
+    def size(self):
+        return int(_lib.lib.sptrans_multi_size(self._h))
+
+    def kernel_launches(self):
+        return sum(int(_lib.lib.sptrans_kernel_launches(C.c_void_p(_lib.lib.sptrans_multi_plan(self._h, r)))) for r in range(self.size()))
+
+    def invtrans(self, nb_fields, scalar_spectra, gp_fields):
+        _wait_for_producers(scalar_spectra, gp_fields)
+        _lib.check(_lib.lib.sptrans_multi_invtrans_scalar(self._h, int(nb_fields), _ptr(scalar_spectra), _ptr(gp_fields)))
+
+    def dirtrans(self, nb_fields, gp_fields, scalar_spectra):
+        _wait_for_producers(scalar_spectra, gp_fields)
+        _lib.check(_lib.lib.sptrans_multi_dirtrans_scalar(self._h, int(nb_fields), _ptr(gp_fields), _ptr(scalar_spectra)))
 
 
 class VorDivToUV:

@@ -25,6 +25,7 @@
 #include "atlas/array.h"
 #include "atlas/field.h"
 #include "atlas/functionspace/Spectral.h"
+#include "atlas/functionspace/StructuredColumns.h"
 #include "atlas/grid.h"
 #include "atlas/runtime/Exception.h"
 #include "atlas/trans/detail/TransFactory.h"
@@ -61,10 +62,45 @@ public:
     }
     TransB200(const Grid& grid, const long truncation, const eckit::Configuration& config = util::NoConfig()):
         TransB200(Cache(), grid, grid.domain(), truncation, config) {}
+    // constructor signature required by TransBuilderFunctionSpace<T> (trans/detail/TransFactory.h:99-113):
+    // Trans(gp_functionspace, sp_functionspace, config) with the key "b200(StructuredColumns,Spectral)"
+    // (TransFactory.cc:206-211), like TransIFSStructuredColumns (trans/ifs/TransIFSStructuredColumns.cc:23-29,35-39).
+    // This backend works on the whole grid of the function space (one GPU holds every point): a StructuredColumns
+    // distributed over several MPI ranks is refused exactly like TransLocal refuses mpi::size() > 1 (TransLocal.cc:338-340).
+    TransB200(const Cache& cache, const FunctionSpace& gp, const FunctionSpace& sp,
+              const eckit::Configuration& config = util::NoConfig()):
+        TransB200(cache, grid_of(gp), grid_of(gp).domain(), truncation_of(sp), config) {
+        spectral_ = functionspace::Spectral(sp);
+    }
 
-    ~TransB200() override { sptrans_plan_destroy(plan_); }
+    ~TransB200() override {
+        if (multi_) {
+            sptrans_multi_destroy(multi_);   // owns the per-device plans (plan_ is the one of device 0)
+        }
+        else {
+            sptrans_plan_destroy(plan_);
+        }
+    }
 
 private:
+    static Grid grid_of(const FunctionSpace& gp) {
+        functionspace::StructuredColumns sc(gp);
+        if (!sc) {
+            throw_NotImplemented("TransB200(gp, sp): the grid-point function space must be StructuredColumns", Here());
+        }
+        if (static_cast<size_t>(sc.sizeOwned()) != static_cast<size_t>(sc.grid().size())) {
+            throw_NotImplemented("TransB200(gp, sp): the StructuredColumns must hold the whole grid on this rank "
+                                 "(like TransLocal, this backend is not MPI-distributed)", Here());
+        }
+        return sc.grid();
+    }
+    static long truncation_of(const FunctionSpace& sp) {
+        functionspace::Spectral s(sp);
+        if (!s) {
+            throw_Exception("TransB200(gp, sp): the spectral function space must be Spectral", Here());
+        }
+        return s.truncation();
+    }
     void write_legendre(const std::string& path) const {
         std::vector<char> blob(sptrans_legendre_cache_size(plan_));
         check(sptrans_export_legendre_cache(plan_, blob.data()));
@@ -114,6 +150,20 @@ private:
             check(sptrans_gaussian_latitudes(nlat / 2, l2.data(), w.data()));
         }
         const unsigned flags = RegularGrid(grid_) ? SPTRANS_GRID_REGULAR : 0u;
+        // config "gpus" = N > 1: the transform is sharded over N devices of this process (zonal wavenumbers x latitude
+        // bands, exchange over NVLink peer memory: sptrans_multi_*); scalar invtrans / dirtrans only in that mode
+        int gpus = 1;
+        config.get("gpus", gpus);
+        if (gpus > 1) {
+            std::vector<int> devices(gpus);
+            for (int r = 0; r < gpus; ++r) {
+                devices[r] = device + r;
+            }
+            check(sptrans_multi_create(&multi_, nlat, nx.data(), lat.data(), w.empty() ? nullptr : w.data(), truncation_, flags,
+                                       gpus, devices.data()));
+            plan_ = sptrans_multi_plan(multi_, 0);
+            return;
+        }
         check(sptrans_plan_create(&plan_, nlat, nx.data(), lat.data(), w.empty() ? nullptr : w.data(), truncation_,
                                   flags, device));
     }
@@ -140,6 +190,10 @@ public:
     }
     void invtrans(const int nb_scalar_fields, const double scalar_spectra[], double gp_fields[],
                   const eckit::Configuration& = util::NoConfig()) const override {
+        if (multi_) {
+            check(sptrans_multi_invtrans_scalar(multi_, nb_scalar_fields, scalar_spectra, gp_fields));
+            return;
+        }
         check(sptrans_invtrans_scalar(plan_, nb_scalar_fields, scalar_spectra, gp_fields));
     }
     void invtrans(const int nb_vordiv_fields, const double vorticity_spectra[], const double divergence_spectra[],
@@ -148,6 +202,10 @@ public:
     }
     void dirtrans(const int nb_fields, const double scalar_fields[], double scalar_spectra[],
                   const eckit::Configuration& = util::NoConfig()) const override {
+        if (multi_) {
+            check(sptrans_multi_dirtrans_scalar(multi_, nb_fields, scalar_fields, scalar_spectra));
+            return;
+        }
         check(sptrans_dirtrans_scalar(plan_, nb_fields, scalar_fields, scalar_spectra));
     }
     void dirtrans(const int nb_fields, const double wind_fields[], double vorticity_spectra[],
@@ -300,8 +358,24 @@ public:
             dirtrans_adj(spfields[f], gpfields[f], config);
         }
     }
-    // adjoint of wind -> vor/div: not provided by this engine either (TransLocal.cc:1661-1667)
-    void dirtrans_wind2vordiv_adj(const Field&, const Field&, Field&, const eckit::Configuration& = util::NoConfig()) const override { ATLAS_NOTIMPLEMENTED; }
+    // adjoint of wind -> vor/div (ATLAS_NOTIMPLEMENTED in TransLocal, TransLocal.cc:1661-1667; the reference's
+    // test_2level_adjoint_test_with_vortdiv, test_transgeneral.cc:1725-1818, runs it through TransIFS)
+    void dirtrans_wind2vordiv_adj(const Field& spvor, const Field& spdiv, Field& gpwind,
+                                  const eckit::Configuration& = util::NoConfig()) const override {
+        const int nlev = levels(spvor, nb_spectral_coefficients(), "vorticity field");
+        ATLAS_ASSERT(levels(spdiv, nb_spectral_coefficients(), "divergence field") == nlev);
+        if (rows_layout(gpwind, nlev)) {
+            check(sptrans_dirtrans_wind2vordiv_adj(plan_, 1, in(spvor), in(spdiv), out(gpwind)));
+        }
+        else {
+            check_components(gpwind, nlev, "wind field");
+            check(sptrans_dirtrans_wind2vordiv_adj_field(plan_, nlev, in(spvor), in(spdiv), out(gpwind)));
+        }
+    }
+    // the engine's tables in the reference's cache layout, for LegendreCacheCreatorB200::create (TransLocal's
+    // export_legendre_, TransLocal.cc:592-647)
+    size_t legendre_cache_size() const { return plan_is_points_ ? 0 : sptrans_legendre_cache_size(plan_); }
+    void export_legendre_cache(void* out) const { check(sptrans_export_legendre_cache(plan_, out)); }
 
 private:
     // Pointer the engine reads: the device copy of the Field if it is allocated and current, else the host copy.
@@ -354,13 +428,18 @@ private:
     Grid grid_;
     int truncation_;
     sptrans_plan* plan_{nullptr};
+    sptrans_multi* multi_{nullptr};   // config "gpus" > 1: the sharded plans of all devices (every other entry point then
+                                      // reports "whole-transform entry points need an unsharded plan" from the C ABI)
     bool plan_is_points_{false};
     mutable functionspace::Spectral spectral_;
 };
 
 // Registration (one translation unit of the plugin / of libatlas must contain):
-//     namespace { static atlas::trans::TransBuilderGrid<atlas::trans::TransB200> builder("b200", "b200"); }
-// exactly like trans/local/TransLocal.cc:57 does for "local".
+//     namespace {
+//     static atlas::trans::TransBuilderGrid<atlas::trans::TransB200> builder("b200", "b200");
+//     static atlas::trans::TransBuilderFunctionSpace<atlas::trans::TransB200> builder_fs("b200(StructuredColumns,Spectral)", "b200");
+//     }
+// exactly like trans/local/TransLocal.cc:57 does for "local" and trans/ifs/TransIFSStructuredColumns.cc:35-39 for "ectrans".
 
 }  // namespace trans
 }  // namespace atlas

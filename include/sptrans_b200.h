@@ -134,6 +134,20 @@ int sptrans_export_legendre_cache(const sptrans_plan* plan, void* out);
  * faster than reading the 8.4 GB file); importing replaces them, e.g. to reproduce a run of the reference bit for bit. */
 int sptrans_import_legendre_cache(sptrans_plan* plan, const void* blob, size_t bytes);
 
+/* LegendreCacheCreatorLocal::uid (trans/local/LegendreCacheCreatorLocal.cc:66-119): the string that names a Legendre
+ * cache file.  `kind` is what the reference derives from the Grid type: a global Gaussian grid ("GaussianN<N>"), a global
+ * regular lon-lat grid with / without pole rows ("L-ny<ny>" / "S-ny<ny>"), a regional regular grid with linear y-spacing
+ * ("Regional-south<ymin>-north<ymax>-ny<ny>"), anything else ("grid-" + first 10 hex digits of eckit::MD5 over
+ * lround(lat_j * 1e8) of the nlat rows).  The option hash is eckit::MD5("flt", bool)[0:10].  prefix "local" reproduces the
+ * reference's strings exactly (the 66 fixtures of src/tests/trans/test_trans_localcache.cc:264-360 are a CPU test here);
+ * this backend's creator uses the same prefix on purpose: its tables are bit-identical to TransLocal's, so cache files are
+ * interchangeable between the two backends.  Returns the length written (without the terminator), or -1. */
+enum { SPTRANS_UID_GAUSSIAN = 0, SPTRANS_UID_LONLAT = 1, SPTRANS_UID_SHIFTED_LONLAT = 2, SPTRANS_UID_REGIONAL = 3, SPTRANS_UID_OTHER = 4 };
+int sptrans_legendre_cache_uid(char* out, size_t out_len, const char* prefix, int truncation, int kind, int n_or_ny,
+                               double south, double north, int nlat, const double* lat_deg, int flt);
+/* LegendreCacheCreatorLocal::estimate (:148-150): T^3 / 2 * 8 bytes */
+size_t sptrans_legendre_cache_estimate(int truncation);
+
 /* Select the arithmetic of the Legendre stage: SPTRANS_PREC_FP64 (default; DMMA, results match the fp64 oracle to
  * 1e-13) or SPTRANS_PREC_TC_SPLIT (tcgen05 kind::tf32 with split operands and fp32 accumulation in tensor memory:
  * fp32-level accuracy, BASELINE config 4).  The reference has one precision only (double, eckit gemm). */
@@ -149,9 +163,16 @@ int sptrans_set_stream(sptrans_plan* plan, void* cuda_stream);
  * sptrans_plan_clone gives a second plan on the same device that BORROWS the tables of `src` (Legendre tables, Fourier
  * tables, geometry) and owns only its streams and workspaces: one transform can be in flight on each, e.g. an inverse
  * and a direct transform whose host<->device copies then use both directions of the PCIe link at once.  Clones must be
- * destroyed before `src`. */
+ * destroyed before `src`.
+ * Dependencies between asynchronous calls on DIFFERENT plans (e.g. the direct transform on the clone reads the grid
+ * fields the inverse on the original is still writing to host memory) are expressed on the device, without host
+ * synchronisation: sptrans_mark(a, &m) marks the end of everything enqueued on plan a so far, sptrans_wait_mark(b, m)
+ * makes the calls issued on plan b from now on wait for it, sptrans_release_mark(m) frees the mark (at any time). */
 int sptrans_set_async(sptrans_plan* plan, int on);
 int sptrans_synchronize(sptrans_plan* plan);
+int sptrans_mark(sptrans_plan* plan, void** mark);
+int sptrans_wait_mark(sptrans_plan* plan, void* mark);
+int sptrans_release_mark(void* mark);
 int sptrans_plan_clone(sptrans_plan* src, sptrans_plan** clone);
 
 /* ---- transforms ------------------------------------------------------------------------------------ */
@@ -308,6 +329,23 @@ int sptrans_invtrans_legendre_peers(sptrans_plan* plan, int nb_fields, const dou
 int sptrans_dirtrans_fourier_peers(sptrans_plan* plan, int nb_fields, const double* d_gp);
 int sptrans_peer_barrier(sptrans_plan* plan);
 int sptrans_peer_advance(sptrans_plan* plan);
+
+/* ---- single-process multi-GPU plan (SURVEY 8e "Process model": one process, N devices).  One host thread drives N
+ * sharded plans, one per device, whose exchange regions are mapped into each other with cudaDeviceEnablePeerAccess;
+ * the transforms take GLOBAL arrays in the reference's layouts (host memory, or device memory under UVA), every device
+ * is given only its share (SPTRANS_SHARD_LOCAL_IO), the device-side barrier of the peer-memory exchange is the only
+ * synchronisation between the devices, and the calls are blocking like the reference's.  This is what the TransB200
+ * adaptor selects with the config key "gpus" (include/atlas_b200/TransB200.h); one-process-per-GPU hosts use the
+ * sptrans_peer_* / sptrans_*_sharded entry points above instead.  `devices` may be NULL (ordinals 0..ndevices-1) and may
+ * name the same device more than once (tests emulate N ranks on one GPU that way). ------------------------------ */
+typedef struct sptrans_multi sptrans_multi;
+int sptrans_multi_create(sptrans_multi** multi, int nlat, const int* nx, const double* lat_deg, const double* weights,
+                         int truncation, unsigned flags, int ndevices, const int* devices);
+int sptrans_multi_destroy(sptrans_multi* multi);
+int sptrans_multi_size(const sptrans_multi* multi);
+sptrans_plan* sptrans_multi_plan(sptrans_multi* multi, int rank);   /* the sharded plan of one device (inspectors, timings) */
+int sptrans_multi_invtrans_scalar(sptrans_multi* multi, int nb_fields, const double* scalar_spectra, double* gp_fields);
+int sptrans_multi_dirtrans_scalar(sptrans_multi* multi, int nb_fields, const double* gp_fields, double* scalar_spectra);
 
 /* kernel time of the last call's stages in milliseconds (CUDA events on the plan's stream):
  * out[0]=pack/unpack+vd2uv, out[1]=Legendre GEMM, out[2]=Fourier, out[3]=H2D, out[4]=D2H,

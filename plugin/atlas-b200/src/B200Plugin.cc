@@ -10,6 +10,7 @@
 #include <string>
 
 #include "atlas/library/Plugin.h"
+#include "atlas_b200/LegendreCacheCreatorB200.h"
 #include "atlas_b200/TransB200.h"
 #include "atlas_b200/VorDivToUVB200.h"
 
@@ -31,6 +32,11 @@ REGISTER_LIBRARY(B200Plugin);
 namespace {
 // backend name "b200", registered for Trans(grid, truncation, config) like "local" and "ectrans" are
 atlas::trans::TransBuilderGrid<atlas::trans::TransB200> register_trans_b200("b200", "b200");
+// ... and for Trans(gp_functionspace, sp_functionspace, config): the key atlas looks up is
+// type + "(" + gp.type() + "," + sp.type() + ")" (trans/detail/TransFactory.cc:206-211), as TransIFSStructuredColumns.cc:35-39
+atlas::trans::TransBuilderFunctionSpace<atlas::trans::TransB200> register_trans_b200_fs("b200(StructuredColumns,Spectral)", "b200");
+// LegendreCacheCreator(grid, truncation, option::type("b200")): same idiom as trans/local/LegendreCacheCreatorLocal.cc:30
+atlas::trans::LegendreCacheCreatorBuilder<atlas::trans::LegendreCacheCreatorB200> register_cache_creator_b200("b200");
 // VorDivToUV(truncation, option::type("b200")): same idiom as trans/local/VorDivToUVLocal.cc:25
 atlas::trans::VorDivToUVBuilder<atlas::trans::VorDivToUVB200> register_vordiv_to_uv_b200("b200");
 }  // namespace

@@ -7,10 +7,18 @@ namespace atlas {
 using idx_t = int;
 class Domain {
 public:
-    explicit Domain(bool global = true): global_(global) {}
+    explicit Domain(bool global = true, double ymin = -90., double ymax = 90.): global_(global), ymin_(ymin), ymax_(ymax) {}
     bool global() const { return global_; }
+    double ymin() const { return ymin_; }
+    double ymax() const { return ymax_; }
 private:
     bool global_;
+    double ymin_, ymax_;
+};
+class RectangularDomain : public Domain {  // domain/Domain.h
+public:
+    RectangularDomain(const Domain& d): Domain(d) {}
+    explicit operator bool() const { return true; }
 };
 class Projection {
 public:
@@ -29,6 +37,9 @@ struct GridData {
     std::vector<int> nx;
     std::vector<double> lat;
     bool gaussian = false, regular = false;
+    bool lonlat_global = false;       // RegularLonLatGrid(grid) holds (global regular lon-lat grid)
+    std::string yspace = "gaussian";  // StructuredGrid::yspace().type()
+    double ymin = -90., ymax = 90.;   // RectangularDomain of a regional grid
     bool structured = true;
     bool global = true;               // domain().global()
     std::vector<PointLonLat> lonlat;  // filled for regional structured grids (Grid::lonlat())
@@ -40,7 +51,7 @@ public:
     explicit Grid(std::shared_ptr<GridData> d): d_(std::move(d)) {}
     explicit operator bool() const { return bool(d_); }
     Projection projection() const { return Projection(); }
-    Domain domain() const { return Domain(d_->global); }
+    Domain domain() const { return Domain(d_->global, d_->ymin, d_->ymax); }
     idx_t size() const {
         if (!d_->structured) return static_cast<idx_t>(d_->points.size());
         idx_t s = 0;
@@ -59,11 +70,22 @@ public:
     idx_t ny() const { return static_cast<idx_t>(d_->nx.size()); }
     idx_t nx(idx_t j) const { return d_->nx[j]; }
     double y(idx_t j) const { return d_->lat[j]; }
+    struct YSpace {
+        std::string t;
+        const std::string& type() const { return t; }
+    };
+    YSpace yspace() const { return YSpace{d_->yspace}; }
 };
 class GaussianGrid : public StructuredGrid {
 public:
     GaussianGrid(const Grid& g): StructuredGrid(g) {}
-    explicit operator bool() const { return d_ && d_->gaussian; }
+    explicit operator bool() const { return d_ && d_->gaussian && d_->global; }
+    long N() const { return static_cast<long>(d_->nx.size() / 2); }
+};
+class RegularLonLatGrid : public StructuredGrid {
+public:
+    RegularLonLatGrid(const Grid& g): StructuredGrid(g) {}
+    explicit operator bool() const { return d_ && d_->lonlat_global; }
 };
 class RegularGrid : public StructuredGrid {
 public:

@@ -2,34 +2,24 @@
 #pragma once
 #include <map>
 #include <string>
+#include "atlas/functionspace/StructuredColumns.h"
+#include "atlas/trans/Cache.h"
 #include "atlas/trans/detail/TransImpl.h"
 namespace atlas {
 namespace trans {
-// trans/Cache.h:41-136: a Cache hands out raw byte entries; only the Legendre entry matters to a backend
-class TransCacheEntry {
-public:
-    TransCacheEntry() = default;
-    TransCacheEntry(const void* data, size_t size): data_(data), size_(size) {}
-    operator bool() const { return size_ != 0; }
-    size_t size() const { return size_; }
-    const void* data() const { return data_; }
-private:
-    const void* data_ = nullptr;
-    size_t size_ = 0;
-};
-class Cache {
-public:
-    Cache() = default;
-    explicit Cache(const TransCacheEntry& legendre): legendre_(legendre) {}
-    const TransCacheEntry& legendre() const { return legendre_; }
-private:
-    TransCacheEntry legendre_;
-};
 class TransFactory {
 public:
     TransFactory(const std::string& name, const std::string& backend): name_(name) { registry()[name] = this; (void)backend; }
     virtual ~TransFactory() = default;
     virtual const TransImpl* make(const Cache&, const Grid&, const Domain&, int, const eckit::Configuration&) = 0;
+    virtual const TransImpl* make(const Cache&, const FunctionSpace&, const FunctionSpace&, const eckit::Configuration&) = 0;
+    // Trans(gp, sp, config): key = type + "(" + gp.type() + "," + sp.type() + ")"  (trans/detail/TransFactory.cc:206-211)
+    static const TransImpl* build(const std::string& type, const FunctionSpace& gp, const FunctionSpace& sp,
+                                  const eckit::Configuration& c) {
+        auto it = registry().find(type + "(" + gp.type() + "," + sp.type() + ")");
+        if (it == registry().end()) throw eckit::Exception("no such Trans backend: " + type);
+        return it->second->make(Cache(), gp, sp, c);
+    }
     static const TransImpl* build(const std::string& type, const Grid& g, int truncation, const eckit::Configuration& c) {
         return build(type, Cache(), g, truncation, c);
     }
@@ -53,8 +43,23 @@ class TransBuilderGrid : public TransFactory {
                           const eckit::Configuration& config) override {
         return new T(cache, grid, domain, truncation, config);
     }
+    const TransImpl* make(const Cache&, const FunctionSpace&, const FunctionSpace&, const eckit::Configuration&) override {
+        throw eckit::Exception("This function should not be called");
+    }
 public:
     TransBuilderGrid(const std::string& name, const std::string& backend): TransFactory(name, backend) {}
+};
+template <class T>
+class TransBuilderFunctionSpace : public TransFactory {  // trans/detail/TransFactory.h:99-113
+    const TransImpl* make(const Cache& cache, const FunctionSpace& gp, const FunctionSpace& sp,
+                          const eckit::Configuration& config) override {
+        return new T(cache, gp, sp, config);
+    }
+    const TransImpl* make(const Cache&, const Grid&, const Domain&, int, const eckit::Configuration&) override {
+        throw eckit::Exception("This function should not be called");
+    }
+public:
+    TransBuilderFunctionSpace(const std::string& name, const std::string& backend): TransFactory(name, backend) {}
 };
 }  // namespace trans
 }  // namespace atlas

@@ -18,6 +18,10 @@ public:
         v = it->second;
         return true;
     }
+    bool getBool(const std::string& key, bool dflt) const {
+        int v = 0;
+        return get(key, v) ? v != 0 : dflt;
+    }
     Configuration& set(const std::string& key, int v) {
         ints_[key] = v;
         return *this;

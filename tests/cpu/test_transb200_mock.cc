@@ -9,14 +9,59 @@
 #include <memory>
 #include <vector>
 
+#include "atlas_b200/LegendreCacheCreatorB200.h"
 #include "atlas_b200/TransB200.h"
 
 namespace {
 static atlas::trans::TransBuilderGrid<atlas::trans::TransB200> builder("b200", "b200");
+// Trans(gp_functionspace, sp_functionspace, option::type("b200")): trans/detail/TransFactory.h:99-113, key TransFactory.cc:206-211
+static atlas::trans::TransBuilderFunctionSpace<atlas::trans::TransB200> builder_fs("b200(StructuredColumns,Spectral)", "b200");
+// LegendreCacheCreator(grid, truncation, option::type("b200")): trans/local/LegendreCacheCreatorLocal.cc:30
+static atlas::trans::LegendreCacheCreatorBuilder<atlas::trans::LegendreCacheCreatorB200> builder_cache("b200");
+}
+
+// host-only part: unique identifiers of the cache creator for the grid kinds the reference distinguishes
+// (trans/local/LegendreCacheCreatorLocal.cc:66-119; expected strings of src/tests/trans/test_trans_localcache.cc:264-360)
+static int check_uids() {
+    using namespace atlas;
+    int bad = 0;
+    auto expect = [&](const Grid& g, int T, const char* want) {
+        std::unique_ptr<trans::LegendreCacheCreatorImpl> c(trans::LegendreCacheCreatorFactory::build("b200", g, T));
+        const std::string got = c->uid();
+        if (got != want || !c->supported() || c->estimate() != size_t(T) * T * T / 2 * 8) {
+            std::printf("uid mismatch: got %s want %s\n", got.c_str(), want);
+            ++bad;
+        }
+    };
+    auto gauss = std::make_shared<GridData>();   // "O320": any global Gaussian grid with N = 320
+    gauss->gaussian = true;
+    gauss->nx.assign(640, 20);
+    gauss->lat.assign(640, 0.);
+    expect(Grid(gauss), 639, "local-T639-GaussianN320-OPT4189816c2e");
+    auto ll = std::make_shared<GridData>();      // "L90": 181 rows from 90 to -90
+    ll->regular = ll->lonlat_global = true;
+    ll->yspace = "linear";
+    ll->nx.assign(181, 360);
+    for (int j = 0; j < 181; ++j) ll->lat.push_back(90. - j);
+    expect(Grid(ll), 20, "local-T20-L-ny181-OPT4189816c2e");
+    auto crop = std::make_shared<GridData>();    // "L90" cropped to latitudes [-20, 20]: regional regular grid, linear spacing
+    crop->regular = true;
+    crop->global = false;
+    crop->yspace = "linear";
+    crop->ymin = -20.;
+    crop->ymax = 20.;
+    crop->nx.assign(41, 21);
+    for (int j = 0; j < 41; ++j) crop->lat.push_back(20. - j);
+    expect(Grid(crop), 20, "local-T20-Regional-south-20-north20-ny41-OPT4189816c2e");
+    crop->yspace = "gaussian";                   // not linear: the reference gives up and hashes the latitudes
+    expect(Grid(crop), 20, "local-T20-grid-7824deccdf-OPT4189816c2e");
+    return bad;
 }
 
 int main() {
     using namespace atlas;
+    if (check_uids() != 0) return 1;
+    if (!trans::LegendreCacheCreatorFactory::has("b200")) return 1;
     const int N = 16, T = 15;
     auto d = std::make_shared<GridData>();
     d->name = "F16";
@@ -89,14 +134,56 @@ int main() {
         threw_u = true;
     }
     if (!threw_u) err3 = 1.;
+    // adjoint of wind -> vor/div through the Field overload: zero spectra give zero wind
+    wind.data()[7] = 3.;
+    t->dirtrans_wind2vordiv_adj(vor, dv, wind);
+    for (idx_t i = 0; i < grid.size() * nlev * 2; ++i) err3 = std::fmax(err3, std::fabs(wind.data()[i]));
+    // Trans(gp_functionspace, sp_functionspace): same plan through the FunctionSpace builder
+    FunctionSpace gpfs(grid, grid.size()), spfs(T);
+    std::unique_ptr<const trans::TransImpl> tf(trans::TransFactory::build("b200", gpfs, spfs, util::NoConfig()));
+    Field gp2("gp2", {grid.size()});
+    tf->invtrans(sp, gp2);
+    for (idx_t i = 0; i < grid.size(); ++i) err3 = std::fmax(err3, std::fabs(gp2.data()[i] - gp.data()[i]));
     bool threw = false;
-    try {
-        t->dirtrans_wind2vordiv_adj(vor, dv, wind);
+    try {   // a StructuredColumns that holds only part of the grid on this rank is refused (TransLocal.cc:338-340 analogue)
+        FunctionSpace part(grid, grid.size() / 2);
+        std::unique_ptr<const trans::TransImpl> bad(trans::TransFactory::build("b200", part, spfs, util::NoConfig()));
     }
     catch (const eckit::NotImplemented&) {
         threw = true;
     }
-    std::printf("TransB200 via factory: invtrans err %.3e, dirtrans err %.3e, multi-level Field err %.3e, NotImplemented thrown: %d\n",
-                err, err2, err3, threw);
-    return (err < 1e-13 && err2 < 1e-13 && err3 < 1e-13 && threw) ? 0 : 1;
+    // LegendreCacheCreator("b200"): the blob it creates is what a Trans built FROM that cache reproduces bit for bit
+    std::unique_ptr<trans::LegendreCacheCreatorImpl> creator(trans::LegendreCacheCreatorFactory::build("b200", grid, T));
+    trans::Cache cache = creator->create();
+    const bool cache_ok = cache.legendre() && cache.legendre().size() > 0;
+    std::unique_ptr<const trans::TransImpl> tc(trans::TransFactory::build("b200", cache, grid, T, util::NoConfig()));
+    Field gp3("gp3", {grid.size()});
+    Field spr("spr", {nspec2});
+    for (idx_t i = 0; i < nspec2; ++i) spr.data()[i] = 1. / (1. + i);
+    spr.data()[1] = 0.;
+    Field gp4("gp4", {grid.size()});
+    t->invtrans(spr, gp3);
+    tc->invtrans(spr, gp4);
+    for (idx_t i = 0; i < grid.size(); ++i)
+        if (gp3.data()[i] != gp4.data()[i]) err3 = 1.;
+    // config "gpus": the single-process multi-device plan behind the same raw-pointer calls (two ranks on device 0 here)
+    {
+        util::Config two;
+        two.set("gpus", 2);
+        two.set("device", 0);
+        std::unique_ptr<const trans::TransImpl> tm;
+        try {
+            tm.reset(trans::TransFactory::build("b200", grid, T, two));
+        }
+        catch (const eckit::Exception&) {   // a box with a single GPU has no device 1: fine, the path is covered by pytest
+        }
+        if (tm) {
+            std::vector<double> g5(grid.size());
+            tm->invtrans(1, spr.data(), g5.data());
+            for (idx_t i = 0; i < grid.size(); ++i) err3 = std::fmax(err3, std::fabs(g5[i] - gp3.data()[i]) > 1e-13 ? 1. : 0.);
+        }
+    }
+    std::printf("TransB200 via factory: invtrans err %.3e, dirtrans err %.3e, multi-level Field err %.3e, partial function space refused: %d, "
+                "cache ok: %d\n", err, err2, err3, threw, cache_ok);
+    return (err < 1e-13 && err2 < 1e-13 && err3 < 1e-13 && threw && cache_ok) ? 0 : 1;
 }

@@ -493,6 +493,100 @@ def test_peer_memory_exchange_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R
         _lib.check(lib.sptrans_peer_free(t._h))
 
 
+@pytest.mark.parametrize("gridname,T,nf,R", [("O48", 47, 5, 2), ("O80", 79, 4, 3), ("L9", 17, 2, 2), ("O160", 159, 9, 8)])
+def test_shard_local_io_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
+    """SPTRANS_SHARD_LOCAL_IO: every rank's spectral array holds only its zonal wavenumbers ([m ascending][n][re/im][field])
+    and its grid array only the rows of its latitude band ([field][northern rows, then their southern mirrors]) -- what
+    bench.py's N > 1 runs and BASELINE config 5 use.  R ranks emulated on one device over the peer-memory exchange;
+    the assembled global results against the CPU oracle."""
+    import ctypes as C
+
+    import atlas_b200
+    from atlas_b200 import _lib
+    from atlas_b200.dist import shard_layout
+    from atlas_b200.trans import _ptr
+    from oracle import pyoracle as po
+
+    torch = torch_cuda
+    lib = _lib.lib
+    grid = atlas_b200.Grid(gridname)
+    npts, nlat = grid.size(), grid.ny()
+    plans = [atlas_b200.Trans(grid, T, rank=r, nranks=R, local_io=True) for r in range(R)]
+    stream = torch.cuda.current_stream().cuda_stream
+    regions = (C.c_void_p * R)()
+    for r, t in enumerate(plans):
+        t.set_stream(stream)
+        _lib.check(lib.sptrans_peer_alloc(t._h, nf, None))
+        reg = C.c_void_p()
+        _lib.check(lib.sptrans_peer_region(t._h, C.byref(reg), None))
+        regions[r] = reg
+    for t in plans:
+        _lib.check(lib.sptrans_peer_attach_ptrs(t._h, R, regions))
+    owner, band, _, _ = shard_layout(grid, T, 0, R)
+    rowoff = np.concatenate([[0], np.cumsum(grid.nx(), dtype=np.int64)])
+
+    def spans(r):
+        j0, j1 = int(band[r]), int(band[r + 1])
+        sp_ = [(int(rowoff[j0]), int(rowoff[j1])), (int(rowoff[nlat - j1]), int(rowoff[nlat - j0]))]
+        if sp_[0][1] > sp_[1][0]:
+            sp_ = [(sp_[0][0], sp_[1][1])]
+        return [(a, b) for a, b in sp_ if b > a]
+
+    def m_slices(r):
+        return [((2 * T + 3 - m) * m // 2 * 2 * nf, (T - m + 1) * 2 * nf) for m in range(T + 1) if owner[m] == r]
+
+    sp = H.synthetic_spectra(T, nf)
+    plan = po.OraclePlan(grid.nx(), grid.y(), T, regular=grid.regular, weights=grid.weights())
+    want = plan.invtrans(nf, sp, mode=2)
+    kw = dict(dtype=torch.float64, device="cuda")
+    d_sp, d_gp, sizes = [], [], []
+    for r, t in enumerate(plans):
+        nsp, stride = t.local_sizes()
+        parts = [sp[o:o + n] for o, n in m_slices(r)]
+        loc = np.concatenate(parts) if parts else np.zeros(0)
+        assert loc.size == nsp * nf and stride >= sum(b - a for a, b in spans(r))
+        d_sp.append(torch.from_numpy(np.ascontiguousarray(loc)).cuda() if loc.size else torch.zeros(2, **kw))
+        d_gp.append(torch.full((max(nf * stride, 2),), float("nan"), **kw))
+        sizes.append((nsp, stride))
+
+    def local_buffer(t):
+        b = C.c_void_p()
+        _lib.check(lib.sptrans_peer_buffer(t._h, C.byref(b)))
+        return b
+
+    for t, a in zip(plans, d_sp):
+        _lib.check(lib.sptrans_invtrans_legendre_peers(t._h, nf, _ptr(a)))
+    for t, g in zip(plans, d_gp):
+        _lib.check(lib.sptrans_invtrans_fourier(t._h, nf, T - 1, local_buffer(t), _ptr(g), 0))
+        _lib.check(lib.sptrans_peer_advance(t._h))
+    got = np.full((nf, npts), np.nan)
+    for r in range(R):
+        loc = d_gp[r].cpu().numpy()[: nf * sizes[r][1]].reshape(nf, sizes[r][1])
+        o = 0
+        for a, b in spans(r):
+            got[:, a:b] = loc[:, o:o + b - a]
+            o += b - a
+    assert H.rel_max(got.reshape(-1), want) < TOL_MAX
+    if grid.weights() is None:
+        return
+    d_back = [torch.full_like(a, float("nan")) for a in d_sp]
+    for t, g in zip(plans, d_gp):
+        _lib.check(lib.sptrans_dirtrans_fourier_peers(t._h, nf, _ptr(g)))
+    for t, b in zip(plans, d_back):
+        _lib.check(lib.sptrans_dirtrans_legendre(t._h, nf, local_buffer(t), _ptr(b)))
+        _lib.check(lib.sptrans_peer_advance(t._h))
+    back = np.full_like(sp, np.nan)
+    for r in range(R):
+        loc = d_back[r].cpu().numpy()
+        o = 0
+        for g0, n in m_slices(r):
+            back[g0:g0 + n] = loc[o:o + n]
+            o += n
+    assert H.rel_max(back, plan.dirtrans(nf, want)) < TOL_MAX
+    for t in plans:
+        _lib.check(lib.sptrans_peer_free(t._h))
+
+
 @pytest.mark.parametrize("gridname,T,nf", [("O32", 31, 4), ("O48", 47, 137), ("O160", 159, 20), ("F24", 23, 3)])
 def test_tensor_core_split_tf32_legendre(gridname, T, nf):
     """BASELINE config 4: Legendre stage on tcgen05 (kind::tf32, operands split hi+lo, fp32 accumulation in TMEM).
@@ -696,5 +790,51 @@ def test_async_cloned_plans_pipelined_host_buffers(torch_cuda, gridname, T, nf):
     other.synchronize()
     assert np.array_equal(h_gp.numpy(), want_gp)
     assert np.array_equal(h_back.numpy(), want_back)
+    # a chain through host memory ordered by device-side marks only: inverse -> host grid fields -> direct transform
+    h_gp.fill_(float("nan"))
+    h_back.fill_(float("nan"))
+    for _ in range(2):
+        trans.invtrans(nf, h_sp.numpy(), h_gp.numpy())
+        m = trans.mark()
+        other.wait_mark(m)
+        other.dirtrans(nf, h_gp.numpy(), h_back.numpy())
+        m2 = other.mark()
+        trans.wait_mark(m2)       # the next inverse overwrites the host grid fields the direct transform is reading
+        trans.release_mark(m)
+        trans.release_mark(m2)
+    other.synchronize()
+    trans.synchronize()
+    assert np.array_equal(h_gp.numpy(), want_gp)
+    assert np.array_equal(h_back.numpy(), want_back)
     trans.set_async(False)
     del other
+
+
+@pytest.mark.parametrize("gridname,T,nf,R", [("O48", 47, 5, 2), ("O160", 159, 9, 4), ("F24", 23, 3, 3)])
+def test_single_process_multi_gpu_plan_emulated(torch_cuda, gridname, T, nf, R):
+    """sptrans_multi_*: one host thread drives R sharded plans whose exchange regions see each other, global arrays in the
+    reference's layouts in, every device given only its share (SPTRANS_SHARD_LOCAL_IO), the device-side barrier the only
+    synchronisation.  Here the R "devices" are all device 0 (the real thing: tests/test_gpu_dist.py on >= 2 GPUs), host and
+    device arrays, against the CPU oracle."""
+    import atlas_b200
+
+    torch = torch_cuda
+    grid, trans, plan = make(gridname, T)
+    del trans
+    mt = atlas_b200.MultiTrans(grid, T, [0] * R)
+    assert mt.size() == R
+    sp = H.synthetic_spectra(T, nf)
+    want = plan.invtrans(nf, sp, mode=2)
+    want_sp = plan.dirtrans(nf, want)
+    for it in range(2):
+        gp = np.full(nf * grid.size(), np.nan)
+        mt.invtrans(nf, sp, gp)
+        assert H.rel_max(gp, want) < TOL_MAX
+        back = np.full_like(sp, np.nan)
+        mt.dirtrans(nf, gp, back)
+        assert H.rel_max(back, want_sp) < TOL_MAX
+    d_sp = torch.from_numpy(sp).cuda()
+    d_gp = torch.full((nf * grid.size(),), float("nan"), dtype=torch.float64, device="cuda")
+    mt.invtrans(nf, d_sp, d_gp)
+    assert H.rel_max(d_gp.cpu().numpy(), want) < TOL_MAX
+    assert mt.kernel_launches() > 0

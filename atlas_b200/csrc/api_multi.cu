@@ -241,11 +241,19 @@ int sptrans_multi_invtrans_scalar(sptrans_multi* m, int nf, const double* spectr
     int rc = prepare(*m, nf, false);
     if (rc) return rc;
     const int R = static_cast<int>(m->plans.size());
-    for (int r = 0; r < R; ++r) {   // enqueue only: no host synchronisation until every device has its work
+    // Enqueue every device's upload + transform first.  Copies from / to PAGEABLE host memory are synchronous with the
+    // host (a device-to-host copy returns only when its stream has drained), so the downloads are issued only after every
+    // device has been given its work: a device waiting at the barrier for a peer this thread has not served yet would
+    // otherwise block the thread for good.
+    for (int r = 0; r < R; ++r) {
         Plan& p = m->plans[r]->p;
         SPT_CUDA(cudaSetDevice(p.device));
         if ((rc = copy_spectra(p, nf, m->d_sp[r], const_cast<double*>(spectra), true))) return rc;
         if ((rc = sptrans_invtrans_sharded(m->plans[r], nf, m->d_sp[r], m->d_gp[r]))) return rc;
+    }
+    for (int r = 0; r < R; ++r) {
+        Plan& p = m->plans[r]->p;
+        SPT_CUDA(cudaSetDevice(p.device));
         if ((rc = copy_grid(p, nf, m->d_gp[r], gp, false))) return rc;
     }
     return finish_all(m);
@@ -260,11 +268,15 @@ int sptrans_multi_dirtrans_scalar(sptrans_multi* m, int nf, const double* gp, do
     int rc = prepare(*m, nf, true);
     if (rc) return rc;
     const int R = static_cast<int>(m->plans.size());
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < R; ++r) {   // uploads + transforms of every device first, downloads afterwards (see the inverse)
         Plan& p = m->plans[r]->p;
         SPT_CUDA(cudaSetDevice(p.device));
         if ((rc = copy_grid(p, nf, m->d_gp[r], const_cast<double*>(gp), true))) return rc;
         if ((rc = sptrans_dirtrans_sharded(m->plans[r], nf, m->d_gp[r], m->d_sp[r]))) return rc;
+    }
+    for (int r = 0; r < R; ++r) {
+        Plan& p = m->plans[r]->p;
+        SPT_CUDA(cudaSetDevice(p.device));
         if ((rc = copy_spectra(p, nf, m->d_sp[r], spectra, false))) return rc;
     }
     return finish_all(m);

@@ -503,6 +503,7 @@ def bench_sharded(args, rank, world, local_rank):
             d_sp.copy_(h_sp, non_blocking=True)
             if not inv_only:
                 s_in.wait_event(ev_used)              # previous direct transform has consumed d_gp_in
+                s_in.wait_stream(s_out)               # ... and the previous step's grid fields have landed in host memory
                 with torch.cuda.stream(s_in):
                     d_gp_in.copy_(h_gp[(i + 1) % 2], non_blocking=True)
                     ev_in.record(s_in)

@@ -23,15 +23,16 @@ public:
     const TransCacheEntry& legendre() const { return legendre_; }
 protected:
     TransCacheEntry legendre_;
+    std::shared_ptr<std::vector<char>> store_;   // entries are shared_ptr in the reference (Cache.h:113-117): copies of a Cache
+                                                 // (also sliced from a LegendreCache) keep the memory alive
 };
 class LegendreCache : public Cache {  // Cache.h:123-128: LegendreCache(size) owns its (host) memory
 public:
-    explicit LegendreCache(size_t size): store_(std::make_shared<std::vector<char>>(size)) {
+    explicit LegendreCache(size_t size) {
+        store_ = std::make_shared<std::vector<char>>(size);
         legendre_ = TransCacheEntry(store_->data(), size);
     }
     LegendreCache(const void* address, size_t size) { legendre_ = TransCacheEntry(address, size); }
-private:
-    std::shared_ptr<std::vector<char>> store_;
 };
 }  // namespace trans
 }  // namespace atlas

@@ -4,5 +4,5 @@ The package holds only what the hot path needs: the CUDA library (csrc/ -> libsp
 C ABI in include/sptrans_b200.h) and a thin host-side mirror of the reference's
 `atlas::trans::Trans` / `atlas::Grid` interface (trans.py, grid.py) for tests and benchmarks.
 """
-from .grid import Grid, StructuredGrid, UnstructuredGrid  # noqa: F401
+from .grid import CroppedGrid, Grid, StructuredGrid, UnstructuredGrid  # noqa: F401
 from .trans import MultiTrans, Trans, VorDivToUV, option  # noqa: F401

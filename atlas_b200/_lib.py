@@ -42,6 +42,8 @@ def _load():
         "sptrans_plan_create": (C.c_int, [C.POINTER(vp), C.c_int, c_int_p, c_double_p, c_double_p, C.c_int, C.c_uint, C.c_int]),
         "sptrans_plan_create_sharded": (C.c_int, [C.POINTER(vp), C.c_int, c_int_p, c_double_p, c_double_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int]),
         "sptrans_plan_create_points": (C.c_int, [C.POINTER(vp), C.c_size_t, c_double_p, c_double_p, C.c_int, C.c_int]),
+        "sptrans_plan_create_cropped": (C.c_int, [C.POINTER(vp), C.c_int, c_int_p, c_double_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int,
+                                                 c_int_p, c_int_p]),
         "sptrans_plan_destroy": (C.c_int, [vp]),
         "sptrans_truncation": (C.c_int, [vp]),
         "sptrans_nb_gridpoints": (C.c_size_t, [vp]),

@@ -203,6 +203,11 @@ int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, 
     }
     tm.mark(marks);
     if (p.g.points) rc = launch_points_inv(p, nf, std::min(p.g.T, trunc), p.d_fourier, d_gp, nb_uv);
+    else if (p.g.cropped) {   // global rows of the band into the work array, then the copy-out of the crop (:1180-1187)
+        if ((rc = ensure(p.d_band, p.band_cap, static_cast<size_t>(p.g.gp_stride) * nf))) return rc;
+        if ((rc = launch_fourier_inv(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, p.d_band, nb_uv))) return rc;
+        rc = launch_crop_gather(p, nf, p.d_band, d_gp);
+    }
     else if (h_gp) rc = fourier_inv_to_host(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, d_gp, nb_uv, h_gp);
     else rc = launch_fourier_inv(p, nf, std::min(p.g.T, trunc - 1), p.d_fourier, d_gp, nb_uv);
     if (rc) return rc;
@@ -253,10 +258,15 @@ struct PointSet {   // sptrans_plan_create_points: per point, its row among the 
     std::vector<int> row;
     std::vector<double> sign, lon, coslatinv;
 };
+struct Crop {       // sptrans_plan_create_cropped
+    int jlat_min, nlat;
+    const int *nx, *jlon_min;
+};
 }  // namespace
 
 static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double* lat_deg, const double* weights,
-                       int truncation, unsigned flags, int device, int rank, int nranks, const PointSet* pts) {
+                       int truncation, unsigned flags, int device, int rank, int nranks, const PointSet* pts,
+                       const Crop* crop = nullptr) {
     if (!out) {
         set_error("sptrans_plan_create: null output pointer");
         return SPTRANS_ERR_INVALID;
@@ -284,6 +294,34 @@ static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double
     if (rc) {
         delete sp;
         return rc;
+    }
+    if (crop) {
+        HostGeom& g = p.g;
+        if (nranks != 1 || crop->nlat < 1 || crop->jlat_min < 0 || crop->jlat_min + crop->nlat > nlat || !crop->nx || !crop->jlon_min) {
+            set_error("sptrans_plan_create_cropped: invalid arguments");
+            delete sp;
+            return SPTRANS_ERR_INVALID;
+        }
+        g.cropped = true;
+        g.crop_jlat_min = crop->jlat_min;
+        g.crop_nx.assign(crop->nx, crop->nx + crop->nlat);
+        g.crop_jlon_min.assign(crop->jlon_min, crop->jlon_min + crop->nlat);
+        int pb = g.nleg, pe = 0;
+        g.crop_npts = 0;
+        for (int r = 0; r < crop->nlat; ++r) {
+            const int jg = crop->jlat_min + r;
+            if (crop->nx[r] < 1 || crop->nx[r] > nx[jg] || crop->jlon_min[r] < 0 || crop->jlon_min[r] >= nx[jg]) {
+                set_error("sptrans_plan_create_cropped: a crop row needs 1 <= nx <= nx(global row) and 0 <= jlon_min < nx(global row)");
+                delete sp;
+                return SPTRANS_ERR_INVALID;
+            }
+            const int pair = jg < g.nleg ? jg : nlat - 1 - jg;
+            pb = std::min(pb, pair);
+            pe = std::max(pe, pair + 1);
+            g.crop_npts += crop->nx[r];
+        }
+        g.pair_begin = pb;   // the Fourier stage runs on the latitude pairs that hold the crop's rows only
+        g.pair_end = pe;
     }
     set_io_layout(p.g, (flags & SPTRANS_SHARD_LOCAL_IO) != 0);
     auto fail = [&](int code) {
@@ -360,6 +398,10 @@ static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double
     if ((rc = upload(p.d_ex_band, p.ex.band_side, p.stream))) return fail(rc);
     if ((rc = generate_legendre_table(p))) return fail(rc);  // (its transpose is built by the first direct transform)
     if ((rc = build_fft_tables(p))) return fail(rc);
+    if (g.cropped) {
+        if ((rc = upload_crop_rows(p))) return fail(rc);
+        g.npts = g.crop_npts;   // grid-point arrays of this plan are [field][crop point]
+    }
     if (cudaStreamSynchronize(p.stream) != cudaSuccess) {
         set_error(std::string("plan setup failed: ") + cudaGetErrorString(cudaGetLastError()));
         return fail(SPTRANS_ERR_CUDA);
@@ -377,6 +419,12 @@ int sptrans_plan_create_sharded(sptrans_plan** out, int nlat, const int* nx, con
 int sptrans_plan_create(sptrans_plan** plan, int nlat, const int* nx, const double* lat_deg, const double* weights,
                         int truncation, unsigned flags, int device) {
     return create_plan(plan, nlat, nx, lat_deg, weights, truncation, flags, device, 0, 1, nullptr);
+}
+
+int sptrans_plan_create_cropped(sptrans_plan** plan, int nlat, const int* nx, const double* lat_deg, int truncation, unsigned flags,
+                                int device, int jlat_min, int nlat_crop, const int* nx_crop, const int* jlon_min) {
+    const Crop crop{jlat_min, nlat_crop, nx_crop, jlon_min};
+    return create_plan(plan, nlat, nx, lat_deg, nullptr, truncation, flags, device, 0, 1, nullptr, &crop);
 }
 
 int sptrans_plan_create_points(sptrans_plan** plan, size_t npoints, const double* lon_deg, const double* lat_deg,
@@ -432,7 +480,7 @@ int sptrans_plan_destroy(sptrans_plan* sp) {
     tc_free(p);
     peer_release(p);
     std::vector<void*> ptrs = {p.d_tiles_inv, p.d_tiles_dir, p.d_tile_counter, p.d_pair_done, p.d_packed, p.d_fourier, p.d_spec,
-                               p.d_spec2, p.d_gp, p.d_rows};
+                               p.d_spec2, p.d_gp, p.d_rows, p.d_band, p.d_crop_rows};
     if (p.parent) p.parent->clones--;   // a clone borrows every table from its parent
     else
         ptrs.insert(ptrs.end(), {p.d_tab, p.d_tabT, p.d_nlat0, p.d_fb_rowoff, p.d_sp_rowoff, p.d_rowoff, p.d_nx, p.d_my_m, p.d_owner,
@@ -693,7 +741,7 @@ int sptrans_invtrans_scalar(sptrans_plan* plan, int nf, const double* spectra, d
         if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
         d_gp = p.d_gp;
     }
-    const bool pipelined = gp_host && !p.g.points;   // D2H of finished field chunks behind the Fourier kernels
+    const bool pipelined = gp_host && !p.g.points && !p.g.cropped;   // D2H of finished field chunks behind the Fourier kernels
     if ((rc = run_inverse(p, nf, T, d_spec, d_gp, 0, tm, marks, slots, pipelined ? gp : nullptr))) return rc;
     if (gp_host && !pipelined) {
         SPT_CUDA(cudaMemcpyAsync(gp, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
@@ -754,7 +802,7 @@ int sptrans_invtrans(sptrans_plan* plan, int nsc, const double* scalar_spectra, 
         if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
         d_gp = p.d_gp;
     }
-    const bool pipelined = gp_host && !p.g.points;
+    const bool pipelined = gp_host && !p.g.points && !p.g.cropped;
     if ((rc = run_inverse(p, nall, T + 1, p.d_spec, d_gp, 2 * nvd, tm, marks, slots, pipelined ? gp : nullptr))) return rc;
     if (gp_host && !pipelined) {
         SPT_CUDA(cudaMemcpyAsync(gp, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
@@ -779,8 +827,8 @@ static int dirtrans_scalar_impl(sptrans_plan* plan, int nf, const double* gp, do
         return SPTRANS_ERR_INVALID;
     }
     if (nf == 0) return SPTRANS_OK;
-    if (p.g.points) {  // TransLocal: ATLAS_NOTIMPLEMENTED (TransLocal.cc:1599-1604, :1671-1676)
-        set_error("direct and adjoint transforms are not available for point-set plans");
+    if (p.g.points || p.g.cropped) {  // TransLocal: ATLAS_NOTIMPLEMENTED (TransLocal.cc:1599-1604, :1671-1676)
+        set_error("direct and adjoint transforms are not available for point-set and cropped-grid plans");
         return SPTRANS_ERR_NOT_IMPLEMENTED;
     }
     if (p.g.nranks != 1) {
@@ -853,8 +901,8 @@ int sptrans_dirtrans_wind2vordiv(sptrans_plan* plan, int nf, const double* wind,
         return SPTRANS_ERR_INVALID;
     }
     if (nf == 0) return SPTRANS_OK;
-    if (p.g.points) {
-        set_error("direct and adjoint transforms are not available for point-set plans");
+    if (p.g.points || p.g.cropped) {
+        set_error("direct and adjoint transforms are not available for point-set and cropped-grid plans");
         return SPTRANS_ERR_NOT_IMPLEMENTED;
     }
     if (p.g.nranks != 1) {
@@ -944,7 +992,7 @@ int sptrans_invtrans_grad(sptrans_plan* plan, int nf, const double* spectra, dou
         if ((rc = ensure(p.d_gp, p.gp_cap, ngp))) return rc;
         d_gp = p.d_gp;
     }
-    const bool pipelined = gp_host && !p.g.points;
+    const bool pipelined = gp_host && !p.g.points && !p.g.cropped;
     if ((rc = run_inverse(p, nall, T + 1, p.d_spec, d_gp, nall, tm, marks, slots, pipelined ? grad : nullptr))) return rc;
     if (gp_host && !pipelined) {
         SPT_CUDA(cudaMemcpyAsync(grad, d_gp, ngp * sizeof(double), cudaMemcpyDeviceToHost, p.stream));

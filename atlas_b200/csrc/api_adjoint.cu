@@ -25,8 +25,8 @@ int adj_args_ok(sptrans_plan* plan, const char* who) {
         return SPTRANS_ERR_INVALID;
     }
     SPT_CUDA(cudaSetDevice(plan->p.device));
-    if (plan->p.g.points) {
-        set_error(std::string(who) + ": direct and adjoint transforms are not available for point-set plans");
+    if (plan->p.g.points || plan->p.g.cropped) {
+        set_error(std::string(who) + ": direct and adjoint transforms are not available for point-set and cropped-grid plans");
         return SPTRANS_ERR_NOT_IMPLEMENTED;
     }
     if (plan->p.g.nranks != 1) {

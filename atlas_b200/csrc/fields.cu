@@ -6,6 +6,9 @@
 // (ecmwf/atlas src/atlas/trans/ifs/TransIFS.cc:610-667 gp, :1392-1437 wind, :2113-2137 gradient), which run on
 // the host there.  Here it is one tiled transpose on the device (32 x 32 doubles through shared memory, both sides
 // coalesced): 2 x 8 bytes of HBM traffic per value.
+#include <algorithm>
+#include <vector>
+
 #include "plan.hpp"
 
 namespace sptrans {
@@ -68,6 +71,64 @@ int launch_gp_repack(Plan& p, int nlev, int ncomp, const double* d_in, double* d
     dim3 block(kTile, 8);
     if (to_rows) gp_repack_kernel<true><<<grid, block, 0, p.stream>>>(d_in, d_out, npts, nlev, ncomp);
     else gp_repack_kernel<false><<<grid, block, 0, p.stream>>>(d_in, d_out, npts, nlev, ncomp);
+    p.launches++;
+    SPT_CUDA(cudaGetLastError());
+    return SPTRANS_OK;
+}
+
+// ---- cropped (regional) structured grids ------------------------------------------------------------------------------
+// The reference transforms the rows of the GLOBAL grid the regional grid is cut from and copies out, per row, the
+// longitudes of the crop starting at jlonMin with wrap-around (TransLocal.cc:501-531, :1180-1187).  Here the Fourier
+// kernels write the global rows of the latitude band into a work array and this kernel does the copy-out.
+struct CropRow {
+    long long src;   // offset of the global row within one field of the band work array
+    long long dst;   // offset of the crop row within one field of the user's array
+    int nxg;         // points of the global row
+    int start;       // first longitude index of the crop (jlonMin)
+    int n;           // points of the crop row
+};
+
+namespace {
+__global__ void crop_gather_kernel(const CropRow* __restrict__ rows, int nf, long long band_stride, long long crop_npts,
+                                   const double* __restrict__ band, double* __restrict__ gp) {
+    const CropRow r = rows[blockIdx.x];
+    for (int f = blockIdx.y; f < nf; f += gridDim.y) {
+        const double* src = band + f * band_stride + r.src;
+        double* dst = gp + f * crop_npts + r.dst;
+        for (int i = threadIdx.x; i < r.n; i += blockDim.x) {
+            int k = r.start + i;
+            if (k >= r.nxg) k -= r.nxg;   // (start < nxg and n <= nxg: one wrap at most)
+            dst[i] = src[k];
+        }
+    }
+}
+}  // namespace
+
+int upload_crop_rows(Plan& p) {
+    const HostGeom& g = p.g;
+    std::vector<CropRow> rows(g.crop_nx.size());
+    long long dst = 0;
+    for (size_t r = 0; r < rows.size(); ++r) {
+        const int jg = g.crop_jlat_min + static_cast<int>(r);
+        rows[r].src = g.gp_rowoff[jg];
+        rows[r].dst = dst;
+        rows[r].nxg = g.nx[jg];
+        rows[r].start = g.crop_jlon_min[r];
+        rows[r].n = g.crop_nx[r];
+        dst += g.crop_nx[r];
+    }
+    SPT_CUDA(cudaMalloc(&p.d_crop_rows, std::max<size_t>(rows.size(), 1) * sizeof(CropRow)));
+    SPT_CUDA(cudaMemcpyAsync(p.d_crop_rows, rows.data(), rows.size() * sizeof(CropRow), cudaMemcpyHostToDevice, p.stream));
+    SPT_CUDA(cudaStreamSynchronize(p.stream));
+    return SPTRANS_OK;
+}
+
+int launch_crop_gather(Plan& p, int nf, const double* d_band, double* d_gp) {
+    const int nrows = static_cast<int>(p.g.crop_nx.size());
+    if (nrows == 0 || nf == 0) return SPTRANS_OK;
+    dim3 grid(nrows, std::min(nf, 64));
+    crop_gather_kernel<<<grid, 128, 0, p.stream>>>(static_cast<const CropRow*>(p.d_crop_rows), nf, p.g.gp_stride, p.g.crop_npts,
+                                                   d_band, d_gp);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
     return SPTRANS_OK;

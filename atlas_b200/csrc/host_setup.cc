@@ -164,9 +164,12 @@ int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, 
         // contiguous bands of latitude pairs with ~equal Fourier-stage cost: a row pair of length n with zonal
         // wavenumbers up to L is one chirp-z transform of length ~ n + 2L (fourier.cu), i.e. ~ M log M work, plus a
         // per-row constant (block set-up)
+        // Rows whose convolution does not fit the register-tiled kernels (n + 2L > 32 * 256) run on the shared-memory-pass
+        // kernels or, beyond the single-CTA limit, on the row-mode kernels: 1.85x the time per unit of work, measured per rank
+        // at TCo2559 on 8 GPUs (profiles/bench_tco2559_r02_n8_inv.json: bands of equal nominal cost took 6.6 ... 13.2 ms)
         auto fcost = [&](int j) {
             const double M = nx[j] + 2.0 * std::max(0, g.mmax[j]);
-            return M * std::log2(M + 2.0) + 2500.;
+            return (M * std::log2(M + 2.0) + 2500.) * (M > 8192. ? 1.85 : 1.0);
         };
         double total = 0;
         for (int j = 0; j < g.nleg; ++j) total += fcost(j);
@@ -213,6 +216,23 @@ void set_io_layout(HostGeom& g, bool local_io) {
     const int T = g.T, nlat = g.nlat;
     g.gp_rowoff.assign(nlat, -1);
     g.spec_off.assign(T + 1, -1);
+    if (g.cropped) {   // work array of the Fourier stage: the rows of the band only; spectra are global
+        long long off = 0;
+        for (int j = g.pair_begin; j < g.pair_end; ++j) {
+            g.gp_rowoff[j] = off;
+            off += g.nx[j];
+        }
+        for (int j = g.pair_end - 1; j >= g.pair_begin; --j) {
+            const int js = nlat - 1 - j;
+            if (js == j) continue;
+            g.gp_rowoff[js] = off;
+            off += g.nx[js];
+        }
+        g.gp_stride = off + (off & 1);
+        for (int m = 0; m <= T; ++m) g.spec_off[m] = static_cast<long long>(2 * T + 3 - m) * m / 2;
+        g.spec_ncoef = static_cast<long long>(T + 1) * (T + 2) / 2;
+        return;
+    }
     if (!g.local_io) {
         for (int j = 0; j < nlat; ++j) g.gp_rowoff[j] = g.rowoff[j];
         g.gp_stride = g.npts;

@@ -316,6 +316,8 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
             if (Kinv > 0) {
                 const int ksteps = round_up(Kinv, kBK) / kBK;
                 for (int l0 = 0; l0 < ncol; l0 += kBM) {
+                    // cropped plans: only the latitude pairs that hold rows of the crop are evaluated
+                    if (g.cropped && (g.nlat0[m] + l0 + kBM <= g.pair_begin || g.nlat0[m] + l0 >= g.pair_end)) continue;
                     for (int n0 = 0; n0 < ld; n0 += kBN) {
                         LegTile t{};
                         t.a_off = g.tab_off[2 * m + par] + l0;

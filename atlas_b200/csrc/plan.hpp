@@ -60,6 +60,14 @@ struct HostGeom {
     // only its own share: grid arrays [field][rows of my latitude band: northern rows, then their southern mirrors],
     // spectral arrays [my zonal wavenumbers ascending][n][re/im][field].
     bool local_io = false;
+    // cropped (regional) structured grids -- a nest of this global grid (TransLocal.cc:371-531): the transform runs on the
+    // latitude pairs [pair_begin, pair_end) that hold the crop's rows, with the GLOBAL grid's zonal truncation and row
+    // lengths, into a band-layout work array; crop row r then takes crop_nx[r] points of global row crop_jlat_min + r
+    // starting at longitude index crop_jlon_min[r], wrapping around (the copy-out of TransLocal.cc:1180-1187)
+    bool cropped = false;
+    int crop_jlat_min = 0;
+    std::vector<int> crop_nx, crop_jlon_min;
+    long long crop_npts = 0;
     std::vector<long long> gp_rowoff;    // [nlat] offset of row j within one field of the grid array (-1: not held)
     long long gp_stride = 0;             // points per field in the grid array
     std::vector<long long> spec_off;     // [T+1] first complex coefficient of zonal wavenumber m at truncation T (-1: not held)
@@ -194,6 +202,8 @@ struct Plan {
     double* d_spec2 = nullptr;    size_t spec2_cap = 0;
     double* d_gp = nullptr;       size_t gp_cap = 0;       // device copy of grid fields (host-pointer mode)
     double* d_rows = nullptr;     size_t rows_cap = 0;     // row-layout image of a Field-layout grid buffer
+    double* d_band = nullptr;     size_t band_cap = 0;     // cropped plans: rows of the latitude band the crop is cut from
+    void* d_crop_rows = nullptr;                           // cropped plans: CropRow[crop rows] (fields.cu)
     void* h_pinned = nullptr;     size_t pinned_cap = 0;
     int precision = 0;           // SPTRANS_PREC_FP64 | SPTRANS_PREC_TC_SPLIT
     void* tc = nullptr;          // TcState (legendre_tc.cu)
@@ -243,7 +253,7 @@ int fourier_truncation(int truncation, int nx, int nxmax, int ndgl, double lat, 
 void gaussian_quadrature(int N, double* lat_deg_2N, double* weights_2N);
 int build_geometry(HostGeom& g, int nlat, const int* nx, const double* lat_deg, const double* weights, int T,
                    bool regular, int rank, int nranks);
-void set_io_layout(HostGeom& g, bool local_io);
+void set_io_layout(HostGeom& g, bool local_io);   // (band layout also for cropped plans)
 std::string legendre_cache_uid(const char* prefix, int truncation, int kind, int n_or_ny, double south, double north, int nlat,
                                const double* lat_deg, bool flt);   // fills gp_rowoff / gp_stride / spec_off / spec_ncoef
 // per-latitude seeds for the device Legendre recurrence: x=cos(theta), s=sin(theta), columns m=0,1 and the diagonal
@@ -305,6 +315,9 @@ int launch_points_inv(Plan& p, int nf, int mlimit, const double* d_fourier, doub
 // ---- fields.cu ----
 // atlas Field layout (node, level, component) <-> transform rows [component * nlev + level][node]
 int launch_gp_repack(Plan& p, int nlev, int ncomp, const double* d_in, double* d_out, bool to_rows);
+// cropped plans: band-layout rows (Fourier stage output) -> the crop's points [field][crop point]
+int upload_crop_rows(Plan& p);
+int launch_crop_gather(Plan& p, int nf, const double* d_band, double* d_gp);
 
 // ---- vordiv.cu ----
 int launch_grad_spectra(cudaStream_t s, int T, int nf, const double* d_sp, double* d_all, uint64_t* launches);

@@ -54,6 +54,76 @@ class StructuredGrid:
         return lon, lat
 
 
+class CroppedGrid:
+    """`atlas::Grid(global_grid, domain)` for a RectangularDomain: the regional grid TransLocal accepts, a cropping of a
+    global structured grid (TransLocal.cc:371-531).  Rows whose latitude lies in [south, north] are kept; in each kept row
+    the points whose longitude, normalised into [west, west + 360), lies in [west, east], ordered west -> east
+    (grid/detail/grid/Structured.cc crops the same way).  `jlat_min`, `nx()` and `jlon_min()` are what the reference derives
+    in its constructor (jlatMin_ :441-447, jlonMin_ :501-531)."""
+
+    regular = False
+
+    def __init__(self, global_grid, west, east, south, north, name=None):
+        if not isinstance(global_grid, StructuredGrid):
+            raise TypeError("CroppedGrid needs a global StructuredGrid")
+        g = self.global_grid = global_grid
+        self.regular = g.regular
+        self.name = name or f"{g.name}[{west},{east}]x[{south},{north}]"
+        eps = 1e-10
+        rows = [j for j in range(g.ny()) if south - eps <= g.y(j) <= north + eps]
+        if not rows or rows != list(range(rows[0], rows[-1] + 1)):
+            raise ValueError("the domain keeps no (contiguous) latitude rows of the global grid")
+        self.jlat_min = rows[0]
+        nxc, start = [], []
+        for j in rows:
+            n = g.nx(j)
+            lon = 360.0 * np.arange(n) / n
+            rel = np.mod(lon - west, 360.0)
+            rel[rel > 360.0 - eps] = 0.0
+            keep = np.nonzero(rel <= (east - west) + eps)[0]
+            if keep.size == 0:
+                raise ValueError(f"the domain keeps no point of global row {j}")
+            first = int(keep[np.argmin(rel[keep])])
+            nxc.append(int(keep.size))
+            start.append(first)
+        self._nx = np.ascontiguousarray(nxc, dtype=np.int32)
+        self._start = np.ascontiguousarray(start, dtype=np.int32)
+        self._rows = rows
+
+    def ny(self):
+        return len(self._rows)
+
+    def nx(self, j=None):
+        return self._nx if j is None else int(self._nx[j])
+
+    def jlon_min(self):
+        return self._start
+
+    def y(self, j=None):
+        lat = self.global_grid.y()[self._rows]
+        return lat if j is None else float(lat[j])
+
+    def size(self):
+        return int(self._nx.sum())
+
+    def weights(self):
+        return None
+
+    def global_indices(self):
+        """index into the global grid's point order of every point of the crop (the copy-out of TransLocal.cc:1180-1187)"""
+        ro = self.global_grid.rowoff()
+        out = []
+        for r, j in enumerate(self._rows):
+            n = self.global_grid.nx(j)
+            out.append(ro[j] + (self._start[r] + np.arange(self._nx[r])) % n)
+        return np.concatenate(out)
+
+    def lonlat(self):
+        lon, lat = self.global_grid.lonlat()
+        idx = self.global_indices()
+        return lon[idx], lat[idx]
+
+
 class UnstructuredGrid:
     """`atlas::UnstructuredGrid(points)` (grid/detail/grid/Unstructured.h): a list of (lon, lat) points in degrees."""
 

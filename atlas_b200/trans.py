@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .grid import Grid, StructuredGrid, UnstructuredGrid
+from .grid import CroppedGrid, Grid, StructuredGrid, UnstructuredGrid
 
 
 class option:
@@ -57,8 +57,8 @@ class Trans:
     def __init__(self, grid, truncation, config=None, device=0, rank=0, nranks=1, local_io=False):
         if isinstance(grid, str):
             grid = Grid(grid)
-        if not isinstance(grid, (StructuredGrid, UnstructuredGrid)):
-            raise TypeError("Trans needs a StructuredGrid or an UnstructuredGrid")
+        if not isinstance(grid, (StructuredGrid, UnstructuredGrid, CroppedGrid)):
+            raise TypeError("Trans needs a StructuredGrid, a CroppedGrid or an UnstructuredGrid")
         cfg = dict(config or {})
         backend = cfg.get("type", "b200")
         if backend != "b200":
@@ -72,6 +72,17 @@ class Trans:
             lon, lat = grid.lonlat()
             _lib.check(_lib.lib.sptrans_plan_create_points(C.byref(self._h), lon.size, lon.ctypes.data_as(_lib.c_double_p),
                                                            lat.ctypes.data_as(_lib.c_double_p), self._T, int(device)))
+            return
+        if isinstance(grid, CroppedGrid):   # Trans(global_grid, domain, truncation): TransLocal.cc:371-531
+            if nranks != 1:
+                raise ValueError("cropped-grid plans are not sharded")
+            g = grid.global_grid
+            gnx, glat = g.nx(), g.y()
+            cnx, start = grid.nx(), grid.jlon_min()
+            _lib.check(_lib.lib.sptrans_plan_create_cropped(
+                C.byref(self._h), g.ny(), gnx.ctypes.data_as(_lib.c_int_p), glat.ctypes.data_as(_lib.c_double_p), self._T,
+                1 if g.regular else 0, int(device), int(grid.jlat_min), grid.ny(), cnx.ctypes.data_as(_lib.c_int_p),
+                start.ctypes.data_as(_lib.c_int_p)))
             return
         nx = grid.nx()
         lat = grid.y()

@@ -542,6 +542,9 @@ def bench_sharded(args, rank, world, local_rank):
         back_err = float((h_gp[(args.steps - 1) % 2].to(dev) - d_gp).abs().max())
         e2e = {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(nb[0].item()),
                "d2h_bytes_per_step": int(nb[1].item()), "host_copy_max_abs_diff": back_err,
+               "aggregate_host_gbs": {"h2d": float(nb[0].item()) / e2e_ms / 1e6, "d2h": float(nb[1].item()) / e2e_ms / 1e6,
+                                      "note": "all ranks together; on this pool's boxes the sum saturates near 55-60 GB/s per direction "
+                                              "whatever the number of GPUs (measured at N = 1, 2, 8), so the end-to-end figure stops scaling"},
                "note": "bytes summed over ranks; every rank copies its own shard from/to pinned host memory as one contiguous "
                        "copy per array; the direct transform of step i reads the grid fields step i-1's inverse produced"}
     out = None

@@ -14,6 +14,7 @@
  */
 #pragma once
 
+#include <cmath>
 #include <cstdio>
 #include <memory>
 #include <sstream>
@@ -37,9 +38,10 @@ namespace trans {
 class TransB200 : public TransImpl {
 public:
     // constructor signature required by TransBuilderGrid<T> (trans/detail/TransFactory.h:116-119)
-    TransB200(const Cache& cache, const Grid& grid, const Domain& /*domain*/, const long truncation,
+    TransB200(const Cache& cache, const Grid& grid, const Domain& domain, const long truncation,
               const eckit::Configuration& config = util::NoConfig()):
-        grid_(grid), truncation_(static_cast<int>(truncation)) {
+        // like TransLocal (TransLocal.cc:322-336): the transform's grid is the given grid cropped to the domain
+        grid_(domain.global() ? grid : Grid(grid, domain)), gridGlobal_(grid), truncation_(static_cast<int>(truncation)) {
         create_plan(config);
         if (!plan_is_points_) {
             // Legendre cache, as TransLocal handles it (TransLocal.cc:608-647): a cache handed in replaces the
@@ -117,12 +119,49 @@ private:
         int device = 0;
         config.get("device", device);
         StructuredGrid g(grid_);
+        if (g && !grid_.domain().global() && StructuredGrid(gridGlobal_) && gridGlobal_.domain().global() && !grid_.projection()) {
+            // Regional grid that is a cropping of a global structured grid (TransLocal.cc:371-531): the global grid's
+            // Legendre functions, per-latitude zonal truncation and row FFTs, then the copy-out of the crop's longitudes.
+            StructuredGrid gg(gridGlobal_);
+            const int nlat_g = static_cast<int>(gg.ny()), nlat_c = static_cast<int>(g.ny());
+            std::vector<int> nx(nlat_g), nxc(nlat_c), jlon(nlat_c);
+            std::vector<double> lat(nlat_g);
+            for (int j = 0; j < nlat_g; ++j) {
+                nx[j]  = static_cast<int>(gg.nx(j));
+                lat[j] = gg.y(j);
+            }
+            int jlat_min = 0;  // :441-447
+            for (int j = 0; j < nlat_g; ++j) {
+                if (gg.y(j) > g.y(0)) {
+                    ++jlat_min;
+                }
+            }
+            auto wrap = [](double angle) {  // :493-499
+                double r = std::fmod(angle, 360.);
+                return r < 0. ? r + 360. : r;
+            };
+            for (int j = 0; j < nlat_c; ++j) {  // jlonMin_: global points of the row west of the crop's first point (:518-529)
+                const double lonmin = wrap(g.x(0, j));
+                const int jg        = j + jlat_min;
+                int count           = 0;
+                for (int i = 0; i < nx[jg]; ++i) {
+                    if (gg.x(i, jg) < lonmin - 1e-9) {
+                        ++count;
+                    }
+                }
+                jlon[j] = count % nx[jg];
+                nxc[j]  = static_cast<int>(g.nx(j));
+            }
+            const unsigned flags = RegularGrid(gridGlobal_) ? SPTRANS_GRID_REGULAR : 0u;
+            check(sptrans_plan_create_cropped(&plan_, nlat_g, nx.data(), lat.data(), truncation_, flags, device, jlat_min, nlat_c,
+                                              nxc.data(), jlon.data()));
+            plan_is_cropped_ = true;
+            return;
+        }
         if (!g || !grid_.domain().global()) {
             // Unstructured grid: the transform is evaluated point by point (TransLocal.cc:740-770, :1289-1392).
-            // Regional structured grids take the same route: for non-nested regular grids that is what TransLocal does
-            // too (no FFT, no zonal truncation: `no_nest`, :397-407, :462-467); a cropped reduced grid is evaluated
-            // WITHOUT the global grid's zonal truncation towards the poles (:468-488), i.e. it keeps terms the reference
-            // drops (below 1e-13 at operational resolutions).  One table row per distinct latitude either way.
+            // Regional REGULAR grids that are not a cropping of a global grid take the same route, which is what TransLocal
+            // does too (no FFT, no zonal truncation: `no_nest`, :397-407, :462-467).  One table row per distinct latitude.
             std::vector<double> lon, lat;
             lon.reserve(grid_.size());
             lat.reserve(grid_.size());
@@ -426,11 +465,13 @@ private:
     }
 
     Grid grid_;
+    Grid gridGlobal_;   // the grid the constructor was given (TransLocal::gridGlobal_, TransLocal.h:213); grid_ = it cropped to the domain
     int truncation_;
     sptrans_plan* plan_{nullptr};
     sptrans_multi* multi_{nullptr};   // config "gpus" > 1: the sharded plans of all devices (every other entry point then
                                       // reports "whole-transform entry points need an unsharded plan" from the C ABI)
     bool plan_is_points_{false};
+    bool plan_is_cropped_{false};
     mutable functionspace::Spectral spectral_;
 };
 

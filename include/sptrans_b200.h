@@ -97,6 +97,16 @@ int sptrans_plan_create_sharded(sptrans_plan** plan, int nlat, const int* nx, co
                                 const double* weights, int truncation, unsigned flags, int device, int rank,
                                 int nranks);
 
+/* Trans(global_grid, domain, truncation) with a NON-global domain: the regional grid is a cropping of a global structured
+ * grid (TransLocal.cc:371-531; anything else is refused there, :410-420).  Rows jlat_min .. jlat_min + nlat_crop - 1 of the
+ * global grid are kept; crop row r holds nx_crop[r] consecutive longitudes of its global row starting at index jlon_min[r]
+ * and wrapping around (jlonMin_, :501-531; copy-out :1180-1187).  The transform uses the GLOBAL grid's per-latitude zonal
+ * truncation (nlat0_, :462-488) and FFTs of the global row lengths, exactly like the reference; grid-point arrays of the
+ * plan are [field][crop point].  Inverse transforms only (scalar, vor/div -> wind, general, gradient), like TransLocal. */
+int sptrans_plan_create_cropped(sptrans_plan** plan, int nlat, const int* nx, const double* lat_deg, int truncation,
+                                unsigned flags, int device, int jlat_min, int nlat_crop, const int* nx_crop,
+                                const int* jlon_min);
+
 /* Trans(UnstructuredGrid, truncation): a plan for `npoints` arbitrary points (lon, lat in degrees), the counterpart of
  * TransLocal's unstructured path (TransLocal.cc:740-770 set-up, :1289-1392 invtrans_unstructured).  Grid-point arrays of
  * such a plan are [field][point]; every zonal wavenumber m <= T enters at every point (no reduced-grid truncation, and

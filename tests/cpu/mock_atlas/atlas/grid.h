@@ -44,11 +44,15 @@ struct GridData {
     bool global = true;               // domain().global()
     std::vector<PointLonLat> lonlat;  // filled for regional structured grids (Grid::lonlat())
     std::vector<PointLonLat> points;  // UnstructuredGrid
+    std::vector<double> xmin;         // first longitude of every row (default 0: global rows)
+    std::vector<double> dx;           // longitude increment of every row (default 360 / nx)
+    std::shared_ptr<GridData> cropped;  // what Grid(this grid, a non-global domain) yields (the mock does not crop itself)
 };
 class Grid {
 public:
     Grid() = default;
     explicit Grid(std::shared_ptr<GridData> d): d_(std::move(d)) {}
+    Grid(const Grid& g, const Domain& domain): d_(domain.global() || !g.d_->cropped ? g.d_ : g.d_->cropped) {}  // grid/Grid.h:83
     explicit operator bool() const { return bool(d_); }
     Projection projection() const { return Projection(); }
     Domain domain() const { return Domain(d_->global, d_->ymin, d_->ymax); }
@@ -70,6 +74,11 @@ public:
     idx_t ny() const { return static_cast<idx_t>(d_->nx.size()); }
     idx_t nx(idx_t j) const { return d_->nx[j]; }
     double y(idx_t j) const { return d_->lat[j]; }
+    double x(idx_t i, idx_t j) const {  // grid/detail/grid/Structured.h:312: xmin + i * dx
+        const double x0 = d_->xmin.empty() ? 0. : d_->xmin[j];
+        const double dx = d_->dx.empty() ? 360. / d_->nx[j] : d_->dx[j];
+        return x0 + i * dx;
+    }
     struct YSpace {
         std::string t;
         const std::string& type() const { return t; }

@@ -29,6 +29,13 @@ public:
         if (it == registry().end()) throw eckit::Exception("no such Trans backend: " + type);
         return it->second->make(cache, g, g.domain(), truncation, c);
     }
+    // Trans(cache, grid, domain, truncation, config): trans/detail/TransFactory.cc:236-258
+    static const TransImpl* build(const std::string& type, const Cache& cache, const Grid& g, int truncation,
+                                  const eckit::Configuration& c, const Domain& domain) {
+        auto it = registry().find(type);
+        if (it == registry().end()) throw eckit::Exception("no such Trans backend: " + type);
+        return it->second->make(cache, g, domain, truncation, c);
+    }
     static bool has(const std::string& type) { return registry().count(type) != 0; }
 private:
     static std::map<std::string, TransFactory*>& registry() {

@@ -166,6 +166,34 @@ int main() {
     tc->invtrans(spr, gp4);
     for (idx_t i = 0; i < grid.size(); ++i)
         if (gp3.data()[i] != gp4.data()[i]) err3 = 1.;
+    // Trans(global_grid, domain, truncation) with a regional domain: the cropped plan (FFT path with the global grid's zonal
+    // truncation, TransLocal.cc:371-531), not the point-by-point path.  Rows 14..17 of F16 (two either side of the equator),
+    // longitudes -11.25 .. 11.25 degrees (5 points, the first two west of Greenwich: jlonMin wraps around).
+    {
+        auto dc = std::make_shared<GridData>();
+        dc->name = "F16-cropped";
+        dc->regular = true;
+        dc->global = false;
+        dc->nx.assign(4, 5);
+        dc->lat.assign(d->lat.begin() + 14, d->lat.begin() + 18);
+        dc->xmin.assign(4, -11.25);
+        dc->dx.assign(4, 5.625);
+        dc->ymin = dc->lat.back();
+        dc->ymax = dc->lat.front();
+        d->cropped = dc;
+        Domain region(false, dc->ymin, dc->ymax);
+        std::unique_ptr<const trans::TransImpl> tr(trans::TransFactory::build("b200", trans::Cache(), grid, T, util::NoConfig(), region));
+        Grid cgrid(grid, region);
+        if (tr->grid().size() != cgrid.size() || cgrid.size() != 20) err3 = 1.;
+        Field gpc("gpc", {cgrid.size()});
+        tr->invtrans(spr, gpc);
+        // the same values as the global transform at the crop's points: global row 14 + r, longitude index (62 + i) % 64
+        for (int r = 0; r < 4; ++r)
+            for (int i = 0; i < 5; ++i) {
+                const double want = gp3.data()[(14 + r) * 64 + (62 + i) % 64];
+                err3 = std::fmax(err3, std::fabs(gpc.data()[r * 5 + i] - want));
+            }
+    }
     // config "gpus": the single-process multi-device plan behind the same raw-pointer calls (two ranks on device 0 here)
     {
         util::Config two;

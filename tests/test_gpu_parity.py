@@ -651,6 +651,21 @@ print("ROWMODE_OK")
         assert r.returncode == 0 and "ROWMODE_OK" in r.stdout, r.stdout[-3000:]
 
 
+def test_shard_local_io_with_row_mode_kernels():
+    """What BASELINE config 5 runs on 8 GPUs -- sharded plans, shard-local I/O arrays AND the row-mode Fourier kernels for
+    the rows beyond the single-CTA limit -- at a small size: the emulated-rank test above in a subprocess whose limit is
+    lowered (SPTRANS_FFT_MAXM is read once per process)."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, SPTRANS_FFT_MAXM="256")
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.abspath(__file__), "-k",
+           "test_shard_local_io_emulated_on_one_gpu and (O48 or L9)"]   # O48: rows beyond 256 take row mode
+    r = subprocess.run(cmd, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-3000:]
+
+
 def test_config5_tco2559_inverse_sample():
     """BASELINE config 5 (TCo2559): the plan builds on one GPU (55 GB of pruned Legendre tables) and the inverse of a
     few fields agrees with the oracle on sampled latitude rows computed independently (direct summation of the

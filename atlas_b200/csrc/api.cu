@@ -397,7 +397,8 @@ static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double
     if ((rc = upload(p.d_ex_m, p.ex.m_side, p.stream))) return fail(rc);
     if ((rc = upload(p.d_ex_band, p.ex.band_side, p.stream))) return fail(rc);
     if ((rc = generate_legendre_table(p))) return fail(rc);  // (its transpose is built by the first direct transform)
-    if ((rc = build_fft_tables(p))) return fail(rc);
+    // (point-set plans evaluate the Fourier sums point by point, points.cu: no FFT tables)
+    if (!g.points && (rc = build_fft_tables(p))) return fail(rc);
     if (g.cropped) {
         if ((rc = upload_crop_rows(p))) return fail(rc);
         g.npts = g.crop_npts;   // grid-point arrays of this plan are [field][crop point]
@@ -448,6 +449,22 @@ int sptrans_plan_create_points(sptrans_plan** plan, size_t npoints, const double
     const bool equator = north.back() == 0.;
     if (equator && north.size() == 1) north.insert(north.begin(), 45.);  // the geometry needs one off-equator row pair
     const int nn = static_cast<int>(north.size());
+    {
+        // One Legendre table row per distinct |latitude|: nn * (T+2)^2 / 2 doubles (plus the Legendre<->Fourier buffer of
+        // the calls).  TransLocal's unstructured path needs O(T^2) memory whatever the number of points (TransLocal.cc:
+        // 1289-1392); a genuinely scattered point set (every latitude distinct) can therefore fit the reference and not
+        // this plan -- fail early and say so instead of running out of device memory half way through.
+        const double table_bytes = 8.0 * nn * (truncation + 2.0) * (truncation + 2.0) / 2.0;
+        size_t free_b = 0, total_b = 0;
+        if (sptrans_device_count() > 0 && device >= 0 && cudaSetDevice(device) == cudaSuccess &&
+            cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && table_bytes > 0.7 * static_cast<double>(free_b)) {
+            set_error("sptrans_plan_create_points: " + std::to_string(nn) + " distinct latitudes at truncation " +
+                      std::to_string(truncation) + " need a Legendre table of " + std::to_string(static_cast<long long>(table_bytes / 1e9)) +
+                      " GB, more than the device can hold; transform the points in batches of fewer distinct latitudes");
+            return SPTRANS_ERR_INVALID;
+        }
+        cudaGetLastError();
+    }
     std::vector<double> lat(north);
     for (int j = nn - 1 - (equator ? 1 : 0); j >= 0; --j) lat.push_back(-north[j]);
     const int nlat = static_cast<int>(lat.size());

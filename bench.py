@@ -291,9 +291,11 @@ def bench_e2e(args, trans, torch, H, T, nf, npts, nspec, sp_host):
     want = mask_mT(sp_np, T, nf)
     scale = float(np.abs(want).max())
 
+    tol = 1e-11 if args.precision == "fp64" else 1e-4   # tf32x3 Legendre stage: fp32-level accuracy (2e-6 per transform)
+
     def check(tag):
         err = float(np.abs(sp2_np - want).max()) / scale
-        if not err < 1e-11:
+        if not err < tol:
             raise SystemExit(f"bench e2e ({tag}): round trip through host buffers differs from the input spectra "
                              f"(m == T column masked): rel max {err:.3e}")
         return err

@@ -84,6 +84,34 @@ def test_field_layout_wind_and_gradient(gridname, T, nlev):
     assert np.array_equal(grad, rows_to_field(g_rows, npts, nlev, 2))
 
 
+@pytest.mark.parametrize("gridname,T,nlev", [("O48", 47, 5), ("F24", 23, 3), ("O160", 159, 11)])
+def test_field_layout_against_oracle(gridname, T, nlev):
+    """Field-layout entry points straight against the CPU oracle (not against the raw-pointer entry points of the same
+    library): spectral Field (nspec2, nlev), grid-point Field (npts, nlev), wind / gradient Field (npts, nlev, 2) with
+    field = component * nlev + level as TransIFS packs them (trans/ifs/TransIFS.cc:610-667, :1392-1437, :2113-2137)."""
+    from oracle import pyoracle as po
+
+    grid, trans = make(gridname, T)
+    plan = po.OraclePlan(grid.nx(), grid.y(), T, regular=grid.regular, weights=grid.weights())
+    npts, nspec2 = grid.size(), trans.nb_spectral_coefficients()
+    sp = H.synthetic_spectra(T, nlev)
+    gpf = np.full((npts, nlev), np.nan)
+    trans.invtrans_field(sp.reshape(nspec2, nlev), gpf)
+    want = plan.invtrans(nlev, sp, mode=2)
+    assert H.compute_rms(field_to_rows(gpf, npts, nlev, 1), want) < 1e-13
+    spf = np.full((nspec2, nlev), np.nan)
+    trans.dirtrans_field(rows_to_field(want, npts, nlev, 1), spf)
+    assert H.rel_max(spf.reshape(-1), plan.dirtrans(nlev, want)) < 1e-12
+    vor, div = H.synthetic_spectra(T, nlev, seed=7), H.synthetic_spectra(T, nlev, seed=8)
+    wind = np.full((npts, nlev, 2), np.nan)
+    trans.invtrans_vordiv2wind_field(vor.reshape(nspec2, nlev), div.reshape(nspec2, nlev), wind)
+    want_w = plan.invtrans(0, None, nlev, vor, div, mode=2)
+    assert H.compute_rms(field_to_rows(wind, npts, nlev, 2), want_w) < 1e-12
+    grad = np.full((npts, nlev, 2), np.nan)
+    trans.invtrans_grad_field(sp.reshape(nspec2, nlev), grad)
+    assert H.compute_rms(field_to_rows(grad, npts, nlev, 2), plan.invtrans_grad(nlev, sp)) < 1e-12
+
+
 def test_field_layout_device_pointers_and_errors():
     import torch
 

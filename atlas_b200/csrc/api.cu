@@ -185,11 +185,10 @@ int run_inverse(Plan& p, int nf, int trunc, const double* d_spec, double* d_gp, 
         if ((rc = tc_prepare_tables(p))) return rc;
         if ((rc = tc_build_tiles(p, nf, trunc, p.g.T))) return rc;
         tm.mark(marks);
-        slots[marks++] = 0;
-        tm.mark(marks);
-        rc = launch_legendre_inv_tc(p, nf, trunc, d_spec, p.d_fourier);
+        rc = launch_legendre_inv_tc(p, nf, trunc, d_spec, p.d_fourier, p.ev[marks + 1]);  // records the next mark after packing
         if (rc) return rc;
-        slots[marks++] = 1;
+        slots[marks++] = 0;   // operand images (split-tf32 spectra)
+        slots[marks++] = 1;   // tcgen05 GEMM
     }
     else {
         tm.mark(marks);
@@ -883,7 +882,8 @@ static int dirtrans_scalar_impl(sptrans_plan* plan, int nf, const double* gp, do
     if (p.precision == SPTRANS_PREC_TC_SPLIT) {
         if ((rc = tc_prepare_tables(p))) return rc;
         if ((rc = tc_build_tiles(p, nf, T, T))) return rc;
-        if ((rc = launch_legendre_dir_tc(p, nf, p.d_fourier, p.d_packed))) return rc;
+        if ((rc = launch_legendre_dir_tc(p, nf, p.d_fourier, p.d_packed, p.ev[marks + 1]))) return rc;
+        slots[marks++] = 0;   // operand images (split-tf32 Fourier rows), then the tcgen05 GEMM
     }
     else if ((rc = launch_legendre_dir(p, nf, p.d_fourier, p.d_packed))) return rc;
     slots[marks++] = 1;

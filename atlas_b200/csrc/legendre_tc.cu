@@ -593,7 +593,7 @@ static int launch_tc_gemm(Plan& p, int nf, const TcTile* tiles, int ntiles, cons
     return SPTRANS_OK;
 }
 
-int launch_legendre_inv_tc(Plan& p, int nf, int trunc, const double* d_spec, double* d_fourier) {
+int launch_legendre_inv_tc(Plan& p, int nf, int trunc, const double* d_spec, double* d_fourier, cudaEvent_t after_pack) {
     TcState* s = tc_state(p);
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
@@ -602,10 +602,11 @@ int launch_legendre_inv_tc(Plan& p, int nf, int trunc, const double* d_spec, dou
                                                        d_spec, s->b_hi, s->b_lo);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
+    if (after_pack) cudaEventRecord(after_pack, p.stream);   // stage timing: operand images | tensor-core GEMM
     return launch_tc_gemm(p, nf, s->d_tiles_inv, s->n_tiles_inv, s->a_inv_hi, s->a_inv_lo, d_fourier);
 }
 
-int launch_legendre_dir_tc(Plan& p, int nf, const double* d_fourier, double* d_packed) {
+int launch_legendre_dir_tc(Plan& p, int nf, const double* d_fourier, double* d_packed, cudaEvent_t after_pack) {
     TcState* s = tc_state(p);
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
@@ -614,6 +615,7 @@ int launch_legendre_dir_tc(Plan& p, int nf, const double* d_fourier, double* d_p
                                                             s->d_b_dir_off, d_fourier, s->b_hi, s->b_lo);
     p.launches++;
     SPT_CUDA(cudaGetLastError());
+    if (after_pack) cudaEventRecord(after_pack, p.stream);
     return launch_tc_gemm(p, nf, s->d_tiles_dir, s->n_tiles_dir, s->a_dir_hi, s->a_dir_lo, d_packed);
 }
 

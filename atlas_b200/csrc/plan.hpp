@@ -282,8 +282,9 @@ int build_transposed_table(Plan& p);   // lazily, by the first direct transform;
 // ---- legendre_tc.cu (tcgen05 split-TF32 path) ----
 int tc_prepare_tables(Plan& p);
 int tc_build_tiles(Plan& p, int nf, int trunc, int dir_trunc);
-int launch_legendre_inv_tc(Plan& p, int nf, int trunc, const double* d_spec, double* d_fourier);
-int launch_legendre_dir_tc(Plan& p, int nf, const double* d_fourier, double* d_packed);
+// after_pack (optional): recorded between the operand-image kernel and the tensor-core GEMM (stage timings)
+int launch_legendre_inv_tc(Plan& p, int nf, int trunc, const double* d_spec, double* d_fourier, cudaEvent_t after_pack = nullptr);
+int launch_legendre_dir_tc(Plan& p, int nf, const double* d_fourier, double* d_packed, cudaEvent_t after_pack = nullptr);
 void tc_free(Plan& p);
 
 // ---- fourier.cu ----

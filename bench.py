@@ -815,6 +815,8 @@ def main():
             src = "half of the measured bf16 cuBLAS rate in MEASURED_PEAKS.json (tf32 runs at half the bf16 rate)"
         except Exception:
             tf32_peak, src = 1590.0 / 2.0, "half of the fallback bf16 figure"
+        # (stage timings of the tensor-core path: "legendre" is the tcgen05 kernel alone, the kernels that build the split-tf32
+        # operand images are under "pack")
         roofline = {"kernel": "legendre_tc_kernel (tcgen05.mma kind::tf32, 3 split products per MAC, TMEM fp32 accumulators)",
                     "bound": "tensor", "achieved": 3.0 * achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": 3.0 * achieved / tf32_peak, "traffic": None, "peak_source": src,

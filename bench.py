@@ -36,6 +36,13 @@ UNIT = "transforms/s"
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (profiles/microbench_f64_r01.txt); no fp64 entry in MEASURED_PEAKS.json
 
 
+CPU_NOTE = ("restatement of TransLocal (+ the quadrature-adjoint dirtrans), OpenMP over zonal wavenumbers and over (field, latitude); "
+            "no BLAS in the image, so the Legendre GEMM is a hand-written AVX-512 / AVX2 micro-kernel (20-30 GFLOP/s per thread "
+            "measured; an MKL/OpenBLAS eckit backend would be ~2x that).  At TCo1279 L137 the GEMM is ~15 % of the CPU time; the "
+            "rest is what the reference does as well: allocating and zero-filling the 7.2 GB Fourier work array per call "
+            "(TransLocal.cc:1426-1428), the split / merge loops (:970-1079) and 350 720 FFTs per direction (:1155-1196)")
+
+
 def metric_name(workload_name):
     _, _, nf = workload(workload_name)
     return f"{workload_name} L{nf} transforms/sec (inv+dir)"
@@ -232,8 +239,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                          "sample": f"{sample}; {len(times)} timed steps of {args.steps} requested (min {min(times):.2f}s, "
                                    f"max {max(times):.2f}s); plan setup {setup_s:.1f}s untimed",
-                         "note": "restatement of TransLocal with a hand-blocked OpenMP GEMM (no BLAS in the image): the reference with an "
-                                 "MKL/OpenBLAS eckit backend would run the Legendre stage several times faster on the same cores"},
+                         "note": CPU_NOTE},
         "steps_timed": len(times),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -875,8 +881,7 @@ def main():
                   f"{nfs} of {nf} fields, full grid, 1 inv + 1 dir, time scaled x{nf}/{nfs}")
         cpu_baseline = {"value": 1.0 / per_step, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                         "sample": f"{sample} (inv {t_inv:.2f}s, dir {t_dir:.2f}s; plan setup {osetup:.1f}s untimed)",
-                        "note": "restatement of TransLocal with a hand-blocked OpenMP GEMM (no BLAS in the image); an MKL/OpenBLAS "
-                                "eckit backend would run the Legendre stage several times faster on the same cores"}
+                        "note": CPU_NOTE}
         if nfs == nf:   # the same inputs went through both: parity of the timed GPU path against the oracle, all fields
             err = H.rel_max(d_gp.cpu().numpy(), gps)
             cpu_baseline["gpu_vs_oracle_invtrans_rel_max"] = err

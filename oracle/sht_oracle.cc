@@ -36,6 +36,7 @@
 #include <vector>
 
 #ifdef _OPENMP
+#include <immintrin.h>
 #include <omp.h>
 #endif
 #include "oracle_internal.h"
@@ -440,44 +441,108 @@ void gemm_naive(const double* A, const double* B, double* C, size_t M, size_t K,
     }
 }
 
-// register-blocked variant for the CPU baseline (same maths, 4 columns at a time)
-void gemm_blocked(const double* A, const double* B, double* C, size_t M, size_t K, size_t N) {
-    constexpr size_t MB = 32;
-    size_t j = 0;
-    for (; j + 4 <= N; j += 4) {
-        for (size_t i0 = 0; i0 < M; i0 += MB) {
-            const size_t mb = std::min(MB, M - i0);
-            double acc[4][MB];
-            for (int c = 0; c < 4; ++c)
-                for (size_t i = 0; i < MB; ++i) acc[c][i] = 0.;
-            if (mb == MB) {
-                for (size_t k = 0; k < K; ++k) {
-                    const double* a = A + i0 + M * k;
-                    const double b0 = B[k + K * j], b1 = B[k + K * (j + 1)], b2 = B[k + K * (j + 2)],
-                                 b3 = B[k + K * (j + 3)];
-#pragma omp simd
-                    for (size_t i = 0; i < MB; ++i) {
-                        acc[0][i] += a[i] * b0;
-                        acc[1][i] += a[i] * b1;
-                        acc[2][i] += a[i] * b2;
-                        acc[3][i] += a[i] * b3;
+// Register-blocked GEMM of the CPU baseline: C(M x N, column-major, ld M) = A(M x K, column-major, ld M) * B, where
+// b(k, n) = B[k * sbk + n * sbn] (sbk = 1, sbn = K: the column-major B of the inverse transform; sbk = K', sbn = 1: a
+// transposed table block in the direct transform).  Same maths as gemm_naive.  The image has no BLAS (eckit's "lapack" /
+// "mkl" backends are what the reference would use on a production host), so this is a plain micro-kernel: 16 rows x 8
+// columns of accumulators in AVX-512 registers (masked loads / stores for the last rows), 8 x 6 in AVX2, chosen at run
+// time -- the library is built in one container and timed on another machine's host cores.
+
+__attribute__((target("avx512f"))) static void gemm_kernel_avx512(const double* A, const double* B, double* C, size_t M, size_t K,
+                                                                  size_t N, size_t sbk, size_t sbn, bool accumulate) {
+    constexpr size_t NR = 8;
+    for (size_t j = 0; j < N; j += NR) {
+        const size_t nb = std::min(NR, N - j);
+        for (size_t i0 = 0; i0 < M; i0 += 16) {
+            const size_t mb = std::min<size_t>(16, M - i0);
+            const __mmask8 m0 = static_cast<__mmask8>(mb >= 8 ? 0xff : (1u << mb) - 1u);
+            const __mmask8 m1 = static_cast<__mmask8>(mb >= 16 ? 0xff : (mb > 8 ? (1u << (mb - 8)) - 1u : 0u));
+            __m512d acc0[NR], acc1[NR];
+            for (size_t c = 0; c < NR; ++c) acc0[c] = acc1[c] = _mm512_setzero_pd();
+            const double* a = A + i0;
+            if (nb == NR) {
+                for (size_t k = 0; k < K; ++k, a += M) {
+                    const __m512d a0 = _mm512_maskz_loadu_pd(m0, a), a1 = _mm512_maskz_loadu_pd(m1, a + 8);
+                    const double* b = B + k * sbk + j * sbn;
+#pragma GCC unroll 8
+                    for (size_t c = 0; c < NR; ++c) {
+                        const __m512d bv = _mm512_set1_pd(b[c * sbn]);
+                        acc0[c] = _mm512_fmadd_pd(a0, bv, acc0[c]);
+                        acc1[c] = _mm512_fmadd_pd(a1, bv, acc1[c]);
                     }
                 }
             }
             else {
-                for (size_t k = 0; k < K; ++k) {
-                    const double* a = A + i0 + M * k;
-                    for (int c = 0; c < 4; ++c) {
-                        const double b = B[k + K * (j + c)];
-                        for (size_t i = 0; i < mb; ++i) acc[c][i] += a[i] * b;
+                for (size_t k = 0; k < K; ++k, a += M) {
+                    const __m512d a0 = _mm512_maskz_loadu_pd(m0, a), a1 = _mm512_maskz_loadu_pd(m1, a + 8);
+                    const double* b = B + k * sbk + j * sbn;
+                    for (size_t c = 0; c < nb; ++c) {
+                        const __m512d bv = _mm512_set1_pd(b[c * sbn]);
+                        acc0[c] = _mm512_fmadd_pd(a0, bv, acc0[c]);
+                        acc1[c] = _mm512_fmadd_pd(a1, bv, acc1[c]);
                     }
                 }
             }
-            for (int c = 0; c < 4; ++c)
-                for (size_t i = 0; i < mb; ++i) C[i0 + i + M * (j + c)] = acc[c][i];
+            for (size_t c = 0; c < nb; ++c) {
+                double* cp = C + i0 + M * (j + c);
+                if (accumulate) {
+                    acc0[c] = _mm512_add_pd(acc0[c], _mm512_maskz_loadu_pd(m0, cp));
+                    acc1[c] = _mm512_add_pd(acc1[c], _mm512_maskz_loadu_pd(m1, cp + 8));
+                }
+                _mm512_mask_storeu_pd(cp, m0, acc0[c]);
+                _mm512_mask_storeu_pd(cp + 8, m1, acc1[c]);
+            }
         }
     }
-    if (j < N) gemm_naive(A, B + K * j, C + M * j, M, K, N - j);
+}
+
+static void gemm_kernel_avx2(const double* A, const double* B, double* C, size_t M, size_t K, size_t N, size_t sbk, size_t sbn,
+                             bool accumulate) {
+    constexpr size_t NR = 6, MR = 8;
+    for (size_t j = 0; j < N; j += NR) {
+        const size_t nb = std::min(NR, N - j);
+        size_t i0 = 0;
+        for (; i0 + MR <= M; i0 += MR) {
+            __m256d acc0[NR], acc1[NR];
+            for (size_t c = 0; c < NR; ++c) acc0[c] = acc1[c] = _mm256_setzero_pd();
+            const double* a = A + i0;
+            for (size_t k = 0; k < K; ++k, a += M) {
+                const __m256d a0 = _mm256_loadu_pd(a), a1 = _mm256_loadu_pd(a + 4);
+                const double* b = B + k * sbk + j * sbn;
+                for (size_t c = 0; c < nb; ++c) {
+                    const __m256d bv = _mm256_set1_pd(b[c * sbn]);
+                    acc0[c] = _mm256_fmadd_pd(a0, bv, acc0[c]);
+                    acc1[c] = _mm256_fmadd_pd(a1, bv, acc1[c]);
+                }
+            }
+            for (size_t c = 0; c < nb; ++c) {
+                double* cp = C + i0 + M * (j + c);
+                if (accumulate) {
+                    acc0[c] = _mm256_add_pd(acc0[c], _mm256_loadu_pd(cp));
+                    acc1[c] = _mm256_add_pd(acc1[c], _mm256_loadu_pd(cp + 4));
+                }
+                _mm256_storeu_pd(cp, acc0[c]);
+                _mm256_storeu_pd(cp + 4, acc1[c]);
+            }
+        }
+        for (; i0 < M; ++i0)   // last rows
+            for (size_t c = 0; c < nb; ++c) {
+                double sum = accumulate ? C[i0 + M * (j + c)] : 0.;
+                for (size_t k = 0; k < K; ++k) sum += A[i0 + M * k] * B[k * sbk + (j + c) * sbn];
+                C[i0 + M * (j + c)] = sum;
+            }
+    }
+}
+
+static void gemm_fast(const double* A, const double* B, double* C, size_t M, size_t K, size_t N, size_t sbk, size_t sbn,
+                      bool accumulate = false) {
+    static const bool have512 = __builtin_cpu_supports("avx512f");
+    if (have512) gemm_kernel_avx512(A, B, C, M, K, N, sbk, sbn, accumulate);
+    else gemm_kernel_avx2(A, B, C, M, K, N, sbk, sbn, accumulate);
+}
+
+void gemm_blocked(const double* A, const double* B, double* C, size_t M, size_t K, size_t N) {
+    gemm_fast(A, B, C, M, K, N, 1, K);
 }
 
 // CPU-baseline variant of invtrans_legendre: same split / GEMM / merge, but threads own blocks of 8 consecutive
@@ -982,19 +1047,7 @@ void dirtrans_general(const Plan& p, int nb_fields, const double* gp, double* sp
                 const double* G = par ? Ga : Gs;
                 // X[i + R*k] = sum_col G[i + R*col] * P[k + K*col]   (tables hold n descending: k = 0 <-> highest n)
                 std::vector<double> X(static_cast<size_t>(R) * K, 0.);
-                for (size_t k0 = 0; k0 < K; k0 += 4) {
-                    const size_t kb = std::min<size_t>(4, K - k0);
-                    for (int col = 0; col < ncols; ++col) {
-                        const double* g = G + static_cast<size_t>(col) * R;
-                        const double* pc = P + K * static_cast<size_t>(col) + k0;
-                        for (size_t kk = 0; kk < kb; ++kk) {
-                            const double pv = pc[kk];
-                            double* x = X.data() + (k0 + kk) * R;
-#pragma omp simd
-                            for (int i = 0; i < R; ++i) x[i] += g[i] * pv;
-                        }
-                    }
-                }
+                gemm_fast(G, P, X.data(), R, ncols, K, K, 1);   // b(col, k) = P[k + K * col]
                 const int ntop = par == 0 ? ((T + 1 - m) % 2 == 0 ? T + 1 : T) : ((T + 1 - m) % 2 == 1 ? T + 1 : T);
                 for (size_t k = 0; k < K; ++k) {
                     const int n = ntop - 2 * static_cast<int>(k);

@@ -17,7 +17,9 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 CASES = [("O64", 63, (-5.0, 5.0, -2.5, 0.0)), ("L9", 8, (0.0, 10.0, -90.0, -10.0)), ("L9", 8, (0.0, 10.0, 10.0, 90.0)),
-         ("O48", 47, (300.0, 420.0, -35.0, 62.0)), ("F24", 23, (10.0, 200.0, -80.0, 10.0))]
+         ("O48", 47, (300.0, 420.0, -35.0, 62.0)), ("F24", 23, (10.0, 200.0, -80.0, 10.0)),
+         ("L9", 17, (350.0, 380.0, -30.0, 30.0)),    # across the equator row of a grid with an odd number of rows, wrapping in longitude
+         ("O160", 159, (0.0, 359.9, 40.0, 90.0))]    # a polar cap: whole rows, northern hemisphere only
 
 
 def make(gridname, T, box):

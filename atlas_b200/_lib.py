@@ -110,6 +110,8 @@ def _load():
         "sptrans_dirtrans_sharded": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_invtrans_legendre_peers": (C.c_int, [vp, C.c_int, vp]),
         "sptrans_dirtrans_fourier_peers": (C.c_int, [vp, C.c_int, vp]),
+        "sptrans_dirtrans_fourier_local": (C.c_int, [vp, C.c_int, vp]),
+        "sptrans_dirtrans_legendre_pull": (C.c_int, [vp, C.c_int, vp]),
         "sptrans_peer_barrier": (C.c_int, [vp]),
         "sptrans_peer_advance": (C.c_int, [vp]),
         "sptrans_multi_create": (C.c_int, [C.POINTER(vp), C.c_int, c_int_p, c_double_p, c_double_p, C.c_int, C.c_uint, C.c_int, c_int_p]),

@@ -1350,6 +1350,47 @@ int sptrans_dirtrans_fourier_peers(sptrans_plan* plan, int nf, const double* d_g
     return fused ? SPTRANS_OK : launch_exchange_push(p, nf);
 }
 
+// Direct transform, exchange by PULL (SPTRANS_DIR_PULL=1; the default stays the push): the Fourier stage writes its rows into the
+// local exchange buffer only, and after the barrier the Legendre GEMM fetches every operand row from the buffer of the rank
+// that owns its latitude band.  Measured (profiles/emul8_timing_r02.txt, profiles/bench_tco1279_r02_n2_pull_vs_push.txt):
+// the push of completed latitude pairs costs the Fourier stage 0.4-0.6 ms per rank at 8 ranks (an extra read + write of every
+// row), which the pull does not have -- but on real NVLink the GEMM's operand copies then run at the link's latency: at N = 2
+// the Fourier stage gains 0.95 ms and the Legendre stage loses 1.4-1.9 ms.  Kept as an option and as the measurement.
+int sptrans_dirtrans_fourier_local(sptrans_plan* plan, int nf, const double* d_gp) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if ((rc = peer_ready(p, nf, "sptrans_dirtrans_fourier_local"))) return rc;
+    if (!d_gp) {
+        set_error("sptrans_dirtrans_fourier_local: null grid-point array");
+        return SPTRANS_ERR_INVALID;
+    }
+    return launch_fourier_dir(p, nf, d_gp, make_peer_dst(p).base[p.g.rank], 0, 0);
+}
+
+int sptrans_dirtrans_legendre_pull(sptrans_plan* plan, int nf, double* d_spectra) {
+    int rc = check_plan(plan);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    if ((rc = peer_ready(p, nf, "sptrans_dirtrans_legendre_pull"))) return rc;
+    if (!d_spectra) {
+        set_error("sptrans_dirtrans_legendre_pull: null spectra");
+        return SPTRANS_ERR_INVALID;
+    }
+    if ((rc = build_tiles(p, nf, p.g.T, p.g.T))) return rc;
+    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
+    if ((rc = launch_legendre_dir_peers(p, nf, make_peer_dst(p), p.d_packed))) return rc;
+    return launch_unpack_spectra(p, nf, p.d_packed, d_spectra);
+}
+
+static bool dir_exchange_push() {
+    static const bool v = [] {
+        const char* e = std::getenv("SPTRANS_DIR_PULL");
+        return !(e && std::atoi(e) != 0);
+    }();
+    return v;
+}
+
 int sptrans_invtrans_sharded(sptrans_plan* plan, int nf, const double* d_spectra, double* d_gp) {
     if (!plan || !d_gp) {
         set_error("sptrans_invtrans_sharded: invalid arguments");
@@ -1380,18 +1421,22 @@ int sptrans_dirtrans_sharded(sptrans_plan* plan, int nf, const double* d_gp, dou
     Plan& p = plan->p;
     int rc;
     cudaEventRecord(p.ev[0], p.stream);
-    if ((rc = sptrans_dirtrans_fourier_peers(plan, nf, d_gp))) return rc;
+    const bool push = dir_exchange_push();   // default; SPTRANS_DIR_PULL=1: the Legendre GEMM pulls its rows instead
+    if ((rc = push ? sptrans_dirtrans_fourier_peers(plan, nf, d_gp) : sptrans_dirtrans_fourier_local(plan, nf, d_gp))) return rc;
     cudaEventRecord(p.ev[1], p.stream);
     if ((rc = launch_peer_barrier(p))) return rc;
     cudaEventRecord(p.ev[2], p.stream);
-    double* local = make_peer_dst(p).base[p.g.rank];
-    if ((rc = build_tiles(p, nf, p.g.T, p.g.T))) return rc;
-    if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
-    if ((rc = launch_legendre_dir(p, nf, local, p.d_packed))) return rc;
-    if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spectra))) return rc;
+    if (push) {
+        double* local = make_peer_dst(p).base[p.g.rank];
+        if ((rc = build_tiles(p, nf, p.g.T, p.g.T))) return rc;
+        if ((rc = ensure(p.d_packed, p.packed_cap, packed_doubles(p, nf)))) return rc;
+        if ((rc = launch_legendre_dir(p, nf, local, p.d_packed))) return rc;
+        if ((rc = launch_unpack_spectra(p, nf, p.d_packed, d_spectra))) return rc;
+    }
+    else if ((rc = sptrans_dirtrans_legendre_pull(plan, nf, d_spectra))) return rc;
     cudaEventRecord(p.ev[3], p.stream);
     p.pending_marks = 4;
-    const int slots[3] = {2, 5, 1};  // fourier + push, exchange wait, legendre (incl. unpack)
+    const int slots[3] = {2, 5, 1};  // fourier (+ push), exchange wait, legendre (pulling its rows; incl. unpack)
     std::memcpy(p.pending_slots, slots, sizeof(slots));
     p.peer.parity ^= 1;
     return SPTRANS_OK;

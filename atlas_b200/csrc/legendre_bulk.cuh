@@ -111,7 +111,7 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
     constexpr int rpw = kBK / (kLegThreads / 32);
     auto load_stage = [&](const LegTile& tl, int kb, int st) {
         const double* Ag = tab + tl.a_off;
-        const double* Bg = B + tl.b_off;
+        const double* Bg = (kDirect && kPeers) ? nullptr : B + tl.b_off;
         double* as = As + st * kBulkAStage;
         double* bs = Bs + st * kBStage;
         uint64_t* bar = &s_full[st];
@@ -128,8 +128,21 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
         __syncwarp();
         if (lane < rpw)
             bulk_g2s(as + (row0 + lane) * kBulkAPitch, Ag + static_cast<long long>(kb * kBK + row0 + lane) * tl.a_pitch, a_bytes, bar);
-        else if (lane < rpw + b_n)
-            bulk_g2s(bs + (row0 + lane - rpw) * kBPitch, Bg + static_cast<long long>(kb * kBK + row0 + lane - rpw) * ldb, b_bytes, bar);
+        else if (lane < rpw + b_n) {
+            const int r = kb * kBK + row0 + lane - rpw;   // row of B = latitude pair tl.lat0 + r (direct) / n-row (inverse)
+            const double* src;
+            if (kDirect && kPeers) {
+                // fused exchange of the direct transform: the Fourier rows of a latitude pair live in the exchange buffer of
+                // the rank that owns its band (same layout on every rank) and are PULLED from there by this TMA copy -- over
+                // NVLink for the peers' bands -- instead of being pushed by the Fourier stage
+                const int lat = tl.lat0 + r;
+                int d = 0;
+                while (d + 1 < dst.nranks && lat >= dst.band[d + 1]) ++d;
+                src = dst.base[d] + tl.b_off + static_cast<long long>(r) * ldb;
+            }
+            else src = Bg + static_cast<long long>(r) * ldb;
+            bulk_g2s(bs + (row0 + lane - rpw) * kBPitch, src, b_bytes, bar);
+        }
     };
     // first kStages-1 stages of a tile; every stage of the ring is free at this point (tile boundary)
     auto prologue = [&](const LegTile& tl) {
@@ -259,7 +272,7 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
                 const int row = row_w + 8 * i + g;
                 if (row < tl.m_valid) {
                     double* Cg;
-                    if (!kPeers) Cg = C + tl.c_off;
+                    if (!kPeers || kDirect) Cg = C + tl.c_off;
                     else {
                         // fused exchange: the row goes straight into the Fourier-side buffer of the rank whose
                         // latitude band contains it (NVLink store; same layout on every rank)
@@ -281,5 +294,5 @@ legendre_dmma_kernel(const LegTile* __restrict__ tiles, int ntiles, int* __restr
         }
         if (next_ti >= ntiles) break;
     }
-    if (kPeers) __threadfence_system();  // remote rows are visible to the peers before this kernel completes
+    if (kPeers && !kDirect) __threadfence_system();  // remote rows are visible to the peers before this kernel completes
 }

@@ -355,6 +355,7 @@ int build_tiles(Plan& p, int nf, int trunc, int dir_trunc) {
 #endif
                         t.b_off = fb_row0 * ld + n0;
                         t.b_rows = ncol;
+                        t.lat0 = g.nlat0[m];   // latitude pair of B row 0 (selects the source rank when the rows are pulled from peers)
                         t.c_off = (g.sp_rowoff[2 * m + par] + r0) * ld + n0;
                         t.m_valid = std::min(kBM, Kdir - r0);
                         t.n_valid = std::min(kBN, ld - n0);
@@ -452,6 +453,9 @@ int launch_legendre_inv_peers(Plan& p, int nf, const double* d_packed, const Pee
 }
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed) {
     return launch_gemm<true, false>(p, nf, p.d_tiles_dir, p.n_tiles_dir, d_fourier, d_packed, PeerDst{});
+}
+int launch_legendre_dir_peers(Plan& p, int nf, const PeerDst& src, double* d_packed) {
+    return launch_gemm<true, true>(p, nf, p.d_tiles_dir, p.n_tiles_dir, nullptr, d_packed, src);
 }
 
 namespace {

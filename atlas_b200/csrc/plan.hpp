@@ -277,6 +277,8 @@ int launch_legendre_inv(Plan& p, int nf, const double* d_packed, double* d_fouri
 // same, every output row stored into the exchange buffer of the rank that owns its latitude band
 int launch_legendre_inv_peers(Plan& p, int nf, const double* d_packed, const PeerDst& dst);
 int launch_legendre_dir(Plan& p, int nf, const double* d_fourier, double* d_packed);
+// same, every Fourier row pulled from the exchange buffer of the rank that owns its latitude band (TMA copies over NVLink)
+int launch_legendre_dir_peers(Plan& p, int nf, const PeerDst& src, double* d_packed);
 int build_transposed_table(Plan& p);   // lazily, by the first direct transform; rebuilt after a cache import
 
 // ---- legendre_tc.cu (tcgen05 split-TF32 path) ----

@@ -336,7 +336,12 @@ int sptrans_dirtrans_sharded(sptrans_plan* plan, int nb_fields, const double* d_
 /* the halves of the two calls above, for hosts that sequence the stages themselves (tests emulate N ranks on
  * one GPU this way): produce into the peers' buffers / barrier kernel / flip to the other buffer pair */
 int sptrans_invtrans_legendre_peers(sptrans_plan* plan, int nb_fields, const double* d_spectra);
-int sptrans_dirtrans_fourier_peers(sptrans_plan* plan, int nb_fields, const double* d_gp);
+int sptrans_dirtrans_fourier_peers(sptrans_plan* plan, int nb_fields, const double* d_gp);   /* Fourier stage + push (round 1) */
+/* direct transform, exchange by pull (sptrans_dirtrans_sharded with SPTRANS_DIR_PULL=1; measured slower than the push on real
+ * NVLink, see api.cu): Fourier stage into the local exchange buffer; after the barrier the Legendre GEMM fetches every
+ * Fourier row from the buffer of the rank that owns its latitude band */
+int sptrans_dirtrans_fourier_local(sptrans_plan* plan, int nb_fields, const double* d_gp);
+int sptrans_dirtrans_legendre_pull(sptrans_plan* plan, int nb_fields, double* d_spectra);
 int sptrans_peer_barrier(sptrans_plan* plan);
 int sptrans_peer_advance(sptrans_plan* plan);
 

@@ -35,11 +35,18 @@ for it in range(3):
     for t, g in zip(plans, d_gp):
         iff.append(timed(lambda t=t, g=g: _lib.check(lib.sptrans_invtrans_fourier(t._h, nf, T - 1, buf(t), _ptr(g), 0))))
         _lib.check(lib.sptrans_peer_advance(t._h))
-    df = [timed(lambda t=t, g=g: _lib.check(lib.sptrans_dirtrans_fourier_peers(t._h, nf, _ptr(g)))) for t, g in zip(plans, d_gp)]
-    dl = []
-    for t, a in zip(plans, d_sp):
-        dl.append(timed(lambda t=t, a=a: _lib.check(lib.sptrans_dirtrans_legendre(t._h, nf, buf(t), _ptr(a)))))
-        _lib.check(lib.sptrans_peer_advance(t._h))
+    pull = os.environ.get("SPTRANS_DIR_PULL", "0") != "0"
+    if pull:
+        df = [timed(lambda t=t, g=g: _lib.check(lib.sptrans_dirtrans_fourier_local(t._h, nf, _ptr(g)))) for t, g in zip(plans, d_gp)]
+        dl = [timed(lambda t=t, a=a: _lib.check(lib.sptrans_dirtrans_legendre_pull(t._h, nf, _ptr(a)))) for t, a in zip(plans, d_sp)]
+        for t in plans:
+            _lib.check(lib.sptrans_peer_advance(t._h))
+    else:
+        df = [timed(lambda t=t, g=g: _lib.check(lib.sptrans_dirtrans_fourier_peers(t._h, nf, _ptr(g)))) for t, g in zip(plans, d_gp)]
+        dl = []
+        for t, a in zip(plans, d_sp):
+            dl.append(timed(lambda t=t, a=a: _lib.check(lib.sptrans_dirtrans_legendre(t._h, nf, buf(t), _ptr(a)))))
+            _lib.check(lib.sptrans_peer_advance(t._h))
     if it == 2:
         res = {"inv_legendre": il, "inv_fourier": iff, "dir_fourier_push": df, "dir_legendre": dl}
 print(json.dumps({k: [round(x, 3) for x in v] for k, v in res.items()}))

@@ -480,6 +480,16 @@ def test_peer_memory_exchange_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R
             _lib.check(lib.sptrans_dirtrans_legendre(t._h, nf, local_buffer(t), _ptr(d_back)))
             _lib.check(lib.sptrans_peer_advance(t._h))
         assert H.rel_max(d_back.cpu().numpy(), want_sp) < TOL_MAX
+        # the same exchange by PULL (what sptrans_dirtrans_sharded does): Fourier rows stay in the owner's buffer and the
+        # Legendre GEMM's TMA copies fetch them from there
+        d_back = torch.full_like(d_sp, float("nan"))
+        for t in plans:
+            _lib.check(lib.sptrans_dirtrans_fourier_local(t._h, nf, _ptr(d_gp)))
+        for t in plans:
+            _lib.check(lib.sptrans_dirtrans_legendre_pull(t._h, nf, _ptr(d_back)))
+        for t in plans:
+            _lib.check(lib.sptrans_peer_advance(t._h))
+        assert H.rel_max(d_back.cpu().numpy(), want_sp) < TOL_MAX
     if R == 1:  # the whole stream-ordered call, barrier kernel included (trivial with one rank)
         d_gp = torch.full((nf * grid.size(),), float("nan"), **kw)
         d_back = torch.full_like(d_sp, float("nan"))
@@ -572,9 +582,10 @@ def test_shard_local_io_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
         return
     d_back = [torch.full_like(a, float("nan")) for a in d_sp]
     for t, g in zip(plans, d_gp):
-        _lib.check(lib.sptrans_dirtrans_fourier_peers(t._h, nf, _ptr(g)))
+        _lib.check(lib.sptrans_dirtrans_fourier_local(t._h, nf, _ptr(g)))
     for t, b in zip(plans, d_back):
-        _lib.check(lib.sptrans_dirtrans_legendre(t._h, nf, local_buffer(t), _ptr(b)))
+        _lib.check(lib.sptrans_dirtrans_legendre_pull(t._h, nf, _ptr(b)))
+    for t in plans:
         _lib.check(lib.sptrans_peer_advance(t._h))
     back = np.full_like(sp, np.nan)
     for r in range(R):

@@ -24,6 +24,8 @@ struct double2 {
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #endif
 
+#include "fft_consts.h"
+
 namespace sptrans {
 namespace fftc {
 
@@ -343,8 +345,48 @@ SPT_HD void dft16(double2* v) {
         v[c + 12] = t[3];
     }
 }
+// Odd-prime radix P (7, 11, 13) for the direct mixed-radix transforms of rows whose length has these factors:
+// y_0 = sum x_j;  y_k, y_{P-k} = x_0 + sum_j c_{jk} (x_j + x_{P-j})  -+  i sgn sum_j s_{jk} (x_j - x_{P-j}),  j, k = 1..(P-1)/2
+// with c, s = cos, sin(2 pi j k / P): (P-1)^2 / 2 real multiply-adds per component instead of (P-1)^2 complex ones.
+template <int P, bool FWD>
+SPT_HD void dft_prime(double2* v) {
+    constexpr int H = (P - 1) / 2;
+    double2 a[H], b[H];
+#pragma unroll
+    for (int j = 1; j <= H; ++j) {
+        a[j - 1] = cadd(v[j], v[P - j]);
+        b[j - 1] = csub(v[j], v[P - j]);
+    }
+    double2 y0 = v[0];
+#pragma unroll
+    for (int j = 0; j < H; ++j) y0 = cadd(y0, a[j]);
+    double2 out[P];
+    out[0] = y0;
+#pragma unroll
+    for (int k = 1; k <= H; ++k) {
+        double2 re = v[0], im = make_double2(0., 0.);
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            const double c = WConst<P>::c((j * k) % P), s = WConst<P>::s((j * k) % P);
+            re.x += c * a[j - 1].x;
+            re.y += c * a[j - 1].y;
+            im.x += s * b[j - 1].x;
+            im.y += s * b[j - 1].y;
+        }
+        // e^{-+ i theta}(x_j) + e^{+- i theta}(x_{P-j}) = cos (x_j + x_{P-j}) -+ i sin (x_j - x_{P-j}); -i (FWD) / +i (INV) times im
+        const double2 r = rot90<FWD>(im);
+        out[k] = cadd(re, r);
+        out[P - k] = csub(re, r);
+    }
+#pragma unroll
+    for (int k = 0; k < P; ++k) v[k] = out[k];
+}
 template <int R, bool FWD>
 SPT_HD void dftN(double2* v) {
+    if (R == 7 || R == 11 || R == 13) {
+        dft_prime<(R == 7 || R == 11 || R == 13) ? R : 7, FWD>(v);
+        return;
+    }
     if (R == 2) dft2<FWD>(v);
     else if (R == 3) dft3<FWD>(v);
     else if (R == 4) dft4<FWD>(v);
@@ -422,9 +464,13 @@ SPT_HD ScheduleG make_schedule_g(int M) {
     ScheduleG s;
     s.npass = 0;
     int a = 0, b = 0, c = 0, r = M;
+    int p7 = 0, p11 = 0, p13 = 0;   // (only the direct transforms of 13-smooth row lengths have these; convolution lengths do not)
     while (r % 2 == 0) { r /= 2; ++a; }
     while (r % 3 == 0) { r /= 3; ++b; }
     while (r % 5 == 0) { r /= 5; ++c; }
+    while (r % 7 == 0) { r /= 7; ++p7; }
+    while (r % 11 == 0) { r /= 11; ++p11; }
+    while (r % 13 == 0) { r /= 13; ++p13; }
     int Nb = M;
     auto push = [&](int R) {
         s.radix[s.npass] = R;
@@ -435,6 +481,9 @@ SPT_HD ScheduleG make_schedule_g(int M) {
         ++s.npass;
         Nb /= R;
     };
+    while (p13 >= 1) { push(13); --p13; }
+    while (p11 >= 1) { push(11); --p11; }
+    while (p7 >= 1) { push(7); --p7; }
     while (b >= 2) { push(9); b -= 2; }
     if (b == 1) push(3);
     while (c >= 1) { push(5); --c; }
@@ -445,57 +494,91 @@ SPT_HD ScheduleG make_schedule_g(int M) {
     return s;
 }
 
+// Where the forward (DIF) transform leaves frequency k: pass p splits k = k_p + R_p k' and sends residue k_p to the k_p-th
+// sub-block of its block, so position = sum_p k_p * (M / (R_0 ... R_p)) -- the mixed-radix digit reversal.  The inverse (DIT)
+// transform expects its input in this order.  Used by the direct (non chirp-z) transforms of smooth row lengths.
+SPT_HD int dif_output_position(const ScheduleG& s, int M, int k) {
+    int pos = 0, span = M;
+    for (int p = 0; p < s.npass; ++p) {
+        const int R = s.radix[p];
+        span /= R;
+        pos += (k % R) * span;
+        k /= R;
+    }
+    return pos;
+}
+// smallest prime factor structure the engine can transform directly: n = 2^a 3^b 5^c 7^d 11^e 13^f
+SPT_HD bool is_13_smooth(int n) {
+    if (n < 1) return false;
+    const int primes[6] = {2, 3, 5, 7, 11, 13};
+    for (int i = 0; i < 6; ++i)
+        while (n % primes[i] == 0) n /= primes[i];
+    return n == 1;
+}
+// slots of one sequence in shared memory: the XOR swizzle permutes within groups of eight
+SPT_HD int swz_len(int M) { return (M + 7) & ~7; }
+
 template <int R>
 SPT_HD void dif_pass_g(double2* X, int nseq, int M, int Nb, int S, unsigned span_magic, unsigned per_magic,
-                       const double2* Wa, const double2* Wb, int tid, int nthr) {
+                       const double2* Wa, const double2* Wb, int tid, int nthr, int ss) {
     const int per = M / R, span = Nb / R;
     for (int w = tid; w < nseq * per; w += nthr) {
         const int sq = nseq == 1 ? 0 : fastdiv(w, per_magic, per), q = w - sq * per;
-        dif_butterfly_g<R>(X + sq * M, q, Nb, span, span_magic, S, Wa, Wb);
+        dif_butterfly_g<R>(X + sq * ss, q, Nb, span, span_magic, S, Wa, Wb);
     }
 }
 template <int R, bool CONJ_FILT>
 SPT_HD void dit_pass_g(double2* X, int nseq, int M, int Nb, int S, unsigned span_magic, unsigned per_magic,
-                       const double2* Wa, const double2* Wb, const double2* filt, int tid, int nthr) {
+                       const double2* Wa, const double2* Wb, const double2* filt, int tid, int nthr, int ss) {
     const int per = M / R, span = Nb / R;
     for (int w = tid; w < nseq * per; w += nthr) {
         const int sq = nseq == 1 ? 0 : fastdiv(w, per_magic, per), q = w - sq * per;
-        dit_butterfly_g<R, CONJ_FILT>(X + sq * M, q, Nb, span, span_magic, S, Wa, Wb, filt);
+        dit_butterfly_g<R, CONJ_FILT>(X + sq * ss, q, Nb, span, span_magic, S, Wa, Wb, filt);
     }
 }
 
+// seq_stride: distance of consecutive sequences in X (0: M; the direct transforms of lengths that are not multiples of 8
+// keep swz_len(M) slots per sequence)
 SPT_HD void fft_dif_g(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb, int tid,
-                      int nthr) {
+                      int nthr, int seq_stride = 0) {
+    const int ss = seq_stride ? seq_stride : M;
     for (int p = 0; p < s.npass; ++p) {
         const int Nb = s.nb[p], S = s.stride[p];
         const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
         switch (s.radix[p]) {
-            case 16: dif_pass_g<16>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 9: dif_pass_g<9>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 8: dif_pass_g<8>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 5: dif_pass_g<5>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 4: dif_pass_g<4>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 3: dif_pass_g<3>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            default: dif_pass_g<2>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 16: dif_pass_g<16>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 13: dif_pass_g<13>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 11: dif_pass_g<11>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 7: dif_pass_g<7>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 9: dif_pass_g<9>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 8: dif_pass_g<8>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 5: dif_pass_g<5>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 4: dif_pass_g<4>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 3: dif_pass_g<3>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            default: dif_pass_g<2>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
         }
         SPT_SYNC();
     }
 }
 template <bool CONJ_FILT>
 SPT_HD void fft_dit_g(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb,
-                      const double2* filt, int tid, int nthr) {
+                      const double2* filt, int tid, int nthr, int seq_stride = 0) {
+    const int ss = seq_stride ? seq_stride : M;
     for (int p = s.npass - 1; p >= 0; --p) {
         const int Nb = s.nb[p], S = s.stride[p];
         const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
         const double2* f = (p == s.npass - 1) ? filt : nullptr;
         switch (s.radix[p]) {
-            case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 9: dit_pass_g<9, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 8: dit_pass_g<8, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 5: dit_pass_g<5, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 4: dit_pass_g<4, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 3: dit_pass_g<3, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            default: dit_pass_g<2, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 13: dit_pass_g<13, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 11: dit_pass_g<11, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 7: dit_pass_g<7, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 9: dit_pass_g<9, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 8: dit_pass_g<8, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 5: dit_pass_g<5, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 4: dit_pass_g<4, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 3: dit_pass_g<3, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            default: dit_pass_g<2, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
         }
         SPT_SYNC();
     }
@@ -558,6 +641,9 @@ SPT_HD void fft_dif_g_gen(double2* X, int nseq, int M, const ScheduleG& s, const
     const unsigned pm0 = s.per_magic[0];
     switch (s.radix[0]) {
         case 16: dif_first_pass_g<16>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        case 13: dif_first_pass_g<13>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        case 11: dif_first_pass_g<11>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
+        case 7: dif_first_pass_g<7>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
         case 9: dif_first_pass_g<9>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
         case 8: dif_first_pass_g<8>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
         case 5: dif_first_pass_g<5>(X, nseq, M, pm0, Wa, Wb, tid, nthr, gen); break;
@@ -570,17 +656,21 @@ SPT_HD void fft_dif_g_gen(double2* X, int nseq, int M, const ScheduleG& s, const
 // remaining forward passes (p >= 1)
 SPT_HD void fft_dif_g_rest(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb, int tid,
                            int nthr) {
+    const int ss = M;
     for (int p = 1; p < s.npass; ++p) {
         const int Nb = s.nb[p], S = s.stride[p];
         const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
         switch (s.radix[p]) {
-            case 16: dif_pass_g<16>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 9: dif_pass_g<9>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 8: dif_pass_g<8>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 5: dif_pass_g<5>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 4: dif_pass_g<4>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            case 3: dif_pass_g<3>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
-            default: dif_pass_g<2>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr); break;
+            case 16: dif_pass_g<16>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 13: dif_pass_g<13>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 11: dif_pass_g<11>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 7: dif_pass_g<7>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 9: dif_pass_g<9>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 8: dif_pass_g<8>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 5: dif_pass_g<5>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 4: dif_pass_g<4>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 3: dif_pass_g<3>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            default: dif_pass_g<2>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
         }
         SPT_SYNC();
     }
@@ -589,18 +679,22 @@ SPT_HD void fft_dif_g_rest(double2* X, int nseq, int M, const ScheduleG& s, cons
 template <bool CONJ_FILT, class Sink>
 SPT_HD void fft_dit_g_sink(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb,
                            const double2* filt, int tid, int nthr, Sink sink) {
+    const int ss = M;
     for (int p = s.npass - 1; p >= 1; --p) {
         const int Nb = s.nb[p], S = s.stride[p];
         const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
         const double2* f = (p == s.npass - 1) ? filt : nullptr;
         switch (s.radix[p]) {
-            case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 9: dit_pass_g<9, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 8: dit_pass_g<8, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 5: dit_pass_g<5, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 4: dit_pass_g<4, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            case 3: dit_pass_g<3, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
-            default: dit_pass_g<2, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr); break;
+            case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 13: dit_pass_g<13, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 11: dit_pass_g<11, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 7: dit_pass_g<7, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 9: dit_pass_g<9, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 8: dit_pass_g<8, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 5: dit_pass_g<5, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 4: dit_pass_g<4, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 3: dit_pass_g<3, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            default: dit_pass_g<2, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
         }
         SPT_SYNC();
     }
@@ -608,6 +702,9 @@ SPT_HD void fft_dit_g_sink(double2* X, int nseq, int M, const ScheduleG& s, cons
     const unsigned pm0 = s.per_magic[0];
     switch (s.radix[0]) {
         case 16: dit_last_pass_g<16, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        case 13: dit_last_pass_g<13, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        case 11: dit_last_pass_g<11, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
+        case 7: dit_last_pass_g<7, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
         case 9: dit_last_pass_g<9, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
         case 8: dit_last_pass_g<8, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;
         case 5: dit_last_pass_g<5, CONJ_FILT>(X, nseq, M, pm0, Wa, Wb, f0, tid, nthr, sink); break;

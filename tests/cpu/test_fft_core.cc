@@ -191,8 +191,52 @@ static int check_g(int n, int L) {
     return (err_inv / nrm < 1e-12 && err_fwd / nrm2 < 1e-12) ? 0 : 1;
 }
 
+// ---- direct transforms of 13-smooth lengths (no chirp-z): forward leaves frequency k at dif_output_position(k), the
+// inverse takes its input in that order.  n need not be a multiple of 8: the buffer has swz_len(n) slots. ----
+static int check_direct(int n) {
+    const ScheduleG sc = make_schedule_g(n);
+    int prod = 1;
+    for (int p = 0; p < sc.npass; ++p) prod *= sc.radix[p];
+    if (prod != n || !is_13_smooth(n)) {
+        printf("direct n=%d: schedule does not cover the length\n", n);
+        return 1;
+    }
+    const int PL = swz_len(n);
+    std::vector<double2> Wa(n / 64 + 1), Wb(64);
+    for (int k = 0; k <= n / 64; ++k) Wa[k] = make_double2(std::cos(-2 * M_PI * (64.0 * k) / n), std::sin(-2 * M_PI * (64.0 * k) / n));
+    for (int k = 0; k < 64; ++k) Wb[k] = make_double2(std::cos(-2 * M_PI * k / n), std::sin(-2 * M_PI * k / n));
+    std::vector<double2> z(n);
+    for (auto& v : z) v = make_double2(urand(), urand());
+    // two sequences back to back, like the kernels hold them
+    std::vector<double2> X(2 * PL, make_double2(0, 0));
+    for (int i = 0; i < n; ++i) X[swz(i)] = X[PL + swz(i)] = z[i];
+    fft_dif_g(X.data(), 2, n, sc, Wa.data(), Wb.data(), 0, 1, PL);   // two sequences, swz_len(n) slots apart
+    double err_f = 0, nrm = 0;
+    for (int k = 0; k < n; k += (n > 1500 ? 11 : 1)) {
+        double re = 0, im = 0;
+        for (int i = 0; i < n; ++i) {
+            const double ang = -2 * M_PI * (double)(((long long)k * i) % n) / n;
+            re += z[i].x * std::cos(ang) - z[i].y * std::sin(ang);
+            im += z[i].x * std::sin(ang) + z[i].y * std::cos(ang);
+        }
+        const double2 got = X[PL + swz(dif_output_position(sc, n, k))];
+        err_f = std::fmax(err_f, std::hypot(got.x - re, got.y - im));
+        nrm = std::fmax(nrm, std::hypot(re, im));
+    }
+    // inverse of the forward = n * identity
+    fft_dit_g<false>(X.data(), 1, n, sc, Wa.data(), Wb.data(), nullptr, 0, 1);
+    double err_i = 0;
+    for (int i = 0; i < n; ++i) err_i = std::fmax(err_i, std::hypot(X[swz(i)].x / n - z[i].x, X[swz(i)].y / n - z[i].y));
+    printf("direct n=%5d passes=%d [", n, sc.npass);
+    for (int p = 0; p < sc.npass; ++p) printf("%d ", sc.radix[p]);
+    printf("]  fwd %.3e  inv %.3e\n", err_f / nrm, err_i);
+    return (err_f / nrm < 1e-12 && err_i < 1e-12) ? 0 : 1;
+}
+
 int main() {
     int bad = 0;
+    const int direct[] = {20, 24, 28, 36, 44, 52, 56, 84, 132, 144, 364, 572, 1092, 1456, 2184, 4004, 5096, 5120, 4732, 3432};
+    for (int n : direct) bad += check_direct(n);
     const int cases[][2] = {{20, 9}, {24, 7}, {28, 0}, {144, 31}, {36, 17}, {1616, 399}, {5136, 1279}, {5132, 1279},
                             {2568, 1279}, {128, 31}, {9, 4}, {7, 3}, {4, 1}};
     for (auto& c : cases) bad += check(c[0], c[1]);

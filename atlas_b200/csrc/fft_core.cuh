@@ -451,6 +451,97 @@ SPT_HD void dit_butterfly_g(double2* X, int q, int Nb, int span, unsigned span_m
     for (int j = 0; j < R; ++j) X[swz(base + j * span)] = v[j];
 }
 
+// Large odd-prime radices (17, 19, 23) of the direct transforms.  Holding P inputs and P outputs would not fit the register
+// budget, so the outputs are produced pair by pair (k, P-k) from the (P-1)/2 sums and differences x_j +- x_{P-j} and stored
+// at once; the twiddles w^k are a running product, w^{P-k} = w^P conj(w^k) with w^P looked up as well.
+template <int P>
+SPT_HD void dif_butterfly_prime(double2* X, int q, int Nb, int span, unsigned span_magic, int S, const double2* Wa,
+                                const double2* Wb) {
+    constexpr int H = (P - 1) / 2;
+    const int blk = fastdiv(q, span_magic, span), t = q - blk * span;
+    const int base = blk * Nb + t;
+    const double2 x0 = X[swz(base)];
+    double2 a[H], b[H];
+    double2 y0 = x0;
+#pragma unroll
+    for (int j = 1; j <= H; ++j) {
+        const double2 u = X[swz(base + j * span)], w = X[swz(base + (P - j) * span)];
+        a[j - 1] = cadd(u, w);
+        b[j - 1] = csub(u, w);
+        y0 = cadd(y0, a[j - 1]);
+    }
+    X[swz(base)] = y0;
+    double2 w1 = make_double2(1., 0.), wP = make_double2(1., 0.), wk = make_double2(1., 0.);
+    if (t != 0) {
+        w1 = twiddle2(Wa, Wb, t * S);
+        wP = twiddle2(Wa, Wb, t * S * P);
+    }
+#pragma unroll
+    for (int k = 1; k <= H; ++k) {
+        double2 re = x0, im = make_double2(0., 0.);
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            const double c = WConst<P>::c((j * k) % P), s = WConst<P>::s((j * k) % P);
+            re.x += c * a[j - 1].x;
+            re.y += c * a[j - 1].y;
+            im.x += s * b[j - 1].x;
+            im.y += s * b[j - 1].y;
+        }
+        const double2 r = rot90<true>(im);
+        double2 yk = cadd(re, r), yq = csub(re, r);
+        if (t != 0) {
+            wk = cmul(wk, w1);
+            yk = cmul(yk, wk);
+            yq = cmul(yq, cmulc(wP, wk));
+        }
+        X[swz(base + k * span)] = yk;
+        X[swz(base + (P - k) * span)] = yq;
+    }
+}
+template <int P>
+SPT_HD void dit_butterfly_prime(double2* X, int q, int Nb, int span, unsigned span_magic, int S, const double2* Wa,
+                                const double2* Wb) {
+    constexpr int H = (P - 1) / 2;
+    const int blk = fastdiv(q, span_magic, span), t = q - blk * span;
+    const int base = blk * Nb + t;
+    const double2 x0 = X[swz(base)];
+    double2 w1 = make_double2(1., 0.), wP = make_double2(1., 0.), wj = make_double2(1., 0.);
+    if (t != 0) {
+        w1 = twiddle2(Wa, Wb, t * S);
+        wP = twiddle2(Wa, Wb, t * S * P);
+    }
+    double2 a[H], b[H];
+    double2 y0 = x0;
+#pragma unroll
+    for (int j = 1; j <= H; ++j) {
+        double2 u = X[swz(base + j * span)], w = X[swz(base + (P - j) * span)];
+        if (t != 0) {
+            wj = cmul(wj, w1);
+            u = cmulc(u, wj);
+            w = cmulc(w, cmulc(wP, wj));
+        }
+        a[j - 1] = cadd(u, w);
+        b[j - 1] = csub(u, w);
+        y0 = cadd(y0, a[j - 1]);
+    }
+    X[swz(base)] = y0;
+#pragma unroll
+    for (int k = 1; k <= H; ++k) {
+        double2 re = x0, im = make_double2(0., 0.);
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            const double c = WConst<P>::c((j * k) % P), s = WConst<P>::s((j * k) % P);
+            re.x += c * a[j - 1].x;
+            re.y += c * a[j - 1].y;
+            im.x += s * b[j - 1].x;
+            im.y += s * b[j - 1].y;
+        }
+        const double2 r = rot90<false>(im);
+        X[swz(base + k * span)] = cadd(re, r);
+        X[swz(base + (P - k) * span)] = csub(re, r);
+    }
+}
+
 struct ScheduleG {
     int npass;
     int radix[10];
@@ -464,13 +555,16 @@ SPT_HD ScheduleG make_schedule_g(int M) {
     ScheduleG s;
     s.npass = 0;
     int a = 0, b = 0, c = 0, r = M;
-    int p7 = 0, p11 = 0, p13 = 0;   // (only the direct transforms of 13-smooth row lengths have these; convolution lengths do not)
+    int p7 = 0, p11 = 0, p13 = 0, p17 = 0, p19 = 0, p23 = 0;   // (only the direct transforms of smooth row lengths have these; convolution lengths do not)
     while (r % 2 == 0) { r /= 2; ++a; }
     while (r % 3 == 0) { r /= 3; ++b; }
     while (r % 5 == 0) { r /= 5; ++c; }
     while (r % 7 == 0) { r /= 7; ++p7; }
     while (r % 11 == 0) { r /= 11; ++p11; }
     while (r % 13 == 0) { r /= 13; ++p13; }
+    while (r % 17 == 0) { r /= 17; ++p17; }
+    while (r % 19 == 0) { r /= 19; ++p19; }
+    while (r % 23 == 0) { r /= 23; ++p23; }
     int Nb = M;
     auto push = [&](int R) {
         s.radix[s.npass] = R;
@@ -481,6 +575,9 @@ SPT_HD ScheduleG make_schedule_g(int M) {
         ++s.npass;
         Nb /= R;
     };
+    while (p23 >= 1) { push(23); --p23; }
+    while (p19 >= 1) { push(19); --p19; }
+    while (p17 >= 1) { push(17); --p17; }
     while (p13 >= 1) { push(13); --p13; }
     while (p11 >= 1) { push(11); --p11; }
     while (p7 >= 1) { push(7); --p7; }
@@ -507,11 +604,11 @@ SPT_HD int dif_output_position(const ScheduleG& s, int M, int k) {
     }
     return pos;
 }
-// smallest prime factor structure the engine can transform directly: n = 2^a 3^b 5^c 7^d 11^e 13^f
-SPT_HD bool is_13_smooth(int n) {
+// lengths the engine can transform directly: no prime factor above 23
+SPT_HD bool is_direct_length(int n) {
     if (n < 1) return false;
-    const int primes[6] = {2, 3, 5, 7, 11, 13};
-    for (int i = 0; i < 6; ++i)
+    const int primes[9] = {2, 3, 5, 7, 11, 13, 17, 19, 23};
+    for (int i = 0; i < 9; ++i)
         while (n % primes[i] == 0) n /= primes[i];
     return n == 1;
 }
@@ -524,7 +621,8 @@ SPT_HD void dif_pass_g(double2* X, int nseq, int M, int Nb, int S, unsigned span
     const int per = M / R, span = Nb / R;
     for (int w = tid; w < nseq * per; w += nthr) {
         const int sq = nseq == 1 ? 0 : fastdiv(w, per_magic, per), q = w - sq * per;
-        dif_butterfly_g<R>(X + sq * ss, q, Nb, span, span_magic, S, Wa, Wb);
+        if constexpr (R >= 17) dif_butterfly_prime<R>(X + sq * ss, q, Nb, span, span_magic, S, Wa, Wb);
+        else dif_butterfly_g<R>(X + sq * ss, q, Nb, span, span_magic, S, Wa, Wb);
     }
 }
 template <int R, bool CONJ_FILT>
@@ -533,12 +631,14 @@ SPT_HD void dit_pass_g(double2* X, int nseq, int M, int Nb, int S, unsigned span
     const int per = M / R, span = Nb / R;
     for (int w = tid; w < nseq * per; w += nthr) {
         const int sq = nseq == 1 ? 0 : fastdiv(w, per_magic, per), q = w - sq * per;
-        dit_butterfly_g<R, CONJ_FILT>(X + sq * ss, q, Nb, span, span_magic, S, Wa, Wb, filt);
+        if constexpr (R >= 17) dit_butterfly_prime<R>(X + sq * ss, q, Nb, span, span_magic, S, Wa, Wb);  // (never filtered)
+        else dit_butterfly_g<R, CONJ_FILT>(X + sq * ss, q, Nb, span, span_magic, S, Wa, Wb, filt);
     }
 }
 
 // seq_stride: distance of consecutive sequences in X (0: M; the direct transforms of lengths that are not multiples of 8
 // keep swz_len(M) slots per sequence)
+template <bool BIGP = false>   // BIGP: the schedule may hold the radices 17, 19, 23 (direct transforms only)
 SPT_HD void fft_dif_g(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb, int tid,
                       int nthr, int seq_stride = 0) {
     const int ss = seq_stride ? seq_stride : M;
@@ -547,6 +647,9 @@ SPT_HD void fft_dif_g(double2* X, int nseq, int M, const ScheduleG& s, const dou
         const unsigned sm_ = s.span_magic[p], pm_ = s.per_magic[p];
         switch (s.radix[p]) {
             case 16: dif_pass_g<16>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 23: if constexpr (BIGP) dif_pass_g<23>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 19: if constexpr (BIGP) dif_pass_g<19>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
+            case 17: if constexpr (BIGP) dif_pass_g<17>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
             case 13: dif_pass_g<13>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
             case 11: dif_pass_g<11>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
             case 7: dif_pass_g<7>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, tid, nthr, ss); break;
@@ -560,7 +663,7 @@ SPT_HD void fft_dif_g(double2* X, int nseq, int M, const ScheduleG& s, const dou
         SPT_SYNC();
     }
 }
-template <bool CONJ_FILT>
+template <bool CONJ_FILT, bool BIGP = false>
 SPT_HD void fft_dit_g(double2* X, int nseq, int M, const ScheduleG& s, const double2* Wa, const double2* Wb,
                       const double2* filt, int tid, int nthr, int seq_stride = 0) {
     const int ss = seq_stride ? seq_stride : M;
@@ -570,6 +673,9 @@ SPT_HD void fft_dit_g(double2* X, int nseq, int M, const ScheduleG& s, const dou
         const double2* f = (p == s.npass - 1) ? filt : nullptr;
         switch (s.radix[p]) {
             case 16: dit_pass_g<16, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 23: if constexpr (BIGP) dit_pass_g<23, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 19: if constexpr (BIGP) dit_pass_g<19, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
+            case 17: if constexpr (BIGP) dit_pass_g<17, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
             case 13: dit_pass_g<13, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
             case 11: dit_pass_g<11, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;
             case 7: dit_pass_g<7, CONJ_FILT>(X, nseq, M, Nb, S, sm_, pm_, Wa, Wb, f, tid, nthr, ss); break;

@@ -295,6 +295,257 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     }
 }
 
+// ---- direct mode (mode 3): rows whose length is 13-smooth need no chirp-z ----
+// x_i + i y_i = sum_{|m| <= L} Z_m e^{2 pi i m i / n} is ONE unnormalised inverse DFT of length n with Z_m stored at
+// frequency m mod n (2L < n: no overlap), instead of two transforms of length M >= n + 2L and three pointwise products.
+// The transforms are the same shared-memory passes (fft_core.cuh), with radices 7, 11 and 13 next to 2..16; the
+// digit-reversed slot of every frequency comes from a table built with the plan (dif_output_position).
+__global__ void __launch_bounds__(kFftThreads)
+direct_tables_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chirp, double2* __restrict__ twid) {
+    const PairMeta pm = cls[blockIdx.x];
+    const int M = pm.M, tid = threadIdx.x, nthr = blockDim.x;
+    double2* Wa = twid + pm.tw_off;
+    double2* Wb = Wa + (M / 64 + 1);
+    for (int k = tid; k <= M / 64; k += nthr) {
+        double s, c;
+        sincospi(-2.0 * (64.0 * k) / M, &s, &c);
+        Wa[k] = make_double2(c, s);
+    }
+    for (int k = tid; k < 64; k += nthr) {
+        double s, c;
+        sincospi(-2.0 * k / M, &s, &c);
+        Wb[k] = make_double2(c, s);
+    }
+    __shared__ ScheduleG sc;
+    if (tid == 0) sc = make_schedule_g(M);
+    __syncthreads();
+    int* pos = reinterpret_cast<int*>(chirp + pm.chirp_off);
+    for (int k = tid; k < M; k += nthr) pos[k] = swz(dif_output_position(sc, M, k));
+}
+
+// Launch shapes of the direct kernels: (threads, resident blocks per SM the register budget is set for).  The passes are
+// short (one or two butterflies per thread), so what matters is how many blocks in different phases share an SM: the global
+// gathers of one block run under the butterflies of the others.
+struct DirectArgs {
+    const PairMeta* meta;
+    int nf, mlimit, nb_uv;
+    const long long* fb_rowoff;
+    const int* nlat0;
+    int nleg;
+    const ScheduleG* scheds;
+    const double2* twid;
+    const double2* chirp;
+    const double* scale_lat;   // inverse: 1/cos(lat); direct: wind scaling (per latitude pair)
+    const double* weights;
+    double2* fb;
+    double* gp;
+    long long npts;
+    int adjoint;
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+fourier_inv_direct_kernel(const __grid_constant__ DirectArgs a, const int2* __restrict__ blocks) {
+    extern __shared__ double2 X[];
+    const int2 bd = blocks[blockIdx.x];
+    const int pair = bd.x, f0 = bd.y & 0xffff, nfb = bd.y >> 16;
+    const PairMeta pm = a.meta[pair];
+    const int tid = threadIdx.x;
+    constexpr int nthr = NT;
+    const int n = pm.n, L = pm.L, PL = swz_len(n), nf = a.nf;
+    const long long npts = a.npts;
+    double* __restrict__ gp = a.gp;
+    const int Lc = min(L, a.mlimit);
+    if (Lc < 0) {
+        for (int w = tid; w < nfb * n; w += nthr) {
+            const int fi = w / n, i = w - fi * n;
+            gp[(f0 + fi) * npts + pm.rowN + i] = 0.;
+            if (pm.has_s) gp[(f0 + fi) * npts + pm.rowS + i] = 0.;
+        }
+        return;
+    }
+    double2* sW = X + pm.F * PL;
+    __shared__ ScheduleG sc;
+    load_schedule(a.scheds + pm.sched, &sc, tid);
+    for (int e = tid; e < nfb * PL; e += nthr) X[e] = make_double2(0., 0.);
+    load_twiddles(a.twid + pm.tw_off, sW, n, tid, nthr);
+    __syncthreads();
+    const int* __restrict__ pos = reinterpret_cast<const int*>(a.chirp + pm.chirp_off);
+    const double2* __restrict__ fb = a.fb;
+    const int tot = nfb * (Lc + 1);
+    const unsigned nfb_magic = fastdiv_magic(static_cast<unsigned>(nfb));  // (tot < 65536)
+    constexpr int kU = 4;  // independent gathers in flight per thread
+    for (int w0 = tid; w0 < tot; w0 += kU * nthr) {
+        double2 cs[kU], ca[kU];
+        int pp[kU], pq[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int w = w0 + u * nthr;
+            if (w < tot) {
+                const int m = fastdiv(w, nfb_magic, nfb), fi = w - m * nfb;
+                const int n0 = a.nlat0[m];
+                const long long is = (a.fb_rowoff[m] + (pair - n0)) * nf + f0 + fi;
+                cs[u] = fb[is];
+                ca[u] = fb[is + static_cast<long long>(a.nleg - n0) * nf];
+                pp[u] = pos[m];
+                pq[u] = pos[m ? n - m : 0];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int w = w0 + u * nthr;
+            if (w < tot) {
+                const int m = fastdiv(w, nfb_magic, nfb), fi = w - m * nfb;
+                if (m == 0) cs[u].y = ca[u].y = 0.;
+                double2 FN, FS;
+                if (pm.has_s) {
+                    FN = cadd(cs[u], ca[u]);
+                    FS = csub(cs[u], ca[u]);
+                }
+                else {
+                    FN = csub(cs[u], ca[u]);
+                    FS = make_double2(0., 0.);
+                }
+                X[fi * PL + pp[u]] = make_double2(FN.x - FS.y, FN.y + FS.x);
+                if (m > 0) X[fi * PL + pq[u]] = make_double2(FN.x + FS.y, FS.x - FN.y);
+            }
+        }
+    }
+    __syncthreads();
+    fft_dit_g<false, true>(X, nfb, n, sc, sW, sW + (n / 64 + 1), nullptr, tid, nthr, PL);
+    for (int fi = 0; fi < nfb; ++fi) {
+        const int f = f0 + fi;
+        const double sn = (f < a.nb_uv) ? a.scale_lat[pair] : 1.;
+        double* __restrict__ gN = gp + f * npts + pm.rowN;
+        double* __restrict__ gS = gp + f * npts + pm.rowS;
+        for (int i = tid; i < n; i += nthr) {
+            const double2 z = X[fi * PL + swz(i)];
+            gN[i] = z.x * sn;
+            if (pm.has_s) gS[i] = z.y * sn;
+        }
+    }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+fourier_dir_direct_kernel(const __grid_constant__ DirectArgs a, const int2* __restrict__ blocks, const int* __restrict__ owner,
+                          const __grid_constant__ PeerDst dst, int me, int* __restrict__ pair_done) {
+    extern __shared__ double2 X[];
+    const int2 bd = blocks[blockIdx.x];
+    const int pair = bd.x, f0 = bd.y & 0xffff, nfb = bd.y >> 16;
+    const PairMeta pm = a.meta[pair];
+    const int tid = threadIdx.x;
+    constexpr int nthr = NT;
+    const int n = pm.n, L = pm.L, PL = swz_len(n), nf = a.nf;
+    if (L < 0) return;
+    const long long npts = a.npts;
+    double2* sW = X + pm.F * PL;
+    __shared__ ScheduleG sc;
+    // the two rows of every field go straight into the interleaved (north, south) sequence: 8-byte asynchronous copies, all in
+    // flight at once
+    for (int fi = 0; fi < nfb; ++fi) {
+        const double* __restrict__ gN = a.gp + (f0 + fi) * npts + pm.rowN;
+        const double* __restrict__ gS = a.gp + (f0 + fi) * npts + pm.rowS;
+        double* Xf = reinterpret_cast<double*>(X + fi * PL);
+        if (pm.has_s) {
+            for (int i = tid; i < n; i += nthr) {
+                double* d = Xf + 2 * swz(i);
+                cp_async8(d, gN + i);
+                cp_async8(d + 1, gS + i);
+            }
+        }
+        else {
+            for (int i = tid; i < n; i += nthr) X[fi * PL + swz(i)] = make_double2(gN[i], 0.);
+        }
+    }
+    load_schedule(a.scheds + pm.sched, &sc, tid);
+    load_twiddles(a.twid + pm.tw_off, sW, n, tid, nthr);
+    cp_async_wait_all();
+    __syncthreads();
+    if (f0 < a.nb_uv) {  // wind components enter as u, v times the latitude's scaling
+        const double sl = a.scale_lat[pair];
+        const int nuv = min(nfb, a.nb_uv - f0);
+        for (int fi = 0; fi < nuv; ++fi)
+            for (int i = tid; i < n; i += nthr) {
+                double2 v = X[fi * PL + swz(i)];
+                v.x *= sl;
+                v.y *= sl;
+                X[fi * PL + swz(i)] = v;
+            }
+        __syncthreads();
+    }
+    fft_dif_g<true>(X, nfb, n, sc, sW, sW + (n / 64 + 1), tid, nthr, PL);
+    const int* __restrict__ pos = reinterpret_cast<const int*>(a.chirp + pm.chirp_off);
+    double2* __restrict__ fb = a.fb;
+    // (weights and conventions: see fourier_dir_kernel)
+    const double wq = a.adjoint ? 1.0 : a.weights[pair];
+    const double hw = 0.5 * wq * (a.adjoint ? 1.0 : 1.0 / n);
+    const int tot = nfb * (L + 1);
+    const unsigned nfb_magic = fastdiv_magic(static_cast<unsigned>(nfb));
+    constexpr int kU = 4;
+    for (int w0 = tid; w0 < tot; w0 += kU * nthr) {
+        long long is[kU], ia[kU];
+        int pp[kU], pq[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int w = w0 + u * nthr;
+            if (w < tot) {
+                const int m = fastdiv(w, nfb_magic, nfb), fi = w - m * nfb;
+                const int n0 = a.nlat0[m];
+                is[u] = (a.fb_rowoff[m] + (pair - n0)) * nf + f0 + fi;
+                ia[u] = is[u] + static_cast<long long>(a.nleg - n0) * nf;
+                pp[u] = pos[m];
+                pq[u] = pos[m ? n - m : 0];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int w = w0 + u * nthr;
+            if (w < tot) {
+                const int m = fastdiv(w, nfb_magic, nfb), fi = w - m * nfb;
+                const double2 Gp = X[fi * PL + pp[u]], Gm = X[fi * PL + pq[u]];
+                // F_N = (G_m + conj(G_-m))/2 ; F_S = (G_m - conj(G_-m))/(2i), each times weight / n
+                const double2 FN = make_double2(hw * (Gp.x + Gm.x), hw * (Gp.y - Gm.y));
+                const double2 FS = make_double2(hw * (Gp.y + Gm.y), -hw * (Gp.x - Gm.x));
+                double2 sy, as;
+                if (pm.has_s) {
+                    sy = cadd(FN, FS);
+                    as = csub(FN, FS);
+                }
+                else sy = as = FN;
+                fb[is[u]] = sy;
+                fb[ia[u]] = as;
+            }
+        }
+    }
+    if (owner) {  // sharded plan: see fourier_dir_kernel
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int nblk = (nf + pm.F - 1) / pm.F;
+            const int done = atomicAdd(pair_done + pair, 1);
+            s_last = (done == nblk - 1);
+            if (s_last) pair_done[pair] = 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            push_pair_rows(pair, L, nf, fb, a.fb_rowoff, a.nlat0, a.nleg, owner, dst, me);
+            __threadfence_system();
+        }
+    }
+}
+
+// (threads, blocks per SM) shapes compiled for the direct kernels; SPTRANS_FFTD_SHAPE picks one for the groups that fit it
+#define SPT_DIRECT_SHAPES(X) X(512, 1) X(256, 2) X(128, 4)
+
 // ---- row mode (mode 1): rows too long for the packed north/south transform (n + 2L > kMaxM, e.g. O2560) ----
 // A real row x_i, i < n, is transformed through z'_k = x_2k + i x_2k+1 (k < n/2):
 //   z'_k = sum_{m=-L..L} G_m e^{2 pi i m k/(n/2)},   G_m = F_m (1 + i w^m),  F_-m = conj(F_m),  w = e^{2 pi i/n}
@@ -559,6 +810,9 @@ int fields_per_block(int M) {
 size_t block_smem_bytes(int M, int F) {
     return (static_cast<size_t>(F) * M + (M / 64 + 1 + 64)) * sizeof(double2);
 }
+size_t direct_smem_bytes(int n, int F) {
+    return (static_cast<size_t>(F) * fftc::swz_len(n) + (n / 64 + 1 + 64)) * sizeof(double2);
+}
 
 }  // namespace
 
@@ -567,7 +821,7 @@ struct FftGroups {
     std::vector<size_t> smem;              // dynamic shared memory of the group (v2: inverse kernel)
     std::vector<size_t> smem_dir;          // v2: direct kernel (its staging area holds two grid rows)
     std::vector<std::vector<int>> pairs;   // pairs per group, costliest first
-    std::vector<int> mode;                 // 0: packed north/south kernels, 1: row kernels, 2: v2 kernels
+    std::vector<int> mode;                 // 0: packed north/south kernels, 1: row kernels, 2: v2 kernels, 3: direct kernels
     std::vector<int> m1;                   // v2: block-level radix of the group
     int nf = -1;                           // block lists below are built for this number of fields
     int nchunks = 0;                       // ... split into this many field chunks (host-pointer pipelines; 1 otherwise)
@@ -637,6 +891,9 @@ int build_fft_tables(Plan& p) {
     // (the kernels keep exchange-buffer row indices as 32-bit integers)
     const bool use_v2 = env_int("SPTRANS_FFT_V2", 1) != 0 && all_even && g.fb_rowoff.back() < 2147483647LL;
     const int v2_min_need = env_int("SPTRANS_FFT2_MIN", 1281);
+    // direct transforms (no chirp-z) of the rows whose length is 13-smooth; SPTRANS_FFT_DIRECT=0 sends every row through
+    // the chirp-z kernels, and so does the test knob SPTRANS_FFT_MAXM unless SPTRANS_FFT_DIRECT=1 is set with it
+    const bool use_direct = env_int("SPTRANS_FFT_DIRECT", std::getenv("SPTRANS_FFT_MAXM") ? 0 : 1) != 0;
     for (int j = 0; j < nleg; ++j) {
         PairMeta pm{};
         pm.n = g.nx[j];
@@ -652,7 +909,11 @@ int build_fft_tables(Plan& p) {
         int M = 0;
         pm.mode = 0;
         pm.m1 = 0;
-        if (use_v2 && pm.L >= 0 && pm.n + 2 * Luse >= v2_min_need) {
+        if (use_direct && pm.L >= 0 && pm.n <= kMaxM && fftc::is_direct_length(pm.n)) {
+            M = pm.n;
+            pm.mode = 3;
+        }
+        if (M == 0 && use_v2 && pm.L >= 0 && pm.n + 2 * Luse >= v2_min_need) {
             int m1 = 0;
             const int M2 = fft2::conv_length_v2(pm.n + 2 * Luse, &m1);
             if (M2 && v2_smem_inv(M2, Luse) <= kSmemLimit && v2_smem_dir(M2, pm.n, Luse) <= kSmemLimit) {
@@ -671,8 +932,9 @@ int build_fft_tables(Plan& p) {
             return SPTRANS_ERR_NOT_IMPLEMENTED;
         }
         pm.M = M;
-        pm.F = (pm.mode || pm.m1) ? 1 : fields_per_block(M);
-        auto key = std::make_pair(pm.n, Luse);
+        pm.F = (pm.mode == 1 || pm.m1) ? 1 : fields_per_block(M);
+        if (pm.mode == 3) pm.F = std::max(1, std::min(16, env_int("SPTRANS_FFTD_POINTS", 4096) / pm.n));
+        auto key = std::make_pair(pm.n, pm.mode == 3 ? -3 : Luse);  // (the direct tables do not depend on the truncation)
         auto it = cls_index.find(key);
         if (it == cls_index.end()) {
             PairMeta c = pm;
@@ -681,8 +943,11 @@ int build_fft_tables(Plan& p) {
             c.filt_off = filt_total;
             c.tw_off = tw_total;
             c.sched = static_cast<int>(classes.size());
-            chirp_total += 2LL * Luse + 1 + (pm.mode ? pm.n / 2 + Luse + 1 : pm.n);
-            filt_total += M;
+            if (pm.mode == 3) chirp_total += (pm.n + 3) / 4;  // swizzled slot of every frequency, n ints
+            else {
+                chirp_total += 2LL * Luse + 1 + (pm.mode ? pm.n / 2 + Luse + 1 : pm.n);
+                filt_total += M;
+            }
             tw_total += pm.m1 ? fft2::kM2 : M / 64 + 1 + 64;
             cls_index[key] = static_cast<int>(classes.size());
             classes.push_back(c);
@@ -709,15 +974,27 @@ int build_fft_tables(Plan& p) {
         SPT_CUDA(cudaStreamSynchronize(p.stream));
         p.d_fft_order = reinterpret_cast<int*>(d_s);  // owned by the plan (freed with it)
     }
-    std::vector<PairMeta> cls1, cls2;
-    for (const PairMeta& c : classes) (c.m1 ? cls2 : cls1).push_back(c);
-    PairMeta *d_cls1 = nullptr, *d_cls2 = nullptr;
+    std::vector<PairMeta> cls1, cls2, cls3;
+    for (const PairMeta& c : classes) (c.mode == 3 ? cls3 : c.m1 ? cls2 : cls1).push_back(c);
+    PairMeta *d_cls1 = nullptr, *d_cls2 = nullptr, *d_cls3 = nullptr;
     const size_t smem_max = block_smem_bytes(kMaxM, 1);
     SPT_CUDA(cudaFuncSetAttribute(chirp_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_dir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_inv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     SPT_CUDA(cudaFuncSetAttribute(fourier_dir_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+#define SPT_ATTR_D(NT, MB)                                                                                                       \
+    SPT_CUDA(cudaFuncSetAttribute(fourier_inv_direct_kernel<NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max)); \
+    SPT_CUDA(cudaFuncSetAttribute(fourier_dir_direct_kernel<NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    SPT_DIRECT_SHAPES(SPT_ATTR_D)
+#undef SPT_ATTR_D
+    if (!cls3.empty()) {
+        SPT_CUDA(cudaMalloc(&d_cls3, cls3.size() * sizeof(PairMeta)));
+        SPT_CUDA(cudaMemcpyAsync(d_cls3, cls3.data(), cls3.size() * sizeof(PairMeta), cudaMemcpyHostToDevice, p.stream));
+        direct_tables_kernel<<<static_cast<int>(cls3.size()), kFftThreads, 0, p.stream>>>(d_cls3, p.d_chirp, p.d_twiddle);
+        p.launches++;
+        SPT_CUDA(cudaGetLastError());
+    }
     if (!cls1.empty()) {
         SPT_CUDA(cudaMalloc(&d_cls1, cls1.size() * sizeof(PairMeta)));
         SPT_CUDA(cudaMemcpyAsync(d_cls1, cls1.data(), cls1.size() * sizeof(PairMeta), cudaMemcpyHostToDevice, p.stream));
@@ -749,7 +1026,7 @@ int build_fft_tables(Plan& p) {
     // launch groups over this rank's latitude band
     FftGroups grp;
     const size_t buckets[] = {28 * 1024, 37 * 1024, 56 * 1024, 75 * 1024, 113 * 1024, smem_max};
-    std::vector<std::vector<int>> by(6);
+    std::vector<std::vector<int>> by(6), by_direct(6);
     std::map<int, std::vector<int>> by_m1;
     std::vector<int> rowmode;
     for (int j = g.pair_begin; j < g.pair_end; ++j) {
@@ -757,14 +1034,14 @@ int build_fft_tables(Plan& p) {
             by_m1[meta[j].m1].push_back(j);
             continue;
         }
-        if (meta[j].mode) {
+        if (meta[j].mode == 1) {
             rowmode.push_back(j);
             continue;
         }
-        const size_t need = block_smem_bytes(meta[j].M, meta[j].F);
+        const size_t need = meta[j].mode == 3 ? direct_smem_bytes(meta[j].n, meta[j].F) : block_smem_bytes(meta[j].M, meta[j].F);
         int b = 0;
         while (need > buckets[b]) ++b;
-        by[b].push_back(j);
+        (meta[j].mode == 3 ? by_direct : by)[b].push_back(j);
     }
     auto add_group = [&](std::vector<int> v, int mode, int m1) {
         std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
@@ -776,6 +1053,7 @@ int build_fft_tables(Plan& p) {
                 need = std::max(need, v2_smem_inv(meta[j].M, std::max(meta[j].L, 0)));
                 need_dir = std::max(need_dir, v2_smem_dir(meta[j].M, meta[j].n, std::max(meta[j].L, 0)));
             }
+            else if (mode == 3) need = std::max(need, direct_smem_bytes(meta[j].n, meta[j].F));
             else need = std::max(need, block_smem_bytes(meta[j].M, mode == 1 ? 1 : meta[j].F));
         }
         grp.smem.push_back(need);
@@ -787,10 +1065,13 @@ int build_fft_tables(Plan& p) {
     for (auto it = by_m1.rbegin(); it != by_m1.rend(); ++it) add_group(it->second, 2, it->first);
     if (!rowmode.empty()) add_group(rowmode, 1, 0);
     for (int b = 5; b >= 0; --b)
+        if (!by_direct[b].empty()) add_group(by_direct[b], 3, 0);
+    for (int b = 5; b >= 0; --b)
         if (!by[b].empty()) add_group(by[b], 0, 0);
     SPT_CUDA(cudaStreamSynchronize(p.stream));
     cudaFree(d_cls1);
     cudaFree(d_cls2);
+    cudaFree(d_cls3);
     fft_state(p).grp = grp;
     fft_state(p).meta = meta;
     return SPTRANS_OK;
@@ -874,6 +1155,28 @@ int fourier_set_chunks(Plan& p, int nf, int nchunks, std::vector<int>* field_bou
     if (rc) return rc;
     if (field_bounds) *field_bounds = fft_state(p).grp.chunk_field;
     return SPTRANS_OK;
+}
+
+static DirectArgs make_direct_args(Plan& p, int nf) {
+    DirectArgs a{};
+    a.meta = reinterpret_cast<const PairMeta*>(p.d_pair_meta);
+    a.nf = nf;
+    a.fb_rowoff = p.d_fb_rowoff;
+    a.nlat0 = p.d_nlat0;
+    a.nleg = p.g.nleg;
+    a.scheds = reinterpret_cast<const ScheduleG*>(p.d_fft_order);
+    a.twid = p.d_twiddle;
+    a.chirp = p.d_chirp;
+    a.npts = p.g.gp_stride;
+    return a;
+}
+// launch shape of a direct group as threads * 16 + blocks per SM (SPTRANS_FFTD_SHAPE="<threads>x<blocks>" for experiments)
+static int direct_shape(size_t smem) {
+    if (smem > 113 * 1024) return 512 * 16 + 1;  // one block per SM
+    int nt = 256, mb = 2;
+    if (smem <= 56 * 1024) nt = 128, mb = 4;  // measured at TCo1279 L137: 11.06 / 11.32 ms per direction against 11.18 / 11.38
+    if (const char* e = std::getenv("SPTRANS_FFTD_SHAPE")) std::sscanf(e, "%dx%d", &nt, &mb);
+    return nt * 16 + mb;
 }
 
 static Fft2Args make_v2_args(Plan& p, const FftGroups& grp, int nf) {
@@ -996,6 +1299,27 @@ int launch_fourier_inv(Plan& p, int nf, int mlimit, const double* d_fourier, dou
                 continue;
             }
             const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;  // one block per SM: 16 warps
+            if (grp.mode[gi] == 3) {
+                DirectArgs a = make_direct_args(p, nf);
+                a.mlimit = mlimit;
+                a.nb_uv = nb_uv;
+                a.scale_lat = lat_scale;
+                a.fb = const_cast<double2*>(reinterpret_cast<const double2*>(d_fourier));
+                a.gp = d_gp;
+                const int shape = direct_shape(grp.smem[gi]);
+                switch (shape) {
+#define SPT_LAUNCH_D(NT, MB)                                                                    \
+    case NT * 16 + MB:                                                                          \
+        fourier_inv_direct_kernel<NT, MB><<<nblk, NT, grp.smem[gi], st>>>(a, blk);              \
+        break;
+                    SPT_DIRECT_SHAPES(SPT_LAUNCH_D)
+#undef SPT_LAUNCH_D
+                    default: set_error("fourier: unsupported shape of the direct kernels"); return SPTRANS_ERR_INVALID;
+                }
+                p.launches++;
+                SPT_CUDA(cudaGetLastError());
+                continue;
+            }
             if (grp.mode[gi]) {
                 fourier_inv_rows_kernel<<<nblk, threads, grp.smem[gi], st>>>(
                     reinterpret_cast<const PairMeta*>(p.d_pair_meta), blk, nf, mlimit, nb_uv,
@@ -1069,6 +1393,28 @@ static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* 
                 continue;
             }
             const int threads = grp.smem[gi] > 113 * 1024 ? 2 * kFftThreads : kFftThreads;
+            if (grp.mode[gi] == 3) {
+                DirectArgs a = make_direct_args(p, nf);
+                a.nb_uv = nb_uv;
+                a.scale_lat = uv_scale;
+                a.weights = p.d_weights;
+                a.fb = reinterpret_cast<double2*>(d_fourier);
+                a.gp = const_cast<double*>(d_gp);
+                a.adjoint = adjoint;
+                const int shape = direct_shape(grp.smem[gi]);
+                switch (shape) {
+#define SPT_LAUNCH_D(NT, MB)                                                                                            \
+    case NT * 16 + MB:                                                                                                  \
+        fourier_dir_direct_kernel<NT, MB><<<nblk, NT, grp.smem[gi], st>>>(a, blk, d_owner, dst, p.g.rank, p.d_pair_done); \
+        break;
+                    SPT_DIRECT_SHAPES(SPT_LAUNCH_D)
+#undef SPT_LAUNCH_D
+                    default: set_error("fourier: unsupported shape of the direct kernels"); return SPTRANS_ERR_INVALID;
+                }
+                p.launches++;
+                SPT_CUDA(cudaGetLastError());
+                continue;
+            }
             if (grp.mode[gi]) {
                 fourier_dir_rows_kernel<<<nblk, threads, grp.smem[gi], st>>>(
                     reinterpret_cast<const PairMeta*>(p.d_pair_meta), blk, nf, nb_uv, d_gp, p.g.gp_stride, p.d_fb_rowoff, p.d_nlat0,

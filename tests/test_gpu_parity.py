@@ -30,6 +30,14 @@ def torch_cuda():
     return torch
 
 
+@pytest.fixture(params=["direct", "chirpz"])
+def fft_path(request, monkeypatch):
+    """Rows whose length has no prime factor above 23 run on the direct mixed-radix kernels by default; the small test grids consist mostly of
+    such rows, so the tests that take this fixture run a second time with every row on the chirp-z kernels."""
+    monkeypatch.setenv("SPTRANS_FFT_DIRECT", "1" if request.param == "direct" else "0")
+    return request.param
+
+
 def make(gridname, T):
     import atlas_b200
     from oracle import pyoracle as po
@@ -94,7 +102,7 @@ def test_legendre_table_vs_reference_golden():
 
 @pytest.mark.parametrize("gridname,T,nf", [("O32", 31, 4), ("O32", 31, 1), ("F24", 23, 3), ("L9", 17, 2),
                                            ("O48", 47, 137), ("O160", 159, 10), ("O80", 79, 75)])
-def test_invtrans_scalar_matches_oracle(gridname, T, nf):
+def test_invtrans_scalar_matches_oracle(gridname, T, nf, fft_path):
     grid, trans, plan = make(gridname, T)
     sp = H.synthetic_spectra(T, nf)
     gp = np.full(nf * grid.size(), np.nan)
@@ -142,7 +150,7 @@ def test_invtrans_vs_closed_form_harmonics(gridname, T, regular):
 
 
 @pytest.mark.parametrize("gridname,T,nsc,nvd", [("O32", 31, 4, 2), ("F24", 23, 0, 1), ("O48", 47, 3, 5), ("L9", 17, 1, 1)])
-def test_invtrans_vordiv_matches_oracle(gridname, T, nsc, nvd):
+def test_invtrans_vordiv_matches_oracle(gridname, T, nsc, nvd, fft_path):
     """TransLocal::invtrans(nscal, sp, nvordiv, vor, div, gp) (TransLocal.cc:1523-1597): T+1 path, u/cos scaling."""
     grid, trans, plan = make(gridname, T)
     sp = H.synthetic_spectra(T, nsc) if nsc else None
@@ -198,7 +206,7 @@ def test_vordiv_to_uv_matches_oracle():
 
 
 @pytest.mark.parametrize("gridname,T,nf", [("O32", 31, 4), ("F24", 23, 3), ("O48", 47, 137), ("O160", 159, 7)])
-def test_dirtrans_matches_oracle(gridname, T, nf):
+def test_dirtrans_matches_oracle(gridname, T, nf, fft_path):
     grid, trans, plan = make(gridname, T)
     sp = H.synthetic_spectra(T, nf)
     gp = plan.invtrans(nf, sp, mode=2)
@@ -223,7 +231,7 @@ def test_dirtrans_unit_harmonic_gives_unit_coefficient():
 
 
 @pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("O160", 159, 4)])
-def test_dirtrans_wind2vordiv_matches_oracle(gridname, T, nf):
+def test_dirtrans_wind2vordiv_matches_oracle(gridname, T, nf, fft_path):
     """TransImpl::dirtrans(nb_fields, wind, vor, div): parity unpinned in the reference (TransLocal: NotImplemented);
     checked against the oracle's definition and as the inverse of invtrans_vordiv2wind."""
     grid, trans, plan = make(gridname, T)
@@ -243,7 +251,7 @@ def test_dirtrans_wind2vordiv_matches_oracle(gridname, T, nf):
 
 
 @pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 5), ("O80", 79, 3)])
-def test_invtrans_grad_matches_oracle_and_closed_form(gridname, T, nf):
+def test_invtrans_grad_matches_oracle_and_closed_form(gridname, T, nf, fft_path):
     """invtrans_grad (TransIFS semantics, ifs/TransIFS.cc:2075-2142): [E-W | N-S]; the oracle evaluates it through
     the reference's own vd2uv + inverse (grad f = irrotational wind of the velocity potential f)."""
     grid, trans, plan = make(gridname, T)
@@ -427,7 +435,7 @@ def test_sharded_path_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
 
 
 @pytest.mark.parametrize("gridname,T,nf,R", [("O48", 47, 5, 2), ("O80", 79, 4, 3), ("F24", 23, 3, 1), ("O48", 47, 137, 4)])
-def test_peer_memory_exchange_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
+def test_peer_memory_exchange_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R, fft_path):
     """The peer-memory exchange with all R ranks living on one device: every plan's exchange region is handed to the
     others as plain pointers (sptrans_peer_attach_ptrs), the inverse Legendre kernel stores each row into the buffer of
     the rank that owns its latitude band, the direct transform pushes rows to the owner of their zonal wavenumber.
@@ -505,7 +513,7 @@ def test_peer_memory_exchange_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R
 
 
 @pytest.mark.parametrize("gridname,T,nf,R", [("O48", 47, 5, 2), ("O80", 79, 4, 3), ("L9", 17, 2, 2), ("O160", 159, 9, 8)])
-def test_shard_local_io_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R):
+def test_shard_local_io_emulated_on_one_gpu(torch_cuda, gridname, T, nf, R, fft_path):
     """SPTRANS_SHARD_LOCAL_IO: every rank's spectral array holds only its zonal wavenumbers ([m ascending][n][re/im][field])
     and its grid array only the rows of its latitude band ([field][northern rows, then their southern mirrors]) -- what
     bench.py's N > 1 runs and BASELINE config 5 use.  R ranks emulated on one device over the peer-memory exchange;
@@ -724,7 +732,7 @@ def test_config5_tco2559_inverse_sample():
 
 
 @pytest.mark.parametrize("gridname,T,nf", [("F24", 23, 2), ("O48", 47, 3), ("L9", 17, 1)])
-def test_invtrans_adjoint_identity(gridname, T, nf):
+def test_invtrans_adjoint_identity(gridname, T, nf, fft_path):
     """<invtrans x, y>_grid == <x, invtrans_adj y>_spec with the spectral inner product that counts m > 0 twice (the
     reference's adjoint test, test_transgeneral.cc:1591-1722, runs this identity through TransIFS; TransLocal has no
     adjoint)."""
@@ -752,6 +760,7 @@ def test_fourier_v2_kernels_match_v1_kernels(torch_cuda, monkeypatch, gridname, 
 
     torch = torch_cuda
     grid = atlas_b200.Grid(gridname)
+    monkeypatch.setenv("SPTRANS_FFT_DIRECT", "0")  # every row on the chirp-z kernels, in both plans
     monkeypatch.setenv("SPTRANS_FFT_V2", "0")
     t1 = atlas_b200.Trans(grid, T, atlas_b200.option.type("b200"))
     monkeypatch.setenv("SPTRANS_FFT_V2", "1")
@@ -780,6 +789,62 @@ def test_fourier_v2_kernels_match_v1_kernels(torch_cuda, monkeypatch, gridname, 
     scale = fb1.abs().max().item()
     err = (fb1 - fb2).abs().max().item()
     assert scale > 0 and err <= 1e-12 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("gridname,T,nf,nb_uv", [("O1280", 1279, 7, 2), ("O400", 399, 137, 0), ("O48", 47, 21, 3),
+                                                 ("F24", 23, 5, 0), ("odd", 7, 19, 1), ("F28", 27, 33, 0)])
+def test_fourier_direct_kernels_match_chirpz_kernels(torch_cuda, monkeypatch, gridname, T, nf, nb_uv):
+    """The direct mixed-radix kernels (rows whose length has no prime factor above 23, no chirp-z) against the
+    chirp-z kernels on the same random exchange buffer / grid fields, whole grid, both directions and the adjoint
+    weighting.  Both evaluate the same trigonometric sums: <= 1e-12 of the field maximum.  The plan with the direct kernels
+    must actually hold direct rows (launch count differs), else the comparison would be vacuous."""
+    import atlas_b200
+
+    torch = torch_cuda
+    if gridname == "odd":  # a reduced Gaussian grid with odd and 2 (mod 4) row lengths, every prime radix among them
+        from atlas_b200.grid import StructuredGrid, gaussian_latitudes
+        lat, w = gaussian_latitudes(16)
+        half = [17, 18, 19, 21, 23, 26, 33, 34, 35, 38, 39, 46, 49, 55, 57, 69]
+        grid = StructuredGrid("odd", np.array(half + half[::-1], dtype=np.int32), lat, w, regular=False)
+    else:
+        grid = atlas_b200.Grid(gridname)
+    nsmooth = sum(1 for n in grid.nx() if all_small_factors(int(n)))
+    assert nsmooth > 0
+    monkeypatch.setenv("SPTRANS_FFT_DIRECT", "0")
+    t1 = atlas_b200.Trans(grid, T, atlas_b200.option.type("b200"))
+    monkeypatch.setenv("SPTRANS_FFT_DIRECT", "1")
+    t2 = atlas_b200.Trans(grid, T, atlas_b200.option.type("b200"))
+    kw = dict(dtype=torch.float64, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    nfb = t1.fourier_elems_per_field() * 2 * nf
+    fb = torch.rand(nfb, generator=g, **kw) - 0.5
+    for mlimit in (T - 1, T // 3):
+        gp1 = torch.full((nf * grid.size(),), 7.0, **kw)
+        gp2 = torch.full((nf * grid.size(),), -7.0, **kw)
+        torch.cuda.synchronize()
+        t1.invtrans_fourier(nf, mlimit, fb, gp1, nb_uv)
+        t2.invtrans_fourier(nf, mlimit, fb, gp2, nb_uv)
+        torch.cuda.synchronize()
+        scale = gp1.abs().max().item()
+        err = (gp1 - gp2).abs().max().item()
+        assert scale > 1.0 and err <= 1e-12 * scale, (mlimit, err, scale)
+    gp = torch.rand(nf * grid.size(), generator=g, **kw) - 0.5
+    fb1 = torch.zeros(nfb, **kw)
+    fb2 = torch.zeros(nfb, **kw)
+    torch.cuda.synchronize()
+    t1.dirtrans_fourier(nf, gp, fb1, nb_uv)
+    t2.dirtrans_fourier(nf, gp, fb2, nb_uv)
+    torch.cuda.synchronize()
+    scale = fb1.abs().max().item()
+    err = (fb1 - fb2).abs().max().item()
+    assert scale > 0 and err <= 1e-12 * scale, (err, scale)
+
+
+def all_small_factors(n):
+    for q in (2, 3, 5, 7, 11, 13, 17, 19, 23):
+        while n % q == 0:
+            n //= q
+    return n == 1
 
 
 @pytest.mark.parametrize("gridname,T,nf", [("O48", 47, 5), ("O160", 159, 23), ("O400", 399, 137)])

@@ -89,6 +89,7 @@ def _load():
         "sptrans_invtrans_grad_adj_field": (C.c_int, [vp, C.c_int, vp, vp]),
         "sptrans_vordiv_to_uv": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]),
         "sptrans_fourier_elems_per_field": (C.c_size_t, [vp]),
+        "sptrans_fourier_path_stats": (C.c_int, [vp, vp]),
         "sptrans_invtrans_legendre": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
         "sptrans_invtrans_fourier": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int]),
         "sptrans_dirtrans_fourier": (C.c_int, [vp, C.c_int, vp, vp, C.c_int]),

@@ -1062,6 +1062,14 @@ int sptrans_vordiv_to_uv(int truncation, int nf, const double* vor, const double
 }
 
 // ---- stage-level API ---------------------------------------------------------------------------------
+int sptrans_fourier_path_stats(sptrans_plan* plan, long long* out8) {
+    if (!plan || !out8) {
+        set_error("sptrans_fourier_path_stats: null argument");
+        return SPTRANS_ERR_INVALID;
+    }
+    fourier_path_stats(plan->p, out8);
+    return SPTRANS_OK;
+}
 size_t sptrans_fourier_elems_per_field(const sptrans_plan* plan) {
     return plan ? static_cast<size_t>(plan->p.g.fb_rowoff.back()) + kBM : 0;
 }

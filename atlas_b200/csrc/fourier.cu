@@ -1077,6 +1077,20 @@ int build_fft_tables(Plan& p) {
     return SPTRANS_OK;
 }
 
+// out[0..3]: grid points per field, out[4..7]: exchange-buffer rows (double2 per field) of the latitude pairs of this rank's
+// band that run on the direct / register-tiled chirp-z / shared-memory-pass chirp-z / row-mode chirp-z kernels
+void fourier_path_stats(Plan& p, long long* out) {
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!p.fft) return;
+    const std::vector<PairMeta>& meta = fft_state(p).meta;
+    for (int j = p.g.pair_begin; j < p.g.pair_end && j < static_cast<int>(meta.size()); ++j) {
+        const PairMeta& pm = meta[j];
+        const int path = pm.mode == 3 ? 0 : pm.m1 ? 1 : pm.mode == 1 ? 3 : 2;
+        out[path] += static_cast<long long>(pm.n) * (pm.has_s ? 2 : 1);
+        out[4 + path] += 2LL * (pm.L + 1);
+    }
+}
+
 void clone_fft_state(Plan& src, Plan& dst) {
     FftState& d = fft_state(dst);
     const FftState& s = fft_state(src);

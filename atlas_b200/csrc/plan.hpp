@@ -292,6 +292,7 @@ void tc_free(Plan& p);
 // ---- fourier.cu ----
 int build_fft_tables(Plan& p);
 void free_fft_tables(Plan& p);
+void fourier_path_stats(Plan& p, long long* out8);  // grid points / exchange rows of this rank's band per Fourier path
 void clone_fft_state(Plan& src, Plan& dst);   // launch groups / per-pair metadata of a plan that borrows src's tables
 // fields < nb_uv are multiplied by d_scale[latitude pair] in the store (default: 1 / cos(lat), the wind scaling)
 // chunk >= 0: only the fields of that chunk of the split set up by fourier_set_chunks (host-pointer pipelines)

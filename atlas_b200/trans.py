@@ -328,6 +328,17 @@ class Trans:
     def fourier_elems_per_field(self):
         return int(_lib.lib.sptrans_fourier_elems_per_field(self._h))
 
+    def fourier_paths(self):
+        """Grid points and exchange-buffer rows (per field) served by each family of Fourier kernels, and the share of the
+        stage's algorithmic bytes (8 B per grid point + 16 B per exchange row) on each."""
+        out = (C.c_longlong * 8)()
+        _lib.check(_lib.lib.sptrans_fourier_path_stats(self._h, C.cast(out, C.c_void_p)))
+        names = ["direct_mixed_radix", "chirpz_register_tiled", "chirpz_smem_passes", "chirpz_row_mode"]
+        byts = [8.0 * out[i] + 16.0 * out[4 + i] for i in range(4)]
+        tot = max(sum(byts), 1.0)
+        return {n: {"grid_points": int(out[i]), "exchange_rows": int(out[4 + i]), "byte_share": byts[i] / tot}
+                for i, n in enumerate(names)}
+
     def invtrans_legendre(self, nf, trunc, d_spec, d_fourier):
         self._sync(d_spec, d_fourier)
         _lib.check(_lib.lib.sptrans_invtrans_legendre(self._h, int(nf), int(trunc), _ptr(d_spec), _ptr(d_fourier)))

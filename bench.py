@@ -583,7 +583,8 @@ def bench_sharded(args, rank, world, local_rank):
         fb_rows0 = sum(2 * max(0, j1 - max(j0, int(nlat0[m]))) for m in mm)
         four_bytes0 = 16.0 * nf * fb_rows0 + 8.0 * nf * stride
         f_ms = [float(stage_all[0][2]), float(stage_all[0][3])]
-        roofline_fourier = {"kernel": "fourier2 / row-mode Fourier kernels on rank 0 (its latitude band)", "bound": "hbm",
+        roofline_fourier = {"kernel": "direct mixed-radix / register-tiled chirp-z / row-mode Fourier kernels on rank 0 (its latitude band)",
+                            "bound": "hbm", "paths": st.trans.fourier_paths(),
                             "achieved": (1 if inv_only else 2) * four_bytes0 / (max(f_ms[0] + f_ms[1], 1e-9) * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                             "bytes_per_launch_group": four_bytes0, "ms_per_launch_group": {"inverse": f_ms[0], "direct": f_ms[1]}}
         roofline_fourier["frac"] = roofline_fourier["achieved"] / hbm
@@ -850,7 +851,9 @@ def main():
     four_bytes = fb_bytes + 8.0 * npts * nf
     f_inv = float(np.mean([a for a, _ in four_ms]))
     f_dir = float(np.mean([b for _, b in four_ms]))
-    roofline_fourier = {"kernel": "fourier2_inv_kernel / fourier2_dir_kernel (+ v1 kernels on short rows): chirp-z in shared memory", "bound": "hbm",
+    roofline_fourier = {"kernel": "fourier2_inv_kernel / fourier2_dir_kernel (register-tiled chirp-z) + fourier_*_direct_kernel (mixed radix, rows "
+                                  "without prime factors above 23) + v1 chirp-z kernels on short rows, all in shared memory", "bound": "hbm",
+                        "paths": trans.fourier_paths(),
                         "achieved": 2 * four_bytes / ((f_inv + f_dir) * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                         "frac": 2 * four_bytes / ((f_inv + f_dir) * 1e-3) / 1e9 / hbm, "traffic": None, "peak_note": hbm_src,
                         "ms_per_launch_group": {"inverse": f_inv, "direct": f_dir}, "share_of_step": (f_inv + f_dir) / ms_per_step}

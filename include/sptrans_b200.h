@@ -285,6 +285,12 @@ int sptrans_vordiv_to_uv(int truncation, int nb_fields, const double* vorticity,
 
 /* number of double2 (re,im) elements per field of the Legendre<->Fourier exchange buffer */
 size_t sptrans_fourier_elems_per_field(const sptrans_plan* plan);
+/* Which Fourier kernels serve the latitude rows of this plan (of this rank's band): out8[0..3] = grid points per field,
+ * out8[4..7] = exchange-buffer rows (one (re,im) pair per field each) on 0: the direct mixed-radix kernels (row length
+ * without prime factors above 23), 1: the register-tiled chirp-z kernels, 2: the shared-memory-pass chirp-z kernels,
+ * 3: the row-mode chirp-z kernels (rows beyond the single-CTA limit).  The reference has one FFTW plan per row length
+ * (TransLocal.cc:1122-1150); here the row length decides the algorithm.  Zero for point-set plans. */
+int sptrans_fourier_path_stats(sptrans_plan* plan, long long* out8);
 /* Legendre stage only: device spectra -> device Fourier buffer  (TransLocal::invtrans_legendre, :939-1097) */
 int sptrans_invtrans_legendre(sptrans_plan* plan, int nb_fields, int truncation_of_data, const double* d_spectra,
                               double* d_fourier);

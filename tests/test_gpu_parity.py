@@ -682,7 +682,8 @@ def test_shard_local_io_with_row_mode_kernels():
            "test_shard_local_io_emulated_on_one_gpu and (O48 or L9)"]   # O48: rows beyond 256 take row mode
     r = subprocess.run(cmd, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=900)
-    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-3000:]
+    # (two grids x {every row on the chirp-z / row-mode kernels, smooth rows on the direct kernels next to them})
+    assert r.returncode == 0 and "4 passed" in r.stdout, r.stdout[-3000:]
 
 
 def test_config5_tco2559_inverse_sample():
@@ -838,6 +839,12 @@ def test_fourier_direct_kernels_match_chirpz_kernels(torch_cuda, monkeypatch, gr
     scale = fb1.abs().max().item()
     err = (fb1 - fb2).abs().max().item()
     assert scale > 0 and err <= 1e-12 * scale, (err, scale)
+    # sptrans_fourier_path_stats: every row is accounted for, the smooth ones on the direct kernels of the second plan only
+    p1, p2 = t1.fourier_paths(), t2.fourier_paths()
+    assert sum(v["grid_points"] for v in p1.values()) == grid.size() == sum(v["grid_points"] for v in p2.values())
+    assert p1["direct_mixed_radix"]["grid_points"] == 0
+    assert p2["direct_mixed_radix"]["grid_points"] == sum(int(n) for n in grid.nx() if all_small_factors(int(n)))
+    assert abs(sum(v["byte_share"] for v in p2.values()) - 1.0) < 1e-12
 
 
 def all_small_factors(n):

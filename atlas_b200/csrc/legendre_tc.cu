@@ -22,8 +22,11 @@
 //   warp 0 lane 0 : producer  -- waits `empty[s]`, arms `full[s]` with the stage byte count, issues 4 bulk copies
 //   warp 1 lane 0 : MMA issuer -- waits `full[s]`, issues 2 k-steps x 3 products x n_inst MMAs, commits to `empty[s]`;
 //                    after the last K chunk commits to `tmem_full`
-//   warps 4..7    : epilogue  -- wait `tmem_full`, tcgen05.ld 32x32b (warp w owns TMEM lanes 32(w%4)..), convert
-//                    fp32 -> fp64, store rows of C, arrive on `tmem_empty`
+//   warps 4..7    : epilogue  -- wait `tmem_full`, tcgen05.ld 32x32b (warp w owns TMEM lanes 32(w%4)..: a thread holds 16
+//                    columns of ONE row), convert fp32 -> fp64, transpose the 32 x 16 block through the warp's own 4 KB of
+//                    shared memory so that the global stores are 128-byte runs along the rows of C (a thread storing its
+//                    own row made every store instruction touch 32 cache lines: the epilogue of a 128 x 288 tile then
+//                    costs as many LSU cycles as the tile's MMAs take), arrive on `tmem_empty`
 // Tiles are assigned round-robin from a cost-sorted list, so all roles walk the same sequence without
 // communicating.
 #include <algorithm>
@@ -39,7 +42,9 @@ namespace {
 constexpr int kTcThreads = 256;
 constexpr int kTcM = 128;        // tile rows = TMEM lanes
 constexpr int kTcKC = 16;        // K chunk per pipeline stage (two K=8 MMA steps)
-constexpr int kTcStages = 4;
+constexpr int kTcStages = 4;      // at most; fewer when the field count makes the stages larger (TcParams::n_stages)
+constexpr int kTcEpiPitch = 17;   // doubles per row of an epilogue warp's 32 x 16 staging block (odd: conflict-free both ways)
+constexpr size_t kTcEpiBytes = 4ull * 32 * kTcEpiPitch * sizeof(double);
 constexpr int kTcMaxN = 512;     // TMEM columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -118,6 +123,7 @@ struct TcParams {
     int n_tot;        // padded columns (multiple of 16) = rows of a B image
     int n_inst;       // MMA instructions per k-step along N
     int n_each;       // columns per MMA instruction (multiple of 16, <= 256)
+    int n_stages;     // depth of the operand ring (<= kTcStages)
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) legendre_tc_kernel(TcParams p) {
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) legendre_tc_kernel(TcParams p) 
                     bulk_g2s(sb + a_bytes, p.a_lo + ao, a_bytes, &bar_full[stage]);
                     bulk_g2s(sb + 2 * a_bytes, p.b_hi + bo, b_bytes, &bar_full[stage]);
                     bulk_g2s(sb + 2 * a_bytes + b_bytes, p.b_lo + bo, b_bytes, &bar_full[stage]);
-                    if (++stage == kTcStages) {
+                    if (++stage == p.n_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) legendre_tc_kernel(TcParams p) 
                         }
                     }
                     umma_commit(&bar_empty[stage]);  // stage buffer reusable once these MMAs have read it
-                    if (++stage == kTcStages) {
+                    if (++stage == p.n_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -214,12 +220,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) legendre_tc_kernel(TcParams p) 
     else if (warp >= 4) {  // ===== epilogue =====
         uint32_t tphase = 0;
         const int lane_grp = warp & 3;  // TMEM lanes 32*lane_grp .. +31
-        const int row = lane_grp * 32 + lane;
+        double* stg = reinterpret_cast<double*>(smem + static_cast<size_t>(p.n_stages) * stage_bytes) + lane_grp * (32 * kTcEpiPitch);
+        const int half = lane >> 4, cl = lane & 15;
         for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x) {
             const TcTile tl = p.tiles[ti];
             mbar_wait(&bar_tmem_full, tphase);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            double* crow = p.C + tl.c_off + static_cast<long long>(row) * p.ldc;
+            double* cblk = p.C + tl.c_off + static_cast<long long>(lane_grp * 32) * p.ldc;
+            const int rows_valid = min(32, tl.m_valid - lane_grp * 32);   // rows of this warp's block inside the tile
             for (int c0 = 0; c0 < p.n_tot; c0 += 16) {
                 uint32_t r[16];
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(c0);
@@ -229,16 +237,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) legendre_tc_kernel(TcParams p) 
                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;");
-                if (row < tl.m_valid) {
+                if (rows_valid > 0 && c0 < p.n_cols) {   // (warp-uniform)
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const int col = c0 + j;
-                        if (col < p.n_cols) {
-                            double2 v = make_double2(static_cast<double>(__uint_as_float(r[j])),
-                                                     static_cast<double>(__uint_as_float(r[j + 1])));
-                            *reinterpret_cast<double2*>(crow + col) = v;
-                        }
+                    for (int j = 0; j < 16; ++j) stg[lane * kTcEpiPitch + j] = static_cast<double>(__uint_as_float(r[j]));
+                    __syncwarp();
+                    const int col = c0 + cl;
+                    if (col < p.n_cols) {
+#pragma unroll 4
+                        for (int rr = half; rr < rows_valid; rr += 2)   // two rows per instruction, 128 bytes each
+                            cblk[static_cast<long long>(rr) * p.ldc + col] = stg[rr * kTcEpiPitch + cl];
                     }
+                    __syncwarp();
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -575,11 +584,14 @@ static int launch_tc_gemm(Plan& p, int nf, const TcTile* tiles, int ntiles, cons
         prm.n_each = prm.n_tot / prm.n_inst;
     }
     const size_t stage_bytes = 2ull * kTcM * kTcKC * 4 + 2ull * prm.n_tot * kTcKC * 4;
-    const size_t smem = stage_bytes * kTcStages + 128;
-    if (smem > 226 * 1024) {  // static shared memory (barriers) comes on top
+    // operand ring + the epilogue warps' staging blocks; static shared memory (barriers) comes on top of the 226 KB
+    const size_t budget = 226 * 1024 - 128 - kTcEpiBytes;
+    prm.n_stages = static_cast<int>(std::min<size_t>(kTcStages, budget / stage_bytes));
+    if (prm.n_stages < 2) {
         set_error("tensor-core Legendre path: stage buffers exceed shared memory for this field count");
         return SPTRANS_ERR_INVALID;
     }
+    const size_t smem = stage_bytes * prm.n_stages + kTcEpiBytes + 128;
     // the opt-in is per device (context), and one process may hold plans on several devices: remembered per ordinal
     static size_t attr_smem[64] = {};
     if (p.device >= 64 || smem > attr_smem[p.device]) {

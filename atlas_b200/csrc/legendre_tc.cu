@@ -309,8 +309,25 @@ __global__ void build_a_images_kernel(int T, const int* __restrict__ my_m, const
     }
 }
 
+// float index of the four K-consecutive elements (row, 4 q .. 4 q + 3) of an R-row B image sequence: 16-byte aligned
+__device__ __forceinline__ long long img_quad(int R, int row, int q) {
+    return static_cast<long long>(q >> 2) * (R * kTcKC) + ((q & 3) * (R >> 3) + (row >> 3)) * 32 + (row & 7) * 4;
+}
+__device__ __forceinline__ void store_split4(const double v[4], float* __restrict__ hi, float* __restrict__ lo, long long dst) {
+    float4 h, l;
+    split_tf32(v[0], h.x, l.x);
+    split_tf32(v[1], h.y, l.y);
+    split_tf32(v[2], h.z, l.z);
+    split_tf32(v[3], h.w, l.w);
+    *reinterpret_cast<float4*>(hi + dst) = h;
+    *reinterpret_cast<float4*>(lo + dst) = l;
+}
+constexpr int kTcPrepZ = 8;   // blocks per (m, parity) of the operand-image kernels
+
 // spectra [m][n][re/im][fld] -> B images of the inverse: B(row = 2 fld + re/im, k = wavenumber index), zero rows /
-// zero coefficients as in pack_spectra_kernel (the `jn <= truncation && jm < truncation` rule, TransLocal.cc:982)
+// zero coefficients as in pack_spectra_kernel (the `jn <= truncation && jm < truncation` rule, TransLocal.cc:982).
+// A thread converts four consecutive k of one row: its loads run along the fields (two 8-byte streams per warp, re and im),
+// its two stores are 16 bytes each and consecutive rows are 16 bytes apart in the image.
 __global__ void pack_spectra_tc_kernel(int T, int nf, int trunc, int n_tot, const int* __restrict__ my_m,
                                        const int* __restrict__ tab_K, const long long* __restrict__ bimg_off,
                                        const double* __restrict__ spec, float* __restrict__ hi, float* __restrict__ lo) {
@@ -320,29 +337,24 @@ __global__ void pack_spectra_tc_kernel(int T, int nf, int trunc, int n_tot, cons
     const int chunks = (K + kTcKC - 1) / kTcKC;
     const long long base = bimg_off[2 * m + par] * (static_cast<long long>(n_tot) * kTcKC);  // bimg_off counts 16-wide K chunks
     const long long ioff = static_cast<long long>(2 * trunc + 3 - m) * m / 2 * nf * 2;
-    const long long total = static_cast<long long>(chunks) * kTcKC * n_tot;
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
-        // source-friendly order: field fastest within (k, imag)
-        const int k = static_cast<int>(e / n_tot);
-        const int r_src = static_cast<int>(e % n_tot);
-        double v = 0.;
-        int r = r_src;
-        if (r_src < 2 * nf) {
-            const int imag = r_src / nf, f = r_src % nf;
-            r = 2 * f + imag;
-            const int n = m + par + 2 * k;
-            if (n <= trunc && m < trunc && k < K) v = spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f];
+    const int total = chunks * (kTcKC / 4) * n_tot;
+    for (int e = blockIdx.z * blockDim.x + threadIdx.x; e < total; e += gridDim.z * blockDim.x) {
+        const int q = e / n_tot, r = e - q * n_tot;
+        double v[4] = {0., 0., 0., 0.};
+        if (r < 2 * nf && m < trunc) {
+            const int f = r >> 1, imag = r & 1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = 4 * q + i, n = m + par + 2 * k;
+                if (n <= trunc && k < K) v[i] = spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f];
+            }
         }
-        float h, l;
-        split_tf32(v, h, l);
-        const int ch = k / kTcKC, kl = k % kTcKC;
-        const long long dst = base + static_cast<long long>(ch) * (n_tot * kTcKC) + img_index(n_tot, r, kl);
-        hi[dst] = h;
-        lo[dst] = l;
+        store_split4(v, hi, lo, base + img_quad(n_tot, r, q));
     }
 }
 
-// exchange buffer [lat][2 fld + re/im] (fp64) -> B images of the direct transform: B(row = r, k = latitude)
+// exchange buffer [lat][2 fld + re/im] (fp64) -> B images of the direct transform: B(row = r, k = latitude); four consecutive
+// latitudes of one row per thread (loads contiguous along the row of the buffer, 16-byte stores)
 __global__ void transpose_fourier_tc_kernel(int nf, int n_tot, const int* __restrict__ my_m, const int* __restrict__ nlat0,
                                             int nleg, const long long* __restrict__ fb_rowoff,
                                             const long long* __restrict__ bimg_off, const double* __restrict__ fb,
@@ -353,18 +365,18 @@ __global__ void transpose_fourier_tc_kernel(int nf, int n_tot, const int* __rest
     const int chunks = (ncol + kTcKC - 1) / kTcKC;
     const long long base = bimg_off[2 * m + par] * (static_cast<long long>(n_tot) * kTcKC);
     const double* src = fb + (fb_rowoff[m] + static_cast<long long>(par) * ncol) * (2 * nf);
-    const long long total = static_cast<long long>(chunks) * kTcKC * n_tot;
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
-        const int jj = static_cast<int>(e / n_tot);
-        const int r = static_cast<int>(e % n_tot);
-        double v = 0.;
-        if (jj < ncol && r < 2 * nf) v = src[static_cast<long long>(jj) * (2 * nf) + r];
-        float h, l;
-        split_tf32(v, h, l);
-        const int ch = jj / kTcKC, kl = jj % kTcKC;
-        const long long dst = base + static_cast<long long>(ch) * (n_tot * kTcKC) + img_index(n_tot, r, kl);
-        hi[dst] = h;
-        lo[dst] = l;
+    const int total = chunks * (kTcKC / 4) * n_tot;
+    for (int e = blockIdx.z * blockDim.x + threadIdx.x; e < total; e += gridDim.z * blockDim.x) {
+        const int q = e / n_tot, r = e - q * n_tot;
+        double v[4] = {0., 0., 0., 0.};
+        if (r < 2 * nf) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int jj = 4 * q + i;
+                if (jj < ncol) v[i] = src[static_cast<long long>(jj) * (2 * nf) + r];
+            }
+        }
+        store_split4(v, hi, lo, base + img_quad(n_tot, r, q));
     }
 }
 
@@ -609,7 +621,7 @@ int launch_legendre_inv_tc(Plan& p, int nf, int trunc, const double* d_spec, dou
     TcState* s = tc_state(p);
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
-    dim3 grid(nm, 2);
+    dim3 grid(nm, 2, kTcPrepZ);
     pack_spectra_tc_kernel<<<grid, 256, 0, p.stream>>>(p.g.T, nf, trunc, n_total_cols(nf), p.d_my_m, s->d_tab_K, s->d_b_inv_off,
                                                        d_spec, s->b_hi, s->b_lo);
     p.launches++;
@@ -622,7 +634,7 @@ int launch_legendre_dir_tc(Plan& p, int nf, const double* d_fourier, double* d_p
     TcState* s = tc_state(p);
     const int nm = static_cast<int>(p.g.my_m.size());
     if (nm == 0) return SPTRANS_OK;
-    dim3 grid(nm, 2);
+    dim3 grid(nm, 2, kTcPrepZ);
     transpose_fourier_tc_kernel<<<grid, 256, 0, p.stream>>>(nf, n_total_cols(nf), p.d_my_m, p.d_nlat0, p.g.nleg, p.d_fb_rowoff,
                                                             s->d_b_dir_off, d_fourier, s->b_hi, s->b_lo);
     p.launches++;

@@ -251,19 +251,23 @@ __global__ void pack_spectra_kernel(int /*T*/, int nf, int trunc, const long lon
     const int k0 = blockIdx.z * kPackRows;
     if (k0 >= rows) return;
     const int kn = min(kPackRows, rows - k0);
-    const int ld = 2 * nf;
     // reference :970; spec_off: the spectral array holds only this rank's zonal wavenumbers (SPTRANS_SHARD_LOCAL_IO)
     const long long ioff = (spec_off ? spec_off[m] : static_cast<long long>(2 * trunc + 3 - m) * m / 2) * nf * 2;
-    for (int e = threadIdx.x; e < kn * ld; e += blockDim.x) {
-        const int k = k0 + e / ld;
-        const int r = e % ld;
-        // read order: field fastest within (k, imag) so that global loads coalesce
-        const int imag = r / nf, f = r % nf;
+    // a thread moves one (re, im) pair: two 8-byte loads along the fields (each stream coalesced), one 16-byte store
+    const bool keep = (m < trunc || (flags & kPackKeepMT));
+    const bool drop_im = (flags & kPackDirAdj) && m == 0;
+    double2* __restrict__ out = reinterpret_cast<double2*>(packed);
+    for (int e = threadIdx.x; e < kn * nf; e += blockDim.x) {
+        const int k = k0 + e / nf;
+        const int f = e % nf;
         const int n = m + p + 2 * k;
-        double v = 0.;
-        if (n <= trunc && (m < trunc || (flags & kPackKeepMT))) v = spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f];
-        if ((flags & kPackDirAdj) && m == 0 && imag) v = 0.;
-        packed[(row0 + k) * ld + 2 * f + imag] = v;
+        double2 v = make_double2(0., 0.);
+        if (n <= trunc && keep) {
+            const double* src = spec + ioff + static_cast<long long>(nf) * (2 * (n - m)) + f;
+            v.x = src[0];
+            v.y = drop_im ? 0. : src[nf];
+        }
+        out[(row0 + k) * nf + f] = v;
     }
 }
 
@@ -278,17 +282,19 @@ __global__ void unpack_spectra_kernel(int T, int nf, const long long* __restrict
     const int k0 = blockIdx.z * kPackRows;
     if (k0 >= K) return;
     const int kn = min(kPackRows, K - k0);
-    const int ld = 2 * nf;
     const long long ioff = (spec_off ? spec_off[m] : static_cast<long long>(2 * T + 3 - m) * m / 2) * nf * 2;
-    for (int e = threadIdx.x; e < kn * ld; e += blockDim.x) {
-        const int k = k0 + e / ld;
-        const int r = e % ld;
-        const int imag = r / nf, f = r % nf;
+    const double2* __restrict__ in = reinterpret_cast<const double2*>(packed);
+    const bool zero_all = drop_mT && m >= T;  // adjoint of the scalar inverse, which ignores the m == T column (:982)
+    for (int e = threadIdx.x; e < kn * nf; e += blockDim.x) {
+        const int k = k0 + e / nf;
+        const int f = e % nf;
         const int n = m + p + 2 * k;
-        double v = packed[(row0 + k) * ld + 2 * f + imag];
-        if (m == 0 && imag == 1) v = 0.;  // Im of the zonal-mean coefficients is identically zero
-        if (drop_mT && m >= T) v = 0.;     // adjoint of the scalar inverse, which ignores the m == T column (:982)
-        spec[ioff + static_cast<long long>(nf) * (imag + 2 * (n - m)) + f] = v;
+        double2 v = in[(row0 + k) * nf + f];
+        if (m == 0) v.y = 0.;  // Im of the zonal-mean coefficients is identically zero
+        if (zero_all) v = make_double2(0., 0.);
+        double* dst = spec + ioff + static_cast<long long>(nf) * (2 * (n - m)) + f;
+        dst[0] = v.x;
+        dst[nf] = v.y;
     }
 }
 

@@ -360,7 +360,7 @@ static int create_plan(sptrans_plan** out, int nlat, const int* nx, const double
     if ((rc = upload(p.d_my_m, g.my_m, p.stream))) return fail(rc);
     if ((rc = upload(p.d_owner, g.owner, p.stream))) return fail(rc);
     if (g.local_io && (rc = upload(p.d_spec_off, g.spec_off, p.stream))) return fail(rc);
-    if ((rc = upload(p.d_pair_done, std::vector<int>(std::max(g.nleg, 1), 0), p.stream))) return fail(rc);
+    if ((rc = upload(p.d_pair_done, std::vector<int>(3 * std::max(g.nleg, 1) + 8, 0), p.stream))) return fail(rc);
     {
         std::vector<double> ci(g.nleg), c(g.nleg);
         for (int j = 0; j < g.nleg; ++j) {
@@ -719,7 +719,7 @@ int sptrans_plan_clone(sptrans_plan* src, sptrans_plan** out) {
         set_error("cudaMalloc failed");
         return fail(SPTRANS_ERR_CUDA);
     }
-    if ((rc = upload(p.d_pair_done, std::vector<int>(std::max(p.g.nleg, 1), 0), p.stream))) return fail(rc);
+    if ((rc = upload(p.d_pair_done, std::vector<int>(3 * std::max(p.g.nleg, 1) + 8, 0), p.stream))) return fail(rc);
     SPT_CUDA(cudaStreamSynchronize(p.stream));
     *out = sp;
     return SPTRANS_OK;

@@ -176,15 +176,15 @@ fourier_inv_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
     }
 }
 
-// Rows (m <= L, parity) of one latitude pair: local exchange buffer -> buffer of the rank that owns m.
+// Rows r0 <= r < r1 (r = 2 m + parity, m <= L) of one latitude pair: local exchange buffer -> buffer of the rank that owns m.
 // One warp per row, up to 5 x 16 B per lane in flight; the rows were written by other blocks, so they are read
 // through L2 (ld.cg).
-__device__ __forceinline__ void push_pair_rows(int pair, int L, int nf, const double2* __restrict__ fb,
+__device__ __forceinline__ void push_pair_rows(int pair, int r0, int r1, int nf, const double2* __restrict__ fb,
                                                const long long* __restrict__ fb_rowoff, const int* __restrict__ nlat0,
                                                int nleg, const int* __restrict__ owner, const PeerDst& dst, int me) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     constexpr int kU = 5;
-    for (int r = warp; r < 2 * (L + 1); r += nw) {
+    for (int r = r0 + warp; r < r1; r += nw) {
         const int m = r >> 1, par = r & 1;
         const int o = owner[m];
         if (o == me) continue;
@@ -202,6 +202,72 @@ __device__ __forceinline__ void push_pair_rows(int pair, int L, int nf, const do
                 if (i0 + 32 * u < nf) out[i0 + 32 * u] = v[u];
         }
     }
+}
+
+// Sharded plans: every row of the exchange buffer belongs to the rank that owns its zonal wavenumber, and the rows of a
+// latitude pair are complete once all the field-group blocks of the pair are through.  The block that completes a pair puts it
+// on a work queue, and EVERY block that finishes -- not just that one -- takes chunks of d_push_rows rows off the queue and ships
+// them (nf double2 = whole rows: long coalesced NVLink stores) while the other SMs keep transforming.  With the completing
+// block shipping all 2 (L + 1) rows alone (5.6 MB at the equator), the last pairs of a launch left one block per pair
+// copying for ~0.4 ms after everybody else had finished.
+// Queue (ints behind the nleg pair counters): [0] tail, [1] head, [8 .. 8 + nleg) pair + 1 once published,
+// [8 + nleg .. 8 + 2 nleg) next chunk of the slot.  Zeroed by the host before the stage.
+__device__ int d_push_rows = 128;  // rows per chunk (8-rank emulation on one B200: 16: 2.18, 32: 1.90, 64: 1.80, 128: 1.73, 256: 1.74 ms per rank;
+                                   // SPTRANS_PUSH_ROWS=0 (measurement): the completing block ships the whole pair alone, 2.21 ms)
+__device__ __forceinline__ void finish_pair_and_push(int pair, int nblk, int* __restrict__ pair_done, int nleg,
+                                                     const PairMeta* __restrict__ meta, int nf, const double2* __restrict__ fb,
+                                                     const long long* __restrict__ fb_rowoff, const int* __restrict__ nlat0,
+                                                     const int* __restrict__ owner, const PeerDst& dst, int me) {
+    __shared__ int s_pair, s_chunk, s_publisher;
+    int* q = pair_done + nleg;
+    const int tid = threadIdx.x;
+    const int cfg_rows = d_push_rows;
+    const int kPushRows = cfg_rows > 0 ? cfg_rows : (1 << 20);
+    __threadfence();   // this block's rows are visible before its arrival is
+    __syncthreads();
+    if (tid == 0) {
+        const int done = atomicAdd(pair_done + pair, 1);
+        s_publisher = (done == nblk - 1);
+        if (done == nblk - 1) {
+            pair_done[pair] = 0;  // ready for the next call
+            __threadfence();
+            const int slot = atomicAdd(q, 1);
+            atomicExch(q + 8 + slot, pair + 1);
+        }
+    }
+    bool pushed = false;
+    for (;;) {
+        __syncthreads();
+        if (cfg_rows <= 0 && !s_publisher) break;
+        if (tid == 0) {
+            int found = -1, chunk = 0;
+            int s = atomicAdd(q + 1, 0);
+            const int tail = atomicAdd(q, 0);
+            while (s < tail) {
+                int pp = atomicAdd(q + 8 + s, 0);
+                while (pp == 0) pp = atomicAdd(q + 8 + s, 0);  // reserved, published within a few instructions by a running block
+                const int nch = (2 * (meta[pp - 1].L + 1) + kPushRows - 1) / kPushRows;
+                const int c = atomicAdd(q + 8 + nleg + s, 1);
+                if (c < nch) {
+                    found = pp - 1;
+                    chunk = c;
+                    break;
+                }
+                atomicMax(q + 1, s + 1);  // slot exhausted
+                ++s;
+            }
+            s_pair = found;
+            s_chunk = chunk;
+        }
+        __syncthreads();
+        const int pp = s_pair;
+        if (pp < 0) break;
+        __threadfence();  // (pairs with the fences of the blocks that wrote the rows)
+        const int r0 = s_chunk * kPushRows;
+        push_pair_rows(pp, r0, min(r0 + kPushRows, 2 * (meta[pp].L + 1)), nf, fb, fb_rowoff, nlat0, nleg, owner, dst, me);
+        pushed = true;
+    }
+    if (pushed) __threadfence_system();  // remote rows are visible to the peers before this kernel completes
 }
 
 __global__ void __launch_bounds__(2 * kFftThreads, 1)
@@ -273,26 +339,8 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
         fb[is] = s;
         fb[ia] = a;
     }
-    if (owner) {
-        // sharded plan: every row belongs to the rank that owns its zonal wavenumber.  The block that completes a
-        // latitude pair (all field groups done) ships the pair's rows -- nf double2 = whole rows, so the NVLink
-        // stores are long and coalesced -- while the other SMs keep transforming: the exchange hides behind the FFTs.
-        __shared__ int s_last;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const int nblk = (nf + pm.F - 1) / pm.F;
-            const int done = atomicAdd(pair_done + pair, 1);
-            s_last = (done == nblk - 1);
-            if (s_last) pair_done[pair] = 0;  // ready for the next call
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            push_pair_rows(pair, L, nf, fb, fb_rowoff, nlat0, nleg, owner, dst, me);
-            __threadfence_system();  // remote rows are visible to the peers before this kernel completes
-        }
-    }
+    if (owner)  // sharded plan: completed pairs are shipped to the owners of their zonal wavenumbers
+        finish_pair_and_push(pair, (nf + pm.F - 1) / pm.F, pair_done, nleg, meta, nf, fb, fb_rowoff, nlat0, owner, dst, me);
 }
 
 // ---- direct mode (mode 3): rows whose length is 13-smooth need no chirp-z ----
@@ -524,23 +572,8 @@ fourier_dir_direct_kernel(const __grid_constant__ DirectArgs a, const int2* __re
             }
         }
     }
-    if (owner) {  // sharded plan: see fourier_dir_kernel
-        __shared__ int s_last;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const int nblk = (nf + pm.F - 1) / pm.F;
-            const int done = atomicAdd(pair_done + pair, 1);
-            s_last = (done == nblk - 1);
-            if (s_last) pair_done[pair] = 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            push_pair_rows(pair, L, nf, fb, a.fb_rowoff, a.nlat0, a.nleg, owner, dst, me);
-            __threadfence_system();
-        }
-    }
+    if (owner)  // sharded plan: see fourier_dir_kernel
+        finish_pair_and_push(pair, (nf + pm.F - 1) / pm.F, pair_done, a.nleg, a.meta, nf, fb, a.fb_rowoff, a.nlat0, owner, dst, me);
 }
 
 // (threads, blocks per SM) shapes compiled for the direct kernels; SPTRANS_FFTD_SHAPE picks one for the groups that fit it
@@ -736,23 +769,8 @@ fourier2_dir_kernel(const __grid_constant__ Fft2Args a, const int2* __restrict__
     extern __shared__ double2 X[];
     const int2 bd = blocks[blockIdx.x];
     fft2::fourier2_dir_body<M1, v2_threads(M1)>(a, bd.x, bd.y & 0xffff, bd.y >> 16, threadIdx.x, X);
-    if (owner) {  // sharded plan: the block that completes a latitude pair ships its rows to their owners (see v1)
-        __shared__ int s_last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int nblk = (a.nf + a.F - 1) / a.F;
-            const int done = atomicAdd(pair_done + bd.x, 1);
-            s_last = (done == nblk - 1);
-            if (s_last) pair_done[bd.x] = 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            push_pair_rows(bd.x, a.meta[bd.x].L, a.nf, a.fb, a.fb_rowoff, a.nlat0, a.nleg, owner, dst, me);
-            __threadfence_system();
-        }
-    }
+    if (owner)  // sharded plan: completed pairs are shipped to the owners of their zonal wavenumbers (see v1)
+        finish_pair_and_push(bd.x, (a.nf + a.F - 1) / a.F, pair_done, a.nleg, a.meta, a.nf, a.fb, a.fb_rowoff, a.nlat0, owner, dst, me);
 }
 
 // Cost model used to pick the convolution length: every pass is one read+write sweep of shared memory;
@@ -1374,6 +1392,13 @@ static int launch_fourier_dir_impl(Plan& p, int nf, const double* d_gp, double* 
     // wind fields enter the vor/div transform as u,v / (a cos(lat)); the adjoint of the inverse wind transform
     // applies the inverse's own 1 / cos(lat)
     const double* uv_scale = adjoint ? p.d_coslatinv : p.d_uvscale;
+    if (d_owner) {  // empty work queue of completed pairs (finish_pair_and_push); the launch groups of all streams share it
+        SPT_CUDA(cudaMemsetAsync(p.d_pair_done + p.g.nleg, 0, (2 * static_cast<size_t>(p.g.nleg) + 8) * sizeof(int), p.stream));
+        if (std::getenv("SPTRANS_PUSH_ROWS")) {  // measurement knob
+            const int v = env_int("SPTRANS_PUSH_ROWS", 128);
+            SPT_CUDA(cudaMemcpyToSymbolAsync(d_push_rows, &v, sizeof(int), 0, cudaMemcpyHostToDevice, p.stream));
+        }
+    }
     StreamFan* fan = fan_begin(p);
     int launched = 0;
     auto launch_groups = [&]() -> int {

@@ -174,7 +174,8 @@ struct Plan {
     int* d_my_m = nullptr;             // [my_m.size()]
     long long* d_spec_off = nullptr;   // [T+1] HostGeom::spec_off (only with SPTRANS_SHARD_LOCAL_IO, else null)
     int* d_owner = nullptr;            // [T+1] rank that owns zonal wavenumber m
-    int* d_pair_done = nullptr;        // [nleg] field-group blocks finished per latitude pair (sharded direct Fourier)
+    int* d_pair_done = nullptr;        // [nleg] field-group blocks finished per latitude pair (sharded direct Fourier), then the
+                                       // work queue of completed pairs whose rows are being shipped ([2 nleg + 8], fourier.cu)
     int* d_pt_row = nullptr;           // point-set plans: see HostGeom
     double* d_pt_sign = nullptr;
     double* d_pt_lon = nullptr;

@@ -29,7 +29,9 @@ def timed(fn):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record(); fn(); e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)
 res = {"inv_legendre": [], "inv_fourier": [], "dir_fourier_push": [], "dir_legendre": []}
-for it in range(3):
+NIT = int(os.environ.get('NIT', '3'))
+acc = {k: [] for k in res}
+for it in range(NIT):
     il = [timed(lambda t=t, a=a: _lib.check(lib.sptrans_invtrans_legendre_peers(t._h, nf, _ptr(a)))) for t, a in zip(plans, d_sp)]
     iff = []
     for t, g in zip(plans, d_gp):
@@ -47,6 +49,8 @@ for it in range(3):
         for t, a in zip(plans, d_sp):
             dl.append(timed(lambda t=t, a=a: _lib.check(lib.sptrans_dirtrans_legendre(t._h, nf, buf(t), _ptr(a)))))
             _lib.check(lib.sptrans_peer_advance(t._h))
-    if it == 2:
-        res = {"inv_legendre": il, "inv_fourier": iff, "dir_fourier_push": df, "dir_legendre": dl}
-print(json.dumps({k: [round(x, 3) for x in v] for k, v in res.items()}))
+    if it >= 1:
+        for k, v in (("inv_legendre", il), ("inv_fourier", iff), ("dir_fourier_push", df), ("dir_legendre", dl)):
+            acc[k].append(v)
+res = {k: list(np.median(np.array(v), axis=0)) for k, v in acc.items()}   # median over the iterations after the first
+print(json.dumps({"tag": os.environ.get("TAG", ""), **{k: [round(float(x), 3) for x in v] for k, v in res.items()}}))

@@ -61,12 +61,105 @@ gp_repack_kernel(const double* __restrict__ in, double* __restrict__ out, long l
     }
 }
 
+// Slab variant (the default): a block moves P consecutive points x ALL fields.  On the Field side that is ONE contiguous run of
+// P * nf doubles (points are adjacent, fields fastest), on the row side nf runs of P doubles; the 32 x 32 tiles above touch the
+// Field side in 256-byte pieces 8 nf bytes apart and reached 2.9 TB/s (5.1 / 4.0 ms per call at TCo1279 L137, measured through
+// the Field entry points; this kernel: 3.6 / 3.1 ms, profiles/field_layout_timing_r02.txt).  Shared memory holds the slab as [point][field] with an odd pitch, so that the row-side accesses (lanes
+// along the points) are conflict free; the Field side walks it linearly (one reciprocal multiply per element for the pitch).
+template <bool TO_ROWS>
+__global__ void __launch_bounds__(256)
+gp_repack_slab_kernel(const double* __restrict__ in, double* __restrict__ out, long long npts, int nlev, int ncomp, int P,
+                      unsigned nf_magic) {
+    extern __shared__ double slab[];
+    const int nf = nlev * ncomp, pitch = nf | 1;
+    const long long p0 = static_cast<long long>(blockIdx.x) * P;
+    const int np = static_cast<int>(min(static_cast<long long>(P), npts - p0));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int total = np * nf;
+    constexpr int kU = 8;               // global accesses in flight per thread (the kernel is pure data movement)
+    const int nseg = (np + 31) >> 5;    // 32-point segments of a row
+    const int nitem = nf * nseg;        // (row, segment) pairs, one warp access each
+    // row side of item `it`: global offset and slab index of this lane's element (-1: beyond the slab)
+    auto row_item = [&](int it, long long& g, int& sidx) {
+        const int r = it / nseg, seg = it - r * nseg;
+        const int c = r / nlev, l = r - c * nlev;
+        const int pp = seg * 32 + lane;
+        g = static_cast<long long>(r) * npts + p0 + pp;
+        sidx = pp < np ? pp * pitch + l * ncomp + c : -1;
+    };
+    auto slab_index = [&](int i) {
+        const int pp = static_cast<int>(__umulhi(static_cast<unsigned>(i), nf_magic));
+        return pp * pitch + (i - pp * nf);
+    };
+    if (TO_ROWS) {
+        // (measured: batching this direction like the other one made it slower -- 6.3 ms against 3.1 ms per call at TCo1279
+        // L137 -- because a row's 512-byte run is then written by two warps at different times; plain loops it is)
+        const double* src = in + p0 * nf;
+        for (int i = tid; i < total; i += 256) slab[slab_index(i)] = src[i];
+        __syncthreads();
+        for (int r = warp; r < nf; r += 8) {
+            const int c = r / nlev, l = r - c * nlev;
+            const int q = l * ncomp + c;
+            double* dst = out + static_cast<long long>(r) * npts + p0;
+            for (int pp = lane; pp < np; pp += 32) dst[pp] = slab[pp * pitch + q];
+        }
+    }
+    else {
+        for (int it0 = warp; it0 < nitem; it0 += 8 * kU) {
+            double v[kU];
+            int sidx[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int it = it0 + 8 * u;
+                sidx[u] = -1;
+                if (it < nitem) {
+                    long long g;
+                    row_item(it, g, sidx[u]);
+                    if (sidx[u] >= 0) v[u] = in[g];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (sidx[u] >= 0) slab[sidx[u]] = v[u];
+        }
+        __syncthreads();
+        double* dst = out + p0 * nf;
+        for (int i0 = tid; i0 < total; i0 += 256 * kU) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (i0 + 256 * u < total) dst[i0 + 256 * u] = slab[slab_index(i0 + 256 * u)];
+        }
+    }
+}
+
 }  // namespace
 
 int launch_gp_repack(Plan& p, int nlev, int ncomp, const double* d_in, double* d_out, bool to_rows) {
     const long long npts = p.g.npts;
     const int nf = nlev * ncomp;
     if (npts == 0 || nf == 0) return SPTRANS_OK;
+    {
+        // points per slab: ~72 KB of shared memory (three blocks per SM), multiples of 32 where the field count allows
+        const int pitch = nf | 1;
+        int P = 9216 / pitch;
+        P = P >= 32 ? std::min(256, P / 32 * 32) : P / 8 * 8;
+        if (nf >= 2 && P >= 8 && static_cast<long long>(P) * nf < 65536) {
+            const size_t smem = static_cast<size_t>(P) * pitch * sizeof(double);
+            static bool attr_set[64] = {};   // (per device, like the Legendre kernels)
+            if (p.device >= 64 || !attr_set[p.device]) {
+                SPT_CUDA(cudaFuncSetAttribute(gp_repack_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+                SPT_CUDA(cudaFuncSetAttribute(gp_repack_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+                if (p.device < 64) attr_set[p.device] = true;
+            }
+            const unsigned magic = static_cast<unsigned>((0x100000000ull + nf - 1) / nf);   // exact i / nf for i < 65536
+            const unsigned nblk = static_cast<unsigned>((npts + P - 1) / P);
+            if (to_rows) gp_repack_slab_kernel<true><<<nblk, 256, smem, p.stream>>>(d_in, d_out, npts, nlev, ncomp, P, magic);
+            else gp_repack_slab_kernel<false><<<nblk, 256, smem, p.stream>>>(d_in, d_out, npts, nlev, ncomp, P, magic);
+            p.launches++;
+            SPT_CUDA(cudaGetLastError());
+            return SPTRANS_OK;
+        }
+    }
     dim3 grid(static_cast<unsigned>((npts + kTile - 1) / kTile), static_cast<unsigned>((nf + kTile - 1) / kTile));
     dim3 block(kTile, 8);
     if (to_rows) gp_repack_kernel<true><<<grid, block, 0, p.stream>>>(d_in, d_out, npts, nlev, ncomp);

@@ -132,6 +132,39 @@ def test_field_layout_device_pointers_and_errors():
     back = np.full((nspec2, nlev), np.nan)
     trans.dirtrans_field(want, back)
     assert np.array_equal(d_back.cpu().numpy(), back)
+    # device-resident wind / gradient / adjoint Fields: the repack runs in field chunks next to the Fourier kernels
+    # (fourier_inv_to_field / fourier_dir_from_field) -- bit-identical to the host-array path (separate transpose pass)
+    for gname, TT, nl in (("O48", 47, 5), ("O160", 159, 9), ("F24", 23, 1)):
+        grid2, trans2 = make(gname, TT)
+        np2, ns2 = grid2.size(), trans2.nb_spectral_coefficients()
+        vor = H.synthetic_spectra(TT, nl, seed=3).reshape(ns2, nl)
+        div = H.synthetic_spectra(TT, nl, seed=4).reshape(ns2, nl)
+        wind_h = np.full((np2, nl, 2), np.nan)
+        trans2.invtrans_vordiv2wind_field(vor, div, wind_h)
+        d_wind = torch.full((np2, nl, 2), float("nan"), dtype=torch.float64, device="cuda")
+        trans2.invtrans_vordiv2wind_field(torch.from_numpy(vor).cuda(), torch.from_numpy(div).cuda(), d_wind)
+        assert np.array_equal(d_wind.cpu().numpy(), wind_h), gname
+        grad_h = np.full((np2, nl, 2), np.nan)
+        trans2.invtrans_grad_field(vor, grad_h)
+        d_grad = torch.full((np2, nl, 2), float("nan"), dtype=torch.float64, device="cuda")
+        trans2.invtrans_grad_field(torch.from_numpy(vor).cuda(), d_grad)
+        assert np.array_equal(d_grad.cpu().numpy(), grad_h), gname
+        gp_h = np.full((np2, nl), np.nan)
+        trans2.invtrans_field(vor, gp_h)
+        d_gp2 = torch.full((np2, nl), float("nan"), dtype=torch.float64, device="cuda")
+        trans2.invtrans_field(torch.from_numpy(vor).cuda(), d_gp2)
+        assert np.array_equal(d_gp2.cpu().numpy(), gp_h), gname
+        if grid2.weights() is not None:
+            sp_h = np.full((ns2, nl), np.nan)
+            trans2.dirtrans_field(gp_h, sp_h)
+            d_sp2 = torch.full((ns2, nl), float("nan"), dtype=torch.float64, device="cuda")
+            trans2.dirtrans_field(d_gp2, d_sp2)
+            assert np.array_equal(d_sp2.cpu().numpy(), sp_h), gname
+        adj_h = np.full((ns2, nl), np.nan)
+        trans2.invtrans_adj_field(gp_h, adj_h)
+        d_adj = torch.full((ns2, nl), float("nan"), dtype=torch.float64, device="cuda")
+        trans2.invtrans_adj_field(d_gp2, d_adj)
+        assert np.array_equal(d_adj.cpu().numpy(), adj_h), gname
     with pytest.raises(ValueError):
         trans.invtrans_field(sp, np.zeros((npts, nlev + 1)))
     with pytest.raises(_lib.SptransError):

@@ -233,8 +233,42 @@ static int check_direct(int n) {
     return (err_f / nrm < 1e-12 && err_i < 1e-12) ? 0 : 1;
 }
 
+// every length the plan may hand to the direct kernels (row lengths up to the single-CTA limit without a prime factor above 23):
+// the schedule covers the length, fits the fixed-size pass arrays, and the digit reversal is a permutation
+static int check_all_direct_schedules(int nmax) {
+    int bad = 0, count = 0, most = 0;
+    std::vector<char> seen;
+    for (int n = 1; n <= nmax; ++n) {
+        if (!is_direct_length(n)) continue;
+        ++count;
+        const ScheduleG sc = make_schedule_g(n);
+        long long prod = 1;
+        for (int p = 0; p < sc.npass; ++p) prod *= sc.radix[p];
+        if (prod != n || sc.npass > 10) {
+            printf("direct schedule n=%d: product %lld, %d passes\n", n, prod, sc.npass);
+            ++bad;
+            continue;
+        }
+        most = sc.npass > most ? sc.npass : most;
+        if (n % 7 == 0 || n < 600) {   // (a subset keeps the test fast)
+            seen.assign(n, 0);
+            for (int k = 0; k < n; ++k) {
+                const int pos = dif_output_position(sc, n, k);
+                if (pos < 0 || pos >= n || seen[pos]) {
+                    printf("direct schedule n=%d: output positions are not a permutation (k=%d)\n", n, k);
+                    ++bad;
+                    break;
+                }
+                seen[pos] = 1;
+            }
+        }
+    }
+    printf("direct schedules: %d lengths up to %d, at most %d passes, %d bad\n", count, nmax, most, bad);
+    return bad;
+}
+
 int main() {
-    int bad = 0;
+    int bad = check_all_direct_schedules(13824);
     const int direct[] = {17, 19, 23, 68, 76, 92, 4301, 7429, 4692, 5060, 4788, 3876, 391, 18, 30, 45, 63, 13, 26, 98, 1001, 77, 20, 24, 28, 36, 44, 52, 56, 84, 132, 144, 364, 572, 1092, 1456, 2184, 4004, 5096, 5120, 4732, 3432};
     for (int n : direct) bad += check_direct(n);
     const int cases[][2] = {{20, 9}, {24, 7}, {28, 0}, {144, 31}, {36, 17}, {1616, 399}, {5136, 1279}, {5132, 1279},

@@ -343,10 +343,10 @@ fourier_dir_kernel(const PairMeta* __restrict__ meta, const int2* __restrict__ b
         finish_pair_and_push(pair, (nf + pm.F - 1) / pm.F, pair_done, nleg, meta, nf, fb, fb_rowoff, nlat0, owner, dst, me);
 }
 
-// ---- direct mode (mode 3): rows whose length is 13-smooth need no chirp-z ----
+// ---- direct mode (mode 3): rows whose length has no prime factor above 23 need no chirp-z ----
 // x_i + i y_i = sum_{|m| <= L} Z_m e^{2 pi i m i / n} is ONE unnormalised inverse DFT of length n with Z_m stored at
 // frequency m mod n (2L < n: no overlap), instead of two transforms of length M >= n + 2L and three pointwise products.
-// The transforms are the same shared-memory passes (fft_core.cuh), with radices 7, 11 and 13 next to 2..16; the
+// The transforms are the same shared-memory passes (fft_core.cuh), with the prime radices 7 .. 23 next to 2 .. 16; the
 // digit-reversed slot of every frequency comes from a table built with the plan (dif_output_position).
 __global__ void __launch_bounds__(kFftThreads)
 direct_tables_kernel(const PairMeta* __restrict__ cls, double2* __restrict__ chirp, double2* __restrict__ twid) {

@@ -909,7 +909,7 @@ int build_fft_tables(Plan& p) {
     // (the kernels keep exchange-buffer row indices as 32-bit integers)
     const bool use_v2 = env_int("SPTRANS_FFT_V2", 1) != 0 && all_even && g.fb_rowoff.back() < 2147483647LL;
     const int v2_min_need = env_int("SPTRANS_FFT2_MIN", 1281);
-    // direct transforms (no chirp-z) of the rows whose length is 13-smooth; SPTRANS_FFT_DIRECT=0 sends every row through
+    // direct transforms (no chirp-z) of the rows whose length has no prime factor above 23; SPTRANS_FFT_DIRECT=0 sends every row through
     // the chirp-z kernels, and so does the test knob SPTRANS_FFT_MAXM unless SPTRANS_FFT_DIRECT=1 is set with it
     const bool use_direct = env_int("SPTRANS_FFT_DIRECT", std::getenv("SPTRANS_FFT_MAXM") ? 0 : 1) != 0;
     for (int j = 0; j < nleg; ++j) {

@@ -191,7 +191,7 @@ static int check_g(int n, int L) {
     return (err_inv / nrm < 1e-12 && err_fwd / nrm2 < 1e-12) ? 0 : 1;
 }
 
-// ---- direct transforms of 13-smooth lengths (no chirp-z): forward leaves frequency k at dif_output_position(k), the
+// ---- direct transforms of lengths without prime factors above 23 (no chirp-z): forward leaves frequency k at dif_output_position(k), the
 // inverse takes its input in that order.  n need not be a multiple of 8: the buffer has swz_len(n) slots. ----
 static int check_direct(int n) {
     const ScheduleG sc = make_schedule_g(n);

@@ -28,3 +28,15 @@ def test_fft2_kernel_bodies_under_thread_emulation():
         r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
         assert r.returncode == 0, r.stdout
         assert "ALL OK" in r.stdout
+
+
+def test_push_work_queue_protocol_on_host_threads():
+    """The work queue through which the blocks of the sharded direct Fourier stage share the shipping of completed latitude
+    pairs (finish_pair_and_push, fourier.cu), modelled with std::atomic on a thread pool: every chunk shipped exactly once."""
+    src = os.path.join(REPO, "tests", "cpu", "test_push_queue.cc")
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "t3")
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-o", exe, src], check=True)
+        r = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout
+        assert "ALL OK" in r.stdout
